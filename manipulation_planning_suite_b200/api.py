@@ -1,0 +1,344 @@
+"""Thin Python binding over the C ABI (include/mps_b200.h) used by tests, bench.py and the
+multi-GPU driver.  Class and method names follow the reference's seams:
+
+  Context.propagate      <- SimEnvStatePropagator::propagate   (ompl/control/SimEnvStatePropagator.cpp:42-118)
+  Context.extend         <- NaiveControlSampler::sampleTo / HybridActionRRT::extend K-loop
+                            (ompl/control/NaiveControlSampler.cpp:34-71, pushing/algorithm/RRT.cpp:449-489)
+  Context.is_valid       <- SimEnvValidityChecker::isValid     (ompl/state/SimEnvState.cpp:1441-1462)
+  NearestNeighbors       <- ompl::NearestNeighbors<MotionPtr> as used by RearrangementRRT
+                            (pushing/algorithm/RRT.cpp:46-51,202,239): add / nearest / clear / size
+
+Every call goes to libmps_b200.so; nothing here computes.  Errors raise MpsError with the
+library's message; a missing library or device is a hard error (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+
+
+class MpsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mps error {code}: {msg}")
+        self.code = code
+
+
+def _fp(a: np.ndarray | None, t=C.c_float):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f32(a, shape=None) -> np.ndarray | None:
+    if a is None:
+        return None
+    out = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        out = out.reshape(shape)
+    return out
+
+
+@dataclass
+class ExtendResult:
+    k: int               # winning rollout (global index) or -1
+    n_ok: int
+    goal_step: int
+    tree_index: int
+    distance: float
+    best_states: np.ndarray    # [L, 3B]
+    best_controls: np.ndarray  # [L, 5]
+    best_flags: np.ndarray     # [L]
+    all_states: np.ndarray | None = None   # [K, L, 3B]
+    all_rest: np.ndarray | None = None     # [K, L]
+    all_flags: np.ndarray | None = None    # [K, L]
+    all_dist: np.ndarray | None = None     # [K]
+    all_steps: np.ndarray | None = None    # [K, L]
+
+
+class Context:
+    """One planner instance on one device (struct mps_ctx)."""
+
+    def __init__(self, scene: abi.Scene, device: int = 0, stream: int | None = None):
+        self.lib = abi.load_library()
+        self.scene = scene
+        self.B = int(scene.n_bodies)
+        h = C.c_void_p()
+        if stream is None:
+            rc = self.lib.mps_ctx_create(C.byref(scene), device, C.byref(h))
+        else:
+            rc = self.lib.mps_ctx_create_on_stream(C.byref(scene), device, C.c_void_p(stream), C.byref(h))
+        if rc != abi.MPS_OK:
+            raise MpsError(rc, (self.lib.mps_last_error(None) or b"").decode())
+        self.h = h
+        self._keep = None  # arrays referenced by an uploaded extend
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mps_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != abi.MPS_OK:
+            raise MpsError(rc, (self.lib.mps_last_error(self.h) or b"").decode())
+
+    def synchronize(self):
+        self._check(self.lib.mps_ctx_synchronize(self.h))
+
+    # ---- propagation ----------------------------------------------------
+    def _extend_in(self, start, controls, n_ctrl=None, dest=None, weights=None, mask=None, compare_f32=False,
+                   goals=None, k_offset=0, ball_center=None, ball_radius=0.0, append_to_tree=False, parent=-1):
+        B = self.B
+        controls = _f32(controls)
+        if controls.ndim == 2:
+            controls = controls[:, None, :]
+        K, L, five = controls.shape
+        assert five == abi.MPS_CONTROL_DIM
+        start = _f32(start, (3 * B,))
+        dest = _f32(dest, (3 * B,))
+        weights = _f32(weights, (B,))
+        ball_center = _f32(ball_center, (3 * B,))
+        n_ctrl_a = None if n_ctrl is None else np.ascontiguousarray(n_ctrl, dtype=np.int32).reshape(K)
+        garr = None
+        ng = 0
+        if goals:
+            ng = len(goals)
+            garr = (abi.Goal * ng)()
+            for i, g in enumerate(goals):
+                garr[i].body, garr[i].x, garr[i].y, garr[i].tol = int(g[0]), float(g[1]), float(g[2]), float(g[3])
+        ein = abi.ExtendIn()
+        ein.start = _fp(start)
+        ein.controls = _fp(controls)
+        ein.n_ctrl = _fp(n_ctrl_a, C.c_int32)
+        ein.K, ein.L = K, L
+        ein.dest = _fp(dest)
+        ein.weights = _fp(weights)
+        full = (1 << B) - 1 if B < 32 else 0xFFFFFFFF
+        ein.mask = full if mask is None else int(mask)
+        ein.compare_f32 = 1 if compare_f32 else 0
+        ein.goals = garr if garr is not None else None
+        ein.n_goals = ng
+        ein.k_offset = int(k_offset)
+        ein.ball_center = _fp(ball_center)
+        ein.ball_radius = float(ball_radius)
+        ein.append_to_tree = 1 if append_to_tree else 0
+        ein.parent = int(parent)
+        keep = (start, controls, n_ctrl_a, dest, weights, ball_center, garr)
+        return ein, keep, K, L
+
+    def _extend_out(self, K, L, dump):
+        B = self.B
+        best = abi.ExtendBest()
+        res = dict(
+            best=best,
+            best_states=np.zeros((L, 3 * B), np.float32),
+            best_controls=np.zeros((L, 5), np.float32),
+            best_flags=np.zeros(L, np.uint32),
+        )
+        eout = abi.ExtendOut()
+        eout.best = C.pointer(best)
+        eout.best_states = _fp(res["best_states"])
+        eout.best_controls = _fp(res["best_controls"])
+        eout.best_flags = _fp(res["best_flags"], C.c_uint32)
+        if dump:
+            res["all_states"] = np.zeros((K, L, 3 * B), np.float32)
+            res["all_rest"] = np.zeros((K, L), np.float32)
+            res["all_flags"] = np.zeros((K, L), np.uint32)
+            res["all_dist"] = np.zeros(K, np.float64)
+            res["all_steps"] = np.zeros((K, L), np.int32)
+            eout.all_states = _fp(res["all_states"])
+            eout.all_rest = _fp(res["all_rest"])
+            eout.all_flags = _fp(res["all_flags"], C.c_uint32)
+            eout.all_dist = _fp(res["all_dist"], C.c_double)
+            eout.all_steps = _fp(res["all_steps"], C.c_int32)
+        return eout, res
+
+    @staticmethod
+    def _result(res) -> ExtendResult:
+        b = res["best"]
+        return ExtendResult(
+            k=b.k, n_ok=b.n_ok, goal_step=b.goal_step, tree_index=b.tree_index, distance=b.distance,
+            best_states=res["best_states"], best_controls=res["best_controls"], best_flags=res["best_flags"],
+            all_states=res.get("all_states"), all_rest=res.get("all_rest"), all_flags=res.get("all_flags"),
+            all_dist=res.get("all_dist"), all_steps=res.get("all_steps"),
+        )
+
+    def extend(self, start, controls, dump=False, **kw) -> ExtendResult:
+        """K rollout chains from `start`, best-of by distance to `dest` (host buffers, synchronous)."""
+        ein, keep, K, L = self._extend_in(start, controls, **kw)
+        eout, res = self._extend_out(K, L, dump)
+        self._check(self.lib.mps_extend(self.h, C.byref(ein), C.byref(eout)))
+        del keep
+        return self._result(res)
+
+    def extend_upload(self, start, controls, **kw):
+        ein, keep, K, L = self._extend_in(start, controls, **kw)
+        self._check(self.lib.mps_extend_upload(self.h, C.byref(ein)))
+        self._ext_shape = (K, L)
+
+    def extend_launch(self):
+        self._check(self.lib.mps_extend_launch(self.h))
+
+    def extend_fetch(self, dump=False) -> ExtendResult:
+        K, L = self._ext_shape
+        eout, res = self._extend_out(K, L, dump)
+        self._check(self.lib.mps_extend_fetch(self.h, C.byref(eout)))
+        return self._result(res)
+
+    def propagate(self, state, control):
+        """bool propagate(state, control /*rest time mutated*/, result). Returns (ok, result, control, flags)."""
+        B = self.B
+        s = _f32(state, (3 * B,)).copy()
+        c = _f32(control, (5,)).copy()
+        out = np.zeros(3 * B, np.float32)
+        ok = C.c_int32(0)
+        fl = C.c_uint32(0)
+        self._check(self.lib.mps_propagate(self.h, _fp(s), _fp(c), _fp(out), C.byref(ok), C.byref(fl)))
+        return bool(ok.value), out, c, int(fl.value)
+
+    def counters(self) -> dict:
+        arr = (C.c_uint64 * 8)()
+        self._check(self.lib.mps_extend_counters(self.h, arr))
+        return dict(steps=arr[0], candidates=arr[1], touching=arr[2], colour_passes=arr[3], launches=arr[4])
+
+    def time_launches(self, what: int, iters: int) -> float:
+        ms = C.c_float(0)
+        self._check(self.lib.mps_time_launches(self.h, what, iters, C.byref(ms)))
+        return float(ms.value)
+
+    # ---- validity -------------------------------------------------------
+    def is_valid(self, states):
+        st = _f32(states).reshape(-1, 3 * self.B)
+        n = st.shape[0]
+        valid = np.zeros(n, np.uint8)
+        flags = np.zeros(n, np.uint32)
+        self._check(self.lib.mps_is_valid_batch(self.h, _fp(st), n, _fp(valid, C.c_uint8), _fp(flags, C.c_uint32)))
+        return valid.astype(bool), flags
+
+    # ---- distance helpers (host, double) ----------------------------------
+    def distance(self, a, b, weights=None, mask=None) -> float:
+        B = self.B
+        out = C.c_double(0)
+        full = (1 << B) - 1 if B < 32 else 0xFFFFFFFF
+        w = _f32(weights, (B,))
+        rc = self.lib.mps_distance(C.byref(self.scene), _fp(_f32(a, (3 * B,))), _fp(_f32(b, (3 * B,))), _fp(w),
+                                   full if mask is None else int(mask), C.byref(out))
+        self._check(rc)
+        return out.value
+
+
+class NearestNeighbors:
+    """Device-resident tree with exact weighted nearest-neighbour queries.
+
+    Mirrors the subset of ompl::NearestNeighbors<MotionPtr> the reference uses
+    (pushing/algorithm/RRT.cpp:46-51, 202, 239, 757; algorithm/Interfaces.cpp:97-100):
+    add, nearest, clear, size — plus parent / control / slice bookkeeping of Motion
+    (ompl/planning/Essentials.cpp:20-93).  Ties resolve to the lowest index.
+    """
+
+    def __init__(self, ctx: Context, capacity: int = 0):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        if capacity:
+            ctx._check(self.lib.mps_tree_reserve(ctx.h, capacity))
+
+    def clear(self):
+        self.ctx._check(self.lib.mps_tree_clear(self.ctx.h))
+
+    def size(self) -> int:
+        n = C.c_int64(0)
+        self.ctx._check(self.lib.mps_tree_size(self.ctx.h, C.byref(n)))
+        return n.value
+
+    def add(self, state, parent: int = -1, control=None, slice_id: int = -1) -> int:
+        idx = C.c_int64(0)
+        s = _f32(state, (3 * self.ctx.B,))
+        c = _f32(control, (5,))
+        self.ctx._check(self.lib.mps_tree_add(self.ctx.h, _fp(s), parent, _fp(c), slice_id, C.byref(idx)))
+        return idx.value
+
+    def add_batch(self, states, parents=None, controls=None, slice_ids=None) -> int:
+        st = _f32(states).reshape(-1, 3 * self.ctx.B)
+        n = st.shape[0]
+        pa = None if parents is None else np.ascontiguousarray(parents, np.int32)
+        co = None if controls is None else _f32(controls).reshape(n, 5)
+        sl = None if slice_ids is None else np.ascontiguousarray(slice_ids, np.int32)
+        first = C.c_int64(0)
+        self.ctx._check(self.lib.mps_tree_add_batch(self.ctx.h, _fp(st), _fp(pa, C.c_int32), _fp(co),
+                                                    _fp(sl, C.c_int32), n, C.byref(first)))
+        return first.value
+
+    def nearest(self, query, weights=None, mask=None, slice_filter: int = -1):
+        B = self.ctx.B
+        full = (1 << B) - 1 if B < 32 else 0xFFFFFFFF
+        idx = C.c_int64(-1)
+        d = C.c_double(0)
+        q = _f32(query, (3 * B,))
+        w = _f32(weights, (B,))
+        self.ctx._check(self.lib.mps_tree_nearest(self.ctx.h, _fp(q), _fp(w), full if mask is None else int(mask),
+                                                  slice_filter, C.byref(idx), C.byref(d)))
+        return idx.value, d.value
+
+    def nearest_batch(self, queries, weights=None, masks=None, slice_filters=None):
+        B = self.ctx.B
+        qs = _f32(queries).reshape(-1, 3 * B)
+        Q = qs.shape[0]
+        w = _f32(weights, (B,))
+        m = None if masks is None else np.ascontiguousarray(masks, np.uint32)
+        f = None if slice_filters is None else np.ascontiguousarray(slice_filters, np.int32)
+        idx = np.zeros(Q, np.int64)
+        d = np.zeros(Q, np.float64)
+        self.ctx._check(self.lib.mps_tree_nearest_batch(self.ctx.h, _fp(qs), Q, _fp(w), _fp(m, C.c_uint32),
+                                                        _fp(f, C.c_int32), _fp(idx, C.c_int64), _fp(d, C.c_double)))
+        return idx, d
+
+    def nearest_upload(self, queries, weights=None, masks=None, slice_filters=None):
+        B = self.ctx.B
+        qs = _f32(queries).reshape(-1, 3 * B)
+        self._Q = qs.shape[0]
+        w = _f32(weights, (B,))
+        m = None if masks is None else np.ascontiguousarray(masks, np.uint32)
+        f = None if slice_filters is None else np.ascontiguousarray(slice_filters, np.int32)
+        self.ctx._check(self.lib.mps_tree_nearest_upload(self.ctx.h, _fp(qs), self._Q, _fp(w), _fp(m, C.c_uint32),
+                                                         _fp(f, C.c_int32)))
+
+    def nearest_launch(self):
+        self.ctx._check(self.lib.mps_tree_nearest_launch(self.ctx.h))
+
+    def nearest_fetch(self):
+        idx = np.zeros(self._Q, np.int64)
+        d = np.zeros(self._Q, np.float64)
+        self.ctx._check(self.lib.mps_tree_nearest_fetch(self.ctx.h, _fp(idx, C.c_int64), _fp(d, C.c_double)))
+        return idx, d
+
+    def get(self, index: int):
+        B = self.ctx.B
+        s = np.zeros(3 * B, np.float32)
+        c = np.zeros(5, np.float32)
+        p = C.c_int32(0)
+        sl = C.c_int32(0)
+        self.ctx._check(self.lib.mps_tree_get(self.ctx.h, index, _fp(s), C.byref(p), _fp(c), C.byref(sl)))
+        return s, p.value, c, sl.value
+
+    def backtrack(self, index: int, max_len: int = 1 << 20) -> np.ndarray:
+        buf = np.zeros(min(max_len, max(self.size(), 1)), np.int64)
+        n = C.c_int64(0)
+        self.ctx._check(self.lib.mps_tree_backtrack(self.ctx.h, index, _fp(buf, C.c_int64), len(buf), C.byref(n)))
+        return buf[: n.value].copy()
+
+    def fill_random(self, n: int, seed: int, n_slices: int = 0):
+        self.ctx._check(self.lib.mps_tree_fill_random(self.ctx.h, n, seed, n_slices))
+
+    def read_states(self, first: int, n: int) -> np.ndarray:
+        out = np.zeros((n, 3 * self.ctx.B), np.float32)
+        self.ctx._check(self.lib.mps_tree_read_states(self.ctx.h, first, n, _fp(out)))
+        return out

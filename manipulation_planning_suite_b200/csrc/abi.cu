@@ -1,0 +1,1003 @@
+// abi.cu — the extern "C" surface of libmps_b200.so (include/mps_b200.h): context, buffers,
+// host<->device staging and kernel launches.  No arithmetic of the hot path lives here except the
+// two host helpers mps_distance / mps_goal_distance (the reference's double expressions).
+//
+// No CPU fallback: every entry point that needs a device fails with MPS_ERR_NO_DEVICE / MPS_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mps_device.cuh"
+#include "nn_scan.h"
+#include "rollout.h"
+
+namespace {
+thread_local std::string g_last_error;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct mps_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    mps_scene scene;
+    DevScene hscene;
+    DevScene* d_scene = nullptr;
+    size_t scene_bytes = 0, warp_bytes = 0;
+    std::string err;
+    unsigned long long launches = 0;
+
+    // extend: device buffers
+    DevBuf d_start, d_controls, d_nctrl, d_dest, d_weights, d_goals, d_ball;
+    DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
+    DevBuf d_best, d_best_states, d_best_controls, d_best_flags;
+    DevBuf d_work, d_counters;
+    // pinned staging
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    RolloutParams rp;
+    SelectParams sp;
+    bool extend_ready = false;
+    int ext_K = 0, ext_L = 0;
+
+    // tree
+    TreeView tree;
+    long long tree_n = 0;      // host mirror of the node count
+    long long tree_upper = 0;  // upper bound including un-fetched device-side appends
+    DevBuf d_tree_size;
+    DevBuf d_tstage_states, d_tstage_parents, d_tstage_controls, d_tstage_slices;
+
+    // nn
+    DevBuf d_queries, d_masks, d_filters, d_nnw, d_out_idx, d_out_dist, d_part_d, d_part_i, d_tickets;
+    NNParams np;
+    bool nn_ready = false;
+    int nn_Q = 0;
+
+    // validity
+    DevBuf d_vstates, d_valid, d_vflags;
+};
+
+static int mps_fail(mps_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+static int mps_fail_cuda(mps_ctx* ctx, cudaError_t e, const char* expr, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at abi.cu:%d: %s", (int)e, cudaGetErrorString(e), line, expr);
+    return mps_fail(ctx, e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MPS_ERR_NO_DEVICE : MPS_ERR_CUDA,
+                    buf);
+}
+
+static int ensure(mps_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.bytes >= bytes) return MPS_OK;
+    if (b.p) {
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaFree(b.p), ctx);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 2;
+    MPS_CUDA_CHECK(cudaMalloc(&b.p, want), ctx);
+    b.bytes = want;
+    return MPS_OK;
+}
+
+static int ensure_stage(mps_ctx* ctx, size_t bytes)
+{
+    if (ctx->h_stage_bytes >= bytes) return MPS_OK;
+    if (ctx->h_stage) {
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaFreeHost(ctx->h_stage), ctx);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_bytes = 0;
+    }
+    size_t want = bytes * 2 + 4096;
+    MPS_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, want), ctx);
+    ctx->h_stage_bytes = want;
+    return MPS_OK;
+}
+
+static void free_buf(DevBuf& b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- scene ------------------------------------------------------------------
+
+static float bounding_radius(int shape, float hx, float hy)
+{
+    if (shape == MPS_SHAPE_DISC) return hx;
+    return sqrtf(hx * hx + hy * hy);
+}
+
+static int validate_scene(const mps_scene* sc, std::string& why)
+{
+    if (!sc) { why = "scene is NULL"; return 0; }
+    if (sc->n_bodies < 2 || sc->n_bodies > MPS_MAX_BODIES) { why = "n_bodies must be in [2, 32]"; return 0; }
+    if (sc->n_statics < 0 || sc->n_statics > MPS_MAX_STATICS) { why = "n_statics must be in [0, 16]"; return 0; }
+    if (sc->robot_id < 0 || sc->robot_id >= sc->n_bodies) { why = "robot_id out of range"; return 0; }
+    if (sc->vel_iters < 1 || sc->vel_iters > 64) { why = "vel_iters must be in [1, 64]"; return 0; }
+    if (!(sc->dt > 0.0f)) { why = "dt must be > 0"; return 0; }
+    if (sc->max_manifolds < 1 || sc->max_manifolds > MPS_MAX_MANIFOLDS) { why = "max_manifolds must be in [1, 64]"; return 0; }
+    for (int i = 0; i < sc->n_bodies; ++i) {
+        if (sc->shape[i] != MPS_SHAPE_BOX && sc->shape[i] != MPS_SHAPE_DISC) { why = "unknown body shape"; return 0; }
+        if (!(sc->hx[i] > 0.0f)) { why = "body half extent must be > 0"; return 0; }
+        if (sc->shape[i] == MPS_SHAPE_BOX && !(sc->hy[i] > 0.0f)) { why = "box hy must be > 0"; return 0; }
+        if (i != sc->robot_id && (!(sc->mass[i] > 0.0f) || !(sc->inertia[i] > 0.0f))) { why = "mass/inertia must be > 0"; return 0; }
+    }
+    for (int i = 0; i < sc->n_statics; ++i) {
+        if (sc->s_shape[i] != MPS_SHAPE_BOX && sc->s_shape[i] != MPS_SHAPE_DISC) { why = "unknown static shape"; return 0; }
+        if (!(sc->s_hx[i] > 0.0f)) { why = "static half extent must be > 0"; return 0; }
+    }
+    for (int i = 0; i < 3; ++i)
+        if (!(sc->accel_limits[i] > 0.0f)) { why = "accel_limits must be > 0"; return 0; }
+    return 1;
+}
+
+// derived constants, same operation order as the physics spec
+static void derive_scene(const mps_scene* sc, DevScene* d)
+{
+    memset(d, 0, sizeof(*d));
+    const int B = sc->n_bodies, S = sc->n_statics;
+    d->B = B;
+    d->S = S;
+    d->robot = sc->robot_id;
+    d->vel_iters = sc->vel_iters;
+    d->Mcap = sc->max_manifolds;
+    d->strict = sc->strict_active_contacts;
+    d->slot_stride = (int)align_up((size_t)(B + S), 4);
+    d->dt = sc->dt;
+    d->t_max = sc->t_max;
+    d->slop = sc->slop;
+    d->beta_dt = sc->baumgarte * (1.0f / sc->dt);
+    d->max_bias = sc->max_bias_vel;
+    d->pen_max = sc->pen_max;
+    d->v_rest2 = sc->v_rest * sc->v_rest;
+    d->w_rest = sc->w_rest;
+    d->ref_tol = 0.1f * sc->slop;
+    d->x_min = sc->x_min;
+    d->x_max = sc->x_max;
+    d->y_min = sc->y_min;
+    d->y_max = sc->y_max;
+    for (int i = 0; i < 3; ++i) d->accel[i] = sc->accel_limits[i];
+    d->static_forbidden = sc->static_forbidden;
+    d->pw = sc->position_weight;
+    d->ow = sc->orientation_weight;
+    for (int i = 0; i < B; ++i) {
+        d->shape[i] = sc->shape[i];
+        d->hx[i] = sc->hx[i];
+        d->hy[i] = sc->hy[i];
+        d->brad[i] = bounding_radius(sc->shape[i], sc->hx[i], sc->hy[i]);
+        d->mass[i] = sc->mass[i];
+        d->inertia[i] = sc->inertia[i];
+        d->mu_c[i] = sc->mu_contact[i];
+        d->pair_forbidden[i] = sc->pair_forbidden[i];
+        if (i == sc->robot_id) {
+            d->inv_m[i] = 0.0f;
+            d->inv_i[i] = 0.0f;
+            d->lin_cap[i] = 0.0f;
+            d->ang_cap[i] = 0.0f;
+        } else {
+            float mg = sc->mass[i] * sc->gravity;
+            float f = sc->mu_ground[i] * mg;
+            d->inv_m[i] = 1.0f / sc->mass[i];
+            d->inv_i[i] = 1.0f / sc->inertia[i];
+            d->lin_cap[i] = sc->dt * f;
+            d->ang_cap[i] = sc->dt * (f * sc->fr_radius[i]);
+        }
+    }
+    for (int k = 0; k < S; ++k) {
+        d->s_shape[k] = sc->s_shape[k];
+        d->s_x[k] = sc->s_x[k];
+        d->s_y[k] = sc->s_y[k];
+        mps_sincos(sc->s_theta[k], &d->s_s[k], &d->s_c[k]);
+        d->s_hx[k] = sc->s_hx[k];
+        d->s_hy[k] = sc->s_hy[k];
+        d->s_brad[k] = bounding_radius(sc->s_shape[k], sc->s_hx[k], sc->s_hy[k]);
+        d->s_mu[k] = sc->s_mu_contact[k];
+    }
+    int P = 0;
+    for (int i = 0; i < B; ++i)
+        for (int j = i + 1; j < B; ++j) d->pairs[P++] = (uint16_t)(i | (j << 8));
+    for (int i = 0; i < B; ++i)
+        for (int k = 0; k < S; ++k) d->pairs[P++] = (uint16_t)(i | ((B + k) << 8));
+    d->P = P;
+}
+
+extern "C" {
+
+int mps_abi_version(void) { return MPS_ABI_VERSION; }
+
+const char* mps_last_error(const mps_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int mps_device_count(int* count)
+{
+    if (!count) return mps_fail(nullptr, MPS_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return mps_fail_cuda(nullptr, e, "cudaGetDeviceCount", __LINE__);
+    }
+    *count = n;
+    return MPS_OK;
+}
+
+void mps_scene_defaults(mps_scene* sc)
+{
+    if (!sc) return;
+    memset(sc, 0, sizeof(*sc));
+    sc->vel_iters = 8;
+    for (int i = 0; i < MPS_MAX_BODIES; ++i) {
+        sc->shape[i] = MPS_SHAPE_BOX;
+        sc->hx[i] = 0.06f;
+        sc->hy[i] = 0.06f;
+        sc->mass[i] = 0.35f;     // magnitudes the reference mentions: LearnedOracle.cpp:314-318
+        sc->inertia[i] = 0.002f;
+        sc->mu_ground[i] = 0.19f;
+        sc->fr_radius[i] = 0.0459f;
+        sc->mu_contact[i] = 0.3f;
+    }
+    for (int i = 0; i < MPS_MAX_STATICS; ++i) {
+        sc->s_shape[i] = MPS_SHAPE_BOX;
+        sc->s_hx[i] = 0.05f;
+        sc->s_hy[i] = 0.05f;
+        sc->s_mu_contact[i] = 0.3f;
+    }
+    // workspace bounds default to +-FLT_MAX (OraclePushPlanner.cpp:61-66)
+    sc->x_min = -FLT_MAX;
+    sc->x_max = FLT_MAX;
+    sc->y_min = -FLT_MAX;
+    sc->y_max = FLT_MAX;
+    sc->accel_limits[0] = 2.0f;
+    sc->accel_limits[1] = 2.0f;
+    sc->accel_limits[2] = 4.0f;
+    sc->position_weight = 1.0;     // SimEnvState.h:224-231
+    sc->orientation_weight = 0.08;
+    sc->dt = 0.01f;
+    sc->t_max = 8.0f;              // SimEnvStatePropagator.h:31, OraclePushPlanner.cpp:52
+    sc->gravity = 9.81f;
+    sc->slop = 0.002f;
+    sc->baumgarte = 0.2f;
+    sc->max_bias_vel = 0.5f;
+    sc->pen_max = 0.01f;
+    sc->v_rest = 0.001f;
+    sc->w_rest = 0.01f;
+    sc->max_manifolds = MPS_MAX_MANIFOLDS;
+    sc->strict_active_contacts = 0;
+}
+
+int mps_ctx_create_on_stream(const mps_scene* scene, int device, void* cuda_stream, mps_ctx** out)
+{
+    if (!out) return mps_fail(nullptr, MPS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    std::string why;
+    if (!validate_scene(scene, why)) return mps_fail(nullptr, MPS_ERR_ARG, "invalid scene: " + why);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return mps_fail(nullptr, MPS_ERR_NO_DEVICE,
+                        "no CUDA device: the extend step has no CPU fallback (cudaGetDeviceCount: " +
+                            std::string(cudaGetErrorString(e)) + ")");
+    if (device < 0 || device >= n) return mps_fail(nullptr, MPS_ERR_ARG, "device index out of range");
+    mps_ctx* ctx = new mps_ctx();
+    ctx->device = device;
+    ctx->scene = *scene;
+    derive_scene(scene, &ctx->hscene);
+    int rc = MPS_OK;
+    do {
+        if ((e = cudaSetDevice(device)) != cudaSuccess) { rc = mps_fail_cuda(nullptr, e, "cudaSetDevice", __LINE__); break; }
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { rc = mps_fail_cuda(nullptr, e, "cudaGetDeviceProperties", __LINE__); break; }
+        if (prop.major < 10) {
+            rc = mps_fail(nullptr, MPS_ERR_NO_DEVICE, "device is not sm_100: libmps_b200 ships sm_100a code only");
+            break;
+        }
+        ctx->num_sms = prop.multiProcessorCount;
+        if (cuda_stream) {
+            ctx->stream = (cudaStream_t)cuda_stream;
+            ctx->own_stream = false;
+        } else {
+            if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = mps_fail_cuda(nullptr, e, "cudaStreamCreate", __LINE__); break; }
+            ctx->own_stream = true;
+        }
+        if ((e = cudaMalloc(&ctx->d_scene, sizeof(DevScene))) != cudaSuccess) { rc = mps_fail_cuda(nullptr, e, "cudaMalloc scene", __LINE__); break; }
+        if ((e = cudaMemcpy(ctx->d_scene, &ctx->hscene, sizeof(DevScene), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = mps_fail_cuda(nullptr, e, "cudaMemcpy scene", __LINE__); break; }
+        ctx->scene_bytes = mps_rollout_scene_bytes();
+        ctx->warp_bytes = mps_rollout_warp_bytes(ctx->hscene);
+        memset(&ctx->tree, 0, sizeof(ctx->tree));
+        ctx->tree.B = scene->n_bodies;
+    } while (0);
+    if (rc != MPS_OK) {
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return MPS_OK;
+}
+
+int mps_ctx_create(const mps_scene* scene, int device, mps_ctx** out)
+{
+    return mps_ctx_create_on_stream(scene, device, nullptr, out);
+}
+
+void mps_ctx_destroy(mps_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_start, &ctx->d_controls, &ctx->d_nctrl, &ctx->d_dest, &ctx->d_weights, &ctx->d_goals,
+                      &ctx->d_ball, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
+                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_best, &ctx->d_best_states, &ctx->d_best_controls,
+                      &ctx->d_best_flags, &ctx->d_work, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
+                      &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
+                      &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_out_idx, &ctx->d_out_dist, &ctx->d_part_d,
+                      &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags};
+    for (DevBuf* b : bufs) free_buf(*b);
+    if (ctx->tree.states) cudaFree(ctx->tree.states);
+    if (ctx->tree.controls) cudaFree(ctx->tree.controls);
+    if (ctx->tree.parent) cudaFree(ctx->tree.parent);
+    if (ctx->tree.slice) cudaFree(ctx->tree.slice);
+    if (ctx->d_scene) cudaFree(ctx->d_scene);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mps_ctx_synchronize(mps_ctx* ctx)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+int mps_ctx_scene(const mps_ctx* ctx, mps_scene* out)
+{
+    if (!ctx || !out) return mps_fail(nullptr, MPS_ERR_ARG, "NULL argument");
+    *out = ctx->scene;
+    return MPS_OK;
+}
+
+// ---- host helpers: the reference's double expressions --------------------------------------------
+
+int mps_distance(const mps_scene* sc, const float* a, const float* b, const float* weights, uint32_t mask, double* out)
+{
+    if (!sc || !a || !b || !out) return mps_fail(nullptr, MPS_ERR_ARG, "NULL argument");
+    double dist = 0.0;
+    for (int i = 0; i < sc->n_bodies; ++i) {
+        if ((mask >> i) & 1u) {
+            double cfg = mps_body_distance(a[3 * i], a[3 * i + 1], a[3 * i + 2], b[3 * i], b[3 * i + 1], b[3 * i + 2],
+                                           sc->position_weight, sc->orientation_weight);
+            double w = weights ? (double)weights[i] : 1.0;
+            dist += w * cfg;
+        }
+    }
+    *out = dist;
+    return MPS_OK;
+}
+
+int mps_goal_distance(const mps_scene* sc, const float* state, const mps_goal* goals, int32_t n_goals, double* out)
+{
+    if (!sc || !state || !out || (n_goals > 0 && !goals)) return mps_fail(nullptr, MPS_ERR_ARG, "NULL argument");
+    double distance = 0.0;
+    for (int g = 0; g < n_goals; ++g) {
+        if (goals[g].body < 0 || goals[g].body >= sc->n_bodies) return mps_fail(nullptr, MPS_ERR_ARG, "goal body out of range");
+        float fx = goals[g].x - state[3 * goals[g].body];
+        float fy = goals[g].y - state[3 * goals[g].body + 1];
+        double dc = sqrt((double)fx * (double)fx + (double)fy * (double)fy);
+        double e = dc - (double)goals[g].tol;
+        distance += e > 0.0 ? e : 0.0;
+    }
+    *out = distance;
+    return MPS_OK;
+}
+
+// ---- tree ---------------------------------------------------------------------------------------
+
+static int tree_alloc(mps_ctx* ctx, TreeView& t, size_t cap)
+{
+    const int B = ctx->scene.n_bodies;
+    memset(&t, 0, sizeof(t));
+    t.B = B;
+    t.cap = cap;
+    MPS_CUDA_CHECK(cudaMalloc(&t.states, sizeof(float) * 3 * B * cap), ctx);
+    MPS_CUDA_CHECK(cudaMalloc(&t.controls, sizeof(float) * MPS_CONTROL_DIM * cap), ctx);
+    MPS_CUDA_CHECK(cudaMalloc(&t.parent, sizeof(int32_t) * cap), ctx);
+    MPS_CUDA_CHECK(cudaMalloc(&t.slice, sizeof(int32_t) * cap), ctx);
+    return MPS_OK;
+}
+
+static int tree_ensure(mps_ctx* ctx, long long need)
+{
+    if (need < 0) return mps_fail(ctx, MPS_ERR_ARG, "negative tree capacity");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    int rc = ensure(ctx, ctx->d_tree_size, sizeof(long long));
+    if (rc) return rc;
+    if (!ctx->tree.states) MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_tree_size.p, 0, sizeof(long long), ctx->stream), ctx);
+    if ((size_t)need <= ctx->tree.cap && ctx->tree.states) return MPS_OK;
+    size_t cap = ctx->tree.cap ? ctx->tree.cap * 2 : 4096;
+    if (cap < (size_t)need) cap = (size_t)need;
+    cap = align_up(cap, 1024);
+    TreeView nt;
+    rc = tree_alloc(ctx, nt, cap);
+    if (rc) return rc;
+    if (ctx->tree.states) {
+        MPS_CUDA_CHECK(mps_launch_tree_copy(ctx->tree, nt, ctx->tree_upper, ctx->stream), ctx);
+        ctx->launches++;
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        cudaFree(ctx->tree.states);
+        cudaFree(ctx->tree.controls);
+        cudaFree(ctx->tree.parent);
+        cudaFree(ctx->tree.slice);
+    }
+    ctx->tree = nt;  // launches read the tree pointers from ctx->tree each time
+    return MPS_OK;
+}
+
+int mps_tree_reserve(mps_ctx* ctx, int64_t capacity)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    return tree_ensure(ctx, capacity);
+}
+
+int mps_tree_clear(mps_ctx* ctx)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    int rc = tree_ensure(ctx, 1);
+    if (rc) return rc;
+    ctx->tree_n = 0;
+    ctx->tree_upper = 0;
+    MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_tree_size.p, 0, sizeof(long long), ctx->stream), ctx);
+    return MPS_OK;
+}
+
+static int tree_sync_size(mps_ctx* ctx)
+{
+    if (ctx->tree_upper == ctx->tree_n) return MPS_OK;
+    long long n = 0;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(&n, ctx->d_tree_size.p, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    ctx->tree_n = n;
+    ctx->tree_upper = n;
+    return MPS_OK;
+}
+
+int mps_tree_size(mps_ctx* ctx, int64_t* n)
+{
+    if (!ctx || !n) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    if (!ctx->tree.states) {
+        *n = 0;
+        return MPS_OK;
+    }
+    int rc = tree_sync_size(ctx);
+    if (rc) return rc;
+    *n = ctx->tree_n;
+    return MPS_OK;
+}
+
+int mps_tree_add_batch(mps_ctx* ctx, const float* states, const int32_t* parents, const float* controls,
+                       const int32_t* slice_ids, int64_t n, int64_t* first_index)
+{
+    if (!ctx || !states || n < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_add_batch");
+    const int B = ctx->scene.n_bodies;
+    int rc = tree_ensure(ctx, 1);
+    if (rc) return rc;
+    if ((rc = tree_sync_size(ctx))) return rc;
+    if ((rc = tree_ensure(ctx, ctx->tree_n + n))) return rc;
+    if (n == 0) {
+        if (first_index) *first_index = ctx->tree_n;
+        return MPS_OK;
+    }
+    const size_t sb = sizeof(float) * 3 * B * (size_t)n, cb = sizeof(float) * MPS_CONTROL_DIM * (size_t)n,
+                 ib = sizeof(int32_t) * (size_t)n;
+    if ((rc = ensure(ctx, ctx->d_tstage_states, sb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tstage_controls, cb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tstage_parents, ib))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tstage_slices, ib))) return rc;
+    if ((rc = ensure_stage(ctx, sb + cb + 2 * ib))) return rc;
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);  // staging buffer reuse
+    char* h = (char*)ctx->h_stage;
+    memcpy(h, states, sb);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tstage_states.p, h, sb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    h += sb;
+    if (controls) {
+        memcpy(h, controls, cb);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tstage_controls.p, h, cb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    }
+    h += cb;
+    if (parents) {
+        memcpy(h, parents, ib);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tstage_parents.p, h, ib, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    }
+    h += ib;
+    if (slice_ids) {
+        memcpy(h, slice_ids, ib);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tstage_slices.p, h, ib, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    }
+    MPS_CUDA_CHECK(mps_launch_tree_append(ctx->tree, ctx->tree_n, n, (const float*)ctx->d_tstage_states.p,
+                                          parents ? (const int32_t*)ctx->d_tstage_parents.p : nullptr,
+                                          controls ? (const float*)ctx->d_tstage_controls.p : nullptr,
+                                          slice_ids ? (const int32_t*)ctx->d_tstage_slices.p : nullptr,
+                                          (long long*)ctx->d_tree_size.p, ctx->stream),
+                   ctx);
+    ctx->launches++;
+    if (first_index) *first_index = ctx->tree_n;
+    ctx->tree_n += n;
+    ctx->tree_upper = ctx->tree_n;
+    return MPS_OK;
+}
+
+int mps_tree_add(mps_ctx* ctx, const float* state, int32_t parent, const float* control, int32_t slice_id,
+                 int64_t* index)
+{
+    return mps_tree_add_batch(ctx, state, &parent, control, &slice_id, 1, index);
+}
+
+int mps_tree_fill_random(mps_ctx* ctx, int64_t n, uint64_t seed, int32_t n_slices)
+{
+    if (!ctx || n < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_fill_random");
+    int rc = tree_ensure(ctx, n > 0 ? n : 1);
+    if (rc) return rc;
+    float x0 = ctx->scene.x_min, x1 = ctx->scene.x_max, y0 = ctx->scene.y_min, y1 = ctx->scene.y_max;
+    if (x0 < -1e6f) x0 = -1.0f;
+    if (x1 > 1e6f) x1 = 1.0f;
+    if (y0 < -1e6f) y0 = -1.0f;
+    if (y1 > 1e6f) y1 = 1.0f;
+    MPS_CUDA_CHECK(mps_launch_tree_fill(ctx->tree, n, seed, n_slices, x0, x1, y0, y1, (long long*)ctx->d_tree_size.p,
+                                        ctx->stream),
+                   ctx);
+    ctx->launches++;
+    ctx->tree_n = n;
+    ctx->tree_upper = n;
+    return MPS_OK;
+}
+
+int mps_tree_read_states(mps_ctx* ctx, int64_t first, int64_t n, float* states)
+{
+    if (!ctx || !states || first < 0 || n < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_read_states");
+    int rc = tree_sync_size(ctx);
+    if (rc) return rc;
+    if (first + n > ctx->tree_n) return mps_fail(ctx, MPS_ERR_ARG, "range beyond the tree size");
+    if (n == 0) return MPS_OK;
+    const size_t sb = sizeof(float) * 3 * ctx->scene.n_bodies * (size_t)n;
+    if ((rc = ensure(ctx, ctx->d_tstage_states, sb))) return rc;
+    MPS_CUDA_CHECK(mps_launch_tree_gather(ctx->tree, first, n, (float*)ctx->d_tstage_states.p, ctx->stream), ctx);
+    ctx->launches++;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(states, ctx->d_tstage_states.p, sb, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+int mps_tree_get(mps_ctx* ctx, int64_t index, float* state, int32_t* parent, float* control, int32_t* slice_id)
+{
+    if (!ctx || index < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_get");
+    int rc = tree_sync_size(ctx);
+    if (rc) return rc;
+    if (index >= ctx->tree_n) return mps_fail(ctx, MPS_ERR_ARG, "tree index out of range");
+    const TreeView& t = ctx->tree;
+    if (state) {
+        MPS_CUDA_CHECK(cudaMemcpy2DAsync(state, sizeof(float), t.states + index, t.cap * sizeof(float), sizeof(float),
+                                         3 * t.B, cudaMemcpyDeviceToHost, ctx->stream),
+                       ctx);
+    }
+    if (control) {
+        MPS_CUDA_CHECK(cudaMemcpy2DAsync(control, sizeof(float), t.controls + index, t.cap * sizeof(float),
+                                         sizeof(float), MPS_CONTROL_DIM, cudaMemcpyDeviceToHost, ctx->stream),
+                       ctx);
+    }
+    if (parent) MPS_CUDA_CHECK(cudaMemcpyAsync(parent, t.parent + index, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    if (slice_id) MPS_CUDA_CHECK(cudaMemcpyAsync(slice_id, t.slice + index, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+int mps_tree_backtrack(mps_ctx* ctx, int64_t index, int64_t* indices, int64_t max_len, int64_t* len)
+{
+    if (!ctx || !indices || !len || index < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_backtrack");
+    int rc = tree_sync_size(ctx);
+    if (rc) return rc;
+    if (index >= ctx->tree_n) return mps_fail(ctx, MPS_ERR_ARG, "tree index out of range");
+    std::vector<int32_t> parents((size_t)ctx->tree_n);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(parents.data(), ctx->tree.parent, sizeof(int32_t) * (size_t)ctx->tree_n,
+                                   cudaMemcpyDeviceToHost, ctx->stream),
+                   ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    std::vector<int64_t> rev;
+    int64_t cur = index;
+    while (cur >= 0) {
+        rev.push_back(cur);
+        if ((long long)rev.size() > ctx->tree_n) return mps_fail(ctx, MPS_ERR_STATE, "parent cycle in the tree");
+        cur = parents[(size_t)cur];
+    }
+    if ((int64_t)rev.size() > max_len) {
+        *len = (int64_t)rev.size();
+        return mps_fail(ctx, MPS_ERR_CAPACITY, "path longer than max_len");
+    }
+    for (size_t i = 0; i < rev.size(); ++i) indices[i] = rev[rev.size() - 1 - i];
+    *len = (int64_t)rev.size();
+    return MPS_OK;
+}
+
+// ---- nearest neighbour ------------------------------------------------------------------------
+
+int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const float* weights,
+                            const uint32_t* masks, const int32_t* slice_filters)
+{
+    if (!ctx || !queries || Q < 1 || Q > 65535) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_nearest_upload");
+    const int B = ctx->scene.n_bodies;
+    int rc = tree_ensure(ctx, 1);
+    if (rc) return rc;
+    const size_t qb = sizeof(float) * 3 * B * (size_t)Q, mb = sizeof(uint32_t) * (size_t)Q, wb = sizeof(float) * B;
+    if ((rc = ensure(ctx, ctx->d_queries, qb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_masks, mb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_filters, mb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_nnw, wb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_out_idx, sizeof(long long) * (size_t)Q))) return rc;
+    if ((rc = ensure(ctx, ctx->d_out_dist, sizeof(double) * (size_t)Q))) return rc;
+    const int max_grid = ctx->num_sms * 4;
+    if ((rc = ensure(ctx, ctx->d_part_d, sizeof(double) * (size_t)Q * max_grid))) return rc;
+    if ((rc = ensure(ctx, ctx->d_part_i, sizeof(long long) * (size_t)Q * max_grid))) return rc;
+    if (ctx->d_tickets.bytes < sizeof(unsigned) * (size_t)Q) {
+        if ((rc = ensure(ctx, ctx->d_tickets, sizeof(unsigned) * (size_t)Q))) return rc;
+        MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.bytes, ctx->stream), ctx);
+    }
+    if ((rc = ensure_stage(ctx, qb + 2 * mb + wb))) return rc;
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    char* h = (char*)ctx->h_stage;
+    memcpy(h, queries, qb);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_queries.p, h, qb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    h += qb;
+    if (masks) {
+        memcpy(h, masks, mb);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_masks.p, h, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    }
+    h += mb;
+    if (slice_filters) {
+        memcpy(h, slice_filters, mb);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_filters.p, h, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    }
+    h += mb;
+    if (weights) {
+        memcpy(h, weights, wb);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nnw.p, h, wb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    }
+    NNParams& np = ctx->np;
+    memset(&np, 0, sizeof(np));
+    np.queries = (const float*)ctx->d_queries.p;
+    np.masks = masks ? (const uint32_t*)ctx->d_masks.p : nullptr;
+    np.filters = slice_filters ? (const int32_t*)ctx->d_filters.p : nullptr;
+    np.weights = weights ? (const float*)ctx->d_nnw.p : nullptr;
+    np.pw = ctx->scene.position_weight;
+    np.ow = ctx->scene.orientation_weight;
+    np.Q = Q;
+    np.out_idx = (long long*)ctx->d_out_idx.p;
+    np.out_dist = (double*)ctx->d_out_dist.p;
+    np.part_d = (double*)ctx->d_part_d.p;
+    np.part_i = (long long*)ctx->d_part_i.p;
+    np.tickets = (unsigned*)ctx->d_tickets.p;
+    ctx->nn_Q = Q;
+    ctx->nn_ready = true;
+    return MPS_OK;
+}
+
+int mps_tree_nearest_launch(mps_ctx* ctx)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    if (!ctx->nn_ready) return mps_fail(ctx, MPS_ERR_STATE, "mps_tree_nearest_upload must precede mps_tree_nearest_launch");
+    int rc = tree_sync_size(ctx);
+    if (rc) return rc;
+    NNParams& np = ctx->np;
+    np.tree = ctx->tree;
+    np.n = ctx->tree_n;
+    np.grid_x = mps_nn_grid_x(np.n, ctx->num_sms);
+    MPS_CUDA_CHECK(mps_launch_nn_scan(np, ctx->stream), ctx);
+    ctx->launches++;
+    return MPS_OK;
+}
+
+int mps_tree_nearest_fetch(mps_ctx* ctx, int64_t* indices, double* distances)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    if (!ctx->nn_ready) return mps_fail(ctx, MPS_ERR_STATE, "nothing to fetch");
+    const int Q = ctx->nn_Q;
+    if (indices) MPS_CUDA_CHECK(cudaMemcpyAsync(indices, ctx->d_out_idx.p, sizeof(long long) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    if (distances) MPS_CUDA_CHECK(cudaMemcpyAsync(distances, ctx->d_out_dist.p, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+int mps_tree_nearest_batch(mps_ctx* ctx, const float* queries, int32_t Q, const float* weights, const uint32_t* masks,
+                           const int32_t* slice_filters, int64_t* indices, double* distances)
+{
+    int rc = mps_tree_nearest_upload(ctx, queries, Q, weights, masks, slice_filters);
+    if (rc) return rc;
+    if ((rc = mps_tree_nearest_launch(ctx))) return rc;
+    return mps_tree_nearest_fetch(ctx, indices, distances);
+}
+
+int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
+                     int64_t* index, double* distance)
+{
+    return mps_tree_nearest_batch(ctx, query, 1, weights, &mask, &slice_filter, index, distance);
+}
+
+// ---- extend -----------------------------------------------------------------------------------
+
+int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
+{
+    if (!ctx || !in) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_upload");
+    if (!in->start || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "start / controls are NULL");
+    if (in->K < 1 || in->L < 1 || in->L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "K must be >= 1 and L in [1, 16]");
+    if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS) return mps_fail(ctx, MPS_ERR_ARG, "n_goals must be in [0, 8]");
+    if (in->n_goals > 0 && !in->goals) return mps_fail(ctx, MPS_ERR_ARG, "goals is NULL");
+    const int B = ctx->scene.n_bodies, K = in->K, L = in->L;
+    for (int g = 0; g < in->n_goals; ++g)
+        if (in->goals[g].body < 0 || in->goals[g].body >= B) return mps_fail(ctx, MPS_ERR_ARG, "goal body out of range");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    const size_t KL = (size_t)K * L;
+    const size_t sb = sizeof(float) * 3 * B, cb = sizeof(float) * MPS_CONTROL_DIM * KL, nb = sizeof(int32_t) * (size_t)K,
+                 wb = sizeof(float) * B, gb = sizeof(mps_goal) * MPS_MAX_GOALS;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_start, sb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_controls, cb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_nctrl, nb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_dest, sb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_weights, wb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_goals, gb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ball, sb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_states, sizeof(float) * 3 * B * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rest, sizeof(float) * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_flags, sizeof(uint32_t) * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_steps, sizeof(int32_t) * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_dist, sizeof(double) * (size_t)K))) return rc;
+    if ((rc = ensure(ctx, ctx->d_nok, sizeof(int32_t) * (size_t)K))) return rc;
+    if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * (size_t)K))) return rc;
+    if ((rc = ensure(ctx, ctx->d_best, sizeof(mps_extend_best)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_best_states, sizeof(float) * 3 * B * L))) return rc;
+    if ((rc = ensure(ctx, ctx->d_best_controls, sizeof(float) * MPS_CONTROL_DIM * L))) return rc;
+    if ((rc = ensure(ctx, ctx->d_best_flags, sizeof(uint32_t) * L))) return rc;
+    if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
+    if (!ctx->d_counters.p) {
+        if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
+        MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
+    }
+    if (in->append_to_tree) {
+        if ((rc = tree_ensure(ctx, ctx->tree_upper + L))) return rc;
+    }
+    // host -> pinned staging -> device
+    if ((rc = ensure_stage(ctx, 3 * sb + cb + nb + wb + gb))) return rc;
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    char* h = (char*)ctx->h_stage;
+    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
+        memcpy(h, src, bytes);
+        cudaError_t e = cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        h += align_up(bytes, 16);
+        return e;
+    };
+    MPS_CUDA_CHECK(up(ctx->d_start, in->start, sb), ctx);
+    MPS_CUDA_CHECK(up(ctx->d_controls, in->controls, cb), ctx);
+    if (in->n_ctrl) MPS_CUDA_CHECK(up(ctx->d_nctrl, in->n_ctrl, nb), ctx);
+    if (in->dest) MPS_CUDA_CHECK(up(ctx->d_dest, in->dest, sb), ctx);
+    if (in->weights) MPS_CUDA_CHECK(up(ctx->d_weights, in->weights, wb), ctx);
+    if (in->n_goals > 0) MPS_CUDA_CHECK(up(ctx->d_goals, in->goals, sizeof(mps_goal) * in->n_goals), ctx);
+    if (in->ball_center) MPS_CUDA_CHECK(up(ctx->d_ball, in->ball_center, sb), ctx);
+
+    RolloutParams& rp = ctx->rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.scene = ctx->d_scene;
+    rp.scene_bytes = ctx->scene_bytes;
+    rp.warp_bytes = ctx->warp_bytes;
+    rp.start = (const float*)ctx->d_start.p;
+    rp.controls = (const float*)ctx->d_controls.p;
+    rp.n_ctrl = in->n_ctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
+    rp.K = K;
+    rp.L = L;
+    rp.dest = in->dest ? (const float*)ctx->d_dest.p : nullptr;
+    rp.weights = in->weights ? (const float*)ctx->d_weights.p : nullptr;
+    rp.mask = in->mask;
+    rp.goals = (const mps_goal*)ctx->d_goals.p;
+    rp.n_goals = in->n_goals;
+    rp.ball_center = in->ball_center ? (const float*)ctx->d_ball.p : nullptr;
+    rp.ball_radius = in->ball_radius;
+    rp.out_states = (float*)ctx->d_states.p;
+    rp.out_rest = (float*)ctx->d_rest.p;
+    rp.out_flags = (uint32_t*)ctx->d_flags.p;
+    rp.out_steps = (int32_t*)ctx->d_steps.p;
+    rp.out_dist = (double*)ctx->d_dist.p;
+    rp.out_nok = (int32_t*)ctx->d_nok.p;
+    rp.out_goal_step = (int32_t*)ctx->d_goal_step.p;
+    rp.work_counter = (unsigned*)ctx->d_work.p;
+    rp.counters = (unsigned long long*)ctx->d_counters.p;
+
+    SelectParams& sp = ctx->sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.K = K;
+    sp.L = L;
+    sp.B = B;
+    sp.has_dest = in->dest ? 1 : 0;
+    sp.compare_f32 = in->compare_f32;
+    sp.k_offset = in->k_offset;
+    sp.dist = rp.out_dist;
+    sp.nok = rp.out_nok;
+    sp.goal_step = rp.out_goal_step;
+    sp.states = rp.out_states;
+    sp.rest = rp.out_rest;
+    sp.flags = rp.out_flags;
+    sp.controls = rp.controls;
+    sp.best = (mps_extend_best*)ctx->d_best.p;
+    sp.best_states = (float*)ctx->d_best_states.p;
+    sp.best_controls = (float*)ctx->d_best_controls.p;
+    sp.best_flags = (uint32_t*)ctx->d_best_flags.p;
+    sp.append = in->append_to_tree;
+    sp.parent = in->parent;
+    ctx->ext_K = K;
+    ctx->ext_L = L;
+    ctx->extend_ready = true;
+    return MPS_OK;
+}
+
+int mps_extend_launch(mps_ctx* ctx)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "mps_extend_upload must precede mps_extend_launch");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    SelectParams& sp = ctx->sp;
+    if (sp.append) {
+        int rc = tree_ensure(ctx, ctx->tree_upper + ctx->ext_L);
+        if (rc) return rc;
+        sp.tree_size = (long long*)ctx->d_tree_size.p;
+        sp.tree_cap = ctx->tree.cap;
+        sp.tree_states = ctx->tree.states;
+        sp.tree_controls = ctx->tree.controls;
+        sp.tree_parent = ctx->tree.parent;
+        sp.tree_slice = ctx->tree.slice;
+        ctx->tree_upper += ctx->ext_L;
+    }
+    MPS_CUDA_CHECK(mps_launch_rollout(ctx->rp, ctx->num_sms, ctx->stream), ctx);
+    MPS_CUDA_CHECK(mps_launch_select(sp, ctx->stream), ctx);
+    ctx->launches += 2;
+    return MPS_OK;
+}
+
+int mps_extend_fetch(mps_ctx* ctx, const mps_extend_out* out)
+{
+    if (!ctx || !out) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_fetch");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "nothing to fetch");
+    const int B = ctx->scene.n_bodies, K = ctx->ext_K, L = ctx->ext_L;
+    const size_t KL = (size_t)K * L;
+    cudaStream_t s = ctx->stream;
+    if (out->best) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best, ctx->d_best.p, sizeof(mps_extend_best), cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_states, ctx->d_best_states.p, sizeof(float) * 3 * B * L, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best_controls) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_controls, ctx->d_best_controls.p, sizeof(float) * MPS_CONTROL_DIM * L, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_flags, ctx->d_best_flags.p, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->all_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_states, ctx->d_states.p, sizeof(float) * 3 * B * KL, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->all_rest) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_rest, ctx->d_rest.p, sizeof(float) * KL, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->all_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_flags, ctx->d_flags.p, sizeof(uint32_t) * KL, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->all_dist) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_dist, ctx->d_dist.p, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->all_steps) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_steps, ctx->d_steps.p, sizeof(int32_t) * KL, cudaMemcpyDeviceToHost, s), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(s), ctx);
+    if (ctx->sp.append) return tree_sync_size(ctx);
+    return MPS_OK;
+}
+
+int mps_extend(mps_ctx* ctx, const mps_extend_in* in, const mps_extend_out* out)
+{
+    int rc = mps_extend_upload(ctx, in);
+    if (rc) return rc;
+    if ((rc = mps_extend_launch(ctx))) return rc;
+    return mps_extend_fetch(ctx, out);
+}
+
+int mps_propagate(mps_ctx* ctx, const float* state_in, float* control, float* state_out, int32_t* ok, uint32_t* flags)
+{
+    if (!ctx || !state_in || !control || !state_out) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_propagate");
+    mps_extend_in in;
+    memset(&in, 0, sizeof(in));
+    in.start = state_in;
+    in.controls = control;
+    in.K = 1;
+    in.L = 1;
+    float rest = 0.0f;
+    uint32_t f = 0;
+    mps_extend_out out;
+    memset(&out, 0, sizeof(out));
+    std::vector<float> res(3 * (size_t)ctx->scene.n_bodies);
+    out.all_states = res.data();
+    out.all_rest = &rest;
+    out.all_flags = &f;
+    int rc = mps_extend(ctx, &in, &out);
+    if (rc) return rc;
+    memcpy(state_out, res.data(), sizeof(float) * res.size());
+    control[4] = rest;
+    if (ok) *ok = (f & MPS_F_OK) ? 1 : 0;
+    if (flags) *flags = f;
+    return MPS_OK;
+}
+
+int mps_extend_counters(mps_ctx* ctx, uint64_t counters[8])
+{
+    if (!ctx || !counters) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    memset(counters, 0, sizeof(uint64_t) * 8);
+    if (ctx->d_counters.p) {
+        MPS_CUDA_CHECK(cudaMemcpyAsync(counters, ctx->d_counters.p, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    }
+    counters[4] = ctx->launches;
+    return MPS_OK;
+}
+
+// ---- validity ---------------------------------------------------------------------------------
+
+int mps_is_valid_batch(mps_ctx* ctx, const float* states, int32_t n, uint8_t* valid, uint32_t* flags)
+{
+    if (!ctx || !states || n < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_is_valid_batch");
+    if (n == 0) return MPS_OK;
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    const size_t sb = sizeof(float) * 3 * ctx->scene.n_bodies * (size_t)n;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_vstates, sb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_valid, (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->d_vflags, sizeof(uint32_t) * (size_t)n))) return rc;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_vstates.p, states, sb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    ValidityParams vp;
+    vp.scene = ctx->d_scene;
+    vp.scene_bytes = ctx->scene_bytes;
+    vp.warp_bytes = ctx->warp_bytes;
+    vp.states = (const float*)ctx->d_vstates.p;
+    vp.n = n;
+    vp.valid = (uint8_t*)ctx->d_valid.p;
+    vp.flags = (uint32_t*)ctx->d_vflags.p;
+    MPS_CUDA_CHECK(mps_launch_validity(vp, ctx->num_sms, ctx->stream), ctx);
+    ctx->launches++;
+    if (valid) MPS_CUDA_CHECK(cudaMemcpyAsync(valid, ctx->d_valid.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    if (flags) MPS_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_vflags.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+// ---- timing -----------------------------------------------------------------------------------
+
+int mps_time_launches(mps_ctx* ctx, int32_t what, int32_t iters, float* elapsed_ms)
+{
+    if (!ctx || !elapsed_ms || iters < 1) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_time_launches");
+    cudaEvent_t e0, e1;
+    MPS_CUDA_CHECK(cudaEventCreate(&e0), ctx);
+    MPS_CUDA_CHECK(cudaEventCreate(&e1), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaEventRecord(e0, ctx->stream), ctx);
+    int rc = MPS_OK;
+    for (int i = 0; i < iters && rc == MPS_OK; ++i) rc = what == 0 ? mps_extend_launch(ctx) : mps_tree_nearest_launch(ctx);
+    cudaError_t e = cudaEventRecord(e1, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    if (e != cudaSuccess) return mps_fail_cuda(ctx, e, "event timing", __LINE__);
+    *elapsed_ms = ms;
+    return MPS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1143 @@
+// rollout.cu — K push rollouts of the planar robot/object contact simulation with the
+// validity / goal / slice-ball tests fused in, one warp per rollout chain (sm_100a).
+//
+// What it replaces in the reference (paths relative to the reference root):
+//   the K-sample loop of NaiveControlSampler::sampleTo      ompl/control/NaiveControlSampler.cpp:46-64
+//   the K-chain loop of HybridActionRRT::extend            pushing/algorithm/RRT.cpp:458-477,531-565
+//   SimEnvStatePropagator::propagate                       ompl/control/SimEnvStatePropagator.cpp:42-118
+//   RampVelocityControl::{computeRamp,getVelocity}          ompl/control/RampVelocityControl.cpp:98-158
+//   SimEnvValidityChecker::isValid + CollisionPolicy       ompl/state/SimEnvState.cpp:1365-1394,1441-1502
+//   SimEnvWorldStateDistanceMeasure::distance              ompl/state/SimEnvWorldStateDistanceMeasure.cpp:34-51
+//   ObjectsRelocationGoal::distanceGoal / isSatisfied      ompl/state/goal/ObjectsRelocationGoal.cpp:108-123
+// The physics step itself follows the spec mps-planar-v1.
+//
+// Mapping to the machine:
+//   * one warp = one rollout chain; lane i owns body i: pose, twist and friction accumulators
+//     live in that lane's registers, poses are mirrored to shared memory for the pair tests;
+//   * broad phase: lane = pair index, 32 pairs per pass, ballot-compacted;
+//   * narrow phase: lane = candidate pair, manifolds written SoA into the warp's shared slice;
+//   * solver: Gauss-Seidel in colour order.  Colour r < B holds the body pairs with
+//     (i + j) mod B == r, colour B + s the pairs (i, static s); a colour touches every body at most
+//     once, so its manifolds are solved by their two owner lanes at the same time, the partner's
+//     twist arriving by warp shuffle.  A sequential CPU sweep in the same order gives the same bits;
+//   * rest test / policy test: warp votes;
+//   * warps pull chain indices from an atomic counter (rollout lengths vary by 10x).
+#include "mps_device.cuh"
+#include "rollout.h"
+
+#define FULL 0xffffffffu
+
+namespace {
+
+// manifold fields in the warp's shared slice, SoA: field f of slot m at man[f * Mcap + m]
+enum { MF_META = 0, MF_NX, MF_NY, MF_FRICTION, MF_P0 };
+enum { PF_RAX = 0, PF_RAY, PF_RBX, PF_RBY, PF_NMASS, PF_TMASS, PF_BIAS, PF_ACCN, PF_ACCT, PF_COUNT };
+#define MF_FIELDS (MF_P0 + 2 * PF_COUNT)
+
+struct Shape {
+    int shape;
+    float x, y, c, s, hx, hy;
+};
+
+struct Manifold {
+    int count;
+    float nx, ny;
+    float rax[2], ray[2], rbx[2], rby[2], sep[2];
+};
+
+__device__ __forceinline__ int collide_disc_disc(const Shape& A, const Shape& Bs, Manifold& m)
+{
+    float dx = Bs.x - A.x;
+    float dy = Bs.y - A.y;
+    float d2 = dx * dx + dy * dy;
+    float R = A.hx + Bs.hx;
+    if (d2 > R * R) return 0;
+    float d = sqrtf(d2);
+    float nx, ny;
+    if (d > 1e-9f) {
+        nx = dx / d;
+        ny = dy / d;
+    } else {
+        nx = 1.0f;
+        ny = 0.0f;
+    }
+    float sep = d - R;
+    float h = A.hx + 0.5f * sep;
+    m.nx = nx;
+    m.ny = ny;
+    m.count = 1;
+    m.rax[0] = nx * h;
+    m.ray[0] = ny * h;
+    m.rbx[0] = m.rax[0] - dx;
+    m.rby[0] = m.ray[0] - dy;
+    m.sep[0] = sep;
+    return 1;
+}
+
+// box X against disc D; a_is_box: body a of the pair is the box
+__device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, bool a_is_box, Manifold& m)
+{
+    float ddx = D.x - X.x;
+    float ddy = D.y - X.y;
+    float lx = ddx * X.c + ddy * X.s;
+    float ly = ddy * X.c - ddx * X.s;
+    float qx = fminf(fmaxf(lx, -X.hx), X.hx);
+    float qy = fminf(fmaxf(ly, -X.hy), X.hy);
+    float r = D.hx;
+    float nlx, nly, sep, spx, spy;
+    if (qx == lx && qy == ly) {
+        float px = X.hx - fabsf(lx);
+        float py = X.hy - fabsf(ly);
+        if (px < py) {
+            nlx = lx >= 0.0f ? 1.0f : -1.0f;
+            nly = 0.0f;
+            sep = -(px + r);
+            spx = nlx * X.hx;
+            spy = ly;
+        } else {
+            nlx = 0.0f;
+            nly = ly >= 0.0f ? 1.0f : -1.0f;
+            sep = -(py + r);
+            spx = lx;
+            spy = nly * X.hy;
+        }
+    } else {
+        float vx = lx - qx;
+        float vy = ly - qy;
+        float d2 = vx * vx + vy * vy;
+        if (d2 > r * r) return 0;
+        float d = sqrtf(d2);
+        nlx = vx / d;
+        nly = vy / d;
+        sep = d - r;
+        spx = qx;
+        spy = qy;
+    }
+    float hs = 0.5f * sep;
+    float cplx = spx + nlx * hs;
+    float cply = spy + nly * hs;
+    float rxx = X.c * cplx - X.s * cply;
+    float rxy = X.s * cplx + X.c * cply;
+    float nx = X.c * nlx - X.s * nly;
+    float ny = X.s * nlx + X.c * nly;
+    float rdx = rxx - ddx;
+    float rdy = rxy - ddy;
+    m.count = 1;
+    m.sep[0] = sep;
+    if (a_is_box) {
+        m.nx = nx;
+        m.ny = ny;
+        m.rax[0] = rxx;
+        m.ray[0] = rxy;
+        m.rbx[0] = rdx;
+        m.rby[0] = rdy;
+    } else {
+        m.nx = -nx;
+        m.ny = -ny;
+        m.rax[0] = rdx;
+        m.ray[0] = rdy;
+        m.rbx[0] = rxx;
+        m.rby[0] = rxy;
+    }
+    return 1;
+}
+
+// rectangle-rectangle: 4-axis SAT, reference face = least penetration (A unless B is better by
+// ref_tol), incident edge clipped to the reference face's side planes
+__device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, float ref_tol, Manifold& m)
+{
+    float dx = Bs.x - A.x;
+    float dy = Bs.y - A.y;
+    float d00 = A.c * Bs.c + A.s * Bs.s;
+    float d01 = A.s * Bs.c - A.c * Bs.s;
+    float ad00 = fabsf(d00);
+    float ad01 = fabsf(d01);
+    float pax = dx * A.c + dy * A.s;
+    float pay = dy * A.c - dx * A.s;
+    float pbx = dx * Bs.c + dy * Bs.s;
+    float pby = dy * Bs.c - dx * Bs.s;
+    float sep_ax = fabsf(pax) - A.hx - (Bs.hx * ad00 + Bs.hy * ad01);
+    float sep_ay = fabsf(pay) - A.hy - (Bs.hx * ad01 + Bs.hy * ad00);
+    float sep_bx = fabsf(pbx) - Bs.hx - (A.hx * ad00 + A.hy * ad01);
+    float sep_by = fabsf(pby) - Bs.hy - (A.hx * ad01 + A.hy * ad00);
+    if (sep_ax > 0.0f || sep_ay > 0.0f || sep_bx > 0.0f || sep_by > 0.0f) return 0;
+    bool a_face_y = sep_ay > sep_ax;
+    bool b_face_y = sep_by > sep_bx;
+    float sep_a = a_face_y ? sep_ay : sep_ax;
+    float sep_b = b_face_y ? sep_by : sep_bx;
+    bool ref_is_b = sep_b > sep_a + ref_tol;
+    float Rc = ref_is_b ? Bs.c : A.c, Rs = ref_is_b ? Bs.s : A.s;
+    float Rhx = ref_is_b ? Bs.hx : A.hx, Rhy = ref_is_b ? Bs.hy : A.hy;
+    float Ic = ref_is_b ? A.c : Bs.c, Is = ref_is_b ? A.s : Bs.s;
+    float Ihx = ref_is_b ? A.hx : Bs.hx, Ihy = ref_is_b ? A.hy : Bs.hy;
+    float ddx = ref_is_b ? -dx : dx;
+    float ddy = ref_is_b ? -dy : dy;
+    bool face_y = ref_is_b ? b_face_y : a_face_y;
+    float ux = face_y ? -Rs : Rc;
+    float uy = face_y ? Rc : Rs;
+    float hu = face_y ? Rhy : Rhx;
+    float ht = face_y ? Rhx : Rhy;
+    float proj = ddx * ux + ddy * uy;
+    float sgn = proj >= 0.0f ? 1.0f : -1.0f;
+    float nrx = sgn * ux;
+    float nry = sgn * uy;
+    float trx = -nry;
+    float tryy = nrx;
+    float e0 = nrx * Ic + nry * Is;
+    float e1 = nry * Ic - nrx * Is;
+    bool inc_y = !(fabsf(e0) >= fabsf(e1));
+    float sm, mx, my, hm, he;
+    if (!inc_y) {
+        sm = e0 > 0.0f ? -1.0f : 1.0f;
+        mx = sm * Ic;
+        my = sm * Is;
+        hm = Ihx;
+        he = Ihy;
+    } else {
+        sm = e1 > 0.0f ? -1.0f : 1.0f;
+        mx = sm * -Is;
+        my = sm * Ic;
+        hm = Ihy;
+        he = Ihx;
+    }
+    float cx = ddx + mx * hm;
+    float cy = ddy + my * hm;
+    float ex = -my;
+    float ey = mx;
+    float v1x = cx + ex * he;
+    float v1y = cy + ey * he;
+    float v2x = cx - ex * he;
+    float v2y = cy - ey * he;
+    float t1 = v1x * trx + v1y * tryy;
+    float t2 = v2x * trx + v2y * tryy;
+    float s1 = (v1x * nrx + v1y * nry) - hu;
+    float s2 = (v2x * nrx + v2y * nry) - hu;
+    if ((t1 > ht && t2 > ht) || (t1 < -ht && t2 < -ht)) return 0;
+    float ct0 = t1, cs0 = s1, ct1 = t2, cs1 = s2;
+    if (t1 > ht) {
+        float al = (ht - t1) / (t2 - t1);
+        cs0 = s1 + al * (s2 - s1);
+        ct0 = ht;
+    } else if (t1 < -ht) {
+        float al = (-ht - t1) / (t2 - t1);
+        cs0 = s1 + al * (s2 - s1);
+        ct0 = -ht;
+    }
+    if (t2 > ht) {
+        float al = (ht - t2) / (t1 - t2);
+        cs1 = s2 + al * (s1 - s2);
+        ct1 = ht;
+    } else if (t2 < -ht) {
+        float al = (-ht - t2) / (t1 - t2);
+        cs1 = s2 + al * (s1 - s2);
+        ct1 = -ht;
+    }
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float csk = k == 0 ? cs0 : cs1;
+        float ctk = k == 0 ? ct0 : ct1;
+        if (csk <= 0.0f) {
+            float h = hu + 0.5f * csk;
+            float rrx = trx * ctk + nrx * h;
+            float rry = tryy * ctk + nry * h;
+            float rix = rrx - ddx;
+            float riy = rry - ddy;
+            // n is 0 or 1 here; written without dynamic register indexing
+            float ax_ = ref_is_b ? rix : rrx, ay_ = ref_is_b ? riy : rry;
+            float bx_ = ref_is_b ? rrx : rix, by_ = ref_is_b ? rry : riy;
+            if (n == 0) {
+                m.rax[0] = ax_; m.ray[0] = ay_; m.rbx[0] = bx_; m.rby[0] = by_; m.sep[0] = csk;
+            } else {
+                m.rax[1] = ax_; m.ray[1] = ay_; m.rbx[1] = bx_; m.rby[1] = by_; m.sep[1] = csk;
+            }
+            ++n;
+        }
+    }
+    if (n == 0) return 0;
+    m.count = n;
+    m.nx = ref_is_b ? -nrx : nrx;
+    m.ny = ref_is_b ? -nry : nry;
+    return n;
+}
+
+__device__ __forceinline__ int collide(const Shape& A, const Shape& Bs, float ref_tol, Manifold& m)
+{
+    if (A.shape == MPS_SHAPE_BOX && Bs.shape == MPS_SHAPE_BOX) return collide_box_box(A, Bs, ref_tol, m);
+    if (A.shape == MPS_SHAPE_BOX && Bs.shape == MPS_SHAPE_DISC) return collide_box_disc(A, Bs, true, m);
+    if (A.shape == MPS_SHAPE_DISC && Bs.shape == MPS_SHAPE_BOX) return collide_box_disc(Bs, A, false, m);
+    return collide_disc_disc(A, Bs, m);
+}
+
+// per-warp working set in shared memory
+struct WarpMem {
+    float* px;  // [32] poses mirrored for the pair tests
+    float* py;
+    float* pc;
+    float* ps;
+    float* man;       // [MF_FIELDS][Mcap]
+    uint8_t* slot;    // [B][slot_stride]
+};
+
+struct DetectResult {
+    bool bad;       // a touching pair the policy forbids
+    bool overflow;  // more touching pairs than Mcap
+    float max_pen;
+    unsigned long long colours;
+    unsigned candidates, touching;
+};
+
+// collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver constants.
+__device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare)
+{
+    const int B = sc.B;
+    const int Mcap = sc.Mcap;
+    {
+        uint32_t* sw = reinterpret_cast<uint32_t*>(W.slot);
+        int words = (B * sc.slot_stride) >> 2;
+        for (int i = lane; i < words; i += 32) sw[i] = 0xffffffffu;
+    }
+    __syncwarp();
+    int nm = 0;
+    bool lane_bad = false, lane_over = false;
+    float lane_pen = 0.0f;
+    unsigned long long lane_col = 0ull;
+    unsigned n_cand = 0, n_touch = 0;
+    for (int base = 0; base < sc.P; base += 32) {
+        int p = base + lane;
+        bool cand = false;
+        int a = 0, b = 0;
+        Shape A, Bs;
+        if (p < sc.P) {
+            unsigned pr = sc.pairs[p];
+            a = pr & 0xff;
+            b = pr >> 8;
+            A.shape = sc.shape[a];
+            A.x = W.px[a];
+            A.y = W.py[a];
+            A.c = W.pc[a];
+            A.s = W.ps[a];
+            A.hx = sc.hx[a];
+            A.hy = sc.hy[a];
+            float rr;
+            if (b < B) {
+                Bs.shape = sc.shape[b];
+                Bs.x = W.px[b];
+                Bs.y = W.py[b];
+                Bs.c = W.pc[b];
+                Bs.s = W.ps[b];
+                Bs.hx = sc.hx[b];
+                Bs.hy = sc.hy[b];
+                rr = sc.brad[a] + sc.brad[b];
+            } else {
+                int k = b - B;
+                Bs.shape = sc.s_shape[k];
+                Bs.x = sc.s_x[k];
+                Bs.y = sc.s_y[k];
+                Bs.c = sc.s_c[k];
+                Bs.s = sc.s_s[k];
+                Bs.hx = sc.s_hx[k];
+                Bs.hy = sc.s_hy[k];
+                rr = sc.brad[a] + sc.s_brad[k];
+            }
+            float dx = Bs.x - A.x;
+            float dy = Bs.y - A.y;
+            cand = !(dx * dx + dy * dy > rr * rr);
+        }
+        unsigned cmask = __ballot_sync(FULL, cand);
+        if (cmask == 0u) continue;
+        n_cand += __popc(cmask);
+        Manifold m;
+        int cnt = 0;
+        if (cand) cnt = collide(A, Bs, sc.ref_tol, m);
+        bool touch = cnt > 0;
+        unsigned tmask = __ballot_sync(FULL, touch);
+        if (tmask == 0u) continue;
+        n_touch += __popc(tmask);
+        if (touch) {
+            float pen = -m.sep[0];
+            if (pen > lane_pen) lane_pen = pen;
+            if (cnt > 1) {
+                pen = -m.sep[1];
+                if (pen > lane_pen) lane_pen = pen;
+            }
+            bool allowed = (b >= B) ? !((sc.static_forbidden >> a) & 1u) : !((sc.pair_forbidden[a] >> b) & 1u);
+            if (!allowed) lane_bad = true;
+            int idx = nm + __popc(tmask & ((1u << lane) - 1u));
+            if (idx < Mcap) {
+                float* mf = W.man + idx;
+                reinterpret_cast<int*>(mf)[MF_META * Mcap] = a | (b << 8) | (cnt << 16);
+                mf[MF_NX * Mcap] = m.nx;
+                mf[MF_NY * Mcap] = m.ny;
+                if (prepare) {
+                    float ma = sc.inv_m[a], ia = sc.inv_i[a];
+                    float mb = 0.0f, ib = 0.0f, mub;
+                    if (b < B) {
+                        mb = sc.inv_m[b];
+                        ib = sc.inv_i[b];
+                        mub = sc.mu_c[b];
+                    } else {
+                        mub = sc.s_mu[b - B];
+                    }
+                    mf[MF_FRICTION * Mcap] = sqrtf(sc.mu_c[a] * mub);
+                    float tx = m.ny, ty = -m.nx;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (k < cnt) {
+                            float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
+                            float rna = rax * m.ny - ray * m.nx;
+                            float rnb = rbx * m.ny - rby * m.nx;
+                            float kn = ((ma + mb) + (ia * rna) * rna) + (ib * rnb) * rnb;
+                            float rta = rax * ty - ray * tx;
+                            float rtb = rbx * ty - rby * tx;
+                            float kt = ((ma + mb) + (ia * rta) * rta) + (ib * rtb) * rtb;
+                            float pen_k = -m.sep[k] - sc.slop;
+                            float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
+                            pf[PF_RAX * Mcap] = rax;
+                            pf[PF_RAY * Mcap] = ray;
+                            pf[PF_RBX * Mcap] = rbx;
+                            pf[PF_RBY * Mcap] = rby;
+                            pf[PF_NMASS * Mcap] = kn > 0.0f ? 1.0f / kn : 0.0f;
+                            pf[PF_TMASS * Mcap] = kt > 0.0f ? 1.0f / kt : 0.0f;
+                            pf[PF_BIAS * Mcap] = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
+                            pf[PF_ACCN * Mcap] = 0.0f;
+                            pf[PF_ACCT * Mcap] = 0.0f;
+                        }
+                    }
+                    W.slot[a * sc.slot_stride + b] = (uint8_t)idx;
+                    int col;
+                    if (b < B) {
+                        W.slot[b * sc.slot_stride + a] = (uint8_t)idx;
+                        col = a + b;
+                        if (col >= B) col -= B;
+                    } else {
+                        col = b;
+                    }
+                    lane_col |= 1ull << col;
+                }
+            } else {
+                lane_over = true;
+            }
+        }
+        nm += __popc(tmask);
+    }
+    DetectResult r;
+    r.bad = __any_sync(FULL, lane_bad);
+    r.overflow = __any_sync(FULL, lane_over);
+    r.max_pen = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(lane_pen)));
+    unsigned lo = __reduce_or_sync(FULL, (unsigned)(lane_col & 0xffffffffull));
+    unsigned hi = __reduce_or_sync(FULL, (unsigned)(lane_col >> 32));
+    r.colours = ((unsigned long long)hi << 32) | lo;
+    r.candidates = n_cand;
+    r.touching = n_touch;
+    __syncwarp();
+    return r;
+}
+
+// registers of the lane that owns body `lane`
+struct Body {
+    float x, y, th, c, s, vx, vy, w;
+    float inv_m, inv_i, mass, inertia, lin_cap, ang_cap;
+    bool dynamic;  // lane < B and not the robot
+    bool live;     // lane < B
+};
+
+__device__ __forceinline__ void publish_pose(const WarpMem& W, const Body& b, int lane)
+{
+    if (b.live) {
+        W.px[lane] = b.x;
+        W.py[lane] = b.y;
+        W.pc[lane] = b.c;
+        W.ps[lane] = b.s;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void set_state(const WarpMem& W, Body& b, int lane, float x, float y, float th)
+{
+    if (b.live) {
+        b.x = x;
+        b.y = y;
+        b.th = mps_wrap_angle(th);
+        mps_sincos(b.th, &b.s, &b.c);
+    }
+    b.vx = 0.0f;
+    b.vy = 0.0f;
+    b.w = 0.0f;
+    publish_pose(W, b, lane);
+}
+
+struct StepStats {
+    unsigned steps, candidates, touching, colour_passes;
+};
+
+// one physics step.  Returns (bad_contact, overflow) as warp-uniform values.
+__device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, int lane, float ux,
+                                             float uy, float uw, bool& bad, bool& overflow, StepStats& st)
+{
+    const int B = sc.B;
+    const int Mcap = sc.Mcap;
+    if (lane == sc.robot) {
+        bd.vx = ux;
+        bd.vy = uy;
+        bd.w = uw;
+    }
+    DetectResult dr = detect(sc, W, lane, true);
+    bad = dr.bad;
+    overflow = dr.overflow;
+    st.steps += 1;
+    st.candidates += dr.candidates;
+    st.touching += dr.touching;
+    if (overflow) return;
+    float acc_lx = 0.0f, acc_ly = 0.0f, acc_a = 0.0f;
+    for (int it = 0; it < sc.vel_iters; ++it) {
+        // support-plane friction: one friction joint to the ground per dynamic body
+        if (bd.dynamic) {
+            float imp = -bd.inertia * bd.w;
+            float old = acc_a;
+            float nw = fminf(fmaxf(old + imp, -bd.ang_cap), bd.ang_cap);
+            acc_a = nw;
+            imp = nw - old;
+            bd.w = bd.w + bd.inv_i * imp;
+            float ix = -bd.mass * bd.vx;
+            float iy = -bd.mass * bd.vy;
+            float ox = acc_lx, oy = acc_ly;
+            float ax = ox + ix, ay = oy + iy;
+            float n2 = ax * ax + ay * ay;
+            float cap = bd.lin_cap;
+            if (n2 > cap * cap) {
+                float sc_ = cap / sqrtf(n2);
+                ax = ax * sc_;
+                ay = ay * sc_;
+            }
+            acc_lx = ax;
+            acc_ly = ay;
+            ix = ax - ox;
+            iy = ay - oy;
+            bd.vx = bd.vx + bd.inv_m * ix;
+            bd.vy = bd.vy + bd.inv_m * iy;
+        }
+        // contacts, colour by colour
+        unsigned long long cm = dr.colours;
+        while (cm) {
+            int col = __ffsll((long long)cm) - 1;
+            cm &= cm - 1ull;
+            st.colour_passes += 1;
+            int j = lane;  // partner lane (self when none)
+            int sl = 0xff;
+            if (bd.live) {
+                if (col < B) {
+                    int jj = col - lane;
+                    if (jj < 0) jj += B;
+                    if (jj != lane) {
+                        j = jj;
+                        sl = W.slot[lane * sc.slot_stride + jj];
+                    }
+                } else {
+                    sl = W.slot[lane * sc.slot_stride + col];
+                }
+            }
+            float ovx = __shfl_sync(FULL, bd.vx, j);
+            float ovy = __shfl_sync(FULL, bd.vy, j);
+            float ow_ = __shfl_sync(FULL, bd.w, j);
+            float om = __shfl_sync(FULL, bd.inv_m, j);
+            float oi = __shfl_sync(FULL, bd.inv_i, j);
+            // lanes that solve a manifold in this colour (both owners of a body pair do, redundantly)
+            const bool act = sl != 0xff;
+            const unsigned amask = __ballot_sync(FULL, act);
+            if (act) {
+                const bool stat = col >= B;
+                const bool is_a = stat || lane < j;
+                float* mf = W.man + sl;
+                int meta = reinterpret_cast<int*>(mf)[MF_META * Mcap];
+                int cnt = meta >> 16;
+                float nx = mf[MF_NX * Mcap], ny = mf[MF_NY * Mcap];
+                float fr = mf[MF_FRICTION * Mcap];
+                float tx = ny, ty = -nx;
+                // everything the pass reads is loaded before anything is written back: the two owner
+                // lanes of a pair must see the same accumulated impulses
+                float rax[2], ray[2], rbx[2], rby[2], nmass[2], tmass[2], bias[2], acc_n[2], acc_t[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
+                    rax[k] = pf[PF_RAX * Mcap];
+                    ray[k] = pf[PF_RAY * Mcap];
+                    rbx[k] = pf[PF_RBX * Mcap];
+                    rby[k] = pf[PF_RBY * Mcap];
+                    nmass[k] = pf[PF_NMASS * Mcap];
+                    tmass[k] = pf[PF_TMASS * Mcap];
+                    bias[k] = pf[PF_BIAS * Mcap];
+                    acc_n[k] = pf[PF_ACCN * Mcap];
+                    acc_t[k] = pf[PF_ACCT * Mcap];
+                }
+                __syncwarp(amask);
+                float ma, ia, mb, ib, vax, vay, wa, vbx, vby, wb;
+                if (is_a) {
+                    ma = bd.inv_m; ia = bd.inv_i; vax = bd.vx; vay = bd.vy; wa = bd.w;
+                    if (stat) {
+                        mb = 0.0f; ib = 0.0f; vbx = 0.0f; vby = 0.0f; wb = 0.0f;
+                    } else {
+                        mb = om; ib = oi; vbx = ovx; vby = ovy; wb = ow_;
+                    }
+                } else {
+                    ma = om; ia = oi; vax = ovx; vay = ovy; wa = ow_;
+                    mb = bd.inv_m; ib = bd.inv_i; vbx = bd.vx; vby = bd.vy; wb = bd.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {  // friction first
+                    if (k < cnt) {
+                        float dvx = (vbx - wb * rby[k]) - (vax - wa * ray[k]);
+                        float dvy = (vby + wb * rbx[k]) - (vay + wa * rax[k]);
+                        float vt = dvx * tx + dvy * ty;
+                        float lambda = tmass[k] * -vt;
+                        float max_f = fr * acc_n[k];
+                        float new_imp = fminf(fmaxf(acc_t[k] + lambda, -max_f), max_f);
+                        lambda = new_imp - acc_t[k];
+                        acc_t[k] = new_imp;
+                        float px = lambda * tx;
+                        float py = lambda * ty;
+                        vax = vax - ma * px;
+                        vay = vay - ma * py;
+                        wa = wa - ia * (rax[k] * py - ray[k] * px);
+                        vbx = vbx + mb * px;
+                        vby = vby + mb * py;
+                        wb = wb + ib * (rbx[k] * py - rby[k] * px);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {  // then non-penetration
+                    if (k < cnt) {
+                        float dvx = (vbx - wb * rby[k]) - (vax - wa * ray[k]);
+                        float dvy = (vby + wb * rbx[k]) - (vay + wa * rax[k]);
+                        float vn = dvx * nx + dvy * ny;
+                        float lambda = -nmass[k] * (vn - bias[k]);
+                        float new_imp = fmaxf(acc_n[k] + lambda, 0.0f);
+                        lambda = new_imp - acc_n[k];
+                        acc_n[k] = new_imp;
+                        float px = lambda * nx;
+                        float py = lambda * ny;
+                        vax = vax - ma * px;
+                        vay = vay - ma * py;
+                        wa = wa - ia * (rax[k] * py - ray[k] * px);
+                        vbx = vbx + mb * px;
+                        vby = vby + mb * py;
+                        wb = wb + ib * (rbx[k] * py - rby[k] * px);
+                    }
+                }
+                if (is_a) {
+                    bd.vx = vax; bd.vy = vay; bd.w = wa;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (k < cnt) {
+                            float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
+                            pf[PF_ACCN * Mcap] = acc_n[k];
+                            pf[PF_ACCT * Mcap] = acc_t[k];
+                        }
+                    }
+                } else {
+                    bd.vx = vbx; bd.vy = vby; bd.w = wb;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (bd.live) {
+        bd.x = bd.x + sc.dt * bd.vx;
+        bd.y = bd.y + sc.dt * bd.vy;
+        bd.th = mps_wrap_angle(bd.th + sc.dt * bd.w);
+        mps_sincos(bd.th, &bd.s, &bd.c);
+    }
+    publish_pose(W, bd, lane);
+}
+
+__device__ __forceinline__ bool at_rest(const DevScene& sc, const Body& bd)
+{
+    bool moving = false;
+    if (bd.live) moving = (bd.vx * bd.vx + bd.vy * bd.vy > sc.v_rest2) || (fabsf(bd.w) > sc.w_rest);
+    return !__any_sync(FULL, moving);
+}
+
+// satisfiesBounds of the reference's compound space, per body in double
+__device__ __forceinline__ bool body_in_bounds(const DevScene& sc, float xf, float yf, float thf)
+{
+    double x = (double)xf, y = (double)yf, th = (double)thf;
+    if (x - MPS_DBL_EPS > (double)sc.x_max || x + MPS_DBL_EPS < (double)sc.x_min) return false;
+    if (y - MPS_DBL_EPS > (double)sc.y_max || y + MPS_DBL_EPS < (double)sc.y_min) return false;
+    if (!(th < MPS_PI_D + MPS_DBL_EPS && th > -MPS_PI_D - MPS_DBL_EPS)) return false;
+    return true;
+}
+
+// isValid(state) with the state already in the lanes (sx, sy, sth = the float state values)
+__device__ __forceinline__ uint32_t state_validity_flags(const DevScene& sc, const WarpMem& W, Body& bd, int lane,
+                                                         float sx, float sy, float sth, StepStats* st)
+{
+    bool oob = bd.live && !body_in_bounds(sc, sx, sy, sth);
+    if (__any_sync(FULL, oob)) return MPS_F_BOUNDS;
+    set_state(W, bd, lane, sx, sy, sth);
+    DetectResult dr = detect(sc, W, lane, false);
+    (void)st;
+    uint32_t f = 0;
+    if (dr.max_pen > sc.pen_max) f |= MPS_F_INFEASIBLE;
+    if (dr.bad) f |= MPS_F_BAD_CONTACT;
+    if (dr.overflow) f |= MPS_F_OVERFLOW;
+    return f;
+}
+
+// sum_i mask_i w_i (pw |dxy_i| + ow arc_i) accumulated in body order, in double
+__device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& bd, int lane, float sx, float sy,
+                                                float sth, const float* __restrict__ other,
+                                                const float* __restrict__ weights, uint32_t mask)
+{
+    double term = 0.0;
+    if (bd.live && ((mask >> lane) & 1u)) {
+        double cfg = mps_body_distance(sx, sy, sth, other[3 * lane], other[3 * lane + 1], other[3 * lane + 2],
+                                       sc.pw, sc.ow);
+        double w = weights ? (double)weights[lane] : 1.0;
+        term = w * cfg;
+    }
+    double dist = 0.0;
+    for (int i = 0; i < sc.B; ++i) {
+        double t = __shfl_sync(FULL, term, i);
+        if ((mask >> i) & 1u) dist += t;
+    }
+    return dist;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevScene& sc = *reinterpret_cast<DevScene*>(smem_raw);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.scene);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevScene) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int B = sc.B;
+    const int Mcap = sc.Mcap;
+    unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)warp * p.warp_bytes;
+    WarpMem W;
+    W.px = reinterpret_cast<float*>(wbase);
+    W.py = W.px + 32;
+    W.pc = W.py + 32;
+    W.ps = W.pc + 32;
+    W.man = W.ps + 32;
+    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_FIELDS * Mcap);
+
+    Body bd;
+    bd.live = lane < B;
+    bd.dynamic = bd.live && lane != sc.robot;
+    {
+        int li = bd.live ? lane : 0;
+        bd.inv_m = bd.live ? sc.inv_m[li] : 0.0f;
+        bd.inv_i = bd.live ? sc.inv_i[li] : 0.0f;
+        bd.mass = sc.mass[li];
+        bd.inertia = sc.inertia[li];
+        bd.lin_cap = sc.lin_cap[li];
+        bd.ang_cap = sc.ang_cap[li];
+    }
+    bd.x = bd.y = bd.th = 0.0f;
+    bd.c = 1.0f;
+    bd.s = 0.0f;
+    bd.vx = bd.vy = bd.w = 0.0f;
+
+    StepStats st = {0u, 0u, 0u, 0u};
+    const int L = p.L;
+
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = (int)atomicAdd(p.work_counter, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= p.K) break;
+        int n = p.n_ctrl ? p.n_ctrl[k] : L;
+        if (n > L) n = L;
+        // start state of the chain
+        float sx = 0.0f, sy = 0.0f, sth = 0.0f;
+        if (bd.live) {
+            sx = p.start[3 * lane];
+            sy = p.start[3 * lane + 1];
+            sth = p.start[3 * lane + 2];
+        }
+        int n_ok = 0, goal_step = -1;
+        int l = 0;
+        for (; l < n; ++l) {
+            const size_t kl = (size_t)k * L + l;
+            const float* ctrl = p.controls + kl * MPS_CONTROL_DIM;
+            uint32_t flags = MPS_F_RAN;
+            unsigned steps0 = st.steps;
+            set_state(W, bd, lane, sx, sy, sth);
+            // RampVelocityControl::computeRamp (rest time reset to 0 before propagating)
+            float v0 = ctrl[0], v1 = ctrl[1], v2 = ctrl[2], t_pl = ctrl[3];
+            float t_acc = fabsf(v0 / sc.accel[0]);
+            {
+                float t = fabsf(v0 / sc.accel[0]);
+                t_acc = t > t_acc ? t : t_acc;
+                t = fabsf(v1 / sc.accel[1]);
+                t_acc = t > t_acc ? t : t_acc;
+                t = fabsf(v2 / sc.accel[2]);
+                t_acc = t > t_acc ? t : t_acc;
+            }
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+            if (t_acc != 0.0f) {
+                float inv = 1.0f / t_acc;
+                a0 = inv * v0;
+                a1 = inv * v1;
+                a2 = inv * v2;
+            }
+            const float T = 2.0f * t_acc + t_pl + 0.0f;
+            const float t_ap = t_acc + t_pl;
+            const double t_dec_end = 2.0 * (double)t_acc + (double)t_pl;
+            float time = 0.0f;
+            bool ok = true;
+            // active phase (SimEnvStatePropagator.cpp:75-83)
+            while (time < T && ok) {
+                float ux, uy, uw;
+                if (time < t_acc) {
+                    ux = time * a0;
+                    uy = time * a1;
+                    uw = time * a2;
+                } else if (time < t_ap) {
+                    ux = v0;
+                    uy = v1;
+                    uw = v2;
+                } else if ((double)time < t_dec_end) {
+                    float s = time - t_acc - t_pl;
+                    ux = v0 - s * a0;
+                    uy = v1 - s * a1;
+                    uw = v2 - s * a2;
+                } else {
+                    ux = 0.0f;
+                    uy = 0.0f;
+                    uw = 0.0f;
+                }
+                bool bad, over;
+                physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, st);
+                time += sc.dt;
+                if (over) {
+                    flags |= MPS_F_OVERFLOW;
+                    ok = false;
+                }
+                if (bad && sc.strict) {
+                    flags |= MPS_F_ACTIVE_CONTACT;
+                    ok = false;
+                }
+            }
+            // rest phase (:86-105)
+            float rest = 0.0f;
+            if (ok) {
+                bool resting = at_rest(sc, bd);
+                while (rest <= sc.t_max && !resting && ok) {
+                    bool bad, over;
+                    physics_step(sc, W, bd, lane, 0.0f, 0.0f, 0.0f, bad, over, st);
+                    ok = !bad;
+                    rest += sc.dt;
+                    if (bad) flags |= MPS_F_REST_CONTACT;
+                    if (over) {
+                        flags |= MPS_F_OVERFLOW;
+                        ok = false;
+                    }
+                    resting = at_rest(sc, bd);
+                }
+                if (!(rest <= sc.t_max && resting)) flags |= MPS_F_NOT_AT_REST;
+                ok = rest <= sc.t_max && resting && ok;
+            }
+            // extractState: theta normalised in double, read back as float
+            float rx = bd.x, ry = bd.y;
+            float rth = (float)mps_normalize_orientation((double)bd.th);
+            uint32_t vf = state_validity_flags(sc, W, bd, lane, rx, ry, rth, &st);
+            flags |= vf;
+            ok = ok && vf == 0u;
+            if (ok) {
+                flags |= MPS_F_OK;
+                // goal test on the result (RRT.cpp:377, :484, :726)
+                if (p.n_goals > 0) {
+                    double gd = 0.0;
+                    for (int g = 0; g < p.n_goals; ++g) {
+                        int gb = p.goals[g].body;
+                        float gx = __shfl_sync(FULL, rx, gb);
+                        float gy = __shfl_sync(FULL, ry, gb);
+                        float fx = p.goals[g].x - gx;
+                        float fy = p.goals[g].y - gy;
+                        double dc = sqrt((double)fx * (double)fx + (double)fy * (double)fy);
+                        double e = dc - (double)p.goals[g].tol;
+                        gd += e > 0.0 ? e : 0.0;
+                    }
+                    if (gd <= MPS_DBL_EPS) {
+                        flags |= MPS_F_GOAL;
+                        if (goal_step < 0) goal_step = l;
+                    }
+                }
+                if (p.ball_center) {
+                    uint32_t arr_mask = ~(1u << sc.robot);
+                    if (B < 32) arr_mask &= (1u << B) - 1u;
+                    double bdist = warp_distance(sc, bd, lane, rx, ry, rth, p.ball_center, p.weights, arr_mask);
+                    if (bdist <= (double)p.ball_radius) flags |= MPS_F_IN_BALL;
+                }
+            }
+            if (bd.live) {
+                float* os = p.out_states + kl * 3 * B + 3 * lane;
+                os[0] = rx;
+                os[1] = ry;
+                os[2] = rth;
+            }
+            if (lane == 0) {
+                p.out_rest[kl] = rest;
+                p.out_flags[kl] = flags;
+                p.out_steps[kl] = (int)(st.steps - steps0);
+            }
+            if (!ok) {
+                ++l;
+                break;
+            }
+            ++n_ok;
+            sx = rx;
+            sy = ry;
+            sth = rth;
+        }
+        // controls of the chain that were never propagated
+        for (; l < L; ++l) {
+            const size_t kl = (size_t)k * L + l;
+            if (bd.live) {
+                float* os = p.out_states + kl * 3 * B + 3 * lane;
+                os[0] = 0.0f;
+                os[1] = 0.0f;
+                os[2] = 0.0f;
+            }
+            if (lane == 0) {
+                p.out_rest[kl] = p.controls[kl * MPS_CONTROL_DIM + 4];
+                p.out_flags[kl] = 0u;
+                p.out_steps[kl] = 0;
+            }
+        }
+        double dist = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+        if (n_ok > 0 && p.dest) dist = warp_distance(sc, bd, lane, sx, sy, sth, p.dest, p.weights, p.mask);
+        if (lane == 0) {
+            p.out_dist[k] = dist;
+            p.out_nok[k] = n_ok;
+            p.out_goal_step[k] = goal_step;
+        }
+    }
+    // counters for the roofline accounting
+    if (lane == 0 && p.counters) {
+        atomicAdd(&p.counters[0], (unsigned long long)st.steps);
+        atomicAdd(&p.counters[1], (unsigned long long)st.candidates);
+        atomicAdd(&p.counters[2], (unsigned long long)st.touching);
+        atomicAdd(&p.counters[3], (unsigned long long)st.colour_passes);
+    }
+}
+
+// argmin over the K chains: strict <, first index wins (NaiveControlSampler.cpp:55, RRT.cpp:467);
+// copies the winner chain into the best buffers and optionally appends it to the tree.
+__global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
+{
+    __shared__ double s_key[32];
+    __shared__ int s_idx[32];
+    const int tid = threadIdx.x;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double best = inf;
+    int best_k = -1;
+    for (int k = tid; k < p.K; k += blockDim.x) {
+        if (p.nok[k] <= 0) continue;
+        double d = p.dist[k];
+        double key = !p.has_dest ? 0.0 : (p.compare_f32 ? (double)(float)d : d);
+        // the reference starts from max() and compares with <: a key that is not below it never wins
+        double limit = p.compare_f32 ? (double)3.402823466e+38f : 1.7976931348623157e+308;
+        if (p.has_dest && !(key < limit)) continue;
+        if (best_k < 0 || key < best) {
+            best = key;
+            best_k = k;
+        }
+    }
+    // warp then block reduction on (key, k): smaller key, then smaller k
+    for (int off = 16; off > 0; off >>= 1) {
+        double ob = __shfl_down_sync(FULL, best, off);
+        int ok = __shfl_down_sync(FULL, best_k, off);
+        if (ok >= 0 && (best_k < 0 || ob < best || (ob == best && ok < best_k))) {
+            best = ob;
+            best_k = ok;
+        }
+    }
+    if ((tid & 31) == 0) {
+        s_key[tid >> 5] = best;
+        s_idx[tid >> 5] = best_k;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int nw = (blockDim.x + 31) >> 5;
+        best = tid < nw ? s_key[tid] : inf;
+        best_k = tid < nw ? s_idx[tid] : -1;
+        for (int off = 16; off > 0; off >>= 1) {
+            double ob = __shfl_down_sync(FULL, best, off);
+            int ok = __shfl_down_sync(FULL, best_k, off);
+            if (ok >= 0 && (best_k < 0 || ob < best || (ob == best && ok < best_k))) {
+                best = ob;
+                best_k = ok;
+            }
+        }
+        if (tid == 0) {
+            s_idx[0] = best_k;
+        }
+    }
+    __syncthreads();
+    best_k = s_idx[0];
+    const int L = p.L, B = p.B;
+    int n_ok = best_k >= 0 ? p.nok[best_k] : 0;
+    int first = -1;
+    if (best_k >= 0 && p.append && tid == 0) {
+        // tree append of the winner chain (RearrangementRRT::addToTree, RRT.cpp:234-244)
+        long long n0 = *p.tree_size;
+        first = (int)n0;
+        *p.tree_size = n0 + n_ok;
+    }
+    if (tid == 0) {
+        p.best->k = best_k < 0 ? -1 : best_k + p.k_offset;
+        p.best->n_ok = n_ok;
+        p.best->goal_step = best_k < 0 ? -1 : p.goal_step[best_k];
+        p.best->distance = best_k < 0 ? inf : p.dist[best_k];
+        p.best->tree_index = (best_k >= 0 && p.append) ? first : -1;
+        s_idx[1] = first;
+    }
+    __syncthreads();
+    first = s_idx[1];
+    for (int i = tid; i < L * 3 * B; i += blockDim.x)
+        p.best_states[i] = best_k < 0 ? 0.0f : p.states[(size_t)best_k * L * 3 * B + i];
+    for (int i = tid; i < L * MPS_CONTROL_DIM; i += blockDim.x) {
+        float v = 0.0f;
+        if (best_k >= 0) {
+            int l = i / MPS_CONTROL_DIM, c = i % MPS_CONTROL_DIM;
+            v = c == 4 ? p.rest[(size_t)best_k * L + l] : p.controls[((size_t)best_k * L + l) * MPS_CONTROL_DIM + c];
+        }
+        p.best_controls[i] = v;
+    }
+    for (int i = tid; i < L; i += blockDim.x) p.best_flags[i] = best_k < 0 ? 0u : p.flags[(size_t)best_k * L + i];
+    if (best_k >= 0 && p.append && first >= 0) {
+        const size_t cap = p.tree_cap;
+        for (int i = tid; i < n_ok * 3 * B; i += blockDim.x) {
+            int l = i / (3 * B), r = i % (3 * B);
+            p.tree_states[(size_t)r * cap + first + l] = p.states[((size_t)best_k * L + l) * 3 * B + r];
+        }
+        for (int i = tid; i < n_ok * MPS_CONTROL_DIM; i += blockDim.x) {
+            int l = i / MPS_CONTROL_DIM, c = i % MPS_CONTROL_DIM;
+            float v = c == 4 ? p.rest[(size_t)best_k * L + l]
+                             : p.controls[((size_t)best_k * L + l) * MPS_CONTROL_DIM + c];
+            p.tree_controls[(size_t)c * cap + first + l] = v;
+        }
+        for (int i = tid; i < n_ok; i += blockDim.x) {
+            p.tree_parent[first + i] = i == 0 ? p.parent : first + i - 1;
+            p.tree_slice[first + i] = -1;
+        }
+    }
+}
+
+// isValid for M states, one warp per state
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DevScene& sc = *reinterpret_cast<DevScene*>(smem_raw);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.scene);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevScene) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int B = sc.B;
+    unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)warp * p.warp_bytes;
+    WarpMem W;
+    W.px = reinterpret_cast<float*>(wbase);
+    W.py = W.px + 32;
+    W.pc = W.py + 32;
+    W.ps = W.pc + 32;
+    W.man = W.ps + 32;
+    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_FIELDS * sc.Mcap);
+    Body bd;
+    bd.live = lane < B;
+    bd.dynamic = false;
+    bd.inv_m = bd.inv_i = bd.mass = bd.inertia = bd.lin_cap = bd.ang_cap = 0.0f;
+    bd.x = bd.y = bd.th = 0.0f;
+    bd.c = 1.0f;
+    bd.s = 0.0f;
+    bd.vx = bd.vy = bd.w = 0.0f;
+    for (int i = blockIdx.x * WARPS + warp; i < p.n; i += gridDim.x * WARPS) {
+        float sx = 0.0f, sy = 0.0f, sth = 0.0f;
+        if (bd.live) {
+            sx = p.states[(size_t)i * 3 * B + 3 * lane];
+            sy = p.states[(size_t)i * 3 * B + 3 * lane + 1];
+            sth = p.states[(size_t)i * 3 * B + 3 * lane + 2];
+        }
+        uint32_t f = state_validity_flags(sc, W, bd, lane, sx, sy, sth, nullptr);
+        if (lane == 0) {
+            p.flags[i] = f;
+            p.valid[i] = f == 0u ? 1 : 0;
+        }
+    }
+}
+
+}  // namespace
+
+size_t mps_rollout_warp_bytes(const DevScene& sc)
+{
+    size_t b = 4 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) + (size_t)sc.B * sc.slot_stride;
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t mps_rollout_scene_bytes() { return (sizeof(DevScene) + 15) & ~(size_t)15; }
+
+#define ROLLOUT_WARPS 4
+
+cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, cudaStream_t stream)
+{
+    RolloutParams p = p_in;
+    size_t smem = p.scene_bytes + (size_t)ROLLOUT_WARPS * p.warp_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ROLLOUT_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int blocks_per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<ROLLOUT_WARPS>,
+                                                                  ROLLOUT_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int want = (p.K + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS;
+    int grid = num_sms * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    rollout_kernel<ROLLOUT_WARPS><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
+{
+    int threads = p.K >= 1024 ? 1024 : ((p.K + 31) / 32) * 32;
+    if (threads < 32) threads = 32;
+    select_kernel<<<1, threads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream)
+{
+    size_t smem = p.scene_bytes + (size_t)ROLLOUT_WARPS * p.warp_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(validity_kernel<ROLLOUT_WARPS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int want = (p.n + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS;
+    int grid = num_sms * 4;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    validity_kernel<ROLLOUT_WARPS><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}

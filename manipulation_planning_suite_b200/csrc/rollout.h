@@ -1,0 +1,74 @@
+// rollout.h — launch interface of rollout.cu (internal to libmps_b200.so)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mps_b200.h"
+
+struct DevScene;
+
+struct RolloutParams {
+    const DevScene* scene;  // device copy
+    size_t scene_bytes;     // shared-memory bytes reserved for the scene copy
+    size_t warp_bytes;      // shared-memory bytes per warp
+    const float* start;     // [3B]
+    const float* controls;  // [K][L][5]
+    const int32_t* n_ctrl;  // [K] or nullptr
+    int K, L;
+    const float* dest;     // [3B] or nullptr
+    const float* weights;  // [B] or nullptr
+    uint32_t mask;
+    const mps_goal* goals;
+    int n_goals;
+    const float* ball_center;  // [3B] or nullptr
+    float ball_radius;
+    float* out_states;    // [K][L][3B]
+    float* out_rest;      // [K][L]
+    uint32_t* out_flags;  // [K][L]
+    int32_t* out_steps;   // [K][L]
+    double* out_dist;     // [K]
+    int32_t* out_nok;     // [K]
+    int32_t* out_goal_step;  // [K]
+    unsigned int* work_counter;
+    unsigned long long* counters;  // [4] or nullptr
+};
+
+struct SelectParams {
+    int K, L, B;
+    int has_dest, compare_f32, k_offset;
+    const double* dist;
+    const int32_t* nok;
+    const int32_t* goal_step;
+    const float* states;
+    const float* rest;
+    const uint32_t* flags;
+    const float* controls;
+    mps_extend_best* best;
+    float* best_states;
+    float* best_controls;
+    uint32_t* best_flags;
+    // optional fused tree append
+    int append, parent;
+    long long* tree_size;
+    size_t tree_cap;
+    float* tree_states;
+    float* tree_controls;
+    int32_t* tree_parent;
+    int32_t* tree_slice;
+};
+
+struct ValidityParams {
+    const DevScene* scene;
+    size_t scene_bytes, warp_bytes;
+    const float* states;  // [n][3B]
+    int n;
+    uint8_t* valid;
+    uint32_t* flags;
+};
+
+size_t mps_rollout_warp_bytes(const DevScene& sc);
+size_t mps_rollout_scene_bytes();
+cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, cudaStream_t stream);
+cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream);
+cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream);

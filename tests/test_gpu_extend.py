@@ -1,0 +1,233 @@
+"""GPU parity of the rollout path against the CPU oracle, through the C ABI.
+
+Bar: states within 1e-4 m / 1e-3 rad per body, flags / rest times / winner identical,
+distances identical as doubles.  The physics spec fixes the operation order, so the expected
+difference is zero; the test asserts the stated tolerance and reports exact-match counts.
+"""
+import numpy as np
+import pytest
+
+from manipulation_planning_suite_b200 import abi, api, scenes
+
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-4
+ANG_TOL = 1e-3
+
+
+def _ang_diff(a, b):
+    d = np.abs(a - b)
+    return np.minimum(d, 2 * np.pi - d)
+
+
+def assert_states_close(got, want, flags, what=""):
+    """got / want: [..., 3B]; rows whose flags carry OVERFLOW are skipped (their state is unspecified)."""
+    g = got.reshape(-1, got.shape[-1] // 3, 3)
+    w = want.reshape(-1, want.shape[-1] // 3, 3)
+    f = flags.reshape(-1)
+    keep = ((f & abi.MPS_F_RAN) != 0) & ((f & abi.MPS_F_OVERFLOW) == 0)
+    dpos = np.abs(g[keep][:, :, :2] - w[keep][:, :, :2]).max() if keep.any() else 0.0
+    dang = _ang_diff(g[keep][:, :, 2], w[keep][:, :, 2]).max() if keep.any() else 0.0
+    assert dpos <= POS_TOL, f"{what}: position differs by {dpos}"
+    assert dang <= ANG_TOL, f"{what}: angle differs by {dang}"
+    return dpos, dang, int((g[keep] == w[keep]).all(axis=(1, 2)).sum()), int(keep.sum())
+
+
+def compare_extend(sc, start, controls, **kw):
+    ctx = api.Context(sc)
+    got = ctx.extend(start, controls, dump=True, **kw)
+    want = ob.extend(sc, start, controls, **kw)
+    assert np.array_equal(got.all_flags, want["all_flags"]), "flags differ"
+    assert np.array_equal(got.all_steps, want["all_steps"]), "step counts differ"
+    assert np.array_equal(got.all_rest, want["all_rest"]), "rest times differ"
+    dpos, dang, exact, n = assert_states_close(got.all_states, want["all_states"], want["all_flags"], "all_states")
+    assert np.array_equal(got.all_dist, want["all_dist"]), "distances differ"
+    assert got.k == want["k"], f"winner differs: {got.k} vs {want['k']}"
+    assert got.n_ok == want["n_ok"]
+    assert got.goal_step == want["goal_step"]
+    if got.k >= 0:
+        assert got.distance == want["distance"]
+        assert np.array_equal(got.best_flags, want["best_flags"])
+        assert np.array_equal(got.best_controls, want["best_controls"])
+        assert_states_close(got.best_states, want["best_states"], want["best_flags"], "best_states")
+    ctx.close()
+    return dict(dpos=dpos, dang=dang, exact=exact, n=n, got=got, want=want)
+
+
+@pytest.mark.parametrize("n_objects,K,seed", [(3, 10, 0), (3, 64, 1), (6, 128, 2), (8, 96, 3), (16, 64, 4)])
+def test_single_control_rollouts_match_oracle(n_objects, K, seed):
+    sc, _ = scenes.make_scene(n_objects, seed=seed)
+    start = scenes.cluttered_start(sc, seed + 10)
+    rng = np.random.RandomState(seed)
+    controls = scenes.sample_controls_towards(rng, sc, start, K, 1)
+    dest = scenes.sample_state(rng, sc)
+    r = compare_extend(sc, start, controls, dest=dest, mask=1 << 1)
+    # contact must actually have happened in this batch, otherwise the test says little
+    moved = np.abs(r["want"]["all_states"][:, 0, 3:] - start[None, 3:]).max(axis=1) > 1e-4
+    assert moved.mean() > 0.3
+    assert r["exact"] == r["n"], f"only {r['exact']} of {r['n']} rollouts bit-identical (within tolerance though)"
+
+
+def test_random_controls_free_space():
+    sc, start = scenes.make_scene(3, seed=1001)
+    rng = np.random.RandomState(5)
+    controls = scenes.sample_controls(rng, 40, 1)
+    compare_extend(sc, start, controls, dest=scenes.sample_state(rng, sc))
+
+
+@pytest.mark.parametrize("compare_f32", [False, True])
+def test_chains_hybrid(compare_f32):
+    sc, _ = scenes.make_scene(6, seed=7)
+    start = scenes.cluttered_start(sc, 17)
+    rng = np.random.RandomState(11)
+    K, L = 48, 4
+    controls = scenes.sample_controls_towards(rng, sc, start, K, L)
+    n_ctrl = rng.randint(1, L + 1, size=K).astype(np.int32)
+    dest = scenes.sample_state(rng, sc)
+    goals = [(1, float(start[3]) + 0.1, float(start[4]), 0.15)]
+    r = compare_extend(sc, start, controls, n_ctrl=n_ctrl, dest=dest, compare_f32=compare_f32, goals=goals,
+                       ball_center=start, ball_radius=0.3)
+    fl = r["want"]["all_flags"]
+    assert ((fl & abi.MPS_F_GOAL) != 0).any(), "no chain reached the goal: weak test"
+    assert ((fl & abi.MPS_F_IN_BALL) != 0).any()
+
+
+def test_invalid_outcomes_and_policy():
+    """Robot driven into a wall (robot-static forbidden) and out of bounds; object-object forbidden pair."""
+    sc, _ = scenes.make_scene(3, seed=3)
+    sc.pair_forbidden[1] |= 1 << 2
+    sc.pair_forbidden[2] |= 1 << 1
+    start = np.array([0.7, 0.0, 0.0, 0.0, 0.5, 0.3, 0.17, 0.5, 0.0, -0.5, -0.5, 1.0], np.float32)
+    controls = np.array([
+        [0.5, 0.0, 0.0, 0.9, 0.0],    # robot into the +x wall / out of bounds
+        [-0.2, 0.0, 0.5, 0.3, 0.0],   # free motion
+        [-0.5, 0.35, 0.0, 0.9, 0.0],  # pushes object 1 into object 2 (forbidden pair)
+        [0.0, 0.0, 0.0, 0.1, 0.0],    # null velocity
+    ], np.float32)
+    r = compare_extend(sc, start, controls, dest=start)
+    fl = r["want"]["all_flags"][:, 0]
+    assert not (fl[0] & abi.MPS_F_OK)
+    assert fl[1] & abi.MPS_F_OK
+
+
+def test_all_invalid_returns_minus_one():
+    sc, _ = scenes.make_scene(3, seed=3)
+    start = np.array([0.9, 0.0, 0.0, 0.0, 0.5, 0.3, 0.3, 0.5, 0.0, -0.5, -0.5, 1.0], np.float32)
+    controls = np.tile(np.array([0.6, 0.0, 0.0, 1.0, 0.0], np.float32), (5, 1))
+    r = compare_extend(sc, start, controls, dest=start)
+    assert r["got"].k == -1 and r["got"].n_ok == 0
+
+
+def test_ties_first_index_wins():
+    sc, start = scenes.make_scene(3, seed=1001)
+    c = np.array([0.1, 0.05, 0.2, 0.3, 0.0], np.float32)
+    controls = np.tile(c, (7, 1))
+    r = compare_extend(sc, start, controls, dest=start)
+    assert r["got"].k == 0
+
+
+def test_strict_active_contacts_flag():
+    sc, _ = scenes.make_scene(3, seed=3)
+    sc.strict_active_contacts = 1
+    sc.pair_forbidden[0] |= 1 << 1
+    sc.pair_forbidden[1] |= 1 << 0
+    start = np.array([0.0, 0.0, 0.0, 0.15, 0.0, 0.3, 0.5, 0.5, 0.0, -0.5, -0.5, 1.0], np.float32)
+    controls = np.array([[0.4, 0.0, 0.0, 0.5, 0.0], [-0.4, 0.0, 0.0, 0.5, 0.0]], np.float32)
+    r = compare_extend(sc, start, controls, dest=start)
+    assert r["want"]["all_flags"][0, 0] & abi.MPS_F_ACTIVE_CONTACT
+
+
+def test_manifold_overflow_flag():
+    sc, _ = scenes.make_scene(8, seed=2)
+    sc.max_manifolds = 2
+    start = scenes.cluttered_start(sc, 4)
+    rng = np.random.RandomState(2)
+    controls = scenes.sample_controls_towards(rng, sc, start, 32, 1)
+    r = compare_extend(sc, start, controls, dest=start)
+    assert ((r["want"]["all_flags"] & abi.MPS_F_OVERFLOW) != 0).any()
+
+
+def test_propagate_single_call_and_alias():
+    sc, _ = scenes.make_scene(3, seed=3)
+    start = np.array([0.0, 0.0, 0.0, 0.15, 0.01, 0.3, 0.32, 0.0, 0.0, 0.5, 0.5, 0.0], np.float32)
+    control = np.array([0.4, 0.0, 0.0, 0.6, 0.123], np.float32)
+    ctx = api.Context(sc)
+    ok, out, c, fl = ctx.propagate(start, control)
+    wok, wout, wc, wfl, _ = ob.propagate(sc, start, control)
+    assert ok == wok and fl == wfl
+    assert np.array_equal(c, wc)
+    assert np.abs(out - wout).max() <= POS_TOL
+    # replay determinism (the reference's verifySolution contract, OraclePushPlanner.cpp:495-519)
+    ok2, out2, c2, _ = ctx.propagate(start, control)
+    assert np.array_equal(out, out2) and np.array_equal(c, c2)
+    ctx.close()
+
+
+def test_is_valid_batch_matches_oracle():
+    sc, _ = scenes.make_scene(6, seed=9)
+    rng = np.random.RandomState(9)
+    states = np.stack([scenes.sample_state(rng, sc) * (1.08 if i % 7 == 0 else 1.0) for i in range(300)])
+    states[5] = scenes.cluttered_start(sc, 1)
+    ctx = api.Context(sc)
+    valid, flags = ctx.is_valid(states)
+    for i in range(len(states)):
+        wok, wfl = ob.is_valid(sc, states[i])
+        assert bool(valid[i]) == wok and int(flags[i]) == wfl, i
+    assert valid.any() and (~valid).any()
+    ctx.close()
+
+
+def test_run_to_run_determinism_large_batch():
+    sc, _ = scenes.make_scene(6, seed=21)
+    start = scenes.cluttered_start(sc, 22)
+    rng = np.random.RandomState(23)
+    controls = scenes.sample_controls_towards(rng, sc, start, 2048, 2)
+    dest = scenes.sample_state(rng, sc)
+    ctx = api.Context(sc)
+    a = ctx.extend(start, controls, dump=True, dest=dest, compare_f32=True)
+    b = ctx.extend(start, controls, dump=True, dest=dest, compare_f32=True)
+    assert a.k == b.k and np.array_equal(a.all_states, b.all_states) and np.array_equal(a.all_flags, b.all_flags)
+    # a sample of the batch against the oracle
+    idx = rng.choice(2048, 48, replace=False)
+    want = ob.extend(sc, start, controls[idx], dest=dest, compare_f32=True)
+    assert np.array_equal(a.all_flags[idx], want["all_flags"])
+    assert_states_close(a.all_states[idx], want["all_states"], want["all_flags"])
+    assert np.array_equal(a.all_dist[idx], want["all_dist"])
+    ctx.close()
+
+
+def test_extend_appends_winner_to_tree():
+    sc, _ = scenes.make_scene(3, seed=3)
+    start = scenes.cluttered_start(sc, 8)
+    rng = np.random.RandomState(3)
+    controls = scenes.sample_controls_towards(rng, sc, start, 16, 2)
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    root = tree.add(start)
+    r = ctx.extend(start, controls, dest=scenes.sample_state(rng, sc), append_to_tree=True, parent=root)
+    assert r.k >= 0 and r.tree_index == 1
+    assert tree.size() == 1 + r.n_ok
+    for l in range(r.n_ok):
+        s, p, c, sl = tree.get(r.tree_index + l)
+        assert np.array_equal(s, r.best_states[l])
+        assert np.array_equal(c, r.best_controls[l])
+        assert p == (root if l == 0 else r.tree_index + l - 1)
+    path = tree.backtrack(r.tree_index + r.n_ok - 1)
+    assert list(path) == list(range(0, r.n_ok + 1))
+    ctx.close()
+
+
+def test_bad_arguments_are_errors_not_crashes():
+    sc, start = scenes.make_scene(3, seed=3)
+    ctx = api.Context(sc)
+    with pytest.raises(api.MpsError):
+        ctx.extend(start, np.zeros((1, 17, 5), np.float32))  # L > 16
+    with pytest.raises(api.MpsError):
+        ctx.extend(start, np.zeros((2, 1, 5), np.float32), goals=[(9, 0.0, 0.0, 0.1)])  # goal body out of range
+    ctx.close()
+    bad = scenes.default_scene()
+    bad.n_bodies = 1
+    with pytest.raises(api.MpsError):
+        api.Context(bad)
