@@ -66,6 +66,7 @@ extern "C" {
 #define MPS_F_BAD_CONTACT (1u << 8) /* result has a contact the policy forbids       */
 #define MPS_F_OVERFLOW (1u << 9)    /* more touching pairs than max_manifolds        */
 #define MPS_F_ACTIVE_CONTACT (1u << 10) /* strict_active_contacts only               */
+#define MPS_F_JAMMED (1u << 11)     /* rest phase aborted: penetration > pen_max for jam_steps steps */
 
 /*
  * Scene = everything that is fixed for a planning problem: bodies, statics,
@@ -126,7 +127,7 @@ typedef struct mps_scene {
     float w_rest;       /* atRest angular threshold */
     int32_t max_manifolds;          /* touching-pair capacity per rollout, <= MPS_MAX_MANIFOLDS */
     int32_t strict_active_contacts; /* 0 = replicate SimEnvStatePropagator.cpp:79 shadowing quirk */
-    int32_t _pad1;
+    int32_t jam_steps;              /* rest phase gives up after this many consecutive steps deeper than pen_max; 0 = never */
 } mps_scene;
 
 /* RelocationGoalSpecification reduced to what distanceGoal reads (ObjectsRelocationGoal.cpp:108-123) */
@@ -252,10 +253,27 @@ int mps_tree_fill_random(mps_ctx* ctx, int64_t n, uint64_t seed, int32_t n_slice
 /* copy node states [first, first+n) back to the host, node-major [n][3B] */
 int mps_tree_read_states(mps_ctx* ctx, int64_t first, int64_t n, float* states);
 
+/* ---- packed winner record (multi-GPU gather) ---------------------------- */
+/* Layout: mps_extend_best | float best_states[L][3B] | float best_controls[L][5] | uint32 best_flags[L],
+ * padded to 8 bytes.  mps_extend_record_to copies the record of the last launch device-to-device
+ * (asynchronously on the ctx stream) into caller-owned device memory, e.g. the input of an NCCL
+ * all-gather. */
+int mps_extend_record_size(mps_ctx* ctx, int64_t* bytes);
+int mps_extend_record_to(mps_ctx* ctx, void* dst_device);
+
 /* ---- timing helper ---------------------------------------------------- */
 /* Runs `iters` back-to-back launches of the uploaded extend (what=0) or NN batch (what=1)
  * on the ctx stream between two CUDA events and returns the elapsed milliseconds. */
 int mps_time_launches(mps_ctx* ctx, int32_t what, int32_t iters, float* elapsed_ms);
+/* Per-launch device time of the rollout kernel: when enabled, every mps_extend_launch brackets the
+ * rollout kernel with CUDA events on the ctx stream (ring of 512 launches).  mps_extend_kernel_times
+ * synchronises, writes the elapsed milliseconds of the recorded launches (oldest first) and clears the ring. */
+int mps_ctx_set_kernel_timing(mps_ctx* ctx, int32_t enabled);
+int mps_extend_kernel_times(mps_ctx* ctx, float* ms, int32_t max_n, int32_t* n);
+/* FP32 FMA microbenchmark on the ctx device: the measured peak the rollout roofline is quoted against */
+int mps_measure_fp32_peak(mps_ctx* ctx, float* tflops);
+/* raw cudaStream_t the ctx enqueues on (for event timing by the caller) */
+int mps_ctx_stream(mps_ctx* ctx, void** cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ MPS_F_INFEASIBLE = 1 << 7
 MPS_F_BAD_CONTACT = 1 << 8
 MPS_F_OVERFLOW = 1 << 9
 MPS_F_ACTIVE_CONTACT = 1 << 10
+MPS_F_JAMMED = 1 << 11
 
 _f32 = C.c_float
 _i32 = C.c_int32
@@ -88,7 +89,7 @@ class Scene(C.Structure):
         ("w_rest", _f32),
         ("max_manifolds", _i32),
         ("strict_active_contacts", _i32),
-        ("_pad1", _i32),
+        ("jam_steps", _i32),
     ]
 
 
@@ -195,6 +196,12 @@ SYMBOLS = {
     "mps_tree_fill_random": (C.c_int, [_ctx, C.c_int64, C.c_uint64, _i32]),
     "mps_tree_read_states": (C.c_int, [_ctx, C.c_int64, C.c_int64, _P(_f32)]),
     "mps_time_launches": (C.c_int, [_ctx, _i32, _i32, _P(_f32)]),
+    "mps_extend_record_size": (C.c_int, [_ctx, _P(C.c_int64)]),
+    "mps_extend_record_to": (C.c_int, [_ctx, C.c_void_p]),
+    "mps_ctx_set_kernel_timing": (C.c_int, [_ctx, _i32]),
+    "mps_extend_kernel_times": (C.c_int, [_ctx, _P(_f32), _i32, _P(_i32)]),
+    "mps_measure_fp32_peak": (C.c_int, [_ctx, _P(_f32)]),
+    "mps_ctx_stream": (C.c_int, [_ctx, _P(C.c_void_p)]),
 }
 
 

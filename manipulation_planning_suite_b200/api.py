@@ -215,6 +215,28 @@ class Context:
         self._check(self.lib.mps_time_launches(self.h, what, iters, C.byref(ms)))
         return float(ms.value)
 
+    def set_kernel_timing(self, enabled: bool):
+        self._check(self.lib.mps_ctx_set_kernel_timing(self.h, 1 if enabled else 0))
+
+    def kernel_times(self) -> np.ndarray:
+        buf = np.zeros(512, np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.mps_extend_kernel_times(self.h, _fp(buf), 512, C.byref(n)))
+        return buf[: n.value].copy()
+
+    def fp32_peak_tflops(self) -> float:
+        v = C.c_float(0)
+        self._check(self.lib.mps_measure_fp32_peak(self.h, C.byref(v)))
+        return float(v.value)
+
+    def record_size(self) -> int:
+        n = C.c_int64(0)
+        self._check(self.lib.mps_extend_record_size(self.h, C.byref(n)))
+        return n.value
+
+    def record_to(self, device_ptr: int):
+        self._check(self.lib.mps_extend_record_to(self.h, C.c_void_p(device_ptr)))
+
     # ---- validity -------------------------------------------------------
     def is_valid(self, states):
         st = _f32(states).reshape(-1, 3 * self.B)

@@ -14,6 +14,7 @@
 
 #include "mps_device.cuh"
 #include "nn_scan.h"
+#include "peak.h"
 #include "rollout.h"
 
 namespace {
@@ -40,7 +41,7 @@ struct mps_ctx {
     // extend: device buffers
     DevBuf d_start, d_controls, d_nctrl, d_dest, d_weights, d_goals, d_ball;
     DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
-    DevBuf d_best, d_best_states, d_best_controls, d_best_flags;
+    DevBuf d_record;  // packed winner record: best | states | controls | flags
     DevBuf d_work, d_counters;
     // pinned staging
     void* h_stage = nullptr;
@@ -65,7 +66,13 @@ struct mps_ctx {
 
     // validity
     DevBuf d_vstates, d_valid, d_vflags;
+
+    // optional per-launch timing of the rollout kernel
+    bool timing = false;
+    std::vector<cudaEvent_t> ev0, ev1;
+    int ev_count = 0;
 };
+#define MPS_EVENT_RING 512
 
 static int mps_fail(mps_ctx* ctx, int code, const std::string& msg)
 {
@@ -122,6 +129,13 @@ static void free_buf(DevBuf& b)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static inline size_t record_bytes(int B, int L)
+{
+    return align_up(sizeof(mps_extend_best) + sizeof(float) * (size_t)L * (3 * B + MPS_CONTROL_DIM) +
+                        sizeof(uint32_t) * (size_t)L,
+                    8);
+}
+
 // ---- scene ------------------------------------------------------------------
 
 static float bounding_radius(int shape, float hx, float hy)
@@ -165,6 +179,7 @@ static void derive_scene(const mps_scene* sc, DevScene* d)
     d->vel_iters = sc->vel_iters;
     d->Mcap = sc->max_manifolds;
     d->strict = sc->strict_active_contacts;
+    d->jam_steps = sc->jam_steps;
     d->slot_stride = (int)align_up((size_t)(B + S), 4);
     d->dt = sc->dt;
     d->t_max = sc->t_max;
@@ -285,6 +300,7 @@ void mps_scene_defaults(mps_scene* sc)
     sc->w_rest = 0.01f;
     sc->max_manifolds = MPS_MAX_MANIFOLDS;
     sc->strict_active_contacts = 0;
+    sc->jam_steps = 25;
 }
 
 int mps_ctx_create_on_stream(const mps_scene* scene, int device, void* cuda_stream, mps_ctx** out)
@@ -348,8 +364,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_start, &ctx->d_controls, &ctx->d_nctrl, &ctx->d_dest, &ctx->d_weights, &ctx->d_goals,
                       &ctx->d_ball, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
-                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_best, &ctx->d_best_states, &ctx->d_best_controls,
-                      &ctx->d_best_flags, &ctx->d_work, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
+                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
                       &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_out_idx, &ctx->d_out_dist, &ctx->d_part_d,
                       &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags};
@@ -360,6 +375,8 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->tree.slice) cudaFree(ctx->tree.slice);
     if (ctx->d_scene) cudaFree(ctx->d_scene);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -772,10 +789,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     if ((rc = ensure(ctx, ctx->d_dist, sizeof(double) * (size_t)K))) return rc;
     if ((rc = ensure(ctx, ctx->d_nok, sizeof(int32_t) * (size_t)K))) return rc;
     if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * (size_t)K))) return rc;
-    if ((rc = ensure(ctx, ctx->d_best, sizeof(mps_extend_best)))) return rc;
-    if ((rc = ensure(ctx, ctx->d_best_states, sizeof(float) * 3 * B * L))) return rc;
-    if ((rc = ensure(ctx, ctx->d_best_controls, sizeof(float) * MPS_CONTROL_DIM * L))) return rc;
-    if ((rc = ensure(ctx, ctx->d_best_flags, sizeof(uint32_t) * L))) return rc;
+    if ((rc = ensure(ctx, ctx->d_record, record_bytes(B, L)))) return rc;
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
@@ -844,10 +858,13 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     sp.rest = rp.out_rest;
     sp.flags = rp.out_flags;
     sp.controls = rp.controls;
-    sp.best = (mps_extend_best*)ctx->d_best.p;
-    sp.best_states = (float*)ctx->d_best_states.p;
-    sp.best_controls = (float*)ctx->d_best_controls.p;
-    sp.best_flags = (uint32_t*)ctx->d_best_flags.p;
+    {
+        char* rec = (char*)ctx->d_record.p;
+        sp.best = (mps_extend_best*)rec;
+        sp.best_states = (float*)(rec + sizeof(mps_extend_best));
+        sp.best_controls = sp.best_states + (size_t)L * 3 * B;
+        sp.best_flags = (uint32_t*)(sp.best_controls + (size_t)L * MPS_CONTROL_DIM);
+    }
     sp.append = in->append_to_tree;
     sp.parent = in->parent;
     ctx->ext_K = K;
@@ -873,7 +890,13 @@ int mps_extend_launch(mps_ctx* ctx)
         sp.tree_slice = ctx->tree.slice;
         ctx->tree_upper += ctx->ext_L;
     }
+    const bool timed = ctx->timing && ctx->ev_count < MPS_EVENT_RING;
+    if (timed) MPS_CUDA_CHECK(cudaEventRecord(ctx->ev0[ctx->ev_count], ctx->stream), ctx);
     MPS_CUDA_CHECK(mps_launch_rollout(ctx->rp, ctx->num_sms, ctx->stream), ctx);
+    if (timed) {
+        MPS_CUDA_CHECK(cudaEventRecord(ctx->ev1[ctx->ev_count], ctx->stream), ctx);
+        ctx->ev_count++;
+    }
     MPS_CUDA_CHECK(mps_launch_select(sp, ctx->stream), ctx);
     ctx->launches += 2;
     return MPS_OK;
@@ -886,10 +909,10 @@ int mps_extend_fetch(mps_ctx* ctx, const mps_extend_out* out)
     const int B = ctx->scene.n_bodies, K = ctx->ext_K, L = ctx->ext_L;
     const size_t KL = (size_t)K * L;
     cudaStream_t s = ctx->stream;
-    if (out->best) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best, ctx->d_best.p, sizeof(mps_extend_best), cudaMemcpyDeviceToHost, s), ctx);
-    if (out->best_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_states, ctx->d_best_states.p, sizeof(float) * 3 * B * L, cudaMemcpyDeviceToHost, s), ctx);
-    if (out->best_controls) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_controls, ctx->d_best_controls.p, sizeof(float) * MPS_CONTROL_DIM * L, cudaMemcpyDeviceToHost, s), ctx);
-    if (out->best_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_flags, ctx->d_best_flags.p, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best, ctx->sp.best, sizeof(mps_extend_best), cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_states, ctx->sp.best_states, sizeof(float) * 3 * B * L, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best_controls) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_controls, ctx->sp.best_controls, sizeof(float) * MPS_CONTROL_DIM * L, cudaMemcpyDeviceToHost, s), ctx);
+    if (out->best_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_flags, ctx->sp.best_flags, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_states, ctx->d_states.p, sizeof(float) * 3 * B * KL, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_rest) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_rest, ctx->d_rest.p, sizeof(float) * KL, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_flags, ctx->d_flags.p, sizeof(uint32_t) * KL, cudaMemcpyDeviceToHost, s), ctx);
@@ -976,7 +999,71 @@ int mps_is_valid_batch(mps_ctx* ctx, const float* states, int32_t n, uint8_t* va
     return MPS_OK;
 }
 
+// ---- packed winner record -----------------------------------------------------------------------
+
+int mps_extend_record_size(mps_ctx* ctx, int64_t* bytes)
+{
+    if (!ctx || !bytes) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "no extend uploaded");
+    *bytes = (int64_t)record_bytes(ctx->scene.n_bodies, ctx->ext_L);
+    return MPS_OK;
+}
+
+int mps_extend_record_to(mps_ctx* ctx, void* dst_device)
+{
+    if (!ctx || !dst_device) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "no extend uploaded");
+    MPS_CUDA_CHECK(cudaMemcpyAsync(dst_device, ctx->d_record.p, record_bytes(ctx->scene.n_bodies, ctx->ext_L),
+                                   cudaMemcpyDeviceToDevice, ctx->stream),
+                   ctx);
+    return MPS_OK;
+}
+
 // ---- timing -----------------------------------------------------------------------------------
+
+int mps_ctx_set_kernel_timing(mps_ctx* ctx, int32_t enabled)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    if (enabled && ctx->ev0.empty()) {
+        ctx->ev0.resize(MPS_EVENT_RING);
+        ctx->ev1.resize(MPS_EVENT_RING);
+        for (int i = 0; i < MPS_EVENT_RING; ++i) {
+            MPS_CUDA_CHECK(cudaEventCreate(&ctx->ev0[i]), ctx);
+            MPS_CUDA_CHECK(cudaEventCreate(&ctx->ev1[i]), ctx);
+        }
+    }
+    ctx->timing = enabled != 0;
+    ctx->ev_count = 0;
+    return MPS_OK;
+}
+
+int mps_extend_kernel_times(mps_ctx* ctx, float* ms, int32_t max_n, int32_t* n)
+{
+    if (!ctx || !ms || !n) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    int cnt = ctx->ev_count < max_n ? ctx->ev_count : max_n;
+    for (int i = 0; i < cnt; ++i) MPS_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ctx->ev0[i], ctx->ev1[i]), ctx);
+    *n = cnt;
+    ctx->ev_count = 0;
+    return MPS_OK;
+}
+
+int mps_measure_fp32_peak(mps_ctx* ctx, float* tflops)
+{
+    if (!ctx || !tflops) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    MPS_CUDA_CHECK(mps_run_fma_peak(ctx->num_sms, ctx->stream, tflops), ctx);
+    return MPS_OK;
+}
+
+int mps_ctx_stream(mps_ctx* ctx, void** cuda_stream)
+{
+    if (!ctx || !cuda_stream) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    *cuda_stream = (void*)ctx->stream;
+    return MPS_OK;
+}
+
 
 int mps_time_launches(mps_ctx* ctx, int32_t what, int32_t iters, float* elapsed_ms)
 {

@@ -20,6 +20,10 @@
 #define NN_THREADS 256
 #define NN_REL_EPS 1.0e-4f
 #define NN_ABS_EPS 1.0e-15f
+#define NN_BODY_BATCH 4
+#define NN_MIN_BLOCKS 3
+#define NN_CAND_CAP 512
+#define NN_CTAS_PER_SM 3
 
 namespace {
 
@@ -66,18 +70,47 @@ __device__ __forceinline__ void take_min(double& bd, long long& bi, double od, l
     }
 }
 
-__global__ void __launch_bounds__(NN_THREADS) nn_scan_kernel(NNParams p)
+// One warp evaluates the reference's double expression for one node: lane i computes body i's term
+// (double sqrt is the expensive part), the terms are then added in body order so the sum has exactly the
+// rounding of the sequential loop in SimEnvWorldStateDistanceMeasure.cpp:41-46.
+__device__ __forceinline__ double warp_exact_distance(const TreeView& t, long long n, const float* s_q,
+                                                      const float* __restrict__ weights, uint32_t mask, double pw,
+                                                      double ow, int lane)
+{
+    double term = 0.0;
+    if (lane < t.B && ((mask >> lane) & 1u)) {
+        float x = t.states[(size_t)(3 * lane) * t.cap + n];
+        float y = t.states[(size_t)(3 * lane + 1) * t.cap + n];
+        float th = t.states[(size_t)(3 * lane + 2) * t.cap + n];
+        double cfg = mps_body_distance(x, y, th, s_q[3 * lane], s_q[3 * lane + 1], s_q[3 * lane + 2], pw, ow);
+        double w = weights ? (double)weights[lane] : 1.0;
+        term = w * cfg;
+    }
+    double dist = 0.0;
+    for (int i = 0; i < t.B; ++i) {
+        double ti = __shfl_sync(FULL, term, i);
+        if ((mask >> i) & 1u) dist += ti;
+    }
+    return dist;
+}
+
+__global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNParams p)
 {
     __shared__ float s_q[3 * MPS_MAX_BODIES];
     __shared__ float s_w[MPS_MAX_BODIES];
     __shared__ int s_act[MPS_MAX_BODIES];
     __shared__ int s_nact;
     __shared__ unsigned int s_bound;
+    __shared__ unsigned int s_ncand;
+    __shared__ unsigned int s_cand_d[NN_CAND_CAP];   // fp32 distance bits of the deferred candidates
+    __shared__ long long s_cand_i[NN_CAND_CAP];      // their node indices
     __shared__ double s_rd[NN_THREADS / 32];
     __shared__ long long s_ri[NN_THREADS / 32];
     __shared__ bool s_last;
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
     const int q = blockIdx.y;
     const int B = p.tree.B;
     uint32_t mask = p.masks ? p.masks[q] : 0xffffffffu;
@@ -96,6 +129,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_scan_kernel(NNParams p)
         }
         s_nact = n;
         s_bound = 0x7f800000u;  // +inf
+        s_ncand = 0u;
     }
     __syncthreads();
     const int nact = s_nact;
@@ -108,21 +142,32 @@ __global__ void __launch_bounds__(NN_THREADS) nn_scan_kernel(NNParams p)
     double best_d = __longlong_as_double(0x7ff0000000000000ll);
     long long best_i = -1;
 
+    // ---- streaming pass: fp32 metric for every node, candidates deferred ------------------------
     for (long long g = (long long)blockIdx.x * NN_THREADS + tid; g < groups; g += (long long)gridDim.x * NN_THREADS) {
         const long long n0 = g << 2;
         float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
-#pragma unroll 4
-        for (int a = 0; a < nact; ++a) {
-            const int i = s_act[a];
-            const float4 X = __ldg(reinterpret_cast<const float4*>(p.tree.states + (size_t)(3 * i) * cap + n0));
-            const float4 Y = __ldg(reinterpret_cast<const float4*>(p.tree.states + (size_t)(3 * i + 1) * cap + n0));
-            const float4 T = __ldg(reinterpret_cast<const float4*>(p.tree.states + (size_t)(3 * i + 2) * cap + n0));
-            const float qx = s_q[3 * i], qy = s_q[3 * i + 1], qth = s_q[3 * i + 2];
-            const float w = s_w[a];
-            d0 += w * body_term_f32(X.x, Y.x, T.x, qx, qy, qth, pwf, owf);
-            d1 += w * body_term_f32(X.y, Y.y, T.y, qx, qy, qth, pwf, owf);
-            d2 += w * body_term_f32(X.z, Y.z, T.z, qx, qy, qth, pwf, owf);
-            d3 += w * body_term_f32(X.w, Y.w, T.w, qx, qy, qth, pwf, owf);
+        for (int a0 = 0; a0 < nact; a0 += NN_BODY_BATCH) {
+            float4 X[NN_BODY_BATCH], Y[NN_BODY_BATCH], T[NN_BODY_BATCH];
+#pragma unroll
+            for (int u = 0; u < NN_BODY_BATCH; ++u) {  // all loads of the batch first: 3 * NN_BODY_BATCH LDG.128 in flight
+                const int a = a0 + u < nact ? a0 + u : nact - 1;
+                const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + n0;
+                X[u] = __ldg(reinterpret_cast<const float4*>(row));
+                Y[u] = __ldg(reinterpret_cast<const float4*>(row + cap));
+                T[u] = __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
+            }
+#pragma unroll
+            for (int u = 0; u < NN_BODY_BATCH; ++u) {
+                if (a0 + u < nact) {
+                    const int i = s_act[a0 + u];
+                    const float qx = s_q[3 * i], qy = s_q[3 * i + 1], qth = s_q[3 * i + 2];
+                    const float w = s_w[a0 + u];
+                    d0 += w * body_term_f32(X[u].x, Y[u].x, T[u].x, qx, qy, qth, pwf, owf);
+                    d1 += w * body_term_f32(X[u].y, Y[u].y, T[u].y, qx, qy, qth, pwf, owf);
+                    d2 += w * body_term_f32(X[u].z, Y[u].z, T[u].z, qx, qy, qth, pwf, owf);
+                    d3 += w * body_term_f32(X[u].w, Y[u].w, T[u].w, qx, qy, qth, pwf, owf);
+                }
+            }
         }
         if (filter >= 0) {
             const int4 sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + n0));
@@ -136,25 +181,45 @@ __global__ void __launch_bounds__(NN_THREADS) nn_scan_kernel(NNParams p)
             if (n0 + 2 >= N) d2 = inf;
             if (n0 + 3 >= N) d3 = inf;
         }
-        float b = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(&s_bound));
-        float thr = b * (1.0f + NN_REL_EPS) + NN_ABS_EPS;
+        // Tighten the CTA bound with this warp's fp32 minimum BEFORE testing against it.
         const float dm = fminf(fminf(d0, d1), fminf(d2, d3));
+        const unsigned am = __activemask();
+        const unsigned wmin = __reduce_min_sync(am, __float_as_uint(dm));  // d >= 0: uint order == float order
+        if (lane == (__ffs(am) - 1)) atomicMin(&s_bound, wmin);
+        __syncwarp(am);
+        const float b = fminf(__uint_as_float(*reinterpret_cast<volatile unsigned int*>(&s_bound)),
+                              __uint_as_float(wmin));
+        const float thr = b * (1.0f + NN_REL_EPS) + NN_ABS_EPS;
         if (dm <= thr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float dj = j == 0 ? d0 : j == 1 ? d1 : j == 2 ? d2 : d3;
                 if (dj <= thr && dj < inf) {
-                    const double e = exact_distance(p.tree, n0 + j, s_q, p.weights, mask, p.pw, p.ow);
-                    if (best_i < 0 || e < best_d) {  // ascending index inside a thread: strict < keeps the lowest
-                        best_d = e;
-                        best_i = n0 + j;
-                    }
-                    if (dj < b) {
-                        atomicMin(&s_bound, __float_as_uint(dj));
-                        b = dj;
-                        thr = b * (1.0f + NN_REL_EPS) + NN_ABS_EPS;
+                    const unsigned slot = atomicAdd(&s_ncand, 1u);
+                    if (slot < NN_CAND_CAP) {
+                        s_cand_d[slot] = __float_as_uint(dj);
+                        s_cand_i[slot] = n0 + j;
+                    } else {
+                        // list full (adversarial orderings): evaluate on the spot
+                        const double e = exact_distance(p.tree, n0 + j, s_q, p.weights, mask, p.pw, p.ow);
+                        take_min(best_d, best_i, e, n0 + j);
                     }
                 }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- deferred exact pass: only candidates still within the final CTA bound ---------------------
+    {
+        const float bf = __uint_as_float(s_bound);
+        const float thr = bf * (1.0f + NN_REL_EPS) + NN_ABS_EPS;
+        const int ncand = (int)min(s_ncand, (unsigned)NN_CAND_CAP);
+        for (int c = warp; c < ncand; c += NN_THREADS / 32) {
+            if (__uint_as_float(s_cand_d[c]) <= thr) {
+                const long long n = s_cand_i[c];
+                const double e = warp_exact_distance(p.tree, n, s_q, p.weights, mask, p.pw, p.ow, lane);
+                if (lane == 0) take_min(best_d, best_i, e, n);
             }
         }
     }
@@ -165,9 +230,9 @@ __global__ void __launch_bounds__(NN_THREADS) nn_scan_kernel(NNParams p)
         long long oi = __shfl_down_sync(FULL, best_i, off);
         take_min(best_d, best_i, od, oi);
     }
-    if ((tid & 31) == 0) {
-        s_rd[tid >> 5] = best_d;
-        s_ri[tid >> 5] = best_i;
+    if (lane == 0) {
+        s_rd[warp] = best_d;
+        s_ri[warp] = best_i;
     }
     __syncthreads();
     if (tid < 32) {
@@ -326,7 +391,7 @@ int mps_nn_grid_x(long long n, int num_sms)
 {
     long long groups = (n + 3) / 4;
     long long want = (groups + NN_THREADS - 1) / NN_THREADS;
-    long long cap = (long long)num_sms * 4;
+    long long cap = (long long)num_sms * NN_CTAS_PER_SM;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int)want;

@@ -30,8 +30,11 @@
 namespace {
 
 // manifold fields in the warp's shared slice, SoA: field f of slot m at man[f * Mcap + m]
-enum { MF_META = 0, MF_NX, MF_NY, MF_FRICTION, MF_P0 };
-enum { PF_RAX = 0, PF_RAY, PF_RBX, PF_RBY, PF_NMASS, PF_TMASS, PF_BIAS, PF_ACCN, PF_ACCT, PF_COUNT };
+enum { MF_META = 0, MF_NX, MF_NY, MF_FRICTION, MF_MANX, MF_MANY, MF_MBNX, MF_MBNY, MF_P0 };
+enum {
+    PF_RNA = 0, PF_RNB, PF_RTA, PF_RTB, PF_IARNA, PF_IBRNB, PF_IARTA, PF_IBRTB,
+    PF_NMASS, PF_TMASS, PF_BIAS, PF_ACCN, PF_ACCT, PF_COUNT
+};
 #define MF_FIELDS (MF_P0 + 2 * PF_COUNT)
 
 struct Shape {
@@ -276,7 +279,9 @@ struct WarpMem {
     float* pc;
     float* ps;
     float* man;       // [MF_FIELDS][Mcap]
-    uint8_t* slot;    // [B][slot_stride]
+    uint8_t* slot;    // [B][slot_stride]: manifold slot of pair (row body, column body|static); never
+                      // cleared — an entry is trusted only if the manifold it names carries the same pair
+    uint16_t* cand;   // [P] broad-phase survivors of the current step
 };
 
 struct DetectResult {
@@ -284,72 +289,92 @@ struct DetectResult {
     bool overflow;  // more touching pairs than Mcap
     float max_pen;
     unsigned long long colours;
+    int nm;         // manifolds stored (<= Mcap)
     unsigned candidates, touching;
 };
 
-// collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver constants.
+__device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpMem& W, int a, int b, Shape& A,
+                                                 Shape& Bs)
+{
+    const int B = sc.B;
+    A.shape = sc.shape[a];
+    A.x = W.px[a];
+    A.y = W.py[a];
+    A.c = W.pc[a];
+    A.s = W.ps[a];
+    A.hx = sc.hx[a];
+    A.hy = sc.hy[a];
+    if (b < B) {
+        Bs.shape = sc.shape[b];
+        Bs.x = W.px[b];
+        Bs.y = W.py[b];
+        Bs.c = W.pc[b];
+        Bs.s = W.ps[b];
+        Bs.hx = sc.hx[b];
+        Bs.hy = sc.hy[b];
+    } else {
+        int k = b - B;
+        Bs.shape = sc.s_shape[k];
+        Bs.x = sc.s_x[k];
+        Bs.y = sc.s_y[k];
+        Bs.c = sc.s_c[k];
+        Bs.s = sc.s_s[k];
+        Bs.hx = sc.s_hx[k];
+        Bs.hy = sc.s_hy[k];
+    }
+}
+
+// collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
 __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare)
 {
     const int B = sc.B;
     const int Mcap = sc.Mcap;
-    {
-        uint32_t* sw = reinterpret_cast<uint32_t*>(W.slot);
-        int words = (B * sc.slot_stride) >> 2;
-        for (int i = lane; i < words; i += 32) sw[i] = 0xffffffffu;
+    // ---- broad phase: lane = pair, bounding circles, survivors compacted into W.cand ------------
+    int ncand = 0;
+    for (int base = 0; base < sc.P; base += 32) {
+        int p = base + lane;
+        bool cand = false;
+        unsigned pr = 0;
+        if (p < sc.P) {
+            pr = sc.pairs[p];
+            int a = pr & 0xff, b = pr >> 8;
+            float bx, by, rr;
+            if (b < B) {
+                bx = W.px[b];
+                by = W.py[b];
+                rr = sc.brad[a] + sc.brad[b];
+            } else {
+                bx = sc.s_x[b - B];
+                by = sc.s_y[b - B];
+                rr = sc.brad[a] + sc.s_brad[b - B];
+            }
+            float dx = bx - W.px[a];
+            float dy = by - W.py[a];
+            cand = !(dx * dx + dy * dy > rr * rr);
+        }
+        unsigned cmask = __ballot_sync(FULL, cand);
+        if (cand) W.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)pr;
+        ncand += __popc(cmask);
     }
     __syncwarp();
+    // ---- narrow phase: lane = candidate, touching manifolds compacted into W.man ----------------
     int nm = 0;
     bool lane_bad = false, lane_over = false;
     float lane_pen = 0.0f;
     unsigned long long lane_col = 0ull;
-    unsigned n_cand = 0, n_touch = 0;
-    for (int base = 0; base < sc.P; base += 32) {
-        int p = base + lane;
-        bool cand = false;
-        int a = 0, b = 0;
-        Shape A, Bs;
-        if (p < sc.P) {
-            unsigned pr = sc.pairs[p];
+    unsigned n_touch = 0;
+    for (int base = 0; base < ncand; base += 32) {
+        int c = base + lane;
+        Manifold m;
+        int cnt = 0, a = 0, b = 0;
+        if (c < ncand) {
+            unsigned pr = W.cand[c];
             a = pr & 0xff;
             b = pr >> 8;
-            A.shape = sc.shape[a];
-            A.x = W.px[a];
-            A.y = W.py[a];
-            A.c = W.pc[a];
-            A.s = W.ps[a];
-            A.hx = sc.hx[a];
-            A.hy = sc.hy[a];
-            float rr;
-            if (b < B) {
-                Bs.shape = sc.shape[b];
-                Bs.x = W.px[b];
-                Bs.y = W.py[b];
-                Bs.c = W.pc[b];
-                Bs.s = W.ps[b];
-                Bs.hx = sc.hx[b];
-                Bs.hy = sc.hy[b];
-                rr = sc.brad[a] + sc.brad[b];
-            } else {
-                int k = b - B;
-                Bs.shape = sc.s_shape[k];
-                Bs.x = sc.s_x[k];
-                Bs.y = sc.s_y[k];
-                Bs.c = sc.s_c[k];
-                Bs.s = sc.s_s[k];
-                Bs.hx = sc.s_hx[k];
-                Bs.hy = sc.s_hy[k];
-                rr = sc.brad[a] + sc.s_brad[k];
-            }
-            float dx = Bs.x - A.x;
-            float dy = Bs.y - A.y;
-            cand = !(dx * dx + dy * dy > rr * rr);
+            Shape A, Bs;
+            load_pair_shapes(sc, W, a, b, A, Bs);
+            cnt = collide(A, Bs, sc.ref_tol, m);
         }
-        unsigned cmask = __ballot_sync(FULL, cand);
-        if (cmask == 0u) continue;
-        n_cand += __popc(cmask);
-        Manifold m;
-        int cnt = 0;
-        if (cand) cnt = collide(A, Bs, sc.ref_tol, m);
         bool touch = cnt > 0;
         unsigned tmask = __ballot_sync(FULL, touch);
         if (tmask == 0u) continue;
@@ -367,8 +392,6 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             if (idx < Mcap) {
                 float* mf = W.man + idx;
                 reinterpret_cast<int*>(mf)[MF_META * Mcap] = a | (b << 8) | (cnt << 16);
-                mf[MF_NX * Mcap] = m.nx;
-                mf[MF_NY * Mcap] = m.ny;
                 if (prepare) {
                     float ma = sc.inv_m[a], ia = sc.inv_i[a];
                     float mb = 0.0f, ib = 0.0f, mub;
@@ -379,7 +402,13 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                     } else {
                         mub = sc.s_mu[b - B];
                     }
+                    mf[MF_NX * Mcap] = m.nx;
+                    mf[MF_NY * Mcap] = m.ny;
                     mf[MF_FRICTION * Mcap] = sqrtf(sc.mu_c[a] * mub);
+                    mf[MF_MANX * Mcap] = ma * m.nx;
+                    mf[MF_MANY * Mcap] = ma * m.ny;
+                    mf[MF_MBNX * Mcap] = mb * m.nx;
+                    mf[MF_MBNY * Mcap] = mb * m.ny;
                     float tx = m.ny, ty = -m.nx;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
@@ -387,16 +416,21 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                             float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
                             float rna = rax * m.ny - ray * m.nx;
                             float rnb = rbx * m.ny - rby * m.nx;
-                            float kn = ((ma + mb) + (ia * rna) * rna) + (ib * rnb) * rnb;
                             float rta = rax * ty - ray * tx;
                             float rtb = rbx * ty - rby * tx;
-                            float kt = ((ma + mb) + (ia * rta) * rta) + (ib * rtb) * rtb;
+                            float iarna = ia * rna, ibrnb = ib * rnb, iarta = ia * rta, ibrtb = ib * rtb;
+                            float kn = ((ma + mb) + iarna * rna) + ibrnb * rnb;
+                            float kt = ((ma + mb) + iarta * rta) + ibrtb * rtb;
                             float pen_k = -m.sep[k] - sc.slop;
                             float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
-                            pf[PF_RAX * Mcap] = rax;
-                            pf[PF_RAY * Mcap] = ray;
-                            pf[PF_RBX * Mcap] = rbx;
-                            pf[PF_RBY * Mcap] = rby;
+                            pf[PF_RNA * Mcap] = rna;
+                            pf[PF_RNB * Mcap] = rnb;
+                            pf[PF_RTA * Mcap] = rta;
+                            pf[PF_RTB * Mcap] = rtb;
+                            pf[PF_IARNA * Mcap] = iarna;
+                            pf[PF_IBRNB * Mcap] = ibrnb;
+                            pf[PF_IARTA * Mcap] = iarta;
+                            pf[PF_IBRTB * Mcap] = ibrtb;
                             pf[PF_NMASS * Mcap] = kn > 0.0f ? 1.0f / kn : 0.0f;
                             pf[PF_TMASS * Mcap] = kt > 0.0f ? 1.0f / kt : 0.0f;
                             pf[PF_BIAS * Mcap] = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
@@ -428,10 +462,32 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
     unsigned lo = __reduce_or_sync(FULL, (unsigned)(lane_col & 0xffffffffull));
     unsigned hi = __reduce_or_sync(FULL, (unsigned)(lane_col >> 32));
     r.colours = ((unsigned long long)hi << 32) | lo;
-    r.candidates = n_cand;
+    r.nm = nm < Mcap ? nm : Mcap;
+    r.candidates = (unsigned)ncand;
     r.touching = n_touch;
     __syncwarp();
     return r;
+}
+
+// manifold slot of body `lane` in colour `col`, or 0xff.  The slot table is never cleared: an entry counts
+// only if it names a live manifold that carries exactly this pair.
+__device__ __forceinline__ int lookup_slot(const DevScene& sc, const WarpMem& W, int lane, int col, int nm)
+{
+    const int B = sc.B;
+    if (lane >= B) return 0xff;
+    int a = lane, b = col;
+    if (col < B) {
+        int j = col - lane;
+        if (j < 0) j += B;
+        if (j == lane) return 0xff;
+        a = lane < j ? lane : j;
+        b = lane < j ? j : lane;
+        col = j;
+    }
+    int sl = W.slot[lane * sc.slot_stride + col];
+    if (sl >= nm) return 0xff;
+    int meta = reinterpret_cast<const int*>(W.man + sl)[MF_META * sc.Mcap];
+    return (meta & 0xffff) == (a | (b << 8)) ? sl : 0xff;
 }
 
 // registers of the lane that owns body `lane`
@@ -471,9 +527,10 @@ struct StepStats {
     unsigned steps, candidates, touching, colour_passes;
 };
 
-// one physics step.  Returns (bad_contact, overflow) as warp-uniform values.
+// one physics step.  bad / overflow / max_pen come back warp-uniform.
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, int lane, float ux,
-                                             float uy, float uw, bool& bad, bool& overflow, StepStats& st)
+                                             float uy, float uw, bool& bad, bool& overflow, float& max_pen,
+                                             StepStats& st)
 {
     const int B = sc.B;
     const int Mcap = sc.Mcap;
@@ -485,160 +542,158 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     DetectResult dr = detect(sc, W, lane, true);
     bad = dr.bad;
     overflow = dr.overflow;
+    max_pen = dr.max_pen;
     st.steps += 1;
     st.candidates += dr.candidates;
     st.touching += dr.touching;
     if (overflow) return;
-    float acc_lx = 0.0f, acc_ly = 0.0f, acc_a = 0.0f;
-    for (int it = 0; it < sc.vel_iters; ++it) {
-        // support-plane friction: one friction joint to the ground per dynamic body
-        if (bd.dynamic) {
-            float imp = -bd.inertia * bd.w;
-            float old = acc_a;
-            float nw = fminf(fmaxf(old + imp, -bd.ang_cap), bd.ang_cap);
-            acc_a = nw;
-            imp = nw - old;
-            bd.w = bd.w + bd.inv_i * imp;
-            float ix = -bd.mass * bd.vx;
-            float iy = -bd.mass * bd.vy;
-            float ox = acc_lx, oy = acc_ly;
-            float ax = ox + ix, ay = oy + iy;
-            float n2 = ax * ax + ay * ay;
-            float cap = bd.lin_cap;
-            if (n2 > cap * cap) {
-                float sc_ = cap / sqrtf(n2);
-                ax = ax * sc_;
-                ay = ay * sc_;
-            }
-            acc_lx = ax;
-            acc_ly = ay;
-            ix = ax - ox;
-            iy = ay - oy;
-            bd.vx = bd.vx + bd.inv_m * ix;
-            bd.vy = bd.vy + bd.inv_m * iy;
+    // support-plane friction, once per step before the contact iterations
+    if (bd.dynamic) {
+        float imp = -bd.inertia * bd.w;
+        imp = fminf(fmaxf(imp, -bd.ang_cap), bd.ang_cap);
+        bd.w = bd.w + bd.inv_i * imp;
+        float ix = -bd.mass * bd.vx;
+        float iy = -bd.mass * bd.vy;
+        float n2 = ix * ix + iy * iy;
+        float cap = bd.lin_cap;
+        if (n2 > cap * cap) {
+            float sc_ = cap / sqrtf(n2);
+            ix = ix * sc_;
+            iy = iy * sc_;
         }
-        // contacts, colour by colour
-        unsigned long long cm = dr.colours;
-        while (cm) {
-            int col = __ffsll((long long)cm) - 1;
-            cm &= cm - 1ull;
-            st.colour_passes += 1;
-            int j = lane;  // partner lane (self when none)
-            int sl = 0xff;
-            if (bd.live) {
-                if (col < B) {
-                    int jj = col - lane;
-                    if (jj < 0) jj += B;
-                    if (jj != lane) {
-                        j = jj;
-                        sl = W.slot[lane * sc.slot_stride + jj];
-                    }
-                } else {
-                    sl = W.slot[lane * sc.slot_stride + col];
-                }
+        bd.vx = bd.vx + bd.inv_m * ix;
+        bd.vy = bd.vy + bd.inv_m * iy;
+    }
+    if (dr.colours != 0ull) {
+        // this lane's manifold slot for each of the first 8 active colours, packed one byte each
+        unsigned long long packed = ~0ull;
+        {
+            unsigned long long cm = dr.colours;
+            for (int ord = 0; cm != 0ull && ord < 8; ++ord) {
+                int col = __ffsll((long long)cm) - 1;
+                cm &= cm - 1ull;
+                unsigned long long sl = (unsigned long long)lookup_slot(sc, W, lane, col, dr.nm);
+                packed = (packed & ~(0xffull << (8 * ord))) | (sl << (8 * ord));
             }
-            float ovx = __shfl_sync(FULL, bd.vx, j);
-            float ovy = __shfl_sync(FULL, bd.vy, j);
-            float ow_ = __shfl_sync(FULL, bd.w, j);
-            float om = __shfl_sync(FULL, bd.inv_m, j);
-            float oi = __shfl_sync(FULL, bd.inv_i, j);
-            // lanes that solve a manifold in this colour (both owners of a body pair do, redundantly)
-            const bool act = sl != 0xff;
-            const unsigned amask = __ballot_sync(FULL, act);
-            if (act) {
+        }
+        for (int it = 0; it < sc.vel_iters; ++it) {
+            unsigned long long cm = dr.colours;
+            int ord = 0;
+            while (cm) {
+                const int col = __ffsll((long long)cm) - 1;
+                cm &= cm - 1ull;
+                st.colour_passes += 1;
+                const int sl = ord < 8 ? (int)((packed >> (8 * ord)) & 0xffull) : lookup_slot(sc, W, lane, col, dr.nm);
+                ++ord;
                 const bool stat = col >= B;
-                const bool is_a = stat || lane < j;
-                float* mf = W.man + sl;
-                int meta = reinterpret_cast<int*>(mf)[MF_META * Mcap];
-                int cnt = meta >> 16;
-                float nx = mf[MF_NX * Mcap], ny = mf[MF_NY * Mcap];
-                float fr = mf[MF_FRICTION * Mcap];
-                float tx = ny, ty = -nx;
-                // everything the pass reads is loaded before anything is written back: the two owner
-                // lanes of a pair must see the same accumulated impulses
-                float rax[2], ray[2], rbx[2], rby[2], nmass[2], tmass[2], bias[2], acc_n[2], acc_t[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
-                    rax[k] = pf[PF_RAX * Mcap];
-                    ray[k] = pf[PF_RAY * Mcap];
-                    rbx[k] = pf[PF_RBX * Mcap];
-                    rby[k] = pf[PF_RBY * Mcap];
-                    nmass[k] = pf[PF_NMASS * Mcap];
-                    tmass[k] = pf[PF_TMASS * Mcap];
-                    bias[k] = pf[PF_BIAS * Mcap];
-                    acc_n[k] = pf[PF_ACCN * Mcap];
-                    acc_t[k] = pf[PF_ACCT * Mcap];
+                int j = lane;  // partner lane (self when none)
+                if (!stat && bd.live) {
+                    j = col - lane;
+                    if (j < 0) j += B;
                 }
-                __syncwarp(amask);
-                float ma, ia, mb, ib, vax, vay, wa, vbx, vby, wb;
-                if (is_a) {
-                    ma = bd.inv_m; ia = bd.inv_i; vax = bd.vx; vay = bd.vy; wa = bd.w;
-                    if (stat) {
-                        mb = 0.0f; ib = 0.0f; vbx = 0.0f; vby = 0.0f; wb = 0.0f;
-                    } else {
-                        mb = om; ib = oi; vbx = ovx; vby = ovy; wb = ow_;
-                    }
-                } else {
-                    ma = om; ia = oi; vax = ovx; vay = ovy; wa = ow_;
-                    mb = bd.inv_m; ib = bd.inv_i; vbx = bd.vx; vby = bd.vy; wb = bd.w;
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {  // friction first
-                    if (k < cnt) {
-                        float dvx = (vbx - wb * rby[k]) - (vax - wa * ray[k]);
-                        float dvy = (vby + wb * rbx[k]) - (vay + wa * rax[k]);
-                        float vt = dvx * tx + dvy * ty;
-                        float lambda = tmass[k] * -vt;
-                        float max_f = fr * acc_n[k];
-                        float new_imp = fminf(fmaxf(acc_t[k] + lambda, -max_f), max_f);
-                        lambda = new_imp - acc_t[k];
-                        acc_t[k] = new_imp;
-                        float px = lambda * tx;
-                        float py = lambda * ty;
-                        vax = vax - ma * px;
-                        vay = vay - ma * py;
-                        wa = wa - ia * (rax[k] * py - ray[k] * px);
-                        vbx = vbx + mb * px;
-                        vby = vby + mb * py;
-                        wb = wb + ib * (rbx[k] * py - rby[k] * px);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {  // then non-penetration
-                    if (k < cnt) {
-                        float dvx = (vbx - wb * rby[k]) - (vax - wa * ray[k]);
-                        float dvy = (vby + wb * rbx[k]) - (vay + wa * rax[k]);
-                        float vn = dvx * nx + dvy * ny;
-                        float lambda = -nmass[k] * (vn - bias[k]);
-                        float new_imp = fmaxf(acc_n[k] + lambda, 0.0f);
-                        lambda = new_imp - acc_n[k];
-                        acc_n[k] = new_imp;
-                        float px = lambda * nx;
-                        float py = lambda * ny;
-                        vax = vax - ma * px;
-                        vay = vay - ma * py;
-                        wa = wa - ia * (rax[k] * py - ray[k] * px);
-                        vbx = vbx + mb * px;
-                        vby = vby + mb * py;
-                        wb = wb + ib * (rbx[k] * py - rby[k] * px);
-                    }
-                }
-                if (is_a) {
-                    bd.vx = vax; bd.vy = vay; bd.w = wa;
+                const float ovx = __shfl_sync(FULL, bd.vx, j);
+                const float ovy = __shfl_sync(FULL, bd.vy, j);
+                const float ow_ = __shfl_sync(FULL, bd.w, j);
+                const bool act = sl != 0xff;
+                const unsigned amask = __ballot_sync(FULL, act);
+                if (act) {
+                    const bool is_a = stat || lane < j;
+                    float* mf = W.man + sl;
+                    const int cnt = reinterpret_cast<const int*>(mf)[MF_META * Mcap] >> 16;
+                    const float nx = mf[MF_NX * Mcap], ny = mf[MF_NY * Mcap];
+                    const float fr = mf[MF_FRICTION * Mcap];
+                    const float manx = mf[MF_MANX * Mcap], many = mf[MF_MANY * Mcap];
+                    const float mbnx = mf[MF_MBNX * Mcap], mbny = mf[MF_MBNY * Mcap];
+                    const float tx = ny, ty = -nx;
+                    // everything the pass reads is loaded before anything is written back: the two owner
+                    // lanes of a pair must see the same accumulated impulses
+                    float rna[2], rnb[2], rta[2], rtb[2], iarna[2], ibrnb[2], iarta[2], ibrtb[2];
+                    float nmass[2], tmass[2], bias[2], acc_n[2], acc_t[2];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         if (k < cnt) {
-                            float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
-                            pf[PF_ACCN * Mcap] = acc_n[k];
-                            pf[PF_ACCT * Mcap] = acc_t[k];
+                            const float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
+                            rna[k] = pf[PF_RNA * Mcap];
+                            rnb[k] = pf[PF_RNB * Mcap];
+                            rta[k] = pf[PF_RTA * Mcap];
+                            rtb[k] = pf[PF_RTB * Mcap];
+                            iarna[k] = pf[PF_IARNA * Mcap];
+                            ibrnb[k] = pf[PF_IBRNB * Mcap];
+                            iarta[k] = pf[PF_IARTA * Mcap];
+                            ibrtb[k] = pf[PF_IBRTB * Mcap];
+                            nmass[k] = pf[PF_NMASS * Mcap];
+                            tmass[k] = pf[PF_TMASS * Mcap];
+                            bias[k] = pf[PF_BIAS * Mcap];
+                            acc_n[k] = pf[PF_ACCN * Mcap];
+                            acc_t[k] = pf[PF_ACCT * Mcap];
                         }
                     }
-                } else {
-                    bd.vx = vbx; bd.vy = vby; bd.w = wb;
+                    __syncwarp(amask);
+                    float vax, vay, wa, vbx, vby, wb;
+                    if (is_a) {
+                        vax = bd.vx; vay = bd.vy; wa = bd.w;
+                        if (stat) {
+                            vbx = 0.0f; vby = 0.0f; wb = 0.0f;
+                        } else {
+                            vbx = ovx; vby = ovy; wb = ow_;
+                        }
+                    } else {
+                        vax = ovx; vay = ovy; wa = ow_;
+                        vbx = bd.vx; vby = bd.vy; wb = bd.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {  // friction first
+                        if (k < cnt) {
+                            float dvx = vbx - vax;
+                            float dvy = vby - vay;
+                            float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, rtb[k], -(wa * rta[k]))));
+                            float lambda = tmass[k] * -vt;
+                            float max_f = fr * acc_n[k];
+                            float new_imp = fminf(fmaxf(acc_t[k] + lambda, -max_f), max_f);
+                            lambda = new_imp - acc_t[k];
+                            acc_t[k] = new_imp;
+                            vax = fmaf(-many, lambda, vax);
+                            vay = fmaf(manx, lambda, vay);
+                            wa = fmaf(-iarta[k], lambda, wa);
+                            vbx = fmaf(mbny, lambda, vbx);
+                            vby = fmaf(-mbnx, lambda, vby);
+                            wb = fmaf(ibrtb[k], lambda, wb);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {  // then non-penetration
+                        if (k < cnt) {
+                            float dvx = vbx - vax;
+                            float dvy = vby - vay;
+                            float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, rnb[k], -(wa * rna[k]))));
+                            float lambda = nmass[k] * (bias[k] - vn);
+                            float new_imp = fmaxf(acc_n[k] + lambda, 0.0f);
+                            lambda = new_imp - acc_n[k];
+                            acc_n[k] = new_imp;
+                            vax = fmaf(-manx, lambda, vax);
+                            vay = fmaf(-many, lambda, vay);
+                            wa = fmaf(-iarna[k], lambda, wa);
+                            vbx = fmaf(mbnx, lambda, vbx);
+                            vby = fmaf(mbny, lambda, vby);
+                            wb = fmaf(ibrnb[k], lambda, wb);
+                        }
+                    }
+                    if (is_a) {
+                        bd.vx = vax; bd.vy = vay; bd.w = wa;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            if (k < cnt) {
+                                float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
+                                pf[PF_ACCN * Mcap] = acc_n[k];
+                                pf[PF_ACCT * Mcap] = acc_t[k];
+                            }
+                        }
+                    } else {
+                        bd.vx = vbx; bd.vy = vby; bd.w = wb;
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     if (bd.live) {
@@ -726,6 +781,7 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
     W.ps = W.pc + 32;
     W.man = W.ps + 32;
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_FIELDS * Mcap);
+    W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
 
     Body bd;
     bd.live = lane < B;
@@ -814,7 +870,8 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
                     uw = 0.0f;
                 }
                 bool bad, over;
-                physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, st);
+                float pen;
+                physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, pen, st);
                 time += sc.dt;
                 if (over) {
                     flags |= MPS_F_OVERFLOW;
@@ -829,14 +886,22 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
             float rest = 0.0f;
             if (ok) {
                 bool resting = at_rest(sc, bd);
+                int jam = 0;
                 while (rest <= sc.t_max && !resting && ok) {
                     bool bad, over;
-                    physics_step(sc, W, bd, lane, 0.0f, 0.0f, 0.0f, bad, over, st);
+                    float pen;
+                    physics_step(sc, W, bd, lane, 0.0f, 0.0f, 0.0f, bad, over, pen, st);
                     ok = !bad;
                     rest += sc.dt;
                     if (bad) flags |= MPS_F_REST_CONTACT;
                     if (over) {
                         flags |= MPS_F_OVERFLOW;
+                        ok = false;
+                    }
+                    // jam rule: wedged deeper than pen_max for jam_steps consecutive rest steps
+                    jam = pen > sc.pen_max ? jam + 1 : 0;
+                    if (sc.jam_steps > 0 && jam >= sc.jam_steps) {
+                        flags |= MPS_F_JAMMED;
                         ok = false;
                     }
                     resting = at_rest(sc, bd);
@@ -1055,6 +1120,7 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
     W.ps = W.pc + 32;
     W.man = W.ps + 32;
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_FIELDS * sc.Mcap);
+    W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
     Body bd;
     bd.live = lane < B;
     bd.dynamic = false;
@@ -1082,7 +1148,8 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
 
 size_t mps_rollout_warp_bytes(const DevScene& sc)
 {
-    size_t b = 4 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) + (size_t)sc.B * sc.slot_stride;
+    size_t b = 4 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) +
+               (((size_t)sc.B * sc.slot_stride + 3) & ~(size_t)3) + sizeof(uint16_t) * (size_t)sc.P;
     return (b + 15) & ~(size_t)15;
 }
 

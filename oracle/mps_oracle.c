@@ -237,7 +237,11 @@ typedef struct orc_manifold {
     int count;
     float nx, ny; /* from a to b */
     float rax[2], ray[2], rbx[2], rby[2], sep[2];
+    /* solver rows (spec §3.4): Jacobian lever arms, effective masses, bias, accumulated impulses */
+    float rna[2], rnb[2], rta[2], rtb[2];
+    float iarna[2], ibrnb[2], iarta[2], ibrtb[2];
     float nmass[2], tmass[2], bias[2], acc_n[2], acc_t[2];
+    float manx, many, mbnx, mbny;
     float friction;
 } orc_manifold;
 
@@ -579,7 +583,7 @@ static int collide(const orc_shape* A, const orc_shape* Bs, float ref_tol, orc_m
     return collide_disc_disc(A, Bs, m);
 }
 
-/* solver constants of one manifold: effective masses, bias, mixed friction */
+/* solver constants of one manifold: Jacobian rows, effective masses, bias, mixed friction */
 static void manifold_prepare(const orc_world* wd, orc_manifold* m)
 {
     const mps_scene* sc = wd->sc;
@@ -595,14 +599,27 @@ static void manifold_prepare(const orc_world* wd, orc_manifold* m)
         mub = sc->s_mu_contact[m->b - B];
     }
     m->friction = sqrtf(sc->mu_contact[m->a] * mub);
+    m->manx = ma * m->nx;
+    m->many = ma * m->ny;
+    m->mbnx = mb * m->nx;
+    m->mbny = mb * m->ny;
     for (k = 0; k < m->count; ++k) {
         float rna = m->rax[k] * m->ny - m->ray[k] * m->nx;
         float rnb = m->rbx[k] * m->ny - m->rby[k] * m->nx;
-        float kn = ((ma + mb) + (ia * rna) * rna) + (ib * rnb) * rnb;
         float rta = m->rax[k] * ty - m->ray[k] * tx;
         float rtb = m->rbx[k] * ty - m->rby[k] * tx;
-        float kt = ((ma + mb) + (ia * rta) * rta) + (ib * rtb) * rtb;
+        float iarna = ia * rna, ibrnb = ib * rnb, iarta = ia * rta, ibrtb = ib * rtb;
+        float kn = ((ma + mb) + iarna * rna) + ibrnb * rnb;
+        float kt = ((ma + mb) + iarta * rta) + ibrtb * rtb;
         float pen = -m->sep[k] - sc->slop;
+        m->rna[k] = rna;
+        m->rnb[k] = rnb;
+        m->rta[k] = rta;
+        m->rtb[k] = rtb;
+        m->iarna[k] = iarna;
+        m->ibrnb[k] = ibrnb;
+        m->iarta[k] = iarta;
+        m->ibrtb[k] = ibrtb;
         m->nmass[k] = kn > 0.0f ? 1.0f / kn : 0.0f;
         m->tmass[k] = kt > 0.0f ? 1.0f / kt : 0.0f;
         m->bias[k] = pen > 0.0f ? fminf(wd->beta_dt * pen, sc->max_bias_vel) : 0.0f;
@@ -658,58 +675,52 @@ static void world_detect(orc_world* wd)
     }
 }
 
+/* One Gauss-Seidel visit of a manifold.  The relative velocity along a row is evaluated as a fused
+ * multiply-add chain (fmaf = one rounding per step, spec §3.4), the impulse applied with one fmaf per
+ * velocity component. */
 static void solve_manifold(orc_world* wd, orc_manifold* m)
 {
     int B = wd->B, k;
     int a = m->a, b = m->b;
-    float ma = wd->inv_m[a], ia = wd->inv_i[a];
-    float mb = 0.0f, ib = 0.0f;
     float vax = wd->vx[a], vay = wd->vy[a], wa = wd->w[a];
     float vbx = 0.0f, vby = 0.0f, wb = 0.0f;
     float nx = m->nx, ny = m->ny, tx = m->ny, ty = -m->nx;
     if (b < B) {
-        mb = wd->inv_m[b];
-        ib = wd->inv_i[b];
         vbx = wd->vx[b];
         vby = wd->vy[b];
         wb = wd->w[b];
     }
     for (k = 0; k < m->count; ++k) { /* friction first (Box2D order) */
-        float dvx = (vbx - wb * m->rby[k]) - (vax - wa * m->ray[k]);
-        float dvy = (vby + wb * m->rbx[k]) - (vay + wa * m->rax[k]);
-        float vt = dvx * tx + dvy * ty;
+        float dvx = vbx - vax;
+        float dvy = vby - vay;
+        float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, m->rtb[k], -(wa * m->rta[k]))));
         float lambda = m->tmass[k] * -vt;
         float max_f = m->friction * m->acc_n[k];
         float new_imp = fminf(fmaxf(m->acc_t[k] + lambda, -max_f), max_f);
-        float px, py;
         lambda = new_imp - m->acc_t[k];
         m->acc_t[k] = new_imp;
-        px = lambda * tx;
-        py = lambda * ty;
-        vax = vax - ma * px;
-        vay = vay - ma * py;
-        wa = wa - ia * (m->rax[k] * py - m->ray[k] * px);
-        vbx = vbx + mb * px;
-        vby = vby + mb * py;
-        wb = wb + ib * (m->rbx[k] * py - m->rby[k] * px);
+        /* P = lambda * t with t = (ny, -nx) */
+        vax = fmaf(-m->many, lambda, vax);
+        vay = fmaf(m->manx, lambda, vay);
+        wa = fmaf(-m->iarta[k], lambda, wa);
+        vbx = fmaf(m->mbny, lambda, vbx);
+        vby = fmaf(-m->mbnx, lambda, vby);
+        wb = fmaf(m->ibrtb[k], lambda, wb);
     }
     for (k = 0; k < m->count; ++k) { /* then non-penetration */
-        float dvx = (vbx - wb * m->rby[k]) - (vax - wa * m->ray[k]);
-        float dvy = (vby + wb * m->rbx[k]) - (vay + wa * m->rax[k]);
-        float vn = dvx * nx + dvy * ny;
-        float lambda = -m->nmass[k] * (vn - m->bias[k]);
+        float dvx = vbx - vax;
+        float dvy = vby - vay;
+        float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, m->rnb[k], -(wa * m->rna[k]))));
+        float lambda = m->nmass[k] * (m->bias[k] - vn);
         float new_imp = fmaxf(m->acc_n[k] + lambda, 0.0f);
-        float px, py;
         lambda = new_imp - m->acc_n[k];
         m->acc_n[k] = new_imp;
-        px = lambda * nx;
-        py = lambda * ny;
-        vax = vax - ma * px;
-        vay = vay - ma * py;
-        wa = wa - ia * (m->rax[k] * py - m->ray[k] * px);
-        vbx = vbx + mb * px;
-        vby = vby + mb * py;
-        wb = wb + ib * (m->rbx[k] * py - m->rby[k] * px);
+        vax = fmaf(-m->manx, lambda, vax);
+        vay = fmaf(-m->many, lambda, vay);
+        wa = fmaf(-m->iarna[k], lambda, wa);
+        vbx = fmaf(m->mbnx, lambda, vbx);
+        vby = fmaf(m->mbny, lambda, vby);
+        wb = fmaf(m->ibrnb[k], lambda, wb);
     }
     wd->vx[a] = vax;
     wd->vy[a] = vay;
@@ -727,48 +738,32 @@ static int world_step(orc_world* wd, const float u[3])
 {
     const mps_scene* sc = wd->sc;
     int B = wd->B, S = wd->S, i, it, col;
-    float acc_lx[MPS_MAX_BODIES], acc_ly[MPS_MAX_BODIES], acc_a[MPS_MAX_BODIES];
     wd->vx[wd->robot] = u[0];
     wd->vy[wd->robot] = u[1];
     wd->w[wd->robot] = u[2];
     world_detect(wd);
     if (wd->overflow) return wd->bad_contact;
+    /* support-plane friction, once per step before the contact iterations: the impulse that brings
+     * the body to rest, capped at dt * mu * m * g (linear, vector norm) and dt * mu * m * g * r (angular) */
     for (i = 0; i < B; ++i) {
-        acc_lx[i] = 0.0f;
-        acc_ly[i] = 0.0f;
-        acc_a[i] = 0.0f;
-    }
-    for (it = 0; it < sc->vel_iters; ++it) {
-        /* support-plane friction (a friction joint to the ground per dynamic body) */
-        for (i = 0; i < B; ++i) {
-            float imp, old, nw, ix, iy, ox, oy, ax, ay, n2, cap;
-            if (i == wd->robot) continue;
-            imp = -sc->inertia[i] * wd->w[i];
-            old = acc_a[i];
-            nw = fminf(fmaxf(old + imp, -wd->ang_cap[i]), wd->ang_cap[i]);
-            acc_a[i] = nw;
-            imp = nw - old;
-            wd->w[i] = wd->w[i] + wd->inv_i[i] * imp;
-            ix = -sc->mass[i] * wd->vx[i];
-            iy = -sc->mass[i] * wd->vy[i];
-            ox = acc_lx[i];
-            oy = acc_ly[i];
-            ax = ox + ix;
-            ay = oy + iy;
-            n2 = ax * ax + ay * ay;
-            cap = wd->lin_cap[i];
-            if (n2 > cap * cap) {
-                float sc_ = cap / sqrtf(n2);
-                ax = ax * sc_;
-                ay = ay * sc_;
-            }
-            acc_lx[i] = ax;
-            acc_ly[i] = ay;
-            ix = ax - ox;
-            iy = ay - oy;
-            wd->vx[i] = wd->vx[i] + wd->inv_m[i] * ix;
-            wd->vy[i] = wd->vy[i] + wd->inv_m[i] * iy;
+        float imp, ix, iy, n2, cap;
+        if (i == wd->robot) continue;
+        imp = -sc->inertia[i] * wd->w[i];
+        imp = fminf(fmaxf(imp, -wd->ang_cap[i]), wd->ang_cap[i]);
+        wd->w[i] = wd->w[i] + wd->inv_i[i] * imp;
+        ix = -sc->mass[i] * wd->vx[i];
+        iy = -sc->mass[i] * wd->vy[i];
+        n2 = ix * ix + iy * iy;
+        cap = wd->lin_cap[i];
+        if (n2 > cap * cap) {
+            float sc_ = cap / sqrtf(n2);
+            ix = ix * sc_;
+            iy = iy * sc_;
         }
+        wd->vx[i] = wd->vx[i] + wd->inv_m[i] * ix;
+        wd->vy[i] = wd->vy[i] + wd->inv_m[i] * iy;
+    }
+    for (it = 0; it < sc->vel_iters && wd->nm > 0; ++it) {
         /* contacts in colour order: colour r < B holds the body pairs with (i + j) mod B == r,
          * colour B + s the pairs (i, static s); inside a colour, ascending i */
         for (col = 0; col < B + S; ++col) {
@@ -910,6 +905,7 @@ static int propagate_impl(const mps_scene* sc, const float* state_in, float* con
     /* rest phase (:86-105) */
     if (ok) {
         float resting_time = 0.0f;
+        int jam = 0;
         u[0] = u[1] = u[2] = 0.0f;
         while (resting_time <= sc->t_max && !world_at_rest(&wd) && ok) {
             int bad = world_step(&wd, u);
@@ -926,6 +922,13 @@ static int propagate_impl(const mps_scene* sc, const float* state_in, float* con
             if (bad) flags |= MPS_F_REST_CONTACT;
             if (wd.overflow) {
                 flags |= MPS_F_OVERFLOW;
+                ok = 0;
+            }
+            /* jam rule (spec §3.6): the robot has stopped; a world that stays deeper than pen_max for
+             * jam_steps consecutive steps is wedged and will not come to rest */
+            jam = wd.max_pen > sc->pen_max ? jam + 1 : 0;
+            if (sc->jam_steps > 0 && jam >= sc->jam_steps) {
+                flags |= MPS_F_JAMMED;
                 ok = 0;
             }
         }
