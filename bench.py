@@ -215,6 +215,9 @@ def run_ours(args):
                     "traffic": None, "kernel_ms": round(k_ms, 4), "share_of_step": round(k_ms * steps / step_ms.sum(), 4),
                     "peak_source": "measured in-run (FMA microbenchmark, csrc/peak.cu)",
                     "physics_steps_per_launch": cnt["steps"] / max(steps, 1),
+                    "candidate_pairs_per_step": round(cnt["candidates"] / max(cnt["steps"], 1), 3),
+                    "touching_pairs_per_step": round(cnt["touching"] / max(cnt["steps"], 1), 3),
+                    "colour_passes_per_step": round(cnt["colour_passes"] / max(cnt["steps"], 1), 3),
                     "note": "latency/divergence-bound contact dynamics on CUDA cores; not a dense contraction"}
 
         # ---- end to end through the host-buffer C ABI (e2e) ------------------------------------

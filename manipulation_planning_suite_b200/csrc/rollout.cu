@@ -29,13 +29,17 @@
 
 namespace {
 
-// manifold fields in the warp's shared slice, SoA: field f of slot m at man[f * Mcap + m]
-enum { MF_META = 0, MF_NX, MF_NY, MF_FRICTION, MF_MANX, MF_MANY, MF_MBNX, MF_MBNY, MF_P0 };
-enum {
-    PF_RNA = 0, PF_RNB, PF_RTA, PF_RTB, PF_IARNA, PF_IBRNB, PF_IARTA, PF_IBRTB,
-    PF_NMASS, PF_TMASS, PF_BIAS, PF_ACCN, PF_ACCT, PF_COUNT
-};
-#define MF_FIELDS (MF_P0 + 2 * PF_COUNT)
+
+// One manifold = 9 float4 (144 B) in the warp's shared slice, read and written with 128-bit accesses:
+//   [0] meta (a | b << 8 | count << 16 | has_bias << 24), nx, ny, friction
+//   [1] ma*nx, ma*ny, mb*nx, mb*ny
+//   [2 + 3k] rna, rnb, rta, rtb          (point k = 0, 1: Jacobian lever arms)
+//   [3 + 3k] ia*rna, ib*rnb, ia*rta, ib*rtb
+//   [4 + 3k] normal mass, tangent mass, bias, -
+//   [8] acc_n0, acc_t0, acc_n1, acc_t1   (accumulated impulses)
+#define MF_VEC4 9
+#define MF_FIELDS (4 * MF_VEC4)
+#define MF_HAS_BIAS (1 << 24)
 
 struct Shape {
     int shape;
@@ -278,7 +282,7 @@ struct WarpMem {
     float* py;
     float* pc;
     float* ps;
-    float* man;       // [MF_FIELDS][Mcap]
+    float4* man;      // [Mcap][MF_VEC4]
     uint8_t* slot;    // [B][slot_stride]: manifold slot of pair (row body, column body|static); never
                       // cleared — an entry is trusted only if the manifold it names carries the same pair
     uint16_t* cand;   // [P] broad-phase survivors of the current step
@@ -338,19 +342,30 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         if (p < sc.P) {
             pr = sc.pairs[p];
             int a = pr & 0xff, b = pr >> 8;
-            float bx, by, rr;
             if (b < B) {
-                bx = W.px[b];
-                by = W.py[b];
-                rr = sc.brad[a] + sc.brad[b];
+                // bounding circles
+                float rr = sc.brad[a] + sc.brad[b];
+                float dx = W.px[b] - W.px[a];
+                float dy = W.py[b] - W.py[a];
+                cand = !(dx * dx + dy * dy > rr * rr);
             } else {
-                bx = sc.s_x[b - B];
-                by = sc.s_y[b - B];
-                rr = sc.brad[a] + sc.s_brad[b - B];
+                // body circle against the static's own box / disc (walls are long: their bounding circle
+                // would make every body a candidate).  Conservative with a small margin; only a filter.
+                const int k = b - B;
+                float dx = W.px[a] - sc.s_x[k];
+                float dy = W.py[a] - sc.s_y[k];
+                float rr = sc.brad[a] * 1.001f + 1e-5f;
+                if (sc.s_shape[k] == MPS_SHAPE_BOX) {
+                    float lx = dx * sc.s_c[k] + dy * sc.s_s[k];
+                    float ly = dy * sc.s_c[k] - dx * sc.s_s[k];
+                    float ex = fmaxf(fabsf(lx) - sc.s_hx[k], 0.0f);
+                    float ey = fmaxf(fabsf(ly) - sc.s_hy[k], 0.0f);
+                    cand = !(ex * ex + ey * ey > rr * rr);
+                } else {
+                    rr += sc.s_hx[k];
+                    cand = !(dx * dx + dy * dy > rr * rr);
+                }
             }
-            float dx = bx - W.px[a];
-            float dy = by - W.py[a];
-            cand = !(dx * dx + dy * dy > rr * rr);
         }
         unsigned cmask = __ballot_sync(FULL, cand);
         if (cand) W.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)pr;
@@ -390,8 +405,8 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             if (!allowed) lane_bad = true;
             int idx = nm + __popc(tmask & ((1u << lane) - 1u));
             if (idx < Mcap) {
-                float* mf = W.man + idx;
-                reinterpret_cast<int*>(mf)[MF_META * Mcap] = a | (b << 8) | (cnt << 16);
+                float4* mf = W.man + idx * MF_VEC4;
+                int meta = a | (b << 8) | (cnt << 16);
                 if (prepare) {
                     float ma = sc.inv_m[a], ia = sc.inv_i[a];
                     float mb = 0.0f, ib = 0.0f, mub;
@@ -402,13 +417,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                     } else {
                         mub = sc.s_mu[b - B];
                     }
-                    mf[MF_NX * Mcap] = m.nx;
-                    mf[MF_NY * Mcap] = m.ny;
-                    mf[MF_FRICTION * Mcap] = sqrtf(sc.mu_c[a] * mub);
-                    mf[MF_MANX * Mcap] = ma * m.nx;
-                    mf[MF_MANY * Mcap] = ma * m.ny;
-                    mf[MF_MBNX * Mcap] = mb * m.nx;
-                    mf[MF_MBNY * Mcap] = mb * m.ny;
+                    mf[1] = make_float4(ma * m.nx, ma * m.ny, mb * m.nx, mb * m.ny);
                     float tx = m.ny, ty = -m.nx;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
@@ -422,22 +431,16 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                             float kn = ((ma + mb) + iarna * rna) + ibrnb * rnb;
                             float kt = ((ma + mb) + iarta * rta) + ibrtb * rtb;
                             float pen_k = -m.sep[k] - sc.slop;
-                            float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
-                            pf[PF_RNA * Mcap] = rna;
-                            pf[PF_RNB * Mcap] = rnb;
-                            pf[PF_RTA * Mcap] = rta;
-                            pf[PF_RTB * Mcap] = rtb;
-                            pf[PF_IARNA * Mcap] = iarna;
-                            pf[PF_IBRNB * Mcap] = ibrnb;
-                            pf[PF_IARTA * Mcap] = iarta;
-                            pf[PF_IBRTB * Mcap] = ibrtb;
-                            pf[PF_NMASS * Mcap] = kn > 0.0f ? 1.0f / kn : 0.0f;
-                            pf[PF_TMASS * Mcap] = kt > 0.0f ? 1.0f / kt : 0.0f;
-                            pf[PF_BIAS * Mcap] = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
-                            pf[PF_ACCN * Mcap] = 0.0f;
-                            pf[PF_ACCT * Mcap] = 0.0f;
+                            float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
+                            if (bias != 0.0f) meta |= MF_HAS_BIAS;
+                            mf[2 + 3 * k] = make_float4(rna, rnb, rta, rtb);
+                            mf[3 + 3 * k] = make_float4(iarna, ibrnb, iarta, ibrtb);
+                            mf[4 + 3 * k] = make_float4(kn > 0.0f ? 1.0f / kn : 0.0f, kt > 0.0f ? 1.0f / kt : 0.0f, bias,
+                                                        0.0f);
                         }
                     }
+                    mf[8] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, sqrtf(sc.mu_c[a] * mub));
                     W.slot[a * sc.slot_stride + b] = (uint8_t)idx;
                     int col;
                     if (b < B) {
@@ -448,6 +451,8 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                         col = b;
                     }
                     lane_col |= 1ull << col;
+                } else {
+                    mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, 0.0f);
                 }
             } else {
                 lane_over = true;
@@ -486,7 +491,7 @@ __device__ __forceinline__ int lookup_slot(const DevScene& sc, const WarpMem& W,
     }
     int sl = W.slot[lane * sc.slot_stride + col];
     if (sl >= nm) return 0xff;
-    int meta = reinterpret_cast<const int*>(W.man + sl)[MF_META * sc.Mcap];
+    int meta = __float_as_int(W.man[sl * MF_VEC4].x);
     return (meta & 0xffff) == (a | (b << 8)) ? sl : 0xff;
 }
 
@@ -533,7 +538,6 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                                              StepStats& st)
 {
     const int B = sc.B;
-    const int Mcap = sc.Mcap;
     if (lane == sc.robot) {
         bd.vx = ux;
         bd.vy = uy;
@@ -576,14 +580,18 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 packed = (packed & ~(0xffull << (8 * ord))) | (sl << (8 * ord));
             }
         }
+        // A manifold whose two bodies have exactly zero twist, that carries no bias and has not been
+        // solved yet this step returns zero impulses: visiting it changes nothing, so it is skipped
+        // (bit-identical to visiting it).  `woke` remembers, per colour ordinal, that it has been solved.
+        unsigned woke = 0u;
         for (int it = 0; it < sc.vel_iters; ++it) {
             unsigned long long cm = dr.colours;
             int ord = 0;
             while (cm) {
                 const int col = __ffsll((long long)cm) - 1;
                 cm &= cm - 1ull;
-                st.colour_passes += 1;
                 const int sl = ord < 8 ? (int)((packed >> (8 * ord)) & 0xffull) : lookup_slot(sc, W, lane, col, dr.nm);
+                const unsigned obit = 1u << (ord & 31);
                 ++ord;
                 const bool stat = col >= B;
                 int j = lane;  // partner lane (self when none)
@@ -594,41 +602,37 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 const float ovx = __shfl_sync(FULL, bd.vx, j);
                 const float ovy = __shfl_sync(FULL, bd.vy, j);
                 const float ow_ = __shfl_sync(FULL, bd.w, j);
-                const bool act = sl != 0xff;
-                const unsigned amask = __ballot_sync(FULL, act);
+                bool act = sl != 0xff;
+                float4 m0;
                 if (act) {
+                    m0 = W.man[sl * MF_VEC4];
+                    const bool moving = (bd.vx != 0.0f) | (bd.vy != 0.0f) | (bd.w != 0.0f) |
+                                        (!stat & ((ovx != 0.0f) | (ovy != 0.0f) | (ow_ != 0.0f)));
+                    act = moving || (__float_as_int(m0.x) & MF_HAS_BIAS) || (woke & obit);
+                }
+                const unsigned amask = __ballot_sync(FULL, act);
+                if (amask == 0u) continue;
+                st.colour_passes += 1;
+                if (act) {
+                    woke |= obit;
                     const bool is_a = stat || lane < j;
-                    float* mf = W.man + sl;
-                    const int cnt = reinterpret_cast<const int*>(mf)[MF_META * Mcap] >> 16;
-                    const float nx = mf[MF_NX * Mcap], ny = mf[MF_NY * Mcap];
-                    const float fr = mf[MF_FRICTION * Mcap];
-                    const float manx = mf[MF_MANX * Mcap], many = mf[MF_MANY * Mcap];
-                    const float mbnx = mf[MF_MBNX * Mcap], mbny = mf[MF_MBNY * Mcap];
+                    float4* mf = W.man + sl * MF_VEC4;
+                    const int cnt = (__float_as_int(m0.x) >> 16) & 0xff;
+                    const float nx = m0.y, ny = m0.z, fr = m0.w;
                     const float tx = ny, ty = -nx;
                     // everything the pass reads is loaded before anything is written back: the two owner
                     // lanes of a pair must see the same accumulated impulses
-                    float rna[2], rnb[2], rta[2], rtb[2], iarna[2], ibrnb[2], iarta[2], ibrtb[2];
-                    float nmass[2], tmass[2], bias[2], acc_n[2], acc_t[2];
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (k < cnt) {
-                            const float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
-                            rna[k] = pf[PF_RNA * Mcap];
-                            rnb[k] = pf[PF_RNB * Mcap];
-                            rta[k] = pf[PF_RTA * Mcap];
-                            rtb[k] = pf[PF_RTB * Mcap];
-                            iarna[k] = pf[PF_IARNA * Mcap];
-                            ibrnb[k] = pf[PF_IBRNB * Mcap];
-                            iarta[k] = pf[PF_IARTA * Mcap];
-                            ibrtb[k] = pf[PF_IBRTB * Mcap];
-                            nmass[k] = pf[PF_NMASS * Mcap];
-                            tmass[k] = pf[PF_TMASS * Mcap];
-                            bias[k] = pf[PF_BIAS * Mcap];
-                            acc_n[k] = pf[PF_ACCN * Mcap];
-                            acc_t[k] = pf[PF_ACCT * Mcap];
-                        }
+                    const float4 mm = mf[1];
+                    const float4 r0 = mf[2], i0 = mf[3], k0 = mf[4];
+                    float4 r1 = r0, i1 = i0, k1 = k0;
+                    if (cnt > 1) {
+                        r1 = mf[5];
+                        i1 = mf[6];
+                        k1 = mf[7];
                     }
+                    float4 acc = mf[8];
                     __syncwarp(amask);
+                    const float manx = mm.x, many = mm.y, mbnx = mm.z, mbny = mm.w;
                     float vax, vay, wa, vbx, vby, wb;
                     if (is_a) {
                         vax = bd.vx; vay = bd.vy; wa = bd.w;
@@ -641,53 +645,73 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                         vax = ovx; vay = ovy; wa = ow_;
                         vbx = bd.vx; vby = bd.vy; wb = bd.w;
                     }
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {  // friction first
-                        if (k < cnt) {
-                            float dvx = vbx - vax;
-                            float dvy = vby - vay;
-                            float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, rtb[k], -(wa * rta[k]))));
-                            float lambda = tmass[k] * -vt;
-                            float max_f = fr * acc_n[k];
-                            float new_imp = fminf(fmaxf(acc_t[k] + lambda, -max_f), max_f);
-                            lambda = new_imp - acc_t[k];
-                            acc_t[k] = new_imp;
-                            vax = fmaf(-many, lambda, vax);
-                            vay = fmaf(manx, lambda, vay);
-                            wa = fmaf(-iarta[k], lambda, wa);
-                            vbx = fmaf(mbny, lambda, vbx);
-                            vby = fmaf(-mbnx, lambda, vby);
-                            wb = fmaf(ibrtb[k], lambda, wb);
-                        }
+                    // friction first (Box2D order), point 0 then point 1
+                    {
+                        float dvx = vbx - vax;
+                        float dvy = vby - vay;
+                        float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r0.w, -(wa * r0.z))));
+                        float lambda = k0.y * -vt;
+                        float max_f = fr * acc.x;
+                        float new_imp = fminf(fmaxf(acc.y + lambda, -max_f), max_f);
+                        lambda = new_imp - acc.y;
+                        acc.y = new_imp;
+                        vax = fmaf(-many, lambda, vax);
+                        vay = fmaf(manx, lambda, vay);
+                        wa = fmaf(-i0.z, lambda, wa);
+                        vbx = fmaf(mbny, lambda, vbx);
+                        vby = fmaf(-mbnx, lambda, vby);
+                        wb = fmaf(i0.w, lambda, wb);
                     }
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {  // then non-penetration
-                        if (k < cnt) {
-                            float dvx = vbx - vax;
-                            float dvy = vby - vay;
-                            float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, rnb[k], -(wa * rna[k]))));
-                            float lambda = nmass[k] * (bias[k] - vn);
-                            float new_imp = fmaxf(acc_n[k] + lambda, 0.0f);
-                            lambda = new_imp - acc_n[k];
-                            acc_n[k] = new_imp;
-                            vax = fmaf(-manx, lambda, vax);
-                            vay = fmaf(-many, lambda, vay);
-                            wa = fmaf(-iarna[k], lambda, wa);
-                            vbx = fmaf(mbnx, lambda, vbx);
-                            vby = fmaf(mbny, lambda, vby);
-                            wb = fmaf(ibrnb[k], lambda, wb);
-                        }
+                    if (cnt > 1) {
+                        float dvx = vbx - vax;
+                        float dvy = vby - vay;
+                        float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
+                        float lambda = k1.y * -vt;
+                        float max_f = fr * acc.z;
+                        float new_imp = fminf(fmaxf(acc.w + lambda, -max_f), max_f);
+                        lambda = new_imp - acc.w;
+                        acc.w = new_imp;
+                        vax = fmaf(-many, lambda, vax);
+                        vay = fmaf(manx, lambda, vay);
+                        wa = fmaf(-i1.z, lambda, wa);
+                        vbx = fmaf(mbny, lambda, vbx);
+                        vby = fmaf(-mbnx, lambda, vby);
+                        wb = fmaf(i1.w, lambda, wb);
+                    }
+                    // then non-penetration
+                    {
+                        float dvx = vbx - vax;
+                        float dvy = vby - vay;
+                        float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r0.y, -(wa * r0.x))));
+                        float lambda = k0.x * (k0.z - vn);
+                        float new_imp = fmaxf(acc.x + lambda, 0.0f);
+                        lambda = new_imp - acc.x;
+                        acc.x = new_imp;
+                        vax = fmaf(-manx, lambda, vax);
+                        vay = fmaf(-many, lambda, vay);
+                        wa = fmaf(-i0.x, lambda, wa);
+                        vbx = fmaf(mbnx, lambda, vbx);
+                        vby = fmaf(mbny, lambda, vby);
+                        wb = fmaf(i0.y, lambda, wb);
+                    }
+                    if (cnt > 1) {
+                        float dvx = vbx - vax;
+                        float dvy = vby - vay;
+                        float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
+                        float lambda = k1.x * (k1.z - vn);
+                        float new_imp = fmaxf(acc.z + lambda, 0.0f);
+                        lambda = new_imp - acc.z;
+                        acc.z = new_imp;
+                        vax = fmaf(-manx, lambda, vax);
+                        vay = fmaf(-many, lambda, vay);
+                        wa = fmaf(-i1.x, lambda, wa);
+                        vbx = fmaf(mbnx, lambda, vbx);
+                        vby = fmaf(mbny, lambda, vby);
+                        wb = fmaf(i1.y, lambda, wb);
                     }
                     if (is_a) {
                         bd.vx = vax; bd.vy = vay; bd.w = wa;
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            if (k < cnt) {
-                                float* pf = mf + (MF_P0 + k * PF_COUNT) * Mcap;
-                                pf[PF_ACCN * Mcap] = acc_n[k];
-                                pf[PF_ACCT * Mcap] = acc_t[k];
-                            }
-                        }
+                        mf[8] = acc;
                     } else {
                         bd.vx = vbx; bd.vy = vby; bd.w = wb;
                     }
@@ -779,8 +803,8 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
     W.py = W.px + 32;
     W.pc = W.py + 32;
     W.ps = W.pc + 32;
-    W.man = W.ps + 32;
-    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_FIELDS * Mcap);
+    W.man = reinterpret_cast<float4*>(W.ps + 32);
+    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
 
     Body bd;
@@ -1118,8 +1142,8 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
     W.py = W.px + 32;
     W.pc = W.py + 32;
     W.ps = W.pc + 32;
-    W.man = W.ps + 32;
-    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_FIELDS * sc.Mcap);
+    W.man = reinterpret_cast<float4*>(W.ps + 32);
+    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * sc.Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
     Body bd;
     bd.live = lane < B;

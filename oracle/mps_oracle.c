@@ -645,16 +645,29 @@ static void world_detect(orc_world* wd)
             float rr, dx, dy;
             orc_manifold m;
             int k;
+            /* broad phase: conservative filters only (they never change the result) */
             if (j < B) {
                 Bs = body_shape(wd, j);
                 rr = wd->brad[i] + wd->brad[j];
+                dx = Bs.x - A.x;
+                dy = Bs.y - A.y;
+                if (dx * dx + dy * dy > rr * rr) continue;
             } else {
                 Bs = static_shape(wd, j - B);
-                rr = wd->brad[i] + wd->st_brad[j - B];
+                dx = A.x - Bs.x;
+                dy = A.y - Bs.y;
+                rr = wd->brad[i] * 1.001f + 1e-5f;
+                if (Bs.shape == MPS_SHAPE_BOX) {
+                    float lx = dx * Bs.c + dy * Bs.s;
+                    float ly = dy * Bs.c - dx * Bs.s;
+                    float ex = fmaxf(fabsf(lx) - Bs.hx, 0.0f);
+                    float ey = fmaxf(fabsf(ly) - Bs.hy, 0.0f);
+                    if (ex * ex + ey * ey > rr * rr) continue;
+                } else {
+                    rr += Bs.hx;
+                    if (dx * dx + dy * dy > rr * rr) continue;
+                }
             }
-            dx = Bs.x - A.x;
-            dy = Bs.y - A.y;
-            if (dx * dx + dy * dy > rr * rr) continue; /* broad phase (conservative) */
             wd->n_candidates++;
             memset(&m, 0, sizeof(m));
             m.a = i;

@@ -231,3 +231,25 @@ def test_bad_arguments_are_errors_not_crashes():
     bad.n_bodies = 1
     with pytest.raises(api.MpsError):
         api.Context(bad)
+
+
+def test_gpu_reproduces_committed_physics_golden():
+    """The CUDA path against the committed fixtures (no oracle involved at run time)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "physics_golden.npz"))
+    i = 0
+    while f"c{i}_meta" in g:
+        n_objects, seed, k, n_ok = [int(x) for x in g[f"c{i}_meta"]]
+        sc, _ = scenes.make_scene(n_objects, seed=seed)
+        ctx = api.Context(sc)
+        r = ctx.extend(g[f"c{i}_start"], g[f"c{i}_controls"], dump=True, dest=g[f"c{i}_dest"], compare_f32=True)
+        assert r.k == k and r.n_ok == n_ok
+        assert np.array_equal(r.all_flags, g[f"c{i}_all_flags"])
+        assert np.array_equal(r.all_rest, g[f"c{i}_all_rest"])
+        assert np.array_equal(r.all_steps, g[f"c{i}_all_steps"])
+        assert np.array_equal(r.all_dist, g[f"c{i}_all_dist"])
+        assert_states_close(r.all_states, g[f"c{i}_all_states"], g[f"c{i}_all_flags"], f"golden case {i}")
+        ctx.close()
+        i += 1
+    assert i == 4
