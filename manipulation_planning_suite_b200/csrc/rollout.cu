@@ -1074,12 +1074,16 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
     best_k = s_idx[0];
     const int L = p.L, B = p.B;
     int n_ok = best_k >= 0 ? p.nok[best_k] : 0;
+    // nodes appended: the chain up to and including the first goal state (HybridActionRRT::extend stops
+    // adding there, RRT.cpp:479-488), else the whole successful prefix
+    int n_app = n_ok;
+    if (best_k >= 0 && p.goal_step[best_k] >= 0) n_app = p.goal_step[best_k] + 1;
     int first = -1;
     if (best_k >= 0 && p.append && tid == 0) {
         // tree append of the winner chain (RearrangementRRT::addToTree, RRT.cpp:234-244)
         long long n0 = *p.tree_size;
         first = (int)n0;
-        *p.tree_size = n0 + n_ok;
+        *p.tree_size = n0 + n_app;
     }
     if (tid == 0) {
         p.best->k = best_k < 0 ? -1 : best_k + p.k_offset;
@@ -1104,17 +1108,17 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
     for (int i = tid; i < L; i += blockDim.x) p.best_flags[i] = best_k < 0 ? 0u : p.flags[(size_t)best_k * L + i];
     if (best_k >= 0 && p.append && first >= 0) {
         const size_t cap = p.tree_cap;
-        for (int i = tid; i < n_ok * 3 * B; i += blockDim.x) {
+        for (int i = tid; i < n_app * 3 * B; i += blockDim.x) {
             int l = i / (3 * B), r = i % (3 * B);
             p.tree_states[(size_t)r * cap + first + l] = p.states[((size_t)best_k * L + l) * 3 * B + r];
         }
-        for (int i = tid; i < n_ok * MPS_CONTROL_DIM; i += blockDim.x) {
+        for (int i = tid; i < n_app * MPS_CONTROL_DIM; i += blockDim.x) {
             int l = i / MPS_CONTROL_DIM, c = i % MPS_CONTROL_DIM;
             float v = c == 4 ? p.rest[(size_t)best_k * L + l]
                              : p.controls[((size_t)best_k * L + l) * MPS_CONTROL_DIM + c];
             p.tree_controls[(size_t)c * cap + first + l] = v;
         }
-        for (int i = tid; i < n_ok; i += blockDim.x) {
+        for (int i = tid; i < n_app; i += blockDim.x) {
             p.tree_parent[first + i] = i == 0 ? p.parent : first + i - 1;
             p.tree_slice[first + i] = -1;
         }

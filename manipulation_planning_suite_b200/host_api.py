@@ -1,0 +1,109 @@
+"""ctypes binding of libmps_host.so: the C++ planner classes (host/mps_host.hpp, mirroring the
+reference's RearrangementRRT family and OraclePushPlanner) driven through mps_host_plan()."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_PKG_DIR, "host", "libmps_host.so")
+
+ALGORITHMS = {"Naive": 0, "OracleRRT": 1, "SliceOracleRRT": 2, "HybridActionRRT": 3}
+
+
+class HostParams(C.Structure):
+    _fields_ = [
+        ("algorithm", C.c_int32), ("time_out", C.c_float), ("goal_bias", C.c_float), ("target_bias", C.c_float),
+        ("robot_bias", C.c_float), ("num_control_samples", C.c_int32), ("action_randomness", C.c_float),
+        ("state_noise", C.c_float), ("do_slice_ball_projection", C.c_int32), ("device", C.c_int32),
+        ("seed", C.c_uint64), ("max_iterations", C.c_int32), ("velocity_limits", C.c_float * 3),
+        ("duration_limits", C.c_float * 2),
+    ]
+
+
+class HostResult(C.Structure):
+    _fields_ = [
+        ("solved", C.c_int32), ("reproducible", C.c_int32), ("num_iterations", C.c_int32),
+        ("num_state_propagations", C.c_int32), ("num_samples", C.c_int32), ("num_nearest_neighbor_queries", C.c_int32),
+        ("runtime_cpu", C.c_float), ("runtime_wall", C.c_float), ("tree_size", C.c_int32), ("num_slices", C.c_int32),
+        ("path_len", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load_host_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise abi.LibraryMissing(f"{HOST_LIB_PATH} not found: run __graft_entry__.build()")
+        abi.load_library()  # libmps_b200.so first (rpath also resolves it)
+        L = C.CDLL(HOST_LIB_PATH)
+        L.mps_host_default_params.argtypes = [C.POINTER(HostParams)]
+        L.mps_host_plan.argtypes = [C.POINTER(abi.Scene), C.POINTER(C.c_float), C.POINTER(abi.Goal), C.c_int32,
+                                    C.POINTER(HostParams), C.POINTER(HostResult), C.POINTER(C.c_float),
+                                    C.POINTER(C.c_float), C.c_int32, C.c_char_p, C.c_int32]
+        L.mps_host_ramp_steer.argtypes = [C.POINTER(C.c_float)] * 6 + [C.c_int32]
+        L.mps_host_max_pushing_distance.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+@dataclass
+class PlanResult:
+    solved: bool
+    reproducible: bool
+    stats: dict
+    path_states: np.ndarray
+    path_controls: np.ndarray
+
+
+def default_params() -> HostParams:
+    p = HostParams()
+    load_host_library().mps_host_default_params(C.byref(p))
+    return p
+
+
+def plan(scene: abi.Scene, start, goals, algorithm="Naive", max_path=4096, **kw) -> PlanResult:
+    """OraclePushPlanner::setup + solve (pushing/OraclePushPlanner.cpp:107-243) on the device."""
+    L = load_host_library()
+    p = default_params()
+    p.algorithm = ALGORITHMS[algorithm] if isinstance(algorithm, str) else int(algorithm)
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown planner parameter {k}")
+        setattr(p, k, v)
+    B = scene.n_bodies
+    s = np.ascontiguousarray(start, np.float32).reshape(3 * B)
+    g = (abi.Goal * len(goals))()
+    for i, (body, x, y, tol) in enumerate(goals):
+        g[i].body, g[i].x, g[i].y, g[i].tol = int(body), float(x), float(y), float(tol)
+    res = HostResult()
+    ps = np.zeros((max_path, 3 * B), np.float32)
+    pc = np.zeros((max_path, 5), np.float32)
+    err = C.create_string_buffer(512)
+    rc = L.mps_host_plan(C.byref(scene), s.ctypes.data_as(C.POINTER(C.c_float)), g, len(goals), C.byref(p), C.byref(res),
+                         ps.ctypes.data_as(C.POINTER(C.c_float)), pc.ctypes.data_as(C.POINTER(C.c_float)), max_path,
+                         err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    n = min(res.path_len, max_path)
+    stats = {f: getattr(res, f) for f, _ in HostResult._fields_}
+    return PlanResult(bool(res.solved), bool(res.reproducible), stats, ps[:n].copy(), pc[:n].copy())
+
+
+def ramp_steer(current, desired, vel_limits=(0.6, 0.6, 1.5), accel_limits=(2.0, 2.0, 4.0), duration_limits=(0.1, 1.0)):
+    L = load_host_library()
+    f = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+    v, a, d, c, e = f(vel_limits), f(accel_limits), f(duration_limits), f(current), f(desired)
+    out = np.zeros((64, 5), np.float32)
+    P = C.POINTER(C.c_float)
+    n = L.mps_host_ramp_steer(v.ctypes.data_as(P), a.ctypes.data_as(P), d.ctypes.data_as(P), c.ctypes.data_as(P),
+                              e.ctypes.data_as(P), out.ctypes.data_as(P), 64)
+    return out[:n].copy()

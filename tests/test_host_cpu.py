@@ -1,0 +1,51 @@
+"""CPU tests of the host-side C++ mirror (libmps_host.so): closed-form oracle pieces that need no device
+(SURVEY.md §8c items 8-9)."""
+import numpy as np
+import pytest
+
+from manipulation_planning_suite_b200 import host_api, scenes
+
+
+def test_max_pushing_distance():
+    # HumanOracle::getMaximalPushingDistance (oracle/HumanOracle.cpp:161-164): sqrt(2*0.1 + 2*0.1) + 0.01*sqrt(0.78)
+    assert host_api.load_host_library().mps_host_max_pushing_distance() == pytest.approx(0.6413, abs=1e-4)
+
+
+@pytest.mark.parametrize("target", [(1.0, 0.5, 0.3), (0.05, 0.0, 0.0), (-0.7, 0.9, -2.0), (0.0, 0.0, 1.0)])
+def test_ramp_computer_steer_reaches_the_target(target):
+    """RampComputer::steer (oracle/RampComputer.cpp:40-92): the ramps' areas add up to the straight-line
+    displacement, every ramp respects the velocity limits and the plateau limit."""
+    vlim, alim = np.array([0.6, 0.6, 1.5]), np.array([2.0, 2.0, 4.0])
+    c = host_api.ramp_steer([0, 0, 0], target)
+    assert len(c) >= 1
+    tot = np.zeros(3)
+    for p in c:
+        v = p[:3].astype(np.float64)
+        assert (np.abs(v) <= vlim + 1e-6).all()
+        assert 0.0 <= p[3] <= 1.0 + 1e-6 and p[4] == 0.0
+        t_acc = np.max(np.abs(v) / alim)
+        tot += v * (t_acc + p[3])
+    assert tot == pytest.approx(np.array(target), abs=2e-5)
+    # all ramps point along the same direction
+    d = np.array(target) / np.linalg.norm(target)
+    for p in c:
+        assert np.cross(p[:3] / np.linalg.norm(p[:3]), d) == pytest.approx(np.zeros(3), abs=1e-5)
+
+
+def test_ramp_computer_zero_distance_gives_no_control():
+    assert len(host_api.ramp_steer([0.3, 0.2, 0.1], [0.3, 0.2, 0.1])) == 0
+
+
+def test_planner_without_device_is_a_hard_error():
+    import ctypes as C
+
+    from manipulation_planning_suite_b200 import abi
+
+    n = C.c_int(0)
+    abi.load_library().mps_device_count(C.byref(n))
+    if n.value > 0:
+        pytest.skip("a CUDA device is present")
+    sc, start = scenes.make_scene(3, seed=1001)
+    with pytest.raises(RuntimeError) as e:
+        host_api.plan(sc, start, [(1, 0.5, 0.5, 0.1)], algorithm="Naive", max_iterations=5)
+    assert "no CPU fallback" in str(e.value)
