@@ -532,6 +532,121 @@ struct StepStats {
     unsigned steps, candidates, touching, colour_passes;
 };
 
+// One colour pass of the Gauss-Seidel sweep: every lane that owns a body with a manifold in this colour
+// solves it (both owners of a body pair do, redundantly and identically; the partner's twist arrives by
+// shuffle).  sl = manifold slot or 0xff, j = partner lane (self when none), stat = static colour.
+__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat)
+{
+    float ovx = 0.0f, ovy = 0.0f, ow_ = 0.0f;
+    if (!stat) {  // warp-uniform
+        ovx = __shfl_sync(FULL, bd.vx, j);
+        ovy = __shfl_sync(FULL, bd.vy, j);
+        ow_ = __shfl_sync(FULL, bd.w, j);
+    }
+    const bool act = sl != 0xff;
+    const unsigned amask = __ballot_sync(FULL, act);
+    if (act) {
+        const bool is_a = stat || lane < j;
+        float4* mf = W.man + sl * MF_VEC4;
+        // everything the pass reads is loaded before anything is written back: the two owner lanes of a
+        // pair must see the same accumulated impulses
+        const float4 m0 = mf[0];
+        const float4 mm = mf[1];
+        const int cnt = (__float_as_int(m0.x) >> 16) & 0xff;
+        const float4 r0 = mf[2], i0 = mf[3], k0 = mf[4];
+        float4 r1 = r0, i1 = i0, k1 = k0;
+        if (cnt > 1) {
+            r1 = mf[5];
+            i1 = mf[6];
+            k1 = mf[7];
+        }
+        float4 acc = mf[8];
+        __syncwarp(amask);
+        const float nx = m0.y, ny = m0.z, fr = m0.w;
+        const float tx = ny, ty = -nx;
+        const float manx = mm.x, many = mm.y, mbnx = mm.z, mbny = mm.w;
+        float vax, vay, wa, vbx, vby, wb;
+        if (is_a) {
+            vax = bd.vx; vay = bd.vy; wa = bd.w;
+            vbx = ovx; vby = ovy; wb = ow_;  // zero for a static partner
+        } else {
+            vax = ovx; vay = ovy; wa = ow_;
+            vbx = bd.vx; vby = bd.vy; wb = bd.w;
+        }
+        // friction first (Box2D order), point 0 then point 1
+        {
+            float dvx = vbx - vax;
+            float dvy = vby - vay;
+            float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r0.w, -(wa * r0.z))));
+            float lambda = k0.y * -vt;
+            float max_f = fr * acc.x;
+            float new_imp = fminf(fmaxf(acc.y + lambda, -max_f), max_f);
+            lambda = new_imp - acc.y;
+            acc.y = new_imp;
+            vax = fmaf(-many, lambda, vax);
+            vay = fmaf(manx, lambda, vay);
+            wa = fmaf(-i0.z, lambda, wa);
+            vbx = fmaf(mbny, lambda, vbx);
+            vby = fmaf(-mbnx, lambda, vby);
+            wb = fmaf(i0.w, lambda, wb);
+        }
+        if (cnt > 1) {
+            float dvx = vbx - vax;
+            float dvy = vby - vay;
+            float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
+            float lambda = k1.y * -vt;
+            float max_f = fr * acc.z;
+            float new_imp = fminf(fmaxf(acc.w + lambda, -max_f), max_f);
+            lambda = new_imp - acc.w;
+            acc.w = new_imp;
+            vax = fmaf(-many, lambda, vax);
+            vay = fmaf(manx, lambda, vay);
+            wa = fmaf(-i1.z, lambda, wa);
+            vbx = fmaf(mbny, lambda, vbx);
+            vby = fmaf(-mbnx, lambda, vby);
+            wb = fmaf(i1.w, lambda, wb);
+        }
+        // then non-penetration
+        {
+            float dvx = vbx - vax;
+            float dvy = vby - vay;
+            float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r0.y, -(wa * r0.x))));
+            float lambda = k0.x * (k0.z - vn);
+            float new_imp = fmaxf(acc.x + lambda, 0.0f);
+            lambda = new_imp - acc.x;
+            acc.x = new_imp;
+            vax = fmaf(-manx, lambda, vax);
+            vay = fmaf(-many, lambda, vay);
+            wa = fmaf(-i0.x, lambda, wa);
+            vbx = fmaf(mbnx, lambda, vbx);
+            vby = fmaf(mbny, lambda, vby);
+            wb = fmaf(i0.y, lambda, wb);
+        }
+        if (cnt > 1) {
+            float dvx = vbx - vax;
+            float dvy = vby - vay;
+            float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
+            float lambda = k1.x * (k1.z - vn);
+            float new_imp = fmaxf(acc.z + lambda, 0.0f);
+            lambda = new_imp - acc.z;
+            acc.z = new_imp;
+            vax = fmaf(-manx, lambda, vax);
+            vay = fmaf(-many, lambda, vay);
+            wa = fmaf(-i1.x, lambda, wa);
+            vbx = fmaf(mbnx, lambda, vbx);
+            vby = fmaf(mbny, lambda, vby);
+            wb = fmaf(i1.y, lambda, wb);
+        }
+        if (is_a) {
+            bd.vx = vax; bd.vy = vay; bd.w = wa;
+            mf[8] = acc;
+        } else {
+            bd.vx = vbx; bd.vy = vby; bd.w = wb;
+        }
+    }
+    __syncwarp();
+}
+
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, int lane, float ux,
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
@@ -569,154 +684,56 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
         bd.vy = bd.vy + bd.inv_m * iy;
     }
     if (dr.colours != 0ull) {
-        // this lane's manifold slot for each of the first 8 active colours, packed one byte each
-        unsigned long long packed = ~0ull;
-        {
-            unsigned long long cm = dr.colours;
-            for (int ord = 0; cm != 0ull && ord < 8; ++ord) {
-                int col = __ffsll((long long)cm) - 1;
-                cm &= cm - 1ull;
-                unsigned long long sl = (unsigned long long)lookup_slot(sc, W, lane, col, dr.nm);
-                packed = (packed & ~(0xffull << (8 * ord))) | (sl << (8 * ord));
-            }
-        }
-        // A manifold whose two bodies have exactly zero twist, that carries no bias and has not been
-        // solved yet this step returns zero impulses: visiting it changes nothing, so it is skipped
-        // (bit-identical to visiting it).  `woke` remembers, per colour ordinal, that it has been solved.
-        unsigned woke = 0u;
-        for (int it = 0; it < sc.vel_iters; ++it) {
-            unsigned long long cm = dr.colours;
-            int ord = 0;
-            while (cm) {
-                const int col = __ffsll((long long)cm) - 1;
-                cm &= cm - 1ull;
-                const int sl = ord < 8 ? (int)((packed >> (8 * ord)) & 0xffull) : lookup_slot(sc, W, lane, col, dr.nm);
-                const unsigned obit = 1u << (ord & 31);
-                ++ord;
-                const bool stat = col >= B;
-                int j = lane;  // partner lane (self when none)
-                if (!stat && bd.live) {
-                    j = col - lane;
-                    if (j < 0) j += B;
-                }
-                const float ovx = __shfl_sync(FULL, bd.vx, j);
-                const float ovy = __shfl_sync(FULL, bd.vy, j);
-                const float ow_ = __shfl_sync(FULL, bd.w, j);
-                bool act = sl != 0xff;
-                float4 m0;
-                if (act) {
-                    m0 = W.man[sl * MF_VEC4];
-                    const bool moving = (bd.vx != 0.0f) | (bd.vy != 0.0f) | (bd.w != 0.0f) |
-                                        (!stat & ((ovx != 0.0f) | (ovy != 0.0f) | (ow_ != 0.0f)));
-                    act = moving || (__float_as_int(m0.x) & MF_HAS_BIAS) || (woke & obit);
-                }
-                const unsigned amask = __ballot_sync(FULL, act);
-                if (amask == 0u) continue;
-                st.colour_passes += 1;
-                if (act) {
-                    woke |= obit;
-                    const bool is_a = stat || lane < j;
-                    float4* mf = W.man + sl * MF_VEC4;
-                    const int cnt = (__float_as_int(m0.x) >> 16) & 0xff;
-                    const float nx = m0.y, ny = m0.z, fr = m0.w;
-                    const float tx = ny, ty = -nx;
-                    // everything the pass reads is loaded before anything is written back: the two owner
-                    // lanes of a pair must see the same accumulated impulses
-                    const float4 mm = mf[1];
-                    const float4 r0 = mf[2], i0 = mf[3], k0 = mf[4];
-                    float4 r1 = r0, i1 = i0, k1 = k0;
-                    if (cnt > 1) {
-                        r1 = mf[5];
-                        i1 = mf[6];
-                        k1 = mf[7];
-                    }
-                    float4 acc = mf[8];
-                    __syncwarp(amask);
-                    const float manx = mm.x, many = mm.y, mbnx = mm.z, mbny = mm.w;
-                    float vax, vay, wa, vbx, vby, wb;
-                    if (is_a) {
-                        vax = bd.vx; vay = bd.vy; wa = bd.w;
-                        if (stat) {
-                            vbx = 0.0f; vby = 0.0f; wb = 0.0f;
-                        } else {
-                            vbx = ovx; vby = ovy; wb = ow_;
+        const int ncol = __popcll(dr.colours);
+        if (ncol <= 4) {
+            // common case: at most 4 active colours.  Slot, partner lane and kind of each are step
+            // constants kept in registers; the sweep is a fully unrolled 4-way pass list.
+            int sl[4], jl[4];
+            bool st_[4];
+            {
+                unsigned long long cm = dr.colours;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    sl[c] = 0xff;
+                    jl[c] = lane;
+                    st_[c] = true;
+                    if (c < ncol) {
+                        const int col = __ffsll((long long)cm) - 1;
+                        cm &= cm - 1ull;
+                        sl[c] = lookup_slot(sc, W, lane, col, dr.nm);
+                        st_[c] = col >= B;
+                        if (!st_[c] && bd.live) {
+                            int j = col - lane;
+                            if (j < 0) j += B;
+                            jl[c] = j;
                         }
-                    } else {
-                        vax = ovx; vay = ovy; wa = ow_;
-                        vbx = bd.vx; vby = bd.vy; wb = bd.w;
-                    }
-                    // friction first (Box2D order), point 0 then point 1
-                    {
-                        float dvx = vbx - vax;
-                        float dvy = vby - vay;
-                        float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r0.w, -(wa * r0.z))));
-                        float lambda = k0.y * -vt;
-                        float max_f = fr * acc.x;
-                        float new_imp = fminf(fmaxf(acc.y + lambda, -max_f), max_f);
-                        lambda = new_imp - acc.y;
-                        acc.y = new_imp;
-                        vax = fmaf(-many, lambda, vax);
-                        vay = fmaf(manx, lambda, vay);
-                        wa = fmaf(-i0.z, lambda, wa);
-                        vbx = fmaf(mbny, lambda, vbx);
-                        vby = fmaf(-mbnx, lambda, vby);
-                        wb = fmaf(i0.w, lambda, wb);
-                    }
-                    if (cnt > 1) {
-                        float dvx = vbx - vax;
-                        float dvy = vby - vay;
-                        float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
-                        float lambda = k1.y * -vt;
-                        float max_f = fr * acc.z;
-                        float new_imp = fminf(fmaxf(acc.w + lambda, -max_f), max_f);
-                        lambda = new_imp - acc.w;
-                        acc.w = new_imp;
-                        vax = fmaf(-many, lambda, vax);
-                        vay = fmaf(manx, lambda, vay);
-                        wa = fmaf(-i1.z, lambda, wa);
-                        vbx = fmaf(mbny, lambda, vbx);
-                        vby = fmaf(-mbnx, lambda, vby);
-                        wb = fmaf(i1.w, lambda, wb);
-                    }
-                    // then non-penetration
-                    {
-                        float dvx = vbx - vax;
-                        float dvy = vby - vay;
-                        float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r0.y, -(wa * r0.x))));
-                        float lambda = k0.x * (k0.z - vn);
-                        float new_imp = fmaxf(acc.x + lambda, 0.0f);
-                        lambda = new_imp - acc.x;
-                        acc.x = new_imp;
-                        vax = fmaf(-manx, lambda, vax);
-                        vay = fmaf(-many, lambda, vay);
-                        wa = fmaf(-i0.x, lambda, wa);
-                        vbx = fmaf(mbnx, lambda, vbx);
-                        vby = fmaf(mbny, lambda, vby);
-                        wb = fmaf(i0.y, lambda, wb);
-                    }
-                    if (cnt > 1) {
-                        float dvx = vbx - vax;
-                        float dvy = vby - vay;
-                        float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
-                        float lambda = k1.x * (k1.z - vn);
-                        float new_imp = fmaxf(acc.z + lambda, 0.0f);
-                        lambda = new_imp - acc.z;
-                        acc.z = new_imp;
-                        vax = fmaf(-manx, lambda, vax);
-                        vay = fmaf(-many, lambda, vay);
-                        wa = fmaf(-i1.x, lambda, wa);
-                        vbx = fmaf(mbnx, lambda, vbx);
-                        vby = fmaf(mbny, lambda, vby);
-                        wb = fmaf(i1.y, lambda, wb);
-                    }
-                    if (is_a) {
-                        bd.vx = vax; bd.vy = vay; bd.w = wa;
-                        mf[8] = acc;
-                    } else {
-                        bd.vx = vbx; bd.vy = vby; bd.w = wb;
                     }
                 }
-                __syncwarp();
+            }
+            st.colour_passes += (unsigned)(ncol * sc.vel_iters);
+            for (int it = 0; it < sc.vel_iters; ++it) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < ncol) solve_pass(W, bd, lane, sl[c], jl[c], st_[c]);
+                }
+            }
+        } else {
+            // general case: walk the colour mask; slots looked up per pass
+            st.colour_passes += (unsigned)(ncol * sc.vel_iters);
+            for (int it = 0; it < sc.vel_iters; ++it) {
+                unsigned long long cm = dr.colours;
+                while (cm) {
+                    const int col = __ffsll((long long)cm) - 1;
+                    cm &= cm - 1ull;
+                    const int slot = lookup_slot(sc, W, lane, col, dr.nm);
+                    const bool stat = col >= B;
+                    int j = lane;
+                    if (!stat && bd.live) {
+                        j = col - lane;
+                        if (j < 0) j += B;
+                    }
+                    solve_pass(W, bd, lane, slot, j, stat);
+                }
             }
         }
     }
@@ -922,8 +939,8 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
                         flags |= MPS_F_OVERFLOW;
                         ok = false;
                     }
-                    // jam rule: wedged deeper than pen_max for jam_steps consecutive rest steps
-                    jam = pen > sc.pen_max ? jam + 1 : 0;
+                    // jam rule: wedged deeper than 2 * slop for jam_steps consecutive rest steps
+                    jam = pen > 2.0f * sc.slop ? jam + 1 : 0;
                     if (sc.jam_steps > 0 && jam >= sc.jam_steps) {
                         flags |= MPS_F_JAMMED;
                         ok = false;

@@ -937,9 +937,10 @@ static int propagate_impl(const mps_scene* sc, const float* state_in, float* con
                 flags |= MPS_F_OVERFLOW;
                 ok = 0;
             }
-            /* jam rule (spec §3.6): the robot has stopped; a world that stays deeper than pen_max for
-             * jam_steps consecutive steps is wedged and will not come to rest */
-            jam = wd.max_pen > sc->pen_max ? jam + 1 : 0;
+            /* jam rule (spec §3.6): the robot has stopped.  A free contact sheds its penetration beyond
+             * the slop by the factor (1 - baumgarte) per step, so a world that stays deeper than 2 * slop
+             * for jam_steps consecutive steps is wedged and will not come to rest */
+            jam = wd.max_pen > 2.0f * sc->slop ? jam + 1 : 0;
             if (sc->jam_steps > 0 && jam >= sc->jam_steps) {
                 flags |= MPS_F_JAMMED;
                 ok = 0;
