@@ -532,16 +532,19 @@ struct StepStats {
     unsigned steps, candidates, touching, colour_passes;
 };
 
-// One colour pass of the Gauss-Seidel sweep: every lane that owns a body with a manifold in this colour
+// One pass of the Gauss-Seidel sweep: every lane that owns a body with a manifold scheduled in this pass
 // solves it (both owners of a body pair do, redundantly and identically; the partner's twist arrives by
-// shuffle).  sl = manifold slot or 0xff, j = partner lane (self when none), stat = static colour.
+// shuffle).  Per lane: sl = manifold slot or 0xff, j = partner lane (self when none or static),
+// stat = the partner is a static.
 __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat)
 {
-    float ovx = 0.0f, ovy = 0.0f, ow_ = 0.0f;
-    if (!stat) {  // warp-uniform
-        ovx = __shfl_sync(FULL, bd.vx, j);
-        ovy = __shfl_sync(FULL, bd.vy, j);
-        ow_ = __shfl_sync(FULL, bd.w, j);
+    float ovx = __shfl_sync(FULL, bd.vx, j);
+    float ovy = __shfl_sync(FULL, bd.vy, j);
+    float ow_ = __shfl_sync(FULL, bd.w, j);
+    if (stat) {
+        ovx = 0.0f;
+        ovy = 0.0f;
+        ow_ = 0.0f;
     }
     const bool act = sl != 0xff;
     const unsigned amask = __ballot_sync(FULL, act);
@@ -686,35 +689,51 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     if (dr.colours != 0ull) {
         const int ncol = __popcll(dr.colours);
         if (ncol <= 4) {
-            // common case: at most 4 active colours.  Slot, partner lane and kind of each are step
-            // constants kept in registers; the sweep is a fully unrolled 4-way pass list.
-            int sl[4], jl[4];
-            bool st_[4];
+            // Common case: at most 4 active colours.  The canonical order is colour by colour, but two
+            // manifolds that share no body commute, so each manifold is scheduled in the earliest ROUND
+            // after every earlier manifold (in canonical order) that shares a body with it:
+            //     round(m) = 1 + max(last round of body a, last round of body b).
+            // Any schedule that keeps the relative order of manifolds sharing a body produces the bits of
+            // the canonical sweep; independent contacts (different islands) now solve concurrently.
+            // Each lane packs its <= 4 entries as round << 16 | static << 15 | partner << 8 | slot.
+            unsigned ent[4];
+            int last = 0;
             {
                 unsigned long long cm = dr.colours;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    sl[c] = 0xff;
-                    jl[c] = lane;
-                    st_[c] = true;
+                    ent[c] = 0u;
                     if (c < ncol) {
                         const int col = __ffsll((long long)cm) - 1;
                         cm &= cm - 1ull;
-                        sl[c] = lookup_slot(sc, W, lane, col, dr.nm);
-                        st_[c] = col >= B;
-                        if (!st_[c] && bd.live) {
-                            int j = col - lane;
+                        const int slc = lookup_slot(sc, W, lane, col, dr.nm);
+                        const bool stc = col >= B;
+                        int j = lane;
+                        if (!stc && bd.live) {
+                            j = col - lane;
                             if (j < 0) j += B;
-                            jl[c] = j;
+                        }
+                        int pl = __shfl_sync(FULL, last, j);
+                        if (stc) pl = 0;
+                        if (slc != 0xff) {
+                            last = (last > pl ? last : pl) + 1;
+                            ent[c] = ((unsigned)last << 16) | (stc ? 0x8000u : 0u) | ((unsigned)(stc ? lane : j) << 8) |
+                                     (unsigned)slc;
                         }
                     }
                 }
             }
-            st.colour_passes += (unsigned)(ncol * sc.vel_iters);
+            const int rounds = __reduce_max_sync(FULL, last);
+            st.colour_passes += (unsigned)(rounds * sc.vel_iters);
             for (int it = 0; it < sc.vel_iters; ++it) {
+                for (int r = 1; r <= rounds; ++r) {
+                    unsigned e = 0u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < ncol) solve_pass(W, bd, lane, sl[c], jl[c], st_[c]);
+                    for (int c = 0; c < 4; ++c)
+                        if ((int)(ent[c] >> 16) == r) e = ent[c];
+                    const int slr = e ? (int)(e & 0xffu) : 0xff;
+                    const int jr = e ? (int)((e >> 8) & 0x7fu) : lane;
+                    solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
                 }
             }
         } else {
