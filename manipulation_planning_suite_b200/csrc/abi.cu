@@ -59,7 +59,9 @@ struct mps_ctx {
     DevBuf d_tstage_states, d_tstage_parents, d_tstage_controls, d_tstage_slices;
 
     // nn
-    DevBuf d_queries, d_masks, d_filters, d_nnw, d_out_idx, d_out_dist, d_part_d, d_part_i, d_tickets;
+    DevBuf d_queries, d_masks, d_filters, d_nnw, d_nn_out, d_part_d, d_part_i, d_tickets;
+    void* h_nn_out = nullptr;  // pinned: idx[Q] | dist[Q]
+    size_t h_nn_out_bytes = 0;
     NNParams np;
     bool nn_ready = false;
     int nn_Q = 0;
@@ -366,7 +368,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
                       &ctx->d_ball, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
                       &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
-                      &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_out_idx, &ctx->d_out_dist, &ctx->d_part_d,
+                      &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_nn_out, &ctx->d_part_d,
                       &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags};
     for (DevBuf* b : bufs) free_buf(*b);
     if (ctx->tree.states) cudaFree(ctx->tree.states);
@@ -375,6 +377,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->tree.slice) cudaFree(ctx->tree.slice);
     if (ctx->d_scene) cudaFree(ctx->d_scene);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_nn_out) cudaFreeHost(ctx->h_nn_out);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -669,34 +672,51 @@ int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const
     if ((rc = ensure(ctx, ctx->d_masks, mb))) return rc;
     if ((rc = ensure(ctx, ctx->d_filters, mb))) return rc;
     if ((rc = ensure(ctx, ctx->d_nnw, wb))) return rc;
-    if ((rc = ensure(ctx, ctx->d_out_idx, sizeof(long long) * (size_t)Q))) return rc;
-    if ((rc = ensure(ctx, ctx->d_out_dist, sizeof(double) * (size_t)Q))) return rc;
-    const int max_grid = ctx->num_sms * 4;
+    if ((rc = ensure(ctx, ctx->d_nn_out, 16 * (size_t)Q))) return rc;
+    if (ctx->h_nn_out_bytes < 16 * (size_t)Q) {
+        if (ctx->h_nn_out) {
+            MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+            MPS_CUDA_CHECK(cudaFreeHost(ctx->h_nn_out), ctx);
+            ctx->h_nn_out = nullptr;
+        }
+        ctx->h_nn_out_bytes = 16 * (size_t)(Q < 256 ? 256 : Q);
+        MPS_CUDA_CHECK(cudaMallocHost(&ctx->h_nn_out, ctx->h_nn_out_bytes), ctx);
+    }
+    const int max_grid = ctx->num_sms * 16;
     if ((rc = ensure(ctx, ctx->d_part_d, sizeof(double) * (size_t)Q * max_grid))) return rc;
     if ((rc = ensure(ctx, ctx->d_part_i, sizeof(long long) * (size_t)Q * max_grid))) return rc;
     if (ctx->d_tickets.bytes < sizeof(unsigned) * (size_t)Q) {
         if ((rc = ensure(ctx, ctx->d_tickets, sizeof(unsigned) * (size_t)Q))) return rc;
         MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.bytes, ctx->stream), ctx);
     }
-    if ((rc = ensure_stage(ctx, qb + 2 * mb + wb))) return rc;
-    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
-    char* h = (char*)ctx->h_stage;
-    memcpy(h, queries, qb);
-    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_queries.p, h, qb, cudaMemcpyHostToDevice, ctx->stream), ctx);
-    h += qb;
-    if (masks) {
-        memcpy(h, masks, mb);
-        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_masks.p, h, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
-    }
-    h += mb;
-    if (slice_filters) {
-        memcpy(h, slice_filters, mb);
-        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_filters.p, h, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
-    }
-    h += mb;
-    if (weights) {
-        memcpy(h, weights, wb);
-        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nnw.p, h, wb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    if (qb + 2 * mb + wb <= 65536) {
+        // small payloads: copy straight from the caller's memory (the driver stages pageable memory before
+        // cudaMemcpyAsync returns), no staging buffer and no synchronise on the query path
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_queries.p, queries, qb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        if (masks) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_masks.p, masks, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        if (slice_filters) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_filters.p, slice_filters, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        if (weights) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nnw.p, weights, wb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    } else {
+        if ((rc = ensure_stage(ctx, qb + 2 * mb + wb))) return rc;
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        char* h = (char*)ctx->h_stage;
+        memcpy(h, queries, qb);
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_queries.p, h, qb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        h += qb;
+        if (masks) {
+            memcpy(h, masks, mb);
+            MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_masks.p, h, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        }
+        h += mb;
+        if (slice_filters) {
+            memcpy(h, slice_filters, mb);
+            MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_filters.p, h, mb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        }
+        h += mb;
+        if (weights) {
+            memcpy(h, weights, wb);
+            MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nnw.p, h, wb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+        }
     }
     NNParams& np = ctx->np;
     memset(&np, 0, sizeof(np));
@@ -707,8 +727,8 @@ int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const
     np.pw = ctx->scene.position_weight;
     np.ow = ctx->scene.orientation_weight;
     np.Q = Q;
-    np.out_idx = (long long*)ctx->d_out_idx.p;
-    np.out_dist = (double*)ctx->d_out_dist.p;
+    np.out_idx = (long long*)ctx->d_nn_out.p;
+    np.out_dist = (double*)((char*)ctx->d_nn_out.p + 8 * (size_t)Q);
     np.part_d = (double*)ctx->d_part_d.p;
     np.part_i = (long long*)ctx->d_part_i.p;
     np.tickets = (unsigned*)ctx->d_tickets.p;
@@ -737,9 +757,11 @@ int mps_tree_nearest_fetch(mps_ctx* ctx, int64_t* indices, double* distances)
     if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
     if (!ctx->nn_ready) return mps_fail(ctx, MPS_ERR_STATE, "nothing to fetch");
     const int Q = ctx->nn_Q;
-    if (indices) MPS_CUDA_CHECK(cudaMemcpyAsync(indices, ctx->d_out_idx.p, sizeof(long long) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
-    if (distances) MPS_CUDA_CHECK(cudaMemcpyAsync(distances, ctx->d_out_dist.p, sizeof(double) * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    // one D2H of idx[Q] | dist[Q] into pinned memory, one synchronise
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nn_out, ctx->d_nn_out.p, 16 * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    if (indices) memcpy(indices, ctx->h_nn_out, 8 * (size_t)Q);
+    if (distances) memcpy(distances, (char*)ctx->h_nn_out + 8 * (size_t)Q, 8 * (size_t)Q);
     return MPS_OK;
 }
 

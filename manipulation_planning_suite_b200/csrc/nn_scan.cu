@@ -17,13 +17,21 @@
 #include "nn_scan.h"
 
 #define FULL 0xffffffffu
+// launch shape (tuned on B200, profiles/tools/nn_tune.sh): threads per CTA, CTAs per SM, bodies whose
+// 3 rows are loaded before the arithmetic starts (3 * NN_BODY_BATCH LDG.128 in flight per thread)
+#ifndef NN_THREADS
 #define NN_THREADS 256
+#endif
+#ifndef NN_CTAS_PER_SM
+#define NN_CTAS_PER_SM 2
+#endif
+#ifndef NN_BODY_BATCH
+#define NN_BODY_BATCH 6
+#endif
+#define NN_MIN_BLOCKS NN_CTAS_PER_SM
 #define NN_REL_EPS 1.0e-4f
 #define NN_ABS_EPS 1.0e-15f
-#define NN_BODY_BATCH 4
-#define NN_MIN_BLOCKS 3
 #define NN_CAND_CAP 512
-#define NN_CTAS_PER_SM 3
 
 namespace {
 
@@ -94,6 +102,10 @@ __device__ __forceinline__ double warp_exact_distance(const TreeView& t, long lo
     return dist;
 }
 
+// STREAM: load the state rows with the evict-first hint (ld.global.cs).  Measured on B200: faster when the
+// scanned rows are about the size of L2 (1 M nodes x 132 B: 29.2 us vs 32.9 us), slower when they are several
+// times larger (4 M nodes: 96 us vs 88 us) - the host picks per launch (mps_launch_nn_scan).
+template <bool STREAM>
 __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNParams p)
 {
     __shared__ float s_q[3 * MPS_MAX_BODIES];
@@ -118,16 +130,14 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
     const int filter = p.filters ? p.filters[q] : -1;
     const float* qg = p.queries + (size_t)q * 3 * B;
     if (tid < 3 * B) s_q[tid] = qg[tid];
+    // active-body list, built in parallel: body i goes to position popc(mask below bit i)
+    if (tid < B && ((mask >> tid) & 1u)) {
+        const int a = __popc(mask & ((1u << tid) - 1u));
+        s_act[a] = tid;
+        s_w[a] = p.weights ? p.weights[tid] : 1.0f;
+    }
     if (tid == 0) {
-        int n = 0;
-        for (int i = 0; i < B; ++i) {
-            if ((mask >> i) & 1u) {
-                s_act[n] = i;
-                s_w[n] = p.weights ? p.weights[i] : 1.0f;
-                ++n;
-            }
-        }
-        s_nact = n;
+        s_nact = __popc(mask);
         s_bound = 0x7f800000u;  // +inf
         s_ncand = 0u;
     }
@@ -152,9 +162,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
             for (int u = 0; u < NN_BODY_BATCH; ++u) {  // all loads of the batch first: 3 * NN_BODY_BATCH LDG.128 in flight
                 const int a = a0 + u < nact ? a0 + u : nact - 1;
                 const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + n0;
-                X[u] = __ldg(reinterpret_cast<const float4*>(row));
-                Y[u] = __ldg(reinterpret_cast<const float4*>(row + cap));
-                T[u] = __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
+                X[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row)) : __ldg(reinterpret_cast<const float4*>(row));
+                Y[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + cap))
+                              : __ldg(reinterpret_cast<const float4*>(row + cap));
+                T[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + 2 * cap))
+                              : __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
             }
 #pragma unroll
             for (int u = 0; u < NN_BODY_BATCH; ++u) {
@@ -243,7 +255,12 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
             long long oi = __shfl_down_sync(FULL, best_i, off);
             take_min(best_d, best_i, od, oi);
         }
-        if (tid == 0) {
+        if (tid == 0 && gridDim.x == 1) {
+            // small trees: one CTA, no cross-CTA hand-off (saves ~4 dependent global round trips)
+            p.out_idx[q] = best_i;
+            p.out_dist[q] = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
+            s_last = false;
+        } else if (tid == 0) {
             p.part_d[(size_t)q * p.grid_x + blockIdx.x] = best_d;
             p.part_i[(size_t)q * p.grid_x + blockIdx.x] = best_i;
             __threadfence();
@@ -400,7 +417,12 @@ int mps_nn_grid_x(long long n, int num_sms)
 cudaError_t mps_launch_nn_scan(const NNParams& p, cudaStream_t stream)
 {
     dim3 grid((unsigned)p.grid_x, (unsigned)p.Q, 1);
-    nn_scan_kernel<<<grid, NN_THREADS, 0, stream>>>(p);
+    // evict-first loads while the scanned rows are within ~2x the 126 MB L2, default policy beyond
+    const double scanned = (double)p.n * 12.0 * p.tree.B;
+    if (scanned < 252.0e6)
+        nn_scan_kernel<true><<<grid, NN_THREADS, 0, stream>>>(p);
+    else
+        nn_scan_kernel<false><<<grid, NN_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
