@@ -211,6 +211,8 @@ int mps_extend_fetch(mps_ctx* ctx, const mps_extend_out* out); /* synchronises *
 /* counters of the last launch: [0] physics steps, [1] candidate pairs, [2] touching manifolds,
  * [3] solver colour passes, [4] kernel launches since ctx creation */
 int mps_extend_counters(mps_ctx* ctx, uint64_t counters[8]);
+/* SM clock cycles the last launch spent on each of its K chains (profiling aid: which chain is the tail) */
+int mps_extend_chain_cycles(mps_ctx* ctx, int64_t* cycles);
 
 /* ---- validity --------------------------------------------------------- */
 /* valid[i] = isValid(states[i]); flags[i] (optional) says why not */

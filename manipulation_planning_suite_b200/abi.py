@@ -175,6 +175,7 @@ SYMBOLS = {
     "mps_extend_launch": (C.c_int, [_ctx]),
     "mps_extend_fetch": (C.c_int, [_ctx, _P(ExtendOut)]),
     "mps_extend_counters": (C.c_int, [_ctx, _P(C.c_uint64)]),
+    "mps_extend_chain_cycles": (C.c_int, [_ctx, _P(C.c_int64)]),
     "mps_is_valid_batch": (C.c_int, [_ctx, _P(_f32), _i32, _P(C.c_uint8), _P(_u32)]),
     "mps_distance": (C.c_int, [_P(Scene), _P(_f32), _P(_f32), _P(_f32), _u32, _P(C.c_double)]),
     "mps_goal_distance": (C.c_int, [_P(Scene), _P(_f32), _P(Goal), _i32, _P(C.c_double)]),

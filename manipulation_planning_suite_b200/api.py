@@ -210,6 +210,12 @@ class Context:
         self._check(self.lib.mps_extend_counters(self.h, arr))
         return dict(steps=arr[0], candidates=arr[1], touching=arr[2], colour_passes=arr[3], launches=arr[4])
 
+    def chain_cycles(self) -> np.ndarray:
+        K = self._ext_shape[0]
+        out = np.zeros(K, np.int64)
+        self._check(self.lib.mps_extend_chain_cycles(self.h, _fp(out, C.c_int64)))
+        return out
+
     def time_launches(self, what: int, iters: int) -> float:
         ms = C.c_float(0)
         self._check(self.lib.mps_time_launches(self.h, what, iters, C.byref(ms)))

@@ -42,7 +42,7 @@ struct mps_ctx {
     DevBuf d_start, d_controls, d_nctrl, d_dest, d_weights, d_goals, d_ball;
     DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
     DevBuf d_record;  // packed winner record: best | states | controls | flags
-    DevBuf d_work, d_counters;
+    DevBuf d_work, d_counters, d_cycles;
     // pinned staging
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -366,7 +366,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_start, &ctx->d_controls, &ctx->d_nctrl, &ctx->d_dest, &ctx->d_weights, &ctx->d_goals,
                       &ctx->d_ball, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
-                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
+                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
                       &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_nn_out, &ctx->d_part_d,
                       &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags};
@@ -813,6 +813,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * (size_t)K))) return rc;
     if ((rc = ensure(ctx, ctx->d_record, record_bytes(B, L)))) return rc;
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * (size_t)K))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
         MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
@@ -864,6 +865,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     rp.out_goal_step = (int32_t*)ctx->d_goal_step.p;
     rp.work_counter = (unsigned*)ctx->d_work.p;
     rp.counters = (unsigned long long*)ctx->d_counters.p;
+    rp.out_cycles = (long long*)ctx->d_cycles.p;
 
     SelectParams& sp = ctx->sp;
     memset(&sp, 0, sizeof(sp));
@@ -976,6 +978,15 @@ int mps_propagate(mps_ctx* ctx, const float* state_in, float* control, float* st
     control[4] = rest;
     if (ok) *ok = (f & MPS_F_OK) ? 1 : 0;
     if (flags) *flags = f;
+    return MPS_OK;
+}
+
+int mps_extend_chain_cycles(mps_ctx* ctx, int64_t* cycles)
+{
+    if (!ctx || !cycles) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "no extend uploaded");
+    MPS_CUDA_CHECK(cudaMemcpyAsync(cycles, ctx->d_cycles.p, sizeof(long long) * (size_t)ctx->ext_K, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     return MPS_OK;
 }
 

@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
         if (k >= p.K) break;
         int n = p.n_ctrl ? p.n_ctrl[k] : L;
         if (n > L) n = L;
+        const long long t_begin = clock64();
         // start state of the chain
         float sx = 0.0f, sy = 0.0f, sth = 0.0f;
         if (bd.live) {
@@ -1043,6 +1044,7 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
             p.out_dist[k] = dist;
             p.out_nok[k] = n_ok;
             p.out_goal_step[k] = goal_step;
+            if (p.out_cycles) p.out_cycles[k] = clock64() - t_begin;
         }
     }
     // counters for the roofline accounting

@@ -32,6 +32,7 @@ struct RolloutParams {
     int32_t* out_goal_step;  // [K]
     unsigned int* work_counter;
     unsigned long long* counters;  // [4] or nullptr
+    long long* out_cycles;         // [K] SM clock cycles spent on each chain (profiling aid) or nullptr
 };
 
 struct SelectParams {
