@@ -255,6 +255,39 @@ int mps_tree_fill_random(mps_ctx* ctx, int64_t n, uint64_t seed, int32_t n_slice
 /* copy node states [first, first+n) back to the host, node-major [n][3B] */
 int mps_tree_read_states(mps_ctx* ctx, int64_t first, int64_t n, float* states);
 
+/* ---- forest: many independent planner instances in one context ----------- */
+/* BASELINE config 5 (multi-seed / multi-problem sweeps): n_instances trees of equal capacity share one
+ * dimension-major SoA; one launch serves a batch of M instances (SURVEY.md §8e "independent planner
+ * instances").  Instance indices are local to the context; node indices are local to their tree. */
+typedef struct mps_forest_extend_in {
+    int32_t M, K, L;          /* M instances in this batch, K chains of <= L controls each */
+    const int32_t* inst_ids;  /* [M] which tree */
+    const int32_t* parents;   /* [M] node of that tree the chains start from (read on device) */
+    const float* controls;    /* [M][K][L][5] */
+    const int32_t* n_ctrl;    /* [M][K] or NULL */
+    const float* dests;       /* [M][3B] or NULL */
+    const uint32_t* masks;    /* [M] or NULL (all bodies) */
+    const float* weights;     /* [B] or NULL */
+    int32_t compare_f32;
+    int32_t n_goals;
+    const mps_goal* goals;    /* shared by all instances */
+    int32_t append_to_tree;   /* winners appended to their own trees */
+    int32_t _pad;
+} mps_forest_extend_in;
+
+int mps_forest_reserve(mps_ctx* ctx, int32_t n_instances, int32_t cap_per_instance);
+/* every tree := { root }, roots [n_instances][3B] */
+int mps_forest_reset(mps_ctx* ctx, const float* roots);
+int mps_forest_sizes(mps_ctx* ctx, int64_t* sizes);
+int mps_forest_nearest(mps_ctx* ctx, int32_t M, const int32_t* inst_ids, const float* queries, const float* weights,
+                       const uint32_t* masks, int64_t* indices, double* distances);
+/* best [M], best_states [M][L][3B], best_controls [M][L][5], best_flags [M][L]; any may be NULL */
+int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_best* best, float* best_states,
+                      float* best_controls, uint32_t* best_flags);
+/* nodes [first, first + n) of one tree: states [n][3B], parents [n], controls [n][5]; any may be NULL */
+int mps_forest_read(mps_ctx* ctx, int32_t inst, int64_t first, int64_t n, float* states, int32_t* parents,
+                    float* controls);
+
 /* ---- packed winner record (multi-GPU gather) ---------------------------- */
 /* Layout: mps_extend_best | float best_states[L][3B] | float best_controls[L][5] | uint32 best_flags[L],
  * padded to 8 bytes.  mps_extend_record_to copies the record of the last launch device-to-device

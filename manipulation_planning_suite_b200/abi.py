@@ -135,6 +135,26 @@ class ExtendBest(C.Structure):
     ]
 
 
+class ForestExtendIn(C.Structure):
+    """struct mps_forest_extend_in"""
+
+    _fields_ = [
+        ("M", _i32), ("K", _i32), ("L", _i32),
+        ("inst_ids", C.POINTER(_i32)),
+        ("parents", C.POINTER(_i32)),
+        ("controls", C.POINTER(_f32)),
+        ("n_ctrl", C.POINTER(_i32)),
+        ("dests", C.POINTER(_f32)),
+        ("masks", C.POINTER(_u32)),
+        ("weights", C.POINTER(_f32)),
+        ("compare_f32", _i32),
+        ("n_goals", _i32),
+        ("goals", C.POINTER(Goal)),
+        ("append_to_tree", _i32),
+        ("_pad", _i32),
+    ]
+
+
 class ExtendOut(C.Structure):
     """struct mps_extend_out"""
 
@@ -197,6 +217,12 @@ SYMBOLS = {
     "mps_tree_fill_random": (C.c_int, [_ctx, C.c_int64, C.c_uint64, _i32]),
     "mps_tree_read_states": (C.c_int, [_ctx, C.c_int64, C.c_int64, _P(_f32)]),
     "mps_time_launches": (C.c_int, [_ctx, _i32, _i32, _P(_f32)]),
+    "mps_forest_reserve": (C.c_int, [_ctx, _i32, _i32]),
+    "mps_forest_reset": (C.c_int, [_ctx, _P(_f32)]),
+    "mps_forest_sizes": (C.c_int, [_ctx, _P(C.c_int64)]),
+    "mps_forest_nearest": (C.c_int, [_ctx, _i32, _P(_i32), _P(_f32), _P(_f32), _P(_u32), _P(C.c_int64), _P(C.c_double)]),
+    "mps_forest_extend": (C.c_int, [_ctx, _P(ForestExtendIn), _P(ExtendBest), _P(_f32), _P(_f32), _P(_u32)]),
+    "mps_forest_read": (C.c_int, [_ctx, _i32, C.c_int64, C.c_int64, _P(_f32), _P(_i32), _P(_f32)]),
     "mps_extend_record_size": (C.c_int, [_ctx, _P(C.c_int64)]),
     "mps_extend_record_to": (C.c_int, [_ctx, C.c_void_p]),
     "mps_ctx_set_kernel_timing": (C.c_int, [_ctx, _i32]),

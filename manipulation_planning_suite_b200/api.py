@@ -370,3 +370,90 @@ class NearestNeighbors:
         out = np.zeros((n, 3 * self.ctx.B), np.float32)
         self.ctx._check(self.lib.mps_tree_read_states(self.ctx.h, first, n, _fp(out)))
         return out
+
+
+class Forest:
+    """Many independent planner instances in one context (mps_forest_*): one tree per instance in a shared
+    dimension-major SoA, batches of M instances per launch (BASELINE config 5)."""
+
+    def __init__(self, ctx: Context, n_instances: int, cap_per_instance: int):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.n = int(n_instances)
+        ctx._check(self.lib.mps_forest_reserve(ctx.h, self.n, int(cap_per_instance)))
+
+    def reset(self, roots):
+        r = _f32(roots).reshape(self.n, 3 * self.ctx.B)
+        self.ctx._check(self.lib.mps_forest_reset(self.ctx.h, _fp(r)))
+
+    def sizes(self) -> np.ndarray:
+        out = np.zeros(self.n, np.int64)
+        self.ctx._check(self.lib.mps_forest_sizes(self.ctx.h, _fp(out, C.c_int64)))
+        return out
+
+    def nearest(self, inst_ids, queries, weights=None, masks=None):
+        B = self.ctx.B
+        ids = np.ascontiguousarray(inst_ids, np.int32)
+        M = len(ids)
+        qs = _f32(queries).reshape(M, 3 * B)
+        w = _f32(weights, (B,))
+        m = None if masks is None else np.ascontiguousarray(masks, np.uint32).reshape(M)
+        idx = np.zeros(M, np.int64)
+        d = np.zeros(M, np.float64)
+        self.ctx._check(self.lib.mps_forest_nearest(self.ctx.h, M, _fp(ids, C.c_int32), _fp(qs), _fp(w),
+                                                    _fp(m, C.c_uint32), _fp(idx, C.c_int64), _fp(d, C.c_double)))
+        return idx, d
+
+    def extend(self, inst_ids, parents, controls, n_ctrl=None, dests=None, masks=None, weights=None,
+               compare_f32=False, goals=None, append=True):
+        B = self.ctx.B
+        ids = np.ascontiguousarray(inst_ids, np.int32)
+        M = len(ids)
+        par = np.ascontiguousarray(parents, np.int32).reshape(M)
+        c = _f32(controls)
+        if c.ndim == 3:
+            c = c[:, :, None, :]
+        assert c.shape[0] == M and c.shape[3] == 5
+        K, L = c.shape[1], c.shape[2]
+        nc = None if n_ctrl is None else np.ascontiguousarray(n_ctrl, np.int32).reshape(M, K)
+        de = None if dests is None else _f32(dests).reshape(M, 3 * B)
+        ma = None if masks is None else np.ascontiguousarray(masks, np.uint32).reshape(M)
+        w = _f32(weights, (B,))
+        garr, ng = None, 0
+        if goals:
+            ng = len(goals)
+            garr = (abi.Goal * ng)()
+            for i, g in enumerate(goals):
+                garr[i].body, garr[i].x, garr[i].y, garr[i].tol = int(g[0]), float(g[1]), float(g[2]), float(g[3])
+        fin = abi.ForestExtendIn()
+        fin.M, fin.K, fin.L = M, K, L
+        fin.inst_ids = _fp(ids, C.c_int32)
+        fin.parents = _fp(par, C.c_int32)
+        fin.controls = _fp(c)
+        fin.n_ctrl = _fp(nc, C.c_int32)
+        fin.dests = _fp(de)
+        fin.masks = _fp(ma, C.c_uint32)
+        fin.weights = _fp(w)
+        fin.compare_f32 = 1 if compare_f32 else 0
+        fin.n_goals = ng
+        fin.goals = garr if garr is not None else None
+        fin.append_to_tree = 1 if append else 0
+        best = (abi.ExtendBest * M)()
+        bs = np.zeros((M, L, 3 * B), np.float32)
+        bc = np.zeros((M, L, 5), np.float32)
+        bf = np.zeros((M, L), np.uint32)
+        self.ctx._check(self.lib.mps_forest_extend(self.ctx.h, C.byref(fin), best, _fp(bs), _fp(bc), _fp(bf, C.c_uint32)))
+        return dict(
+            k=np.array([b.k for b in best], np.int32), n_ok=np.array([b.n_ok for b in best], np.int32),
+            goal_step=np.array([b.goal_step for b in best], np.int32),
+            tree_index=np.array([b.tree_index for b in best], np.int32),
+            distance=np.array([b.distance for b in best], np.float64), states=bs, controls=bc, flags=bf)
+
+    def read(self, inst: int, first: int, n: int):
+        B = self.ctx.B
+        st = np.zeros((n, 3 * B), np.float32)
+        pa = np.zeros(n, np.int32)
+        co = np.zeros((n, 5), np.float32)
+        self.ctx._check(self.lib.mps_forest_read(self.ctx.h, int(inst), int(first), int(n), _fp(st), _fp(pa, C.c_int32),
+                                                 _fp(co)))
+        return st, pa, co

@@ -66,6 +66,12 @@ struct mps_ctx {
     bool nn_ready = false;
     int nn_Q = 0;
 
+    // forest (multi-instance batches)
+    TreeView forest;
+    int f_ninst = 0;
+    size_t f_seg = 0;
+    DevBuf d_fsizes, d_finst, d_fparents, d_fmasks, d_fbest, d_fbest_states, d_fbest_controls, d_fbest_flags, d_froots;
+
     // validity
     DevBuf d_vstates, d_valid, d_vflags;
 
@@ -345,6 +351,8 @@ int mps_ctx_create_on_stream(const mps_scene* scene, int device, void* cuda_stre
         ctx->warp_bytes = mps_rollout_warp_bytes(ctx->hscene);
         memset(&ctx->tree, 0, sizeof(ctx->tree));
         ctx->tree.B = scene->n_bodies;
+        memset(&ctx->forest, 0, sizeof(ctx->forest));
+        ctx->forest.B = scene->n_bodies;
     } while (0);
     if (rc != MPS_OK) {
         delete ctx;
@@ -369,12 +377,18 @@ void mps_ctx_destroy(mps_ctx* ctx)
                       &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
                       &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_nn_out, &ctx->d_part_d,
-                      &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags};
+                      &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags, &ctx->d_fsizes,
+                      &ctx->d_finst, &ctx->d_fparents, &ctx->d_fmasks, &ctx->d_fbest, &ctx->d_fbest_states,
+                      &ctx->d_fbest_controls, &ctx->d_fbest_flags, &ctx->d_froots};
     for (DevBuf* b : bufs) free_buf(*b);
     if (ctx->tree.states) cudaFree(ctx->tree.states);
     if (ctx->tree.controls) cudaFree(ctx->tree.controls);
     if (ctx->tree.parent) cudaFree(ctx->tree.parent);
     if (ctx->tree.slice) cudaFree(ctx->tree.slice);
+    if (ctx->forest.states) cudaFree(ctx->forest.states);
+    if (ctx->forest.controls) cudaFree(ctx->forest.controls);
+    if (ctx->forest.parent) cudaFree(ctx->forest.parent);
+    if (ctx->forest.slice) cudaFree(ctx->forest.slice);
     if (ctx->d_scene) cudaFree(ctx->d_scene);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_nn_out) cudaFreeHost(ctx->h_nn_out);
@@ -872,6 +886,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     sp.K = K;
     sp.L = L;
     sp.B = B;
+    sp.M = 1;
     sp.has_dest = in->dest ? 1 : 0;
     sp.compare_f32 = in->compare_f32;
     sp.k_offset = in->k_offset;
@@ -908,6 +923,7 @@ int mps_extend_launch(mps_ctx* ctx)
         if (rc) return rc;
         sp.tree_size = (long long*)ctx->d_tree_size.p;
         sp.tree_cap = ctx->tree.cap;
+        sp.tree_seg = ctx->tree.cap;
         sp.tree_states = ctx->tree.states;
         sp.tree_controls = ctx->tree.controls;
         sp.tree_parent = ctx->tree.parent;
@@ -1029,6 +1045,246 @@ int mps_is_valid_batch(mps_ctx* ctx, const float* states, int32_t n, uint8_t* va
     if (valid) MPS_CUDA_CHECK(cudaMemcpyAsync(valid, ctx->d_valid.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), ctx);
     if (flags) MPS_CUDA_CHECK(cudaMemcpyAsync(flags, ctx->d_vflags.p, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), ctx);
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+
+// ---- forest: many independent planner instances batched per launch ----------------------------------
+
+int mps_forest_reserve(mps_ctx* ctx, int32_t n_instances, int32_t cap_per_instance)
+{
+    if (!ctx || n_instances < 1 || cap_per_instance < 1) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_forest_reserve");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    if (ctx->forest.states) {
+        cudaFree(ctx->forest.states);
+        cudaFree(ctx->forest.controls);
+        cudaFree(ctx->forest.parent);
+        cudaFree(ctx->forest.slice);
+        memset(&ctx->forest, 0, sizeof(ctx->forest));
+    }
+    const size_t seg = align_up((size_t)cap_per_instance, 32);
+    int rc = tree_alloc(ctx, ctx->forest, seg * (size_t)n_instances);
+    if (rc) return rc;
+    ctx->f_ninst = n_instances;
+    ctx->f_seg = seg;
+    if ((rc = ensure(ctx, ctx->d_fsizes, sizeof(long long) * (size_t)n_instances))) return rc;
+    MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_fsizes.p, 0, sizeof(long long) * (size_t)n_instances, ctx->stream), ctx);
+    return MPS_OK;
+}
+
+int mps_forest_reset(mps_ctx* ctx, const float* roots)
+{
+    if (!ctx || !roots) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_forest_reset");
+    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    const int B = ctx->scene.n_bodies, n = ctx->f_ninst;
+    const size_t sb = sizeof(float) * 3 * B * (size_t)n;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_froots, sb))) return rc;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_froots.p, roots, sb, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    MPS_CUDA_CHECK(mps_launch_forest_roots(ctx->forest, ctx->f_seg, n, (const float*)ctx->d_froots.p,
+                                           (long long*)ctx->d_fsizes.p, ctx->stream),
+                   ctx);
+    ctx->launches++;
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+int mps_forest_sizes(mps_ctx* ctx, int64_t* sizes)
+{
+    if (!ctx || !sizes) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    MPS_CUDA_CHECK(cudaMemcpyAsync(sizes, ctx->d_fsizes.p, sizeof(long long) * (size_t)ctx->f_ninst, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    return MPS_OK;
+}
+
+static int check_inst_ids(mps_ctx* ctx, const int32_t* ids, int M)
+{
+    for (int m = 0; m < M; ++m)
+        if (ids[m] < 0 || ids[m] >= ctx->f_ninst) return mps_fail(ctx, MPS_ERR_ARG, "instance id out of range");
+    return MPS_OK;
+}
+
+int mps_forest_nearest(mps_ctx* ctx, int32_t M, const int32_t* inst_ids, const float* queries, const float* weights,
+                       const uint32_t* masks, int64_t* indices, double* distances)
+{
+    if (!ctx || M < 1 || M > 65535 || !inst_ids || !queries) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_forest_nearest");
+    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    int rc = check_inst_ids(ctx, inst_ids, M);
+    if (rc) return rc;
+    // queries / masks / weights go through the plain query path's buffers
+    if ((rc = mps_tree_nearest_upload(ctx, queries, M, weights, masks, nullptr))) return rc;
+    if ((rc = ensure(ctx, ctx->d_finst, sizeof(int32_t) * (size_t)M))) return rc;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_finst.p, inst_ids, sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, ctx->stream), ctx);
+    NNParams np = ctx->np;
+    np.tree = ctx->forest;
+    np.n = (long long)ctx->f_seg;  // grid sizing only; the kernel reads the real size of each segment
+    np.inst_ids = (const int32_t*)ctx->d_finst.p;
+    np.seg_sizes = (const long long*)ctx->d_fsizes.p;
+    np.seg = ctx->f_seg;
+    np.grid_x = mps_nn_grid_x((long long)ctx->f_seg, ctx->num_sms);
+    int cap_grid = ctx->num_sms * 16 / (M < 1 ? 1 : M);
+    if (cap_grid < 1) cap_grid = 1;
+    if (np.grid_x > cap_grid) np.grid_x = cap_grid;  // many small trees: a few CTAs each
+    MPS_CUDA_CHECK(mps_launch_nn_scan(np, ctx->stream), ctx);
+    ctx->launches++;
+    return mps_tree_nearest_fetch(ctx, indices, distances);
+}
+
+int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_best* best, float* best_states,
+                      float* best_controls, uint32_t* best_flags)
+{
+    if (!ctx || !in || !in->inst_ids || !in->parents || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_forest_extend");
+    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    const int B = ctx->scene.n_bodies, M = in->M, K = in->K, L = in->L;
+    if (M < 1 || K < 1 || L < 1 || L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "M, K >= 1 and L in [1, 16]");
+    if ((long long)M * K > (1ll << 24)) return mps_fail(ctx, MPS_ERR_ARG, "M * K too large");
+    if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS || (in->n_goals > 0 && !in->goals)) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
+    int rc = check_inst_ids(ctx, in->inst_ids, M);
+    if (rc) return rc;
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    const size_t KT = (size_t)M * K, KL = KT * L;
+    const size_t cb = sizeof(float) * MPS_CONTROL_DIM * KL, nb = sizeof(int32_t) * KT, db = sizeof(float) * 3 * B * (size_t)M,
+                 mb = sizeof(int32_t) * (size_t)M, wb = sizeof(float) * B;
+    if ((rc = ensure(ctx, ctx->d_controls, cb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_nctrl, nb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_dest, db))) return rc;
+    if ((rc = ensure(ctx, ctx->d_weights, wb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_goals, sizeof(mps_goal) * MPS_MAX_GOALS))) return rc;
+    if ((rc = ensure(ctx, ctx->d_finst, mb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_fparents, mb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_fmasks, mb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_states, sizeof(float) * 3 * B * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rest, sizeof(float) * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_flags, sizeof(uint32_t) * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_steps, sizeof(int32_t) * KL))) return rc;
+    if ((rc = ensure(ctx, ctx->d_dist, sizeof(double) * KT))) return rc;
+    if ((rc = ensure(ctx, ctx->d_nok, sizeof(int32_t) * KT))) return rc;
+    if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * KT))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * KT))) return rc;
+    if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
+    if (!ctx->d_counters.p) {
+        if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
+        MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
+    }
+    if ((rc = ensure(ctx, ctx->d_fbest, sizeof(mps_extend_best) * (size_t)M))) return rc;
+    if ((rc = ensure(ctx, ctx->d_fbest_states, sizeof(float) * 3 * B * L * (size_t)M))) return rc;
+    if ((rc = ensure(ctx, ctx->d_fbest_controls, sizeof(float) * MPS_CONTROL_DIM * L * (size_t)M))) return rc;
+    if ((rc = ensure(ctx, ctx->d_fbest_flags, sizeof(uint32_t) * L * (size_t)M))) return rc;
+    cudaStream_t st = ctx->stream;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_controls.p, in->controls, cb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->n_ctrl) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nctrl.p, in->n_ctrl, nb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->dests) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_dest.p, in->dests, db, cudaMemcpyHostToDevice, st), ctx);
+    if (in->weights) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_weights.p, in->weights, wb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->n_goals > 0) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_goals.p, in->goals, sizeof(mps_goal) * in->n_goals, cudaMemcpyHostToDevice, st), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_finst.p, in->inst_ids, mb, cudaMemcpyHostToDevice, st), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_fparents.p, in->parents, mb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->masks) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_fmasks.p, in->masks, mb, cudaMemcpyHostToDevice, st), ctx);
+
+    RolloutParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.scene = ctx->d_scene;
+    rp.scene_bytes = ctx->scene_bytes;
+    rp.warp_bytes = ctx->warp_bytes;
+    rp.controls = (const float*)ctx->d_controls.p;
+    rp.n_ctrl = in->n_ctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
+    rp.K = (int)KT;
+    rp.L = L;
+    rp.dest = in->dests ? (const float*)ctx->d_dest.p : nullptr;
+    rp.weights = in->weights ? (const float*)ctx->d_weights.p : nullptr;
+    rp.mask = B < 32 ? (1u << B) - 1u : 0xffffffffu;
+    rp.goals = (const mps_goal*)ctx->d_goals.p;
+    rp.n_goals = in->n_goals;
+    rp.out_states = (float*)ctx->d_states.p;
+    rp.out_rest = (float*)ctx->d_rest.p;
+    rp.out_flags = (uint32_t*)ctx->d_flags.p;
+    rp.out_steps = (int32_t*)ctx->d_steps.p;
+    rp.out_dist = (double*)ctx->d_dist.p;
+    rp.out_nok = (int32_t*)ctx->d_nok.p;
+    rp.out_goal_step = (int32_t*)ctx->d_goal_step.p;
+    rp.work_counter = (unsigned*)ctx->d_work.p;
+    rp.counters = (unsigned long long*)ctx->d_counters.p;
+    rp.out_cycles = (long long*)ctx->d_cycles.p;
+    rp.K_per = K;
+    rp.inst_ids = (const int32_t*)ctx->d_finst.p;
+    rp.parents = (const int32_t*)ctx->d_fparents.p;
+    rp.f_states = ctx->forest.states;
+    rp.f_cols = ctx->forest.cap;
+    rp.f_seg = ctx->f_seg;
+    rp.masks = in->masks ? (const uint32_t*)ctx->d_fmasks.p : nullptr;
+
+    SelectParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.K = K;
+    sp.L = L;
+    sp.B = B;
+    sp.M = M;
+    sp.has_dest = in->dests ? 1 : 0;
+    sp.compare_f32 = in->compare_f32;
+    sp.dist = rp.out_dist;
+    sp.nok = rp.out_nok;
+    sp.goal_step = rp.out_goal_step;
+    sp.states = rp.out_states;
+    sp.rest = rp.out_rest;
+    sp.flags = rp.out_flags;
+    sp.controls = rp.controls;
+    sp.best = (mps_extend_best*)ctx->d_fbest.p;
+    sp.best_states = (float*)ctx->d_fbest_states.p;
+    sp.best_controls = (float*)ctx->d_fbest_controls.p;
+    sp.best_flags = (uint32_t*)ctx->d_fbest_flags.p;
+    sp.append = in->append_to_tree;
+    sp.tree_size = (long long*)ctx->d_fsizes.p;
+    sp.tree_cap = ctx->forest.cap;
+    sp.tree_seg = ctx->f_seg;
+    sp.tree_states = ctx->forest.states;
+    sp.tree_controls = ctx->forest.controls;
+    sp.tree_parent = ctx->forest.parent;
+    sp.tree_slice = ctx->forest.slice;
+    sp.inst_ids = rp.inst_ids;
+    sp.parents = rp.parents;
+    MPS_CUDA_CHECK(mps_launch_rollout(rp, ctx->num_sms, st), ctx);
+    MPS_CUDA_CHECK(mps_launch_select(sp, st), ctx);
+    ctx->launches += 2;
+    ctx->extend_ready = false;  // the plain extend's cached parameters no longer describe the buffers
+    if (best) MPS_CUDA_CHECK(cudaMemcpyAsync(best, sp.best, sizeof(mps_extend_best) * (size_t)M, cudaMemcpyDeviceToHost, st), ctx);
+    if (best_states) MPS_CUDA_CHECK(cudaMemcpyAsync(best_states, sp.best_states, sizeof(float) * 3 * B * L * (size_t)M, cudaMemcpyDeviceToHost, st), ctx);
+    if (best_controls) MPS_CUDA_CHECK(cudaMemcpyAsync(best_controls, sp.best_controls, sizeof(float) * MPS_CONTROL_DIM * L * (size_t)M, cudaMemcpyDeviceToHost, st), ctx);
+    if (best_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(best_flags, sp.best_flags, sizeof(uint32_t) * L * (size_t)M, cudaMemcpyDeviceToHost, st), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(st), ctx);
+    return MPS_OK;
+}
+
+int mps_forest_read(mps_ctx* ctx, int32_t inst, int64_t first, int64_t n, float* states, int32_t* parents,
+                    float* controls)
+{
+    if (!ctx || inst < 0 || first < 0 || n < 0) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_forest_read");
+    if (!ctx->forest.states || inst >= ctx->f_ninst) return mps_fail(ctx, MPS_ERR_ARG, "no such instance");
+    if ((size_t)(first + n) > ctx->f_seg) return mps_fail(ctx, MPS_ERR_ARG, "range beyond the tree capacity");
+    if (n == 0) return MPS_OK;
+    const TreeView& t = ctx->forest;
+    const size_t col = (size_t)inst * ctx->f_seg + (size_t)first;
+    // dimension-major rows -> node-major host arrays: one strided 2-D copy per array
+    if (states) {
+        std::vector<float> tmp((size_t)n * 3 * t.B);
+        MPS_CUDA_CHECK(cudaMemcpy2DAsync(tmp.data(), (size_t)n * sizeof(float), t.states + col, t.cap * sizeof(float),
+                                         (size_t)n * sizeof(float), 3 * t.B, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        for (int64_t i = 0; i < n; ++i)
+            for (int r = 0; r < 3 * t.B; ++r) states[(size_t)i * 3 * t.B + r] = tmp[(size_t)r * n + i];
+    }
+    if (controls) {
+        std::vector<float> tmp((size_t)n * MPS_CONTROL_DIM);
+        MPS_CUDA_CHECK(cudaMemcpy2DAsync(tmp.data(), (size_t)n * sizeof(float), t.controls + col, t.cap * sizeof(float),
+                                         (size_t)n * sizeof(float), MPS_CONTROL_DIM, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        for (int64_t i = 0; i < n; ++i)
+            for (int c = 0; c < MPS_CONTROL_DIM; ++c) controls[(size_t)i * MPS_CONTROL_DIM + c] = tmp[(size_t)c * n + i];
+    }
+    if (parents) {
+        MPS_CUDA_CHECK(cudaMemcpyAsync(parents, t.parent + col, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    }
     return MPS_OK;
 }
 

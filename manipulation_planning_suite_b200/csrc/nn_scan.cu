@@ -145,7 +145,13 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
     const int nact = s_nact;
     const float pwf = (float)p.pw, owf = (float)p.ow;
     const size_t cap = p.tree.cap;
-    const long long N = p.n;
+    long long N = p.n;
+    size_t col0 = 0;  // first column of the scanned segment
+    if (p.inst_ids) {
+        const int inst = p.inst_ids[q];
+        col0 = (size_t)inst * p.seg;
+        N = p.seg_sizes[inst];
+    }
     const long long groups = (N + 3) >> 2;
     const float inf = __uint_as_float(0x7f800000u);
 
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
 #pragma unroll
             for (int u = 0; u < NN_BODY_BATCH; ++u) {  // all loads of the batch first: 3 * NN_BODY_BATCH LDG.128 in flight
                 const int a = a0 + u < nact ? a0 + u : nact - 1;
-                const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + n0;
+                const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + col0 + n0;
                 X[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row)) : __ldg(reinterpret_cast<const float4*>(row));
                 Y[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + cap))
                               : __ldg(reinterpret_cast<const float4*>(row + cap));
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
             }
         }
         if (filter >= 0) {
-            const int4 sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + n0));
+            const int4 sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + col0 + n0));
             if (sl.x != filter) d0 = inf;
             if (sl.y != filter) d1 = inf;
             if (sl.z != filter) d2 = inf;
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
                         s_cand_i[slot] = n0 + j;
                     } else {
                         // list full (adversarial orderings): evaluate on the spot
-                        const double e = exact_distance(p.tree, n0 + j, s_q, p.weights, mask, p.pw, p.ow);
+                        const double e = exact_distance(p.tree, (long long)col0 + n0 + j, s_q, p.weights, mask, p.pw, p.ow);
                         take_min(best_d, best_i, e, n0 + j);
                     }
                 }
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
         for (int c = warp; c < ncand; c += NN_THREADS / 32) {
             if (__uint_as_float(s_cand_d[c]) <= thr) {
                 const long long n = s_cand_i[c];
-                const double e = warp_exact_distance(p.tree, n, s_q, p.weights, mask, p.pw, p.ow, lane);
+                const double e = warp_exact_distance(p.tree, (long long)col0 + n, s_q, p.weights, mask, p.pw, p.ow, lane);
                 if (lane == 0) take_min(best_d, best_i, e, n);
             }
         }
@@ -392,6 +398,24 @@ __global__ void tree_copy_kernel(TreeView src, TreeView dst, long long n)
     }
 }
 
+// every tree of the forest := { root }
+__global__ void forest_roots_kernel(TreeView t, size_t seg, int n_inst, const float* __restrict__ roots, long long* sizes)
+{
+    const int dims = 3 * t.B;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)n_inst * dims;
+         e += (long long)gridDim.x * blockDim.x) {
+        int inst = (int)(e / dims), r = (int)(e % dims);
+        t.states[(size_t)r * t.cap + (size_t)inst * seg] = roots[e];
+    }
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_inst; e += (long long)gridDim.x * blockDim.x) {
+        const size_t col = (size_t)e * seg;
+        for (int c = 0; c < MPS_CONTROL_DIM; ++c) t.controls[(size_t)c * t.cap + col] = 0.0f;
+        t.parent[col] = -1;
+        t.slice[col] = -1;
+        sizes[e] = 1;
+    }
+}
+
 int grid_for(long long work, int threads, int max_blocks)
 {
     long long b = (work + threads - 1) / threads;
@@ -457,5 +481,13 @@ cudaError_t mps_launch_tree_copy(const TreeView& src, const TreeView& dst, long 
     if (n <= 0) return cudaSuccess;
     int blocks = grid_for(n * 3 * src.B, 256, 1184);
     tree_copy_kernel<<<blocks, 256, 0, stream>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_forest_roots(const TreeView& forest, size_t seg, int n_inst, const float* roots, long long* sizes,
+                                    cudaStream_t stream)
+{
+    int blocks = grid_for((long long)n_inst * 3 * forest.B, 256, 1184);
+    forest_roots_kernel<<<blocks, 256, 0, stream>>>(forest, seg, n_inst, roots, sizes);
     return cudaGetLastError();
 }

@@ -30,6 +30,10 @@ struct NNParams {
     double* part_d;      // [Q][grid_x]
     long long* part_i;   // [Q][grid_x]
     unsigned int* tickets;  // [Q], zero on entry, zero on exit
+    // forest queries (multi-instance): query q scans segment inst_ids[q] = columns [inst * seg, inst * seg + seg_sizes[inst])
+    const int32_t* inst_ids;      // [Q] or nullptr (plain tree: columns [0, n))
+    const long long* seg_sizes;   // [segments]
+    size_t seg;
     int grid_x;
 };
 
@@ -43,3 +47,5 @@ cudaError_t mps_launch_tree_fill(const TreeView& t, long long n, unsigned long l
 cudaError_t mps_launch_tree_gather(const TreeView& t, long long first, long long n, float* out_states,
                                    cudaStream_t stream);
 cudaError_t mps_launch_tree_copy(const TreeView& src, const TreeView& dst, long long n, cudaStream_t stream);
+cudaError_t mps_launch_forest_roots(const TreeView& forest, size_t seg, int n_inst, const float* roots, long long* sizes,
+                                    cudaStream_t stream);

@@ -873,7 +873,20 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
         const long long t_begin = clock64();
         // start state of the chain
         float sx = 0.0f, sy = 0.0f, sth = 0.0f;
-        if (bd.live) {
+        const float* dest = p.dest;
+        uint32_t dmask = p.mask;
+        if (p.K_per > 0) {
+            // multi-instance batch: start = a node of this instance's forest segment
+            const int m = k / p.K_per;
+            const size_t col = (size_t)p.inst_ids[m] * p.f_seg + (size_t)p.parents[m];
+            if (bd.live) {
+                sx = p.f_states[(size_t)(3 * lane) * p.f_cols + col];
+                sy = p.f_states[(size_t)(3 * lane + 1) * p.f_cols + col];
+                sth = p.f_states[(size_t)(3 * lane + 2) * p.f_cols + col];
+            }
+            if (dest) dest += (size_t)m * 3 * B;
+            if (p.masks) dmask = p.masks[m];
+        } else if (bd.live) {
             sx = p.start[3 * lane];
             sy = p.start[3 * lane + 1];
             sth = p.start[3 * lane + 2];
@@ -1039,7 +1052,7 @@ __global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
             }
         }
         double dist = __longlong_as_double(0x7ff0000000000000ll);  // +inf
-        if (n_ok > 0 && p.dest) dist = warp_distance(sc, bd, lane, sx, sy, sth, p.dest, p.weights, p.mask);
+        if (n_ok > 0 && dest) dist = warp_distance(sc, bd, lane, sx, sy, sth, dest, p.weights, dmask);
         if (lane == 0) {
             p.out_dist[k] = dist;
             p.out_nok[k] = n_ok;
@@ -1063,10 +1076,12 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
     __shared__ double s_key[32];
     __shared__ int s_idx[32];
     const int tid = threadIdx.x;
+    const int m = blockIdx.x;  // instance
+    const int k_base = m * p.K;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     double best = inf;
     int best_k = -1;
-    for (int k = tid; k < p.K; k += blockDim.x) {
+    for (int k = k_base + tid; k < k_base + p.K; k += blockDim.x) {
         if (p.nok[k] <= 0) continue;
         double d = p.dist[k];
         double key = !p.has_dest ? 0.0 : (p.compare_f32 ? (double)(float)d : d);
@@ -1116,49 +1131,60 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
     // adding there, RRT.cpp:479-488), else the whole successful prefix
     int n_app = n_ok;
     if (best_k >= 0 && p.goal_step[best_k] >= 0) n_app = p.goal_step[best_k] + 1;
+    const int seg_id = p.inst_ids ? p.inst_ids[m] : 0;
     int first = -1;
     if (best_k >= 0 && p.append && tid == 0) {
         // tree append of the winner chain (RearrangementRRT::addToTree, RRT.cpp:234-244)
-        long long n0 = *p.tree_size;
-        first = (int)n0;
-        *p.tree_size = n0 + n_app;
+        long long n0 = p.tree_size[seg_id];
+        if ((size_t)(n0 + n_app) <= p.tree_seg) {
+            first = (int)n0;
+            p.tree_size[seg_id] = n0 + n_app;
+        } else {
+            first = -2;  // segment full: nothing appended
+        }
     }
+    mps_extend_best* rec = p.best + m;
     if (tid == 0) {
-        p.best->k = best_k < 0 ? -1 : best_k + p.k_offset;
-        p.best->n_ok = n_ok;
-        p.best->goal_step = best_k < 0 ? -1 : p.goal_step[best_k];
-        p.best->distance = best_k < 0 ? inf : p.dist[best_k];
-        p.best->tree_index = (best_k >= 0 && p.append) ? first : -1;
+        rec->k = best_k < 0 ? -1 : best_k - k_base + p.k_offset;
+        rec->n_ok = n_ok;
+        rec->goal_step = best_k < 0 ? -1 : p.goal_step[best_k];
+        rec->distance = best_k < 0 ? inf : p.dist[best_k];
+        rec->tree_index = (best_k >= 0 && p.append) ? first : -1;
         s_idx[1] = first;
     }
     __syncthreads();
     first = s_idx[1];
+    float* bs = p.best_states + (size_t)m * L * 3 * B;
+    float* bc = p.best_controls + (size_t)m * L * MPS_CONTROL_DIM;
+    uint32_t* bf = p.best_flags + (size_t)m * L;
     for (int i = tid; i < L * 3 * B; i += blockDim.x)
-        p.best_states[i] = best_k < 0 ? 0.0f : p.states[(size_t)best_k * L * 3 * B + i];
+        bs[i] = best_k < 0 ? 0.0f : p.states[(size_t)best_k * L * 3 * B + i];
     for (int i = tid; i < L * MPS_CONTROL_DIM; i += blockDim.x) {
         float v = 0.0f;
         if (best_k >= 0) {
             int l = i / MPS_CONTROL_DIM, c = i % MPS_CONTROL_DIM;
             v = c == 4 ? p.rest[(size_t)best_k * L + l] : p.controls[((size_t)best_k * L + l) * MPS_CONTROL_DIM + c];
         }
-        p.best_controls[i] = v;
+        bc[i] = v;
     }
-    for (int i = tid; i < L; i += blockDim.x) p.best_flags[i] = best_k < 0 ? 0u : p.flags[(size_t)best_k * L + i];
+    for (int i = tid; i < L; i += blockDim.x) bf[i] = best_k < 0 ? 0u : p.flags[(size_t)best_k * L + i];
     if (best_k >= 0 && p.append && first >= 0) {
         const size_t cap = p.tree_cap;
+        const size_t col0 = (size_t)seg_id * p.tree_seg + (size_t)first;
+        const int parent = p.parents ? p.parents[m] : p.parent;
         for (int i = tid; i < n_app * 3 * B; i += blockDim.x) {
             int l = i / (3 * B), r = i % (3 * B);
-            p.tree_states[(size_t)r * cap + first + l] = p.states[((size_t)best_k * L + l) * 3 * B + r];
+            p.tree_states[(size_t)r * cap + col0 + l] = p.states[((size_t)best_k * L + l) * 3 * B + r];
         }
         for (int i = tid; i < n_app * MPS_CONTROL_DIM; i += blockDim.x) {
             int l = i / MPS_CONTROL_DIM, c = i % MPS_CONTROL_DIM;
             float v = c == 4 ? p.rest[(size_t)best_k * L + l]
                              : p.controls[((size_t)best_k * L + l) * MPS_CONTROL_DIM + c];
-            p.tree_controls[(size_t)c * cap + first + l] = v;
+            p.tree_controls[(size_t)c * cap + col0 + l] = v;
         }
         for (int i = tid; i < n_app; i += blockDim.x) {
-            p.tree_parent[first + i] = i == 0 ? p.parent : first + i - 1;
-            p.tree_slice[first + i] = -1;
+            p.tree_parent[col0 + i] = i == 0 ? parent : first + i - 1;
+            p.tree_slice[col0 + i] = -1;
         }
     }
 }
@@ -1253,7 +1279,7 @@ cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
 {
     int threads = p.K >= 1024 ? 1024 : ((p.K + 31) / 32) * 32;
     if (threads < 32) threads = 32;
-    select_kernel<<<1, threads, 0, stream>>>(p);
+    select_kernel<<<p.M, threads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -33,10 +33,19 @@ struct RolloutParams {
     unsigned int* work_counter;
     unsigned long long* counters;  // [4] or nullptr
     long long* out_cycles;         // [K] SM clock cycles spent on each chain (profiling aid) or nullptr
+    // multi-instance batches (BASELINE cfg 5): K = M * K_per chains, instance m = k / K_per starts from node
+    // parents[m] of forest segment inst_ids[m] and measures its distance to dest + m * 3B under masks[m]
+    int K_per;                // 0 = single instance
+    const int32_t* inst_ids;  // [M]
+    const int32_t* parents;   // [M]
+    const float* f_states;    // forest states, dimension-major
+    size_t f_cols, f_seg;     // row stride of the forest / columns per segment
+    const uint32_t* masks;    // [M] or nullptr (= mask)
 };
 
 struct SelectParams {
-    int K, L, B;
+    int K, L, B;   // K chains per instance; the grid has one CTA per instance
+    int M;         // instances (1 for the plain extend)
     int has_dest, compare_f32, k_offset;
     const double* dist;
     const int32_t* nok;
@@ -51,8 +60,11 @@ struct SelectParams {
     uint32_t* best_flags;
     // optional fused tree append
     int append, parent;
-    long long* tree_size;
-    size_t tree_cap;
+    long long* tree_size;      // [segments]
+    size_t tree_cap;           // row stride (total columns)
+    size_t tree_seg;           // columns per segment (= tree_cap for the plain tree)
+    const int32_t* inst_ids;   // [M] segment of instance m, or nullptr (segment 0)
+    const int32_t* parents;    // [M] parent node (local index) of instance m, or nullptr (= parent)
     float* tree_states;
     float* tree_controls;
     int32_t* tree_parent;

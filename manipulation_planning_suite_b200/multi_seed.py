@@ -1,0 +1,122 @@
+"""Multi-seed sweep: many independent NaiveRRT instances advanced in lockstep on one device
+(BASELINE config 5: "4096 independent NaiveRRT instances ... time-to-solution").
+
+Each instance is the reference's RearrangementRRT::plan loop with NaiveRearrangementRRT::extend
+(pushing/algorithm/RRT.cpp:79-143, 171-204, 246-257, 358-390): sample (goal-biased or uniform valid
+state) -> nearest tree node under the full metric -> K random controls propagated, best by the active
+object's distance -> append.  All instances still running share one validity launch, one nearest-
+neighbour launch and one extend launch per iteration (api.Forest); host code only draws random numbers
+and keeps the bookkeeping.  Instances never interact: results depend on the seed, not on which other
+instances are batched with them or on how many GPUs the sweep is split over.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi, api, scenes
+
+
+@dataclass
+class SweepResult:
+    solved_iteration: np.ndarray          # [n] iteration at which the instance reached the goal, -1 if not
+    solved_time: np.ndarray               # [n] wall seconds at that moment, nan if not
+    tree_sizes: np.ndarray                # [n]
+    iterations: int
+    rollouts: int                         # propagated controls over the whole sweep
+    wall_s: float
+    goal_nodes: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # [n] node index of the goal state
+
+
+def _rng_for(seed: int, instance_ids: np.ndarray, iteration: int) -> np.random.RandomState:
+    # one stream per (seed, iteration); instance-specific draws are taken from fixed positions of it,
+    # so an instance's randomness does not depend on which other instances are still active
+    return np.random.RandomState((seed * 1000003 + iteration) % (2**31 - 1))
+
+
+def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int, num_control_samples: int = 10,
+                    max_iterations: int = 500, seed: int = 1, goal_bias: float = 0.2, target_bias: float = 0.25,
+                    robot_bias: float = 0.0, wall_timeout: float = 1e9, instance_offset: int = 0,
+                    candidates_per_sample: int = 8) -> SweepResult:
+    sc = ctx.scene
+    B = sc.n_bodies
+    K = int(num_control_samples)
+    forest = api.Forest(ctx, n_instances, max_iterations + 2)
+    forest.reset(np.tile(np.asarray(start, np.float32), (n_instances, 1)))
+    targets = [int(g[0]) for g in goals]
+    solved_it = np.full(n_instances, -1, np.int64)
+    solved_t = np.full(n_instances, np.nan)
+    goal_nodes = np.full(n_instances, -1, np.int64)
+    active = np.arange(n_instances, dtype=np.int32)
+    rollouts = 0
+    t0 = time.perf_counter()
+    it = 0
+    C = candidates_per_sample
+    for it in range(max_iterations):
+        if len(active) == 0 or time.perf_counter() - t0 > wall_timeout:
+            break
+        rng = _rng_for(seed, active, it)
+        # per-instance draws are indexed by the GLOBAL instance id so that sharding does not change them
+        gid = active.astype(np.int64) + instance_offset
+        n_glob = int(gid.max()) + 1
+        u_goal = rng.rand(n_glob)[gid]
+        u_obj = rng.rand(n_glob)[gid]
+        obj_uniform = rng.randint(0, B, size=n_glob)[gid]
+        tgt_pick = np.minimum(rng.randint(0, len(targets) + 1, size=n_glob), len(targets) - 1)[gid]  # :133-136 quirk
+        M = len(active)
+        # ---- sample(): goal-biased or uniform VALID state; C candidates each, one validity launch ----
+        cand = np.zeros((n_glob, C, 3 * B), np.float32)
+        cand[:, :, 0::3] = rng.uniform(sc.x_min, sc.x_max, size=(n_glob, C, B))
+        cand[:, :, 1::3] = rng.uniform(sc.y_min, sc.y_max, size=(n_glob, C, B))
+        cand[:, :, 2::3] = rng.uniform(-np.pi, np.pi, size=(n_glob, C, B))
+        ball = rng.normal(size=(n_glob, C, len(targets), 2))
+        ball /= np.maximum(np.linalg.norm(ball, axis=-1, keepdims=True), 1e-12)
+        ball *= np.sqrt(rng.uniform(size=(n_glob, C, len(targets), 1)))
+        cand = cand[gid]
+        ball = ball[gid]
+        is_goal = u_goal < goal_bias
+        for gi, g in enumerate(goals):  # ObjectsRelocationGoal::sampleGoal: targets inside their goal discs
+            b = int(g[0])
+            cand[is_goal, :, 3 * b] = g[1] + g[3] * ball[is_goal, :, gi, 0]
+            cand[is_goal, :, 3 * b + 1] = g[2] + g[3] * ball[is_goal, :, gi, 1]
+        valid, _ = ctx.is_valid(cand.reshape(M * C, 3 * B))
+        valid = valid.reshape(M, C)
+        first = np.where(valid.any(axis=1), valid.argmax(axis=1), C - 1)
+        samples = cand[np.arange(M), first]
+        # active object: target of the goal, else sampleActiveObject (RRT.cpp:246-257)
+        obj = np.where(u_obj < target_bias, np.asarray(targets)[tgt_pick],
+                       np.where(u_obj < target_bias + robot_bias, sc.robot_id, obj_uniform))
+        obj = np.where(is_goal, np.asarray(targets)[tgt_pick], obj).astype(np.int64)
+        # ---- selectTreeNode(): nearest node under the full metric (RRT.cpp:192-204) ----
+        near, _ = forest.nearest(active, samples)
+        # ---- extend(): K random controls, best by the active object's distance, appended (:358-390) ----
+        controls = scenes.sample_controls(rng, n_glob * K, 1).reshape(n_glob, K, 1, 5)[gid]
+        res = forest.extend(active, near, controls, dests=samples, masks=(1 << obj).astype(np.uint32), goals=goals,
+                            append=True)
+        rollouts += M * K
+        reached = (res["flags"][:, 0] & abi.MPS_F_GOAL) != 0
+        reached &= res["k"] >= 0
+        if reached.any():
+            now = time.perf_counter() - t0
+            ids = active[reached]
+            solved_it[ids] = it
+            solved_t[ids] = now
+            goal_nodes[ids] = res["tree_index"][reached]
+            active = active[~reached]
+    wall = time.perf_counter() - t0
+    return SweepResult(solved_it, solved_t, forest.sizes(), it + 1, rollouts, wall, goal_nodes), forest
+
+
+def extract_path(forest: api.Forest, inst: int, goal_node: int):
+    """root .. goal_node of one instance: (states [n][3B], controls [n][5])"""
+    n = goal_node + 1
+    st, pa, co = forest.read(inst, 0, n)
+    idx = []
+    cur = goal_node
+    while cur >= 0:
+        idx.append(cur)
+        cur = int(pa[cur])
+    idx = idx[::-1]
+    return st[idx], co[idx]
