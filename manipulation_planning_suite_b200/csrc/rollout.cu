@@ -818,8 +818,12 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
     return dist;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) rollout_kernel(RolloutParams p)
+// MINB = CTAs per SM the register allocation is held to.  Two instantiations are built: MINB = 3 (up to 168
+// registers, no spills) for launches with few chains, where one warp per scheduler runs alone and only its
+// own dependent-instruction latency matters, and MINB = 4 (128 registers) for launches that fill the machine,
+// where resident warps per SM decide the throughput.
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevScene& sc = *reinterpret_cast<DevScene*>(smem_raw);
@@ -1249,19 +1253,19 @@ size_t mps_rollout_scene_bytes() { return (sizeof(DevScene) + 15) & ~(size_t)15;
 
 #define ROLLOUT_WARPS 4
 
-cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, cudaStream_t stream)
+template <int MINB>
+static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
 {
-    RolloutParams p = p_in;
     size_t smem = p.scene_bytes + (size_t)ROLLOUT_WARPS * p.warp_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ROLLOUT_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ROLLOUT_WARPS, MINB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     int blocks_per_sm = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<ROLLOUT_WARPS>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<ROLLOUT_WARPS, MINB>,
                                                                   ROLLOUT_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -1271,8 +1275,16 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, cudaStrea
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    rollout_kernel<ROLLOUT_WARPS><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
+    rollout_kernel<ROLLOUT_WARPS, MINB><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, cudaStream_t stream)
+{
+    RolloutParams p = p_in;
+    // few chains (at most ~3 CTAs of 4 warps per SM): latency build; otherwise the occupancy build
+    if ((long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3) return launch_rollout_t<3>(p, num_sms, stream);
+    return launch_rollout_t<4>(p, num_sms, stream);
 }
 
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
