@@ -115,6 +115,16 @@ def flop_model(B: int, S: int, vel_iters: int, counters: dict) -> float:
             + 2.0 * 55.0 * vel_iters * counters["touching"])
 
 
+def ncu_traffic(kernel: str):
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or None"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -212,7 +222,7 @@ def run_ours(args):
         achieved_tf = flops_per_launch / (k_ms * 1e-3) / 1e12
         roofline = {"kernel": "rollout_kernel", "bound": "fp32", "achieved": round(achieved_tf, 4),
                     "peak": round(fp32_peak, 2), "unit": "TFLOP/s", "frac": round(achieved_tf / fp32_peak, 5),
-                    "traffic": None, "kernel_ms": round(k_ms, 4), "share_of_step": round(k_ms * steps / step_ms.sum(), 4),
+                    "traffic": ncu_traffic("rollout_kernel"), "kernel_ms": round(k_ms, 4), "share_of_step": round(k_ms * steps / step_ms.sum(), 4),
                     "peak_source": "measured in-run (FMA microbenchmark, csrc/peak.cu)",
                     "physics_steps_per_launch": cnt["steps"] / max(steps, 1),
                     "candidate_pairs_per_step": round(cnt["candidates"] / max(cnt["steps"], 1), 3),
@@ -336,7 +346,7 @@ def bench_nn(api, scenes, device):
             "queries_per_s": round(1e3 / ms, 1), "us_per_query": round(ms * 1e3, 2),
             "e2e_queries_per_s": round(1e3 / e2e_ms, 1),
             "roofline": {"kernel": "nn_scan_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm,
-                         "unit": "GB/s", "frac": round(gbs / hbm, 4), "traffic": None, "peak_source": src,
+                         "unit": "GB/s", "frac": round(gbs / hbm, 4), "traffic": ncu_traffic("nn_scan_kernel"), "peak_source": src,
                          "algorithmic_bytes_per_launch": bytes_alg}}
 
 
