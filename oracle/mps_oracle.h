@@ -77,6 +77,16 @@ int orc_step_once(const mps_scene* sc, float* pose /*[3B]*/, float* vel /*[3B]*/
 /* contact query at a state: writes up to max_m manifolds (a, b, count, nx, ny, sep0, sep1) */
 int orc_contacts(const mps_scene* sc, const float* state, int32_t* ab, float* data, int32_t max_m);
 
+/* mps_gnat.c: restatement of ompl::NearestNeighborsGNAT, the structure behind the reference's _tree
+ * (pushing/algorithm/RRT.cpp:46-51,202): the CPU baseline of the nearest-neighbour queries */
+typedef struct orc_gnat orc_gnat;
+orc_gnat* orc_gnat_create(const mps_scene* sc, const float* weights, uint32_t mask);
+void orc_gnat_free(orc_gnat* g);
+int orc_gnat_add(orc_gnat* g, const float* state);
+int orc_gnat_size(const orc_gnat* g);
+int orc_gnat_nearest(orc_gnat* g, const float* query, double* dist_out);
+long orc_gnat_distance_evaluations(const orc_gnat* g);
+
 /* mps_oracle_mt.c: pthread fan-out used by the host-CPU baseline */
 int orc_extend_mt(const mps_scene* sc, const mps_extend_in* in, const mps_extend_out* out, int n_threads);
 int orc_nn_linear_batch_mt(const mps_scene* sc, const float* states, const int32_t* slice_ids, int64_t n,

@@ -53,8 +53,51 @@ def lib():
         L.orc_propagate_trace.argtypes = [_P(abi.Scene), _P(_f), _P(_f), _P(_f), C.c_int32, _P(C.c_int32)]
         L.orc_step_once.argtypes = [_P(abi.Scene), _P(_f), _P(_f), _P(_f), _P(C.c_int32)]
         L.orc_contacts.argtypes = [_P(abi.Scene), _P(_f), _P(C.c_int32), _P(_f), C.c_int32]
+        L.orc_gnat_create.restype = C.c_void_p
+        L.orc_gnat_create.argtypes = [_P(abi.Scene), _P(_f), C.c_uint32]
+        L.orc_gnat_free.argtypes = [C.c_void_p]
+        L.orc_gnat_add.argtypes = [C.c_void_p, _P(_f)]
+        L.orc_gnat_size.argtypes = [C.c_void_p]
+        L.orc_gnat_nearest.argtypes = [C.c_void_p, _P(_f), _P(C.c_double)]
+        L.orc_gnat_distance_evaluations.restype = C.c_long
+        L.orc_gnat_distance_evaluations.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+class Gnat:
+    """orc_gnat: CPU restatement of ompl::NearestNeighborsGNAT (oracle/mps_gnat.c)"""
+
+    def __init__(self, sc, weights=None, mask=None):
+        B = sc.n_bodies
+        full = (1 << B) - 1 if B < 32 else 0xFFFFFFFF
+        self.sc = sc
+        w = f32(weights)
+        self.h = lib().orc_gnat_create(C.byref(sc), fp(w), full if mask is None else int(mask))
+
+    def add(self, state):
+        s = f32(state)
+        return lib().orc_gnat_add(self.h, fp(s))
+
+    def add_many(self, states):
+        st = f32(states).reshape(-1, 3 * self.sc.n_bodies)
+        for i in range(len(st)):
+            lib().orc_gnat_add(self.h, fp(st[i]))
+
+    def nearest(self, q):
+        d = C.c_double(0)
+        qq = f32(q)
+        i = lib().orc_gnat_nearest(self.h, fp(qq), C.byref(d))
+        return int(i), d.value
+
+    def distance_evaluations(self):
+        return lib().orc_gnat_distance_evaluations(self.h)
+
+    def __del__(self):
+        try:
+            lib().orc_gnat_free(self.h)
+        except Exception:
+            pass
 
 
 def fp(a, t=_f):

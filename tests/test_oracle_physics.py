@@ -213,3 +213,31 @@ def test_oracle_reproduces_committed_physics_golden():
             assert np.array_equal(r[key], g[f"c{i}_{key}"]), (i, key)
         i += 1
     assert i == 4
+
+
+def test_gnat_restatement_is_exact():
+    """oracle/mps_gnat.c (ompl::NearestNeighborsGNAT restated) against the linear scan: same distance, and the
+    same index whenever the minimum is unique; far fewer distance evaluations than a scan."""
+    sc = _scene(6)
+    rng = np.random.RandomState(12)
+    N = 6000
+    states = np.stack([scenes.sample_state(rng, sc) for _ in range(N)])
+    for mask in (None, 0b1111110, 1):
+        g = ob.Gnat(sc, mask=mask)
+        g.add_many(states)
+        e0 = g.distance_evaluations()
+        for _ in range(40):
+            q = scenes.sample_state(rng, sc)
+            gi, gd = g.nearest(q)
+            wi, wd = ob.nn_linear(sc, states, q, mask=mask)
+            assert gd == wd
+            if mask is None:
+                assert gi == wi
+        if mask is None:
+            assert (g.distance_evaluations() - e0) / 40 < N
+    g = ob.Gnat(sc)
+    assert g.nearest(states[0]) == (-1, np.inf)
+    dup = np.concatenate([states[:300], states[:300]])
+    g.add_many(dup)
+    i, d = g.nearest(states[17])
+    assert d == 0.0 and i in (17, 317)
