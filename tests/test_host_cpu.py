@@ -49,3 +49,23 @@ def test_planner_without_device_is_a_hard_error():
     with pytest.raises(RuntimeError) as e:
         host_api.plan(sc, start, [(1, 0.5, 0.5, 0.1)], algorithm="Naive", max_iterations=5)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_solution_file_roundtrip_is_lossless(tmp_path):
+    """saveSolution / loadSolution format (OraclePushPlanner.cpp:260-385)."""
+    from manipulation_planning_suite_b200 import solution_io
+
+    rng = np.random.RandomState(3)
+    states = rng.uniform(-1, 1, size=(5, 12)).astype(np.float32)
+    controls = rng.uniform(-1, 1, size=(5, 5)).astype(np.float32)
+    stats = dict(num_iterations=17, num_state_propagations=170, num_samples=17, num_nearest_neighbor_queries=17,
+                 runtime=0.25, success=1, reproducible=1)
+    p = tmp_path / "sol.txt"
+    solution_io.save_solution(str(p), states, controls, stats)
+    lines = p.read_text().split("\n")
+    assert lines[0] == "4,0,3,3,3,3" and lines[1] == "5" and lines[3] == "5"
+    sol = solution_io.load_solution(str(p), n_objects=4)
+    assert np.array_equal(sol.states, states) and np.array_equal(sol.controls, controls)
+    assert sol.stats["num_state_propagations"] == 170 and sol.stats["success"] == 1
+    with pytest.raises(ValueError):
+        solution_io.load_solution(str(p), n_objects=5)
