@@ -34,13 +34,14 @@
 extern "C" {
 #endif
 
-#define MPS_ABI_VERSION 1
+#define MPS_ABI_VERSION 2
 
 #define MPS_MAX_BODIES 32   /* B: robot + movable objects (one warp lane per body) */
 #define MPS_MAX_STATICS 16  /* S: static obstacles (walls, fixed boxes) */
 #define MPS_MAX_GOALS 8
 #define MPS_CONTROL_DIM 5   /* (vx, vy, omega, t_plateau, t_rest) RampVelocityControl.cpp:34-61 */
 #define MPS_MAX_MANIFOLDS 64
+#define MPS_MAX_CHAIN 64     /* controls per chain (L) */
 
 /* status codes */
 #define MPS_OK 0
@@ -153,7 +154,10 @@ typedef struct mps_extend_in {
     float ball_radius;
     int32_t append_to_tree; /* 1: the winner chain is appended to the ctx tree on device */
     int32_t parent;         /* tree index of `start` (used when append_to_tree) */
-    int32_t _pad;
+    int32_t stop_at_goal;   /* 1 = a chain ends at its first goal state (the shortcutters' forwardPropagatePath,
+                               RRT.cpp:966-968,1011-1013); 0 = the whole chain is propagated */
+    const float* starts;    /* [K][3B] optional per-chain start states (candidate replays of the shortcutters,
+                               RRT.cpp:946-1034); NULL = every chain starts from `start` */
 } mps_extend_in;
 
 /* Winner of an extend (strict <, first index wins; NaiveControlSampler.cpp:55, RRT.cpp:467). */

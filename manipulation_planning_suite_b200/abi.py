@@ -9,13 +9,13 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-MPS_ABI_VERSION = 1
+MPS_ABI_VERSION = 2
 MPS_MAX_BODIES = 32
 MPS_MAX_STATICS = 16
 MPS_MAX_GOALS = 8
 MPS_CONTROL_DIM = 5
 MPS_MAX_MANIFOLDS = 64
-MPS_MAX_CHAIN = 16
+MPS_MAX_CHAIN = 64
 
 MPS_OK = 0
 MPS_ERR_ARG = -1
@@ -119,7 +119,8 @@ class ExtendIn(C.Structure):
         ("ball_radius", _f32),
         ("append_to_tree", _i32),
         ("parent", _i32),
-        ("_pad", _i32),
+        ("stop_at_goal", _i32),
+        ("starts", C.POINTER(_f32)),
     ]
 
 

@@ -96,14 +96,15 @@ class Context:
 
     # ---- propagation ----------------------------------------------------
     def _extend_in(self, start, controls, n_ctrl=None, dest=None, weights=None, mask=None, compare_f32=False,
-                   goals=None, k_offset=0, ball_center=None, ball_radius=0.0, append_to_tree=False, parent=-1):
+                   goals=None, k_offset=0, ball_center=None, ball_radius=0.0, append_to_tree=False, parent=-1,
+                   starts=None, stop_at_goal=False):
         B = self.B
         controls = _f32(controls)
         if controls.ndim == 2:
             controls = controls[:, None, :]
         K, L, five = controls.shape
         assert five == abi.MPS_CONTROL_DIM
-        start = _f32(start, (3 * B,))
+        start = None if start is None else _f32(start, (3 * B,))
         dest = _f32(dest, (3 * B,))
         weights = _f32(weights, (B,))
         ball_center = _f32(ball_center, (3 * B,))
@@ -132,7 +133,10 @@ class Context:
         ein.ball_radius = float(ball_radius)
         ein.append_to_tree = 1 if append_to_tree else 0
         ein.parent = int(parent)
-        keep = (start, controls, n_ctrl_a, dest, weights, ball_center, garr)
+        starts_a = None if starts is None else _f32(starts).reshape(K, 3 * B)
+        ein.starts = _fp(starts_a)
+        ein.stop_at_goal = 1 if stop_at_goal else 0
+        keep = (start, controls, n_ctrl_a, dest, weights, ball_center, garr, starts_a)
         return ein, keep, K, L
 
     def _extend_out(self, K, L, dump):

@@ -799,8 +799,8 @@ int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uin
 int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
 {
     if (!ctx || !in) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_upload");
-    if (!in->start || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "start / controls are NULL");
-    if (in->K < 1 || in->L < 1 || in->L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "K must be >= 1 and L in [1, 16]");
+    if ((!in->start && !in->starts) || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "start / controls are NULL");
+    if (in->K < 1 || in->L < 1 || in->L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "K must be >= 1 and L in [1, 64]");
     if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS) return mps_fail(ctx, MPS_ERR_ARG, "n_goals must be in [0, 8]");
     if (in->n_goals > 0 && !in->goals) return mps_fail(ctx, MPS_ERR_ARG, "goals is NULL");
     const int B = ctx->scene.n_bodies, K = in->K, L = in->L;
@@ -811,7 +811,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     const size_t sb = sizeof(float) * 3 * B, cb = sizeof(float) * MPS_CONTROL_DIM * KL, nb = sizeof(int32_t) * (size_t)K,
                  wb = sizeof(float) * B, gb = sizeof(mps_goal) * MPS_MAX_GOALS;
     int rc;
-    if ((rc = ensure(ctx, ctx->d_start, sb))) return rc;
+    if ((rc = ensure(ctx, ctx->d_start, in->starts ? sb * (size_t)K : sb))) return rc;
     if ((rc = ensure(ctx, ctx->d_controls, cb))) return rc;
     if ((rc = ensure(ctx, ctx->d_nctrl, nb))) return rc;
     if ((rc = ensure(ctx, ctx->d_dest, sb))) return rc;
@@ -836,7 +836,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
         if ((rc = tree_ensure(ctx, ctx->tree_upper + L))) return rc;
     }
     // host -> pinned staging -> device
-    if ((rc = ensure_stage(ctx, 3 * sb + cb + nb + wb + gb))) return rc;
+    if ((rc = ensure_stage(ctx, 3 * sb + cb + nb + wb + gb + (in->starts ? sb * (size_t)K + 64 : 0) + 256))) return rc;
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     char* h = (char*)ctx->h_stage;
     auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
@@ -845,7 +845,10 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
         h += align_up(bytes, 16);
         return e;
     };
-    MPS_CUDA_CHECK(up(ctx->d_start, in->start, sb), ctx);
+    if (in->starts)
+        MPS_CUDA_CHECK(up(ctx->d_start, in->starts, sb * (size_t)K), ctx);
+    else
+        MPS_CUDA_CHECK(up(ctx->d_start, in->start, sb), ctx);
     MPS_CUDA_CHECK(up(ctx->d_controls, in->controls, cb), ctx);
     if (in->n_ctrl) MPS_CUDA_CHECK(up(ctx->d_nctrl, in->n_ctrl, nb), ctx);
     if (in->dest) MPS_CUDA_CHECK(up(ctx->d_dest, in->dest, sb), ctx);
@@ -859,6 +862,8 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     rp.scene_bytes = ctx->scene_bytes;
     rp.warp_bytes = ctx->warp_bytes;
     rp.start = (const float*)ctx->d_start.p;
+    rp.start_stride = in->starts ? (size_t)3 * B : 0;
+    rp.stop_at_goal = in->stop_at_goal;
     rp.controls = (const float*)ctx->d_controls.p;
     rp.n_ctrl = in->n_ctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
     rp.K = K;
@@ -1138,7 +1143,7 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     if (!ctx || !in || !in->inst_ids || !in->parents || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_forest_extend");
     if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
     const int B = ctx->scene.n_bodies, M = in->M, K = in->K, L = in->L;
-    if (M < 1 || K < 1 || L < 1 || L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "M, K >= 1 and L in [1, 16]");
+    if (M < 1 || K < 1 || L < 1 || L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "M, K >= 1 and L in [1, 64]");
     if ((long long)M * K > (1ll << 24)) return mps_fail(ctx, MPS_ERR_ARG, "M * K too large");
     if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS || (in->n_goals > 0 && !in->goals)) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
     int rc = check_inst_ids(ctx, in->inst_ids, M);

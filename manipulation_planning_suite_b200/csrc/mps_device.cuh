@@ -18,7 +18,6 @@
 #define MPS_TWO_PI_F (2.0f * 3.14159265358979323846f)
 #define MPS_DBL_EPS 2.2204460492503131e-16
 
-#define MPS_MAX_CHAIN 16
 #define MPS_MAX_PAIRS (MPS_MAX_BODIES * (MPS_MAX_BODIES - 1) / 2 + MPS_MAX_BODIES * MPS_MAX_STATICS)
 
 // Scene as the kernels see it: the mps_scene of the ABI plus the derived constants

@@ -891,9 +891,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             if (dest) dest += (size_t)m * 3 * B;
             if (p.masks) dmask = p.masks[m];
         } else if (bd.live) {
-            sx = p.start[3 * lane];
-            sy = p.start[3 * lane + 1];
-            sth = p.start[3 * lane + 2];
+            const float* st0 = p.start + (size_t)k * p.start_stride;
+            sx = st0[3 * lane];
+            sy = st0[3 * lane + 1];
+            sth = st0[3 * lane + 2];
         }
         int n_ok = 0, goal_step = -1;
         int l = 0;
@@ -1039,6 +1040,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             sx = rx;
             sy = ry;
             sth = rth;
+            if (p.stop_at_goal && goal_step >= 0) {
+                ++l;
+                break;
+            }
         }
         // controls of the chain that were never propagated
         for (; l < L; ++l) {

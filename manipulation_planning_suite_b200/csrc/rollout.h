@@ -12,10 +12,12 @@ struct RolloutParams {
     const DevScene* scene;  // device copy
     size_t scene_bytes;     // shared-memory bytes reserved for the scene copy
     size_t warp_bytes;      // shared-memory bytes per warp
-    const float* start;     // [3B]
+    const float* start;     // [3B], or [K][3B] when start_stride != 0
+    size_t start_stride;    // 0 or 3B
     const float* controls;  // [K][L][5]
     const int32_t* n_ctrl;  // [K] or nullptr
     int K, L;
+    int stop_at_goal;       // chains end at their first goal state
     const float* dest;     // [3B] or nullptr
     const float* weights;  // [B] or nullptr
     uint32_t mask;

@@ -1236,6 +1236,27 @@ bool OraclePushPlanner::setup(PlanningProblem& problem)
         break;
     }
     }
+    // createShortcutAlgorithm (:731-768)
+    _shortcutter.reset();
+    switch (problem.shortcut_type) {
+    case ShortcutType::NaiveShortcut:
+        _shortcutter = std::make_shared<algorithm::NaiveShortcutter>(_si, robot_oracle);
+        break;
+    case ShortcutType::LocalShortcut:
+        _shortcutter = std::make_shared<algorithm::LocalShortcutter>(_si, robot_oracle, problem.robot_id);
+        break;
+    case ShortcutType::LocalOracleShortcut:
+        _shortcutter = std::make_shared<algorithm::LocalOracleShortcutter>(_si, robot_oracle, pushing_oracle, problem.robot_id);
+        break;
+    case ShortcutType::OracleShortcut:
+        _shortcutter = std::make_shared<algorithm::OracleShortcutter>(_si, robot_oracle, pushing_oracle, problem.robot_id);
+        break;
+    case ShortcutType::NoShortcut:
+        break;
+    default:
+        throw std::runtime_error("Invalid shortcut configuration encountered");
+    }
+    if (_shortcutter) _shortcutter->setBatchSize(problem.shortcut_batch_size);
     _is_initialized = true;
     return true;
 }
@@ -1258,7 +1279,22 @@ bool OraclePushPlanner::solve(PlanningSolution& solution)
     solution.solved = _algorithm->plan(pq, solution.stats);
     solution.path = pq->path;
     if (solution.solved) solution.stats.reproducible = verifySolution(solution);
+    _path_len_before_shortcut = solution.path ? solution.path->getNumMotions() : 0;
+    if (_shortcutter && solution.solved) shortcutSolution(solution);
     return solution.solved;
+}
+
+void OraclePushPlanner::shortcutSolution(PlanningSolution& solution)
+{
+    // :229-238
+    if (!_shortcutter || !solution.path) return;
+    auto cost_fn = std::make_shared<algorithm::ActionDurationCost>(_problem.control_limits.acceleration_limits);
+    algorithm::Shortcutter::ShortcutQuery sq(_goal, cost_fn, _problem.robot_id);
+    sq.stopping_condition = _problem.stopping_condition;
+    _shortcutter->shortcut(solution.path, sq, _problem.max_shortcut_time);
+    solution.stats.cost_before_shortcut = sq.cost_before_shortcut;
+    solution.stats.cost_after_shortcut = sq.cost_after_shortcut;
+    solution.stats.reproducible_after_shortcut = verifySolution(solution);
 }
 
 bool OraclePushPlanner::verifySolution(PlanningSolution& solution)
@@ -1309,75 +1345,142 @@ struct DebugInit {
 } g_debug_init;
 }  // namespace
 
+namespace {
+void problem_from_params(pushing::PlanningProblem& problem, const mps_scene* scene, const float* start,
+                         const mps_goal* goals, int32_t n_goals, const mps_host_params* params)
+{
+    problem.scene = *scene;
+    problem.start_state = ompl::state::SimEnvWorldState((unsigned int)scene->n_bodies);
+    std::memcpy(problem.start_state.values.data(), start, sizeof(float) * 3 * (size_t)scene->n_bodies);
+    problem.robot_id = (unsigned int)scene->robot_id;
+    for (int g = 0; g < n_goals; ++g) {
+        ompl::state::goal::RelocationGoalSpecification s;
+        s.id = (unsigned int)goals[g].body;
+        s.goal_position[0] = goals[g].x;
+        s.goal_position[1] = goals[g].y;
+        s.position_tolerance = goals[g].tol;
+        problem.relocation_goals.push_back(s);
+    }
+    problem.algorithm_type = (pushing::AlgorithmType)params->algorithm;
+    problem.planning_time_out = params->time_out;
+    problem.goal_bias = params->goal_bias;
+    problem.target_bias = params->target_bias;
+    problem.robot_bias = params->robot_bias;
+    problem.num_control_samples = (unsigned int)params->num_control_samples;
+    problem.action_noise = params->action_randomness;
+    problem.state_noise = params->state_noise;
+    problem.do_slice_ball_projection = params->do_slice_ball_projection != 0;
+    problem.seed = params->seed;
+    problem.device = params->device;
+    problem.max_iterations = (unsigned int)params->max_iterations;
+    problem.shortcut_type = (pushing::ShortcutType)params->shortcut_type;
+    problem.max_shortcut_time = params->max_shortcut_time;
+    problem.shortcut_batch_size = params->shortcut_batch_size > 0 ? (unsigned int)params->shortcut_batch_size : 1u;
+    for (int i = 0; i < 3; ++i) {
+        problem.control_limits.velocity_limits[i] = params->velocity_limits[i];
+        problem.control_limits.acceleration_limits[i] = scene->accel_limits[i];
+    }
+    problem.control_limits.duration_limits[0] = params->duration_limits[0];
+    problem.control_limits.duration_limits[1] = params->duration_limits[1];
+}
+
+void fill_result(mps_host_result* result, const pushing::OraclePushPlanner& planner,
+                 const pushing::PlanningSolution& solution, const mps_scene* scene, float* path_states,
+                 float* path_controls, int32_t max_path)
+{
+    result->solved = solution.solved ? 1 : 0;
+    result->reproducible = solution.stats.reproducible ? 1 : 0;
+    result->num_iterations = (int32_t)solution.stats.num_iterations;
+    result->num_state_propagations = (int32_t)solution.stats.num_state_propagations;
+    result->num_samples = (int32_t)solution.stats.num_samples;
+    result->num_nearest_neighbor_queries = (int32_t)solution.stats.num_nearest_neighbor_queries;
+    result->runtime_cpu = solution.stats.runtime;
+    result->runtime_wall = solution.stats.wall_time;
+    result->tree_size = (int32_t)planner.getAlgorithm()->treeSize();
+    auto slice_rrt = std::dynamic_pointer_cast<pushing::algorithm::SliceBasedOracleRRT>(planner.getAlgorithm());
+    result->num_slices = slice_rrt ? (int32_t)slice_rrt->numSlices() : 0;
+    result->cost_before_shortcut = solution.stats.cost_before_shortcut;
+    result->cost_after_shortcut = solution.stats.cost_after_shortcut;
+    result->reproducible_after_shortcut = solution.stats.reproducible_after_shortcut ? 1 : 0;
+    if (planner.getShortcutter()) {
+        const auto& st = planner.getShortcutter()->statistics();
+        result->shortcut_candidates = (int32_t)st.num_candidates;
+        result->shortcut_launches = (int32_t)st.num_launches;
+        result->shortcut_propagations = (int32_t)st.num_propagations;
+        result->shortcut_accepted = (int32_t)st.num_accepted;
+    }
+    result->path_len = 0;
+    if (solution.solved && solution.path) {
+        const size_t dim = 3 * (size_t)scene->n_bodies;
+        int32_t n = (int32_t)solution.path->motions.size();
+        result->path_len = n;
+        for (int32_t i = 0; i < n && i < max_path; ++i) {
+            if (path_states) std::memcpy(path_states + (size_t)i * dim, solution.path->motions[i]->state.values.data(), dim * sizeof(float));
+            if (path_controls) std::memcpy(path_controls + (size_t)i * 5, solution.path->motions[i]->control.data(), 5 * sizeof(float));
+        }
+    }
+}
+
+int report(const std::exception& e, char* err, int32_t err_len)
+{
+    if (err && err_len > 0) {
+        std::strncpy(err, e.what(), (size_t)err_len - 1);
+        err[err_len - 1] = 0;
+    }
+    return -1;
+}
+}  // namespace
+
 extern "C" int mps_host_plan(const mps_scene* scene, const float* start, const mps_goal* goals, int32_t n_goals,
                              const mps_host_params* params, mps_host_result* result, float* path_states,
                              float* path_controls, int32_t max_path, char* err, int32_t err_len)
 {
     try {
         pushing::PlanningProblem problem;
-        problem.scene = *scene;
-        problem.start_state = ompl::state::SimEnvWorldState((unsigned int)scene->n_bodies);
-        std::memcpy(problem.start_state.values.data(), start, sizeof(float) * 3 * (size_t)scene->n_bodies);
-        problem.robot_id = (unsigned int)scene->robot_id;
-        for (int g = 0; g < n_goals; ++g) {
-            ompl::state::goal::RelocationGoalSpecification s;
-            s.id = (unsigned int)goals[g].body;
-            s.goal_position[0] = goals[g].x;
-            s.goal_position[1] = goals[g].y;
-            s.position_tolerance = goals[g].tol;
-            problem.relocation_goals.push_back(s);
-        }
-        problem.algorithm_type = (pushing::AlgorithmType)params->algorithm;
-        problem.planning_time_out = params->time_out;
-        problem.goal_bias = params->goal_bias;
-        problem.target_bias = params->target_bias;
-        problem.robot_bias = params->robot_bias;
-        problem.num_control_samples = (unsigned int)params->num_control_samples;
-        problem.action_noise = params->action_randomness;
-        problem.state_noise = params->state_noise;
-        problem.do_slice_ball_projection = params->do_slice_ball_projection != 0;
-        problem.seed = params->seed;
-        problem.device = params->device;
-        problem.max_iterations = (unsigned int)params->max_iterations;
-        for (int i = 0; i < 3; ++i) {
-            problem.control_limits.velocity_limits[i] = params->velocity_limits[i];
-            problem.control_limits.acceleration_limits[i] = scene->accel_limits[i];
-        }
-        problem.control_limits.duration_limits[0] = params->duration_limits[0];
-        problem.control_limits.duration_limits[1] = params->duration_limits[1];
+        problem_from_params(problem, scene, start, goals, n_goals, params);
         pushing::OraclePushPlanner planner;
         planner.setup(problem);
         pushing::PlanningSolution solution;
         planner.solve(solution);
         std::memset(result, 0, sizeof(*result));
-        result->solved = solution.solved ? 1 : 0;
-        result->reproducible = solution.stats.reproducible ? 1 : 0;
-        result->num_iterations = (int32_t)solution.stats.num_iterations;
-        result->num_state_propagations = (int32_t)solution.stats.num_state_propagations;
-        result->num_samples = (int32_t)solution.stats.num_samples;
-        result->num_nearest_neighbor_queries = (int32_t)solution.stats.num_nearest_neighbor_queries;
-        result->runtime_cpu = solution.stats.runtime;
-        result->runtime_wall = solution.stats.wall_time;
-        result->tree_size = (int32_t)planner.getAlgorithm()->treeSize();
-        auto slice_rrt = std::dynamic_pointer_cast<pushing::algorithm::SliceBasedOracleRRT>(planner.getAlgorithm());
-        result->num_slices = slice_rrt ? (int32_t)slice_rrt->numSlices() : 0;
-        result->path_len = 0;
-        if (solution.solved && solution.path) {
-            const size_t dim = 3 * (size_t)scene->n_bodies;
-            int32_t n = (int32_t)solution.path->motions.size();
-            result->path_len = n;
-            for (int32_t i = 0; i < n && i < max_path; ++i) {
-                if (path_states) std::memcpy(path_states + (size_t)i * dim, solution.path->motions[i]->state.values.data(), dim * sizeof(float));
-                if (path_controls) std::memcpy(path_controls + (size_t)i * 5, solution.path->motions[i]->control.data(), 5 * sizeof(float));
-            }
-        }
+        fill_result(result, planner, solution, scene, path_states, path_controls, max_path);
+        result->path_len_before_shortcut = (int32_t)planner.pathLengthBeforeShortcut();
         return 0;
     } catch (const std::exception& e) {
-        if (err && err_len > 0) {
-            std::strncpy(err, e.what(), (size_t)err_len - 1);
-            err[err_len - 1] = 0;
+        return report(e, err, err_len);
+    }
+}
+
+extern "C" int mps_host_shortcut(const mps_scene* scene, const mps_goal* goals, int32_t n_goals,
+                                 const mps_host_params* params, const float* in_states, const float* in_controls,
+                                 int32_t n_path, mps_host_result* result, float* path_states, float* path_controls,
+                                 int32_t max_path, char* err, int32_t err_len)
+{
+    try {
+        if (n_path < 1) throw std::invalid_argument("mps_host_shortcut: empty path");
+        pushing::PlanningProblem problem;
+        problem_from_params(problem, scene, in_states, goals, n_goals, params);
+        pushing::OraclePushPlanner planner;
+        planner.setup(problem);
+        pushing::PlanningSolution solution;
+        solution.path = std::make_shared<ompl::planning::essentials::Path>();
+        const size_t dim = 3 * (size_t)scene->n_bodies;
+        for (int32_t i = 0; i < n_path; ++i) {
+            auto m = std::make_shared<ompl::planning::essentials::Motion>((unsigned int)scene->n_bodies);
+            std::memcpy(m->state.values.data(), in_states + (size_t)i * dim, dim * sizeof(float));
+            std::memcpy(m->control.data(), in_controls + (size_t)i * 5, 5 * sizeof(float));
+            if (i > 0) m->parent = solution.path->motions.back();
+            solution.path->motions.push_back(m);
         }
-        return -1;
+        solution.solved = true;
+        solution.stats.reproducible = planner.verifySolution(solution);
+        planner.shortcutSolution(solution);
+        std::memset(result, 0, sizeof(*result));
+        fill_result(result, planner, solution, scene, path_states, path_controls, max_path);
+        result->path_len_before_shortcut = n_path;
+        return 0;
+    } catch (const std::exception& e) {
+        return report(e, err, err_len);
     }
 }
 
@@ -1401,6 +1504,9 @@ extern "C" void mps_host_default_params(mps_host_params* p)
     p->velocity_limits[2] = 1.5f;
     p->duration_limits[0] = 0.1f;  // :70-71
     p->duration_limits[1] = 1.0f;
+    p->shortcut_type = 3;          // LocalShortcut, :87-88
+    p->max_shortcut_time = 5.0f;
+    p->shortcut_batch_size = 256;
 }
 
 // oracle helpers exposed for the known-answer tests of the "next" rows (RampComputer / HumanOracle)

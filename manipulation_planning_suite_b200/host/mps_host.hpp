@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdint>
 #include <ctime>
+#include <deque>
 #include <functional>
 #include <limits>
 #include <map>
@@ -404,6 +405,8 @@ struct PlanningStatistics {  // algorithm/Interfaces.h:39-127
     float wall_time = 0.0f;     // additionally: wall clock seconds
     bool success = false;
     bool reproducible = false;
+    float cost_before_shortcut = 0.0f, cost_after_shortcut = 0.0f;  // Interfaces.h:46-49
+    bool reproducible_after_shortcut = false;
 };
 
 // ompl::base::ParamSet stand-in: string-typed set / get with declared setters (RRT.cpp:145-169)
@@ -528,7 +531,7 @@ protected:
     oracle::OracleControlSamplerPtr _oracle_sampler;
     unsigned int _num_control_samples = 10;
     float _action_randomness = 0.0001f;
-    static const int kMaxChain = 16;
+    static const int kMaxChain = MPS_MAX_CHAIN;
 };
 
 class OracleRearrangementRRT : public RearrangementRRT {
@@ -588,10 +591,157 @@ protected:
     float _slice_ball_radius = 0.0f;
     unsigned int _robot_id_cached = 0;
 };
+// ----------------------------------------------------------------------------------- shortcutting
+// CostFunction (ompl/planning/Essentials.cpp:197-211) and ActionDurationCost (pushing/Costs.cpp:12-17)
+class CostFunction {
+public:
+    virtual ~CostFunction() = default;
+    // cost of taking the action stored in `second` from the state in `first`
+    virtual double cost(const ompl::planning::essentials::Motion& first,
+                        const ompl::planning::essentials::Motion& second) const = 0;
+    // accumulates over the motions 0..limit (all when limit < 0); starts with prev = motion 0, so the control
+    // stored in motion 0 is counted as well (Essentials.cpp:203-209)
+    virtual double cost(const ompl::planning::essentials::Path& path, int limit = -1) const;
+};
+typedef std::shared_ptr<CostFunction> CostFunctionPtr;
+
+class ActionDurationCost : public CostFunction {
+public:
+    explicit ActionDurationCost(const float accel_limits[3]);
+    using CostFunction::cost;
+    double cost(const ompl::planning::essentials::Motion& first,
+                const ompl::planning::essentials::Motion& second) const override;
+    double duration(const std::array<float, 5>& control) const;  // RampVelocityControl::getMaxDuration
+
+private:
+    float _accel_limits[3];
+};
+
+// Shortcutter (RRT.h:313-412, RRT.cpp:889-1034).  The reference tries one candidate (start_id, end_id) at a
+// time: build the replacement actions on the host, forward propagate them and the rest of the old path, accept
+// when the goal is still reached at lower cost.  Here every candidate of a round is an independent control
+// chain with its own start state, so a whole round is propagated by batched launches (mps_extend with
+// `starts`, `stop_at_goal`) and the candidates are then examined in the reference's order; the first
+// acceptable one is taken, exactly the candidate the sequential loop would have accepted.
+class Shortcutter {
+public:
+    struct ShortcutQuery {  // RRT.h:319-335
+        ompl::state::goal::ObjectsRelocationGoalPtr goal_region;
+        CostFunctionPtr cost_function;
+        unsigned int robot_id = 0;
+        std::function<bool()> stopping_condition = []() { return false; };
+        float cost_before_shortcut = 0.0f, cost_after_shortcut = 0.0f;
+        ShortcutQuery(ompl::state::goal::ObjectsRelocationGoalPtr goal_region_in, CostFunctionPtr cost_function_in,
+                      unsigned int robot_id_in)
+            : goal_region(goal_region_in), cost_function(cost_function_in), robot_id(robot_id_in)
+        {
+        }
+    };
+    struct Statistics {
+        unsigned int num_candidates = 0;      // candidate shortcuts evaluated
+        unsigned int num_launches = 0;        // batched propagate launches
+        unsigned int num_propagations = 0;    // controls propagated on the device
+        unsigned int num_accepted = 0;
+    };
+    explicit Shortcutter(SpaceInformationPtr si);
+    virtual ~Shortcutter() = default;
+    virtual void shortcut(ompl::planning::essentials::PathPtr iopath, ShortcutQuery& sq, float max_time) = 0;
+    virtual std::string getName() const = 0;
+    const Statistics& statistics() const { return _stats; }
+    // candidates per batched launch (upper bound; 1 reproduces the reference's one-at-a-time evaluation)
+    void setBatchSize(unsigned int n) { _batch_size = n > 0 ? n : 1; }
+
+protected:
+    typedef ompl::planning::essentials::Motion Motion;
+    typedef ompl::planning::essentials::MotionPtr MotionPtr;
+    typedef ompl::planning::essentials::Path Path;
+    typedef ompl::planning::essentials::PathPtr PathPtr;
+    typedef std::array<float, 5> ControlParams;
+    // one candidate shortcut being propagated: `appended` grows by the motions that propagated successfully
+    struct Candidate {
+        unsigned int start_id = 0, end_id = 0, object_id = 0;
+        int stage = 0;                        // next stage nextControls() is asked for
+        std::deque<ControlParams> pending;    // controls of the current stage not yet propagated
+        std::vector<MotionPtr> appended;      // forwardPropagatePath's path->append(new_motion)
+        ompl::state::SimEnvWorldState last;   // state the next control starts from
+        bool valid = true, goal = false, done = false;
+    };
+    // fills c.pending with the controls of stage c.stage given c.last; returns false when there is no further
+    // stage (c stays valid), may set c.valid = false to abort the candidate (e.g. oracle gave no control)
+    virtual bool nextControls(Candidate& c, const Path& current_path, ShortcutQuery& sq) = 0;
+    // forwardPropagatePath (RRT.cpp:946-1034) for all candidates at once
+    void propagateCandidates(std::vector<Candidate>& cands, const Path& current_path, ShortcutQuery& sq);
+    void initCandidate(Candidate& c, const Path& current_path, unsigned int start_id, unsigned int end_id) const;
+    void finish(PathPtr iopath, const Path& current_path, ShortcutQuery& sq, double initial_cost, double cost) const;
+
+    SpaceInformationPtr _si;
+    util::time::Timer _timer;
+    Statistics _stats;
+    unsigned int _batch_size = 256;
+};
+typedef std::shared_ptr<Shortcutter> ShortcutterPtr;
+
+class NaiveShortcutter : public Shortcutter {  // RRT.cpp:1054-1171
+public:
+    NaiveShortcutter(SpaceInformationPtr si, oracle::RobotOraclePtr robot_oracle);
+    void shortcut(PathPtr iopath, ShortcutQuery& sq, float max_time) override;
+    std::string getName() const override { return "NaiveShortcutter"; }
+
+protected:
+    bool nextControls(Candidate& c, const Path& current_path, ShortcutQuery& sq) override;
+    void createAllPairs(std::vector<std::pair<unsigned int, unsigned int>>& all_pairs, unsigned int n) const;
+    oracle::RobotOraclePtr _robot_oracle;
+};
+
+class LocalShortcutter : public Shortcutter {  // RRT.cpp:1177-1305
+public:
+    LocalShortcutter(SpaceInformationPtr si, oracle::RobotOraclePtr robot_oracle, unsigned int robot_id);
+    void shortcut(PathPtr iopath, ShortcutQuery& sq, float max_time) override;
+    std::string getName() const override { return "LocalShortcutter"; }
+
+protected:
+    bool nextControls(Candidate& c, const Path& current_path, ShortcutQuery& sq) override;
+    oracle::RobotOraclePtr _robot_oracle;
+    unsigned int _robot_id;
+};
+
+class LocalOracleShortcutter : public LocalShortcutter {  // RRT.cpp:1310-1411
+public:
+    LocalOracleShortcutter(SpaceInformationPtr si, oracle::RobotOraclePtr robot_oracle,
+                           oracle::PushingOraclePtr pushing_oracle, unsigned int robot_id);
+    std::string getName() const override { return "LocalOracleShortcutter"; }
+
+protected:
+    bool nextControls(Candidate& c, const Path& current_path, ShortcutQuery& sq) override;
+    unsigned int selectObject(const ompl::state::SimEnvWorldState& start_state,
+                              const ompl::state::SimEnvWorldState& end_state) const;  // :1326-1345
+    oracle::OracleControlSamplerPtr _oracle_sampler;
+};
+
+class OracleShortcutter : public Shortcutter {  // RRT.cpp:1416-1688
+public:
+    OracleShortcutter(SpaceInformationPtr si, oracle::RobotOraclePtr robot_oracle, oracle::PushingOraclePtr pushing_oracle,
+                      unsigned int robot_id);
+    void shortcut(PathPtr iopath, ShortcutQuery& sq, float max_time) override;
+    std::string getName() const override { return "OracleShortcutter"; }
+
+protected:
+    typedef std::pair<unsigned int, unsigned int> IndexPair;
+    typedef std::deque<IndexPair> PairQueue;
+    typedef std::vector<unsigned int> ObjectIds;
+    typedef std::map<IndexPair, ObjectIds> PairMap;
+    bool nextControls(Candidate& c, const Path& current_path, ShortcutQuery& sq) override;
+    void fillPairQueue(PairQueue& all_pairs, unsigned int n) const;                                  // :1505-1519
+    unsigned int selectObject(const Path& current_path, const IndexPair& current_pair, PairMap& pair_to_objects,
+                              PairQueue& pair_queue, unsigned int robot_id) const;                   // :1521-1571
+    oracle::OracleControlSamplerPtr _oracle_sampler;
+};
 }  // namespace algorithm
 
 // ---------------------------------------------------------------------------------- OraclePushPlanner
 enum class AlgorithmType { Naive = 0, OracleRRT = 1, SliceOracleRRT = 2, HybridActionRRT = 3 };
+// PlanningProblem::ShortcutType, OraclePushPlanner.h:48-54 (same values)
+enum class ShortcutType { NaiveShortcut = 0, OracleShortcut = 1, NoShortcut = 2, LocalShortcut = 3, LocalOracleShortcut = 4 };
 
 struct PlanningProblem {  // OraclePushPlanner.cpp:40-91 (the fields the path reads)
     mps_scene scene;
@@ -605,6 +755,9 @@ struct PlanningProblem {  // OraclePushPlanner.cpp:40-91 (the fields the path re
     bool do_slice_ball_projection = true;
     unsigned int num_control_samples = 10;
     AlgorithmType algorithm_type = AlgorithmType::Naive;
+    ShortcutType shortcut_type = ShortcutType::LocalShortcut;  // OraclePushPlanner.cpp:87-88
+    float max_shortcut_time = 5.0f;
+    unsigned int shortcut_batch_size = 256;
     std::vector<float> object_weights;  // empty = 1.0 each (prepareDistanceWeights :610-622)
     uint64_t seed = 1;
     int device = 0;
@@ -622,14 +775,20 @@ class OraclePushPlanner {
 public:
     bool setup(PlanningProblem& problem);       // OraclePushPlanner.cpp:107-173
     bool solve(PlanningSolution& solution);     // :175-243
+    void shortcutSolution(PlanningSolution& solution);  // :229-238, also usable on a loaded solution
     bool verifySolution(PlanningSolution& solution);  // :495-519: replay every control, check the goal
     algorithm::SpaceInformationPtr getSpaceInformation() const { return _si; }
     std::shared_ptr<algorithm::RearrangementRRT> getAlgorithm() const { return _algorithm; }
+    algorithm::ShortcutterPtr getShortcutter() const { return _shortcutter; }
+    unsigned int pathLengthBeforeShortcut() const { return _path_len_before_shortcut; }
+    ompl::state::goal::ObjectsRelocationGoalPtr getGoal() const { return _goal; }
 
 private:
     PlanningProblem _problem;
     algorithm::SpaceInformationPtr _si;
     std::shared_ptr<algorithm::RearrangementRRT> _algorithm;
+    algorithm::ShortcutterPtr _shortcutter;
+    unsigned int _path_len_before_shortcut = 0;
     ompl::state::goal::ObjectsRelocationGoalPtr _goal;
     bool _is_initialized = false;
 };

@@ -23,6 +23,9 @@ typedef struct mps_host_params {
     int32_t max_iterations;      /* 0 = unlimited */
     float velocity_limits[3];
     float duration_limits[2];
+    int32_t shortcut_type;       /* PlanningProblem::ShortcutType: 0 Naive, 1 Oracle, 2 none, 3 Local, 4 LocalOracle */
+    float max_shortcut_time;     /* CPU seconds */
+    int32_t shortcut_batch_size; /* candidates per batched launch; 1 = the reference's one-at-a-time evaluation */
 } mps_host_params;
 
 typedef struct mps_host_result {
@@ -30,6 +33,10 @@ typedef struct mps_host_result {
     int32_t num_iterations, num_state_propagations, num_samples, num_nearest_neighbor_queries;
     float runtime_cpu, runtime_wall;
     int32_t tree_size, num_slices, path_len;
+    float cost_before_shortcut, cost_after_shortcut;   /* PlanningStatistics, Interfaces.h:46-49 */
+    int32_t reproducible_after_shortcut;
+    int32_t path_len_before_shortcut;
+    int32_t shortcut_candidates, shortcut_launches, shortcut_propagations, shortcut_accepted;
 } mps_host_result;
 
 void mps_host_default_params(mps_host_params* p);
@@ -37,6 +44,11 @@ void mps_host_default_params(mps_host_params* p);
 int mps_host_plan(const mps_scene* scene, const float* start, const mps_goal* goals, int32_t n_goals,
                   const mps_host_params* params, mps_host_result* result, float* path_states, float* path_controls,
                   int32_t max_path, char* err, int32_t err_len);
+/* shortcuts a given solution path (OraclePushPlanner::solve's shortcut step, OraclePushPlanner.cpp:229-238):
+ * in_states [n_path][3B] / in_controls [n_path][5] as written by mps_host_plan */
+int mps_host_shortcut(const mps_scene* scene, const mps_goal* goals, int32_t n_goals, const mps_host_params* params,
+                      const float* in_states, const float* in_controls, int32_t n_path, mps_host_result* result,
+                      float* path_states, float* path_controls, int32_t max_path, char* err, int32_t err_len);
 /* RampComputer::steer (oracle/RampComputer.cpp:40-92) */
 int mps_host_ramp_steer(const float* vel_limits, const float* accel_limits, const float* duration_limits,
                         const float* current, const float* desired, float* controls_out, int32_t max_controls);

@@ -1043,16 +1043,16 @@ int orc_extend(const mps_scene* sc, const mps_extend_in* in, const mps_extend_ou
     float best_f = FLT_MAX;
     float cur[3 * MPS_MAX_BODIES], res[3 * MPS_MAX_BODIES];
     /* scratch for the running chain */
-    float chain_states[16][3 * MPS_MAX_BODIES];
-    float chain_ctrl[16][5];
-    uint32_t chain_flags[16];
-    if (L > 16 || L < 1 || K < 0) return MPS_ERR_ARG;
+    static __thread float chain_states[MPS_MAX_CHAIN][3 * MPS_MAX_BODIES];
+    float chain_ctrl[MPS_MAX_CHAIN][5];
+    uint32_t chain_flags[MPS_MAX_CHAIN];
+    if (L > MPS_MAX_CHAIN || L < 1 || K < 0) return MPS_ERR_ARG;
     for (k = 0; k < K; ++k) {
         int n = in->n_ctrl ? in->n_ctrl[k] : L;
         int n_ok = 0, goal_step = -1;
         double d = INFINITY;
         if (n > L) n = L;
-        memcpy(cur, in->start, sizeof(float) * 3 * (size_t)B);
+        memcpy(cur, in->starts ? in->starts + (size_t)k * 3 * B : in->start, sizeof(float) * 3 * (size_t)B);
         for (l = 0; l < L; ++l) {
             chain_flags[l] = 0;
             for (i = 0; i < 5; ++i) chain_ctrl[l][i] = in->controls[((size_t)k * L + l) * 5 + i];
@@ -1081,6 +1081,7 @@ int orc_extend(const mps_scene* sc, const mps_extend_in* in, const mps_extend_ou
             if (!ok) break;
             ++n_ok;
             memcpy(cur, res, sizeof(float) * 3 * (size_t)B);
+            if (in->stop_at_goal && goal_step >= 0) break; /* forwardPropagatePath RRT.cpp:966-968 */
         }
         if (n_ok > 0 && in->dest) d = orc_distance(sc, chain_states[n_ok - 1], in->dest, in->weights, in->mask);
         for (l = 0; l < L; ++l) {

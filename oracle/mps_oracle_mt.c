@@ -54,6 +54,7 @@ int orc_extend_mt(const mps_scene* sc, const mps_extend_in* in, const mps_extend
         j->in.K = k1 - k0;
         j->in.controls = in->controls + (size_t)k0 * L * 5;
         j->in.n_ctrl = in->n_ctrl ? in->n_ctrl + k0 : 0;
+        j->in.starts = in->starts ? in->starts + (size_t)k0 * 3 * B : 0;
         j->in.k_offset = in->k_offset + k0;
         memset(&j->out, 0, sizeof(j->out));
         j->best_states = (float*)calloc((size_t)L * 3 * B, sizeof(float));

@@ -154,14 +154,15 @@ def contacts(sc, state, max_m=64):
 
 
 def extend(sc, start, controls, n_ctrl=None, dest=None, weights=None, mask=None, compare_f32=False, goals=None,
-           k_offset=0, ball_center=None, ball_radius=0.0, threads=0):
+           k_offset=0, ball_center=None, ball_radius=0.0, threads=0, starts=None, stop_at_goal=False):
     """Same inputs / outputs as manipulation_planning_suite_b200.api.Context.extend(dump=True)."""
     B = sc.n_bodies
     controls = f32(controls)
     if controls.ndim == 2:
         controls = controls[:, None, :]
     K, L, _ = controls.shape
-    start = f32(start).reshape(3 * B)
+    start = None if start is None else f32(start).reshape(3 * B)
+    starts_a = None if starts is None else f32(starts).reshape(K, 3 * B)
     dest = None if dest is None else f32(dest).reshape(3 * B)
     weights = None if weights is None else f32(weights).reshape(B)
     ball_center = None if ball_center is None else f32(ball_center).reshape(3 * B)
@@ -188,6 +189,8 @@ def extend(sc, start, controls, n_ctrl=None, dest=None, weights=None, mask=None,
     ein.k_offset = k_offset
     ein.ball_center = fp(ball_center)
     ein.ball_radius = ball_radius
+    ein.starts = fp(starts_a)
+    ein.stop_at_goal = 1 if stop_at_goal else 0
     best = abi.ExtendBest()
     res = dict(
         best=best,

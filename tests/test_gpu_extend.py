@@ -223,7 +223,7 @@ def test_bad_arguments_are_errors_not_crashes():
     sc, start = scenes.make_scene(3, seed=3)
     ctx = api.Context(sc)
     with pytest.raises(api.MpsError):
-        ctx.extend(start, np.zeros((1, 17, 5), np.float32))  # L > 16
+        ctx.extend(start, np.zeros((1, abi.MPS_MAX_CHAIN + 1, 5), np.float32))  # L > MPS_MAX_CHAIN
     with pytest.raises(api.MpsError):
         ctx.extend(start, np.zeros((2, 1, 5), np.float32), goals=[(9, 0.0, 0.0, 0.1)])  # goal body out of range
     ctx.close()
@@ -253,3 +253,30 @@ def test_gpu_reproduces_committed_physics_golden():
         ctx.close()
         i += 1
     assert i == 4
+
+
+@pytest.mark.parametrize("stop_at_goal", [False, True])
+def test_per_chain_starts_long_chains_and_stop_at_goal(stop_at_goal):
+    """The shortcutters' candidate replays (RRT.cpp:946-1034): every chain has its own start state, chains are
+    longer than an extend's (L = 24 here, limit MPS_MAX_CHAIN = 64) and end at their first goal state."""
+    sc, _ = scenes.make_scene(4, seed=21)
+    rng = np.random.RandomState(5)
+    K, L = 40, 24
+    starts = np.stack([scenes.cluttered_start(sc, 100 + (k % 7)) for k in range(K)])
+    controls = np.stack([scenes.sample_controls_towards(rng, sc, starts[k], 1, L)[0] for k in range(K)])
+    n_ctrl = rng.randint(1, L + 1, size=K).astype(np.int32)
+    goals = [(1, float(starts[0][3]) + 0.05, float(starts[0][4]), 0.2)]
+    r = compare_extend(sc, None, controls, n_ctrl=n_ctrl, goals=goals, starts=starts, stop_at_goal=stop_at_goal)
+    fl = r["want"]["all_flags"]
+    goal = (fl & abi.MPS_F_GOAL) != 0
+    assert goal.any(), "no chain reached the goal: weak test"
+    ran = (fl & abi.MPS_F_RAN) != 0
+    if stop_at_goal:
+        # nothing is propagated behind the first goal state of a chain
+        first = np.where(goal.any(axis=1), goal.argmax(axis=1), L)
+        for k in range(K):
+            assert not ran[k, first[k] + 1:].any()
+    else:
+        assert any(ran[k, goal[k].argmax() + 1:].any() for k in range(K) if goal[k].any())
+    # chains that share a start state and controls prefix agree; different starts give different results
+    assert len({tuple(r["want"]["all_states"][k, 0]) for k in range(K)}) > 7
