@@ -21,6 +21,13 @@ namespace {
 thread_local std::string g_last_error;
 }
 
+// words per chain written by the rollout kernel's cycle counters (8 in the -DMPS_PHASE_PROF profiling build)
+#ifdef MPS_PHASE_PROF
+#define MPS_CYCLE_WORDS 8
+#else
+#define MPS_CYCLE_WORDS 1
+#endif
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -239,11 +246,18 @@ static void derive_scene(const mps_scene* sc, DevScene* d)
         d->s_brad[k] = bounding_radius(sc->s_shape[k], sc->s_hx[k], sc->s_hy[k]);
         d->s_mu[k] = sc->s_mu_contact[k];
     }
+    // The pair table is laid out in the solver's canonical order — colour r < B holds the body pairs with
+    // (i + j) mod B == r, colour B + k the pairs (i, static k), ascending i inside a colour — so the manifold
+    // list the detection compacts from it is already in solve order (rollout.cu: round scheduling).
     int P = 0;
-    for (int i = 0; i < B; ++i)
-        for (int j = i + 1; j < B; ++j) d->pairs[P++] = (uint16_t)(i | (j << 8));
-    for (int i = 0; i < B; ++i)
-        for (int k = 0; k < S; ++k) d->pairs[P++] = (uint16_t)(i | ((B + k) << 8));
+    for (int r = 0; r < B; ++r)
+        for (int i = 0; i < B; ++i) {
+            int j = r - i;
+            if (j < 0) j += B;
+            if (j > i) d->pairs[P++] = (uint16_t)(i | (j << 8));
+        }
+    for (int k = 0; k < S; ++k)
+        for (int i = 0; i < B; ++i) d->pairs[P++] = (uint16_t)(i | ((B + k) << 8));
     d->P = P;
 }
 
@@ -827,7 +841,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * (size_t)K))) return rc;
     if ((rc = ensure(ctx, ctx->d_record, record_bytes(B, L)))) return rc;
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
-    if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * (size_t)K))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * (size_t)K * MPS_CYCLE_WORDS))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
         MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
@@ -1006,7 +1020,7 @@ int mps_extend_chain_cycles(mps_ctx* ctx, int64_t* cycles)
 {
     if (!ctx || !cycles) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
     if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "no extend uploaded");
-    MPS_CUDA_CHECK(cudaMemcpyAsync(cycles, ctx->d_cycles.p, sizeof(long long) * (size_t)ctx->ext_K, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(cycles, ctx->d_cycles.p, sizeof(long long) * (size_t)ctx->ext_K * MPS_CYCLE_WORDS, cudaMemcpyDeviceToHost, ctx->stream), ctx);
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     return MPS_OK;
 }
@@ -1167,7 +1181,7 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     if ((rc = ensure(ctx, ctx->d_dist, sizeof(double) * KT))) return rc;
     if ((rc = ensure(ctx, ctx->d_nok, sizeof(int32_t) * KT))) return rc;
     if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * KT))) return rc;
-    if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * KT))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * KT * MPS_CYCLE_WORDS))) return rc;
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;

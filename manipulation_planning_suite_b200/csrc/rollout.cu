@@ -329,49 +329,57 @@ __device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpM
 }
 
 // collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
-__device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare)
+__device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare,
+                                               long long* t_mid = nullptr)
 {
     const int B = sc.B;
     const int Mcap = sc.Mcap;
     // ---- broad phase: lane = pair, bounding circles, survivors compacted into W.cand ------------
-    int ncand = 0;
-    for (int base = 0; base < sc.P; base += 32) {
-        int p = base + lane;
-        bool cand = false;
-        unsigned pr = 0;
-        if (p < sc.P) {
-            pr = sc.pairs[p];
-            int a = pr & 0xff, b = pr >> 8;
-            if (b < B) {
-                // bounding circles
-                float rr = sc.brad[a] + sc.brad[b];
-                float dx = W.px[b] - W.px[a];
-                float dy = W.py[b] - W.py[a];
-                cand = !(dx * dx + dy * dy > rr * rr);
-            } else {
-                // body circle against the static's own box / disc (walls are long: their bounding circle
-                // would make every body a candidate).  Conservative with a small margin; only a filter.
-                const int k = b - B;
-                float dx = W.px[a] - sc.s_x[k];
-                float dy = W.py[a] - sc.s_y[k];
-                float rr = sc.brad[a] * 1.001f + 1e-5f;
-                if (sc.s_shape[k] == MPS_SHAPE_BOX) {
-                    float lx = dx * sc.s_c[k] + dy * sc.s_s[k];
-                    float ly = dy * sc.s_c[k] - dx * sc.s_s[k];
-                    float ex = fmaxf(fabsf(lx) - sc.s_hx[k], 0.0f);
-                    float ey = fmaxf(fabsf(ly) - sc.s_hy[k], 0.0f);
-                    cand = !(ex * ex + ey * ey > rr * rr);
-                } else {
-                    rr += sc.s_hx[k];
-                    cand = !(dx * dx + dy * dy > rr * rr);
-                }
-            }
+    // two chunks of 32 pairs per trip so that their loads and tests overlap
+    auto pair_test = [&](int p, unsigned& pr) -> bool {
+        if (p >= sc.P) return false;
+        pr = sc.pairs[p];
+        const int a = pr & 0xff, b = pr >> 8;
+        if (b < B) {
+            // bounding circles
+            float rr = sc.brad[a] + sc.brad[b];
+            float dx = W.px[b] - W.px[a];
+            float dy = W.py[b] - W.py[a];
+            return !(dx * dx + dy * dy > rr * rr);
         }
-        unsigned cmask = __ballot_sync(FULL, cand);
-        if (cand) W.cand[ncand + __popc(cmask & ((1u << lane) - 1u))] = (uint16_t)pr;
-        ncand += __popc(cmask);
+        // body circle against the static's own box / disc (walls are long: their bounding circle
+        // would make every body a candidate).  Conservative with a small margin; only a filter.
+        const int k = b - B;
+        float dx = W.px[a] - sc.s_x[k];
+        float dy = W.py[a] - sc.s_y[k];
+        float rr = sc.brad[a] * 1.001f + 1e-5f;
+        if (sc.s_shape[k] == MPS_SHAPE_BOX) {
+            float lx = dx * sc.s_c[k] + dy * sc.s_s[k];
+            float ly = dy * sc.s_c[k] - dx * sc.s_s[k];
+            float ex = fmaxf(fabsf(lx) - sc.s_hx[k], 0.0f);
+            float ey = fmaxf(fabsf(ly) - sc.s_hy[k], 0.0f);
+            return !(ex * ex + ey * ey > rr * rr);
+        }
+        rr += sc.s_hx[k];
+        return !(dx * dx + dy * dy > rr * rr);
+    };
+    int ncand = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < sc.P; base += 64) {
+        unsigned pr0 = 0, pr1 = 0;
+        const bool c0 = pair_test(base + lane, pr0);
+        const bool c1 = pair_test(base + 32 + lane, pr1);
+        const unsigned m0 = __ballot_sync(FULL, c0);
+        const unsigned m1 = __ballot_sync(FULL, c1);
+        const int n0 = __popc(m0);
+        if (c0) W.cand[ncand + __popc(m0 & lt)] = (uint16_t)pr0;
+        if (c1) W.cand[ncand + n0 + __popc(m1 & lt)] = (uint16_t)pr1;
+        ncand += n0 + __popc(m1);
     }
     __syncwarp();
+#ifdef MPS_PHASE_PROF
+    if (t_mid) *t_mid = clock64();
+#endif
     // ---- narrow phase: lane = candidate, touching manifolds compacted into W.man ----------------
     int nm = 0;
     bool lane_bad = false, lane_over = false;
@@ -530,7 +538,17 @@ __device__ __forceinline__ void set_state(const WarpMem& W, Body& b, int lane, f
 
 struct StepStats {
     unsigned steps, candidates, touching, colour_passes;
+#ifdef MPS_PHASE_PROF
+    long long ph[6];  // broad phase, narrow phase, round scheduling, solver rounds, friction + integration, contact steps
+#endif
 };
+#ifdef MPS_PHASE_PROF
+#define PH_T(var) long long var = clock64()
+#define PH_ADD(i, a, b) st.ph[i] += (b) - (a)
+#else
+#define PH_T(var)
+#define PH_ADD(i, a, b)
+#endif
 
 // One pass of the Gauss-Seidel sweep: every lane that owns a body with a manifold scheduled in this pass
 // solves it (both owners of a body pair do, redundantly and identically; the partner's twist arrives by
@@ -661,7 +679,16 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
         bd.vy = uy;
         bd.w = uw;
     }
+    PH_T(t0);
+#ifdef MPS_PHASE_PROF
+    long long t_mid = t0;
+    DetectResult dr = detect(sc, W, lane, true, &t_mid);
+#else
     DetectResult dr = detect(sc, W, lane, true);
+#endif
+    PH_T(t1);
+    PH_ADD(0, t0, t_mid);
+    PH_ADD(1, t_mid, t1);
     bad = dr.bad;
     overflow = dr.overflow;
     max_pen = dr.max_pen;
@@ -695,36 +722,36 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             //     round(m) = 1 + max(last round of body a, last round of body b).
             // Any schedule that keeps the relative order of manifolds sharing a body produces the bits of
             // the canonical sweep; independent contacts (different islands) now solve concurrently.
-            // Each lane packs its <= 4 entries as round << 16 | static << 15 | partner << 8 | slot.
-            unsigned ent[4];
-            int last = 0;
-            {
-                unsigned long long cm = dr.colours;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    ent[c] = 0u;
-                    if (c < ncol) {
-                        const int col = __ffsll((long long)cm) - 1;
-                        cm &= cm - 1ull;
-                        const int slc = lookup_slot(sc, W, lane, col, dr.nm);
-                        const bool stc = col >= B;
-                        int j = lane;
-                        if (!stc && bd.live) {
-                            j = col - lane;
-                            if (j < 0) j += B;
-                        }
-                        int pl = __shfl_sync(FULL, last, j);
-                        if (stc) pl = 0;
-                        if (slc != 0xff) {
-                            last = (last > pl ? last : pl) + 1;
-                            ent[c] = ((unsigned)last << 16) | (stc ? 0x8000u : 0u) | ((unsigned)(stc ? lane : j) << 8) |
-                                     (unsigned)slc;
-                        }
-                    }
+            // Each lane packs its <= 4 entries (one per colour at most) as
+            // round << 16 | static << 15 | partner << 8 | slot.
+            unsigned ent[4] = {0u, 0u, 0u, 0u};
+            int last = 0, ne = 0;
+            // the manifold list is in canonical order (the pair table is): walk it once
+            for (int m = 0; m < dr.nm; ++m) {
+                const int meta = __float_as_int(W.man[m * MF_VEC4].x);
+                const int a = meta & 0xff, b = (meta >> 8) & 0xff;
+                const bool stc = b >= B;
+                int r = __shfl_sync(FULL, last, a);
+                if (!stc) {
+                    const int lb = __shfl_sync(FULL, last, b);
+                    r = r > lb ? r : lb;
+                }
+                r += 1;
+                if (lane == a || (!stc && lane == b)) {
+                    last = r;
+                    const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) |
+                                       ((unsigned)(stc ? lane : (lane == a ? b : a)) << 8) | (unsigned)m;
+                    if (ne == 0) ent[0] = e;
+                    else if (ne == 1) ent[1] = e;
+                    else if (ne == 2) ent[2] = e;
+                    else ent[3] = e;
+                    ++ne;
                 }
             }
             const int rounds = __reduce_max_sync(FULL, last);
             st.colour_passes += (unsigned)(rounds * sc.vel_iters);
+            PH_T(t2);
+            PH_ADD(2, t1, t2);
             for (int it = 0; it < sc.vel_iters; ++it) {
                 for (int r = 1; r <= rounds; ++r) {
                     unsigned e = 0u;
@@ -736,6 +763,11 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
                 }
             }
+            PH_T(t3);
+            PH_ADD(3, t2, t3);
+#ifdef MPS_PHASE_PROF
+            st.ph[5] += 1;
+#endif
         } else {
             // general case: walk the colour mask; slots looked up per pass
             st.colour_passes += (unsigned)(ncol * sc.vel_iters);
@@ -763,6 +795,8 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
         mps_sincos(bd.th, &bd.s, &bd.c);
     }
     publish_pose(W, bd, lane);
+    PH_T(t4);
+    PH_ADD(4, t1, t4);  // includes phases 2 and 3
 }
 
 __device__ __forceinline__ bool at_rest(const DevScene& sc, const Body& bd)
@@ -875,6 +909,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         int n = p.n_ctrl ? p.n_ctrl[k] : L;
         if (n > L) n = L;
         const long long t_begin = clock64();
+#ifdef MPS_PHASE_PROF
+        for (int i = 0; i < 6; ++i) st.ph[i] = 0;
+#endif
         // start state of the chain
         float sx = 0.0f, sy = 0.0f, sth = 0.0f;
         const float* dest = p.dest;
@@ -1066,7 +1103,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             p.out_dist[k] = dist;
             p.out_nok[k] = n_ok;
             p.out_goal_step[k] = goal_step;
+#ifdef MPS_PHASE_PROF
+            if (p.out_cycles) {
+                p.out_cycles[(size_t)k * 8] = clock64() - t_begin;
+                for (int i = 0; i < 6; ++i) p.out_cycles[(size_t)k * 8 + 1 + i] = st.ph[i];
+                p.out_cycles[(size_t)k * 8 + 7] = 0;
+            }
+#else
             if (p.out_cycles) p.out_cycles[k] = clock64() - t_begin;
+#endif
         }
     }
     // counters for the roofline accounting
