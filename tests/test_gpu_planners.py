@@ -214,3 +214,33 @@ def _check_solution_states_only(sc, goals, r):
         assert ok and np.array_equal(out, r.path_states[i])
         st = out
     assert _goal_satisfied(st, goals)
+
+
+# ---------------------------------------------------------------------------------------------------
+# DataGenerator (pushing/oracle/DataGenerator.cpp:56-116): one batched launch per file
+# ---------------------------------------------------------------------------------------------------
+def test_data_generator_triplets_replay_on_the_oracle(tmp_path):
+    from manipulation_planning_suite_b200 import data_generator as dg
+    sc, _ = scenes.make_scene(1, seed=4)          # robot + one object, as the reference's generator worlds
+    gen = dg.DataGenerator(sc, object_id=1, seed=11)
+    f = tmp_path / "train.csv"
+    info = gen.generate_data(str(f), 96, annotation="0.35, 0.19")
+    assert info["propagations"] == 96 and 0 < info["lines"] <= 96
+    assert info["launches"] <= 30, "state validation and propagation must be batched (rejection rounds + 1 extend)"
+    s, r, c, notes = dg.read_triplets(str(f), sc.n_bodies)
+    assert len(s) == info["lines"] and notes[0] == "0.35, 0.19"
+    moved = 0
+    for i in range(len(s)):
+        assert np.all(s[i, 0:3] == 0.0)                                       # robot at the origin (:203-206)
+        assert np.hypot(s[i, 3], s[i, 4]) < gen.max_distance                  # object within reach (:216-217)
+        ok, out, cc, _, _ = ob.propagate(sc, s[i], c[i])
+        assert ok and np.array_equal(out, r[i]) and cc[4] == c[i, 4]
+        moved += int(np.abs(r[i, 3:6] - s[i, 3:6]).max() > 1e-5)
+    assert moved >= 3, "no sampled push moved the object: weak test"
+    # state + dynamics noise: per-sample worlds, same file format
+    noisy = dg.DataGenerator(sc, 1, dg.Parameters(0.005, 0.05, 0.05, 0.02), seed=12)
+    info2 = noisy.generate_data(str(f), 8, deterministic=False, num_noise_samples=3)
+    s2, r2, c2, _ = dg.read_triplets(str(f), sc.n_bodies)
+    assert info2["propagations"] <= 24 and len(s2) == info2["lines"] > 0
+    gen.close()
+    noisy.close()

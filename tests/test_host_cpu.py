@@ -69,3 +69,22 @@ def test_solution_file_roundtrip_is_lossless(tmp_path):
     assert sol.stats["num_state_propagations"] == 170 and sol.stats["success"] == 1
     with pytest.raises(ValueError):
         solution_io.load_solution(str(p), n_objects=5)
+
+
+def test_data_triplet_csv_round_trip(tmp_path):
+    """OracleDataDumper format (util/Serialize.cpp:73-119): state, result, control[, annotation] per line."""
+    from manipulation_planning_suite_b200 import data_generator as dg
+    rng = np.random.RandomState(3)
+    B = 3
+    starts = rng.uniform(-1, 1, size=(7, 3 * B)).astype(np.float32)
+    results = rng.uniform(-1, 1, size=(7, 3 * B)).astype(np.float32)
+    controls = rng.uniform(-1, 1, size=(7, 5)).astype(np.float32)
+    f = tmp_path / "data.csv"
+    dg.write_triplets(str(f), starts, results, controls, annotation="box, 0.35")
+    lines = f.read_text().splitlines()
+    assert len(lines) == 7 and all(len(ln.split(", ")) == 2 * 3 * B + 5 + 2 for ln in lines)
+    s, r, c, notes = dg.read_triplets(str(f), B)
+    assert np.array_equal(s, starts) and np.array_equal(r, results) and np.array_equal(c, controls)
+    assert notes == ["box, 0.35"] * 7
+    dg.write_triplets(str(f), starts[:2], results[:2], controls[:2])   # no annotation: no trailing field
+    assert len(f.read_text().splitlines()[0].split(", ")) == 2 * 3 * B + 5
