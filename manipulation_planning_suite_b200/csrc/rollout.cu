@@ -288,6 +288,27 @@ struct WarpMem {
     uint16_t* cand;   // [P] broad-phase survivors of the current step
 };
 
+// State a chain carries from one physics step to the next (registers).
+//  * Candidate list with a skin: the broad phase keeps every pair within reach + MPS_SKIN and is rebuilt only
+//    when a body has moved more than MPS_SKIN_MOVE from where it was at the last rebuild (bounding circles do
+//    not care about rotation).  Each step re-applies the exact reach test to the listed pairs, so the pairs that
+//    enter the narrow phase are the same as with a fresh broad phase.
+//  * Round schedule of the solver, reused while the list of touching pairs is unchanged.
+#define MPS_SKIN 0.04f
+#define MPS_SKIN_MOVE2 (0.018f * 0.018f) /* (0.45 * MPS_SKIN)^2: two bodies together stay below the skin */
+struct StepCache {
+    float rx, ry;  // this lane's body position at the last rebuild
+    int n_list;    // pairs in W.cand, < 0: none
+    unsigned ent[4];
+    int rounds, nm;       // nm < 0: no schedule
+    unsigned sig0, sig1;  // pair of manifold slot `lane` / `lane + 32` the schedule was built for
+    __device__ __forceinline__ void reset()
+    {
+        n_list = -1;
+        nm = -1;
+    }
+};
+
 struct DetectResult {
     bool bad;       // a touching pair the policy forbids
     bool overflow;  // more touching pairs than Mcap
@@ -330,19 +351,18 @@ __device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpM
 
 // collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
 __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare,
-                                               long long* t_mid = nullptr)
+                                               StepCache& cache, long long* t_mid = nullptr)
 {
     const int B = sc.B;
     const int Mcap = sc.Mcap;
     // ---- broad phase: lane = pair, bounding circles, survivors compacted into W.cand ------------
-    // two chunks of 32 pairs per trip so that their loads and tests overlap
-    auto pair_test = [&](int p, unsigned& pr) -> bool {
-        if (p >= sc.P) return false;
-        pr = sc.pairs[p];
+    // reach test of one pair; skin = 0 is the exact test of the physics spec
+    auto pair_near = [&](unsigned pr, float skin) -> bool {
         const int a = pr & 0xff, b = pr >> 8;
         if (b < B) {
             // bounding circles
             float rr = sc.brad[a] + sc.brad[b];
+            rr = rr + skin;
             float dx = W.px[b] - W.px[a];
             float dy = W.py[b] - W.py[a];
             return !(dx * dx + dy * dy > rr * rr);
@@ -354,6 +374,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         float dy = W.py[a] - sc.s_y[k];
         float rr = sc.brad[a] * 1.001f + 1e-5f;
         if (sc.s_shape[k] == MPS_SHAPE_BOX) {
+            rr = rr + skin;
             float lx = dx * sc.s_c[k] + dy * sc.s_s[k];
             float ly = dy * sc.s_c[k] - dx * sc.s_s[k];
             float ex = fmaxf(fabsf(lx) - sc.s_hx[k], 0.0f);
@@ -361,39 +382,73 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             return !(ex * ex + ey * ey > rr * rr);
         }
         rr += sc.s_hx[k];
+        rr = rr + skin;
         return !(dx * dx + dy * dy > rr * rr);
     };
-    int ncand = 0;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < sc.P; base += 64) {
-        unsigned pr0 = 0, pr1 = 0;
-        const bool c0 = pair_test(base + lane, pr0);
-        const bool c1 = pair_test(base + 32 + lane, pr1);
-        const unsigned m0 = __ballot_sync(FULL, c0);
-        const unsigned m1 = __ballot_sync(FULL, c1);
-        const int n0 = __popc(m0);
-        if (c0) W.cand[ncand + __popc(m0 & lt)] = (uint16_t)pr0;
-        if (c1) W.cand[ncand + n0 + __popc(m1 & lt)] = (uint16_t)pr1;
-        ncand += n0 + __popc(m1);
+    bool rebuild = cache.n_list < 0;
+    if (!rebuild) {
+        bool moved = false;
+        if (lane < B) {
+            float dx = W.px[lane] - cache.rx;
+            float dy = W.py[lane] - cache.ry;
+            moved = dx * dx + dy * dy > MPS_SKIN_MOVE2;
+        }
+        rebuild = __any_sync(FULL, moved);
     }
-    __syncwarp();
+    if (rebuild) {
+        // two chunks of 32 pairs per trip so that their loads and tests overlap
+        int nl = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int base = 0; base < sc.P; base += 64) {
+            const int p0 = base + lane, p1 = base + 32 + lane;
+            unsigned pr0 = 0, pr1 = 0;
+            bool c0 = false, c1 = false;
+            if (p0 < sc.P) {
+                pr0 = sc.pairs[p0];
+                c0 = pair_near(pr0, MPS_SKIN);
+            }
+            if (p1 < sc.P) {
+                pr1 = sc.pairs[p1];
+                c1 = pair_near(pr1, MPS_SKIN);
+            }
+            const unsigned m0 = __ballot_sync(FULL, c0);
+            const unsigned m1 = __ballot_sync(FULL, c1);
+            const int n0 = __popc(m0);
+            if (c0) W.cand[nl + __popc(m0 & lt)] = (uint16_t)pr0;
+            if (c1) W.cand[nl + n0 + __popc(m1 & lt)] = (uint16_t)pr1;
+            nl += n0 + __popc(m1);
+        }
+        cache.n_list = nl;
+        if (lane < B) {
+            cache.rx = W.px[lane];
+            cache.ry = W.py[lane];
+        }
+        __syncwarp();
+    }
+    const int nlist = cache.n_list;
+    int ncand = 0;
 #ifdef MPS_PHASE_PROF
     if (t_mid) *t_mid = clock64();
 #endif
-    // ---- narrow phase: lane = candidate, touching manifolds compacted into W.man ----------------
+    // ---- narrow phase: lane = listed pair; pairs out of exact reach drop out first ----------------
     int nm = 0;
     bool lane_bad = false, lane_over = false;
     float lane_pen = 0.0f;
     unsigned long long lane_col = 0ull;
     unsigned n_touch = 0;
-    for (int base = 0; base < ncand; base += 32) {
+    for (int base = 0; base < nlist; base += 32) {
         int c = base + lane;
         Manifold m;
         int cnt = 0, a = 0, b = 0;
-        if (c < ncand) {
+        bool near = false;
+        if (c < nlist) {
             unsigned pr = W.cand[c];
             a = pr & 0xff;
             b = pr >> 8;
+            near = pair_near(pr, 0.0f);
+        }
+        ncand += __popc(__ballot_sync(FULL, near));
+        if (near) {
             Shape A, Bs;
             load_pair_shapes(sc, W, a, b, A, Bs);
             cnt = collide(A, Bs, sc.ref_tol, m);
@@ -554,7 +609,8 @@ struct StepStats {
 // solves it (both owners of a body pair do, redundantly and identically; the partner's twist arrives by
 // shuffle).  Per lane: sl = manifold slot or 0xff, j = partner lane (self when none or static),
 // stat = the partner is a static.
-__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat)
+__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat,
+                                           bool solo = false)
 {
     float ovx = __shfl_sync(FULL, bd.vx, j);
     float ovy = __shfl_sync(FULL, bd.vy, j);
@@ -660,10 +716,11 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane,
         }
         if (is_a) {
             bd.vx = vax; bd.vy = vay; bd.w = wa;
-            mf[8] = acc;
         } else {
             bd.vx = vbx; bd.vy = vby; bd.w = wb;
         }
+        // the accumulated impulses are written by body a's lane, or by the only lane there is
+        if (is_a || solo) mf[8] = acc;
     }
     __syncwarp();
 }
@@ -671,7 +728,7 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane,
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, int lane, float ux,
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
-                                             StepStats& st)
+                                             StepStats& st, StepCache& cache)
 {
     const int B = sc.B;
     if (lane == sc.robot) {
@@ -682,9 +739,9 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     PH_T(t0);
 #ifdef MPS_PHASE_PROF
     long long t_mid = t0;
-    DetectResult dr = detect(sc, W, lane, true, &t_mid);
+    DetectResult dr = detect(sc, W, lane, true, cache, &t_mid);
 #else
-    DetectResult dr = detect(sc, W, lane, true);
+    DetectResult dr = detect(sc, W, lane, true, cache);
 #endif
     PH_T(t1);
     PH_ADD(0, t0, t_mid);
@@ -723,32 +780,55 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             // Any schedule that keeps the relative order of manifolds sharing a body produces the bits of
             // the canonical sweep; independent contacts (different islands) now solve concurrently.
             // Each lane packs its <= 4 entries (one per colour at most) as
-            // round << 16 | static << 15 | partner << 8 | slot.
-            unsigned ent[4] = {0u, 0u, 0u, 0u};
-            int last = 0, ne = 0;
-            // the manifold list is in canonical order (the pair table is): walk it once
-            for (int m = 0; m < dr.nm; ++m) {
-                const int meta = __float_as_int(W.man[m * MF_VEC4].x);
-                const int a = meta & 0xff, b = (meta >> 8) & 0xff;
-                const bool stc = b >= B;
-                int r = __shfl_sync(FULL, last, a);
-                if (!stc) {
-                    const int lb = __shfl_sync(FULL, last, b);
-                    r = r > lb ? r : lb;
+            // round << 16 | static << 15 | solo << 14 | partner << 8 | slot.
+            // The schedule depends only on which pair sits in which manifold slot: reuse the last one while
+            // that list is unchanged (contact sets persist over many steps).
+            const unsigned sig0 =
+                lane < dr.nm ? (unsigned)(__float_as_int(W.man[lane * MF_VEC4].x) & 0xffff) : 0xffffffffu;
+            const unsigned sig1 =
+                lane + 32 < dr.nm ? (unsigned)(__float_as_int(W.man[(lane + 32) * MF_VEC4].x) & 0xffff) : 0xffffffffu;
+            const bool same = __all_sync(FULL, cache.nm == dr.nm && sig0 == cache.sig0 && sig1 == cache.sig1);
+            if (!same) {
+                unsigned e0 = 0u, e1 = 0u, e2 = 0u, e3 = 0u;
+                int last = 0, ne = 0;
+                // the manifold list is in canonical order (the pair table is): walk it once
+                for (int m = 0; m < dr.nm; ++m) {
+                    const int meta = __float_as_int(W.man[m * MF_VEC4].x);
+                    const int a = meta & 0xff, b = (meta >> 8) & 0xff;
+                    const bool stc = b >= B;
+                    // the robot is kinematic: its twist is only read, so manifolds that share nothing but the
+                    // robot commute and the robot neither waits nor is waited for
+                    const bool dyn_a = a != sc.robot;
+                    const bool dyn_b = !stc && b != sc.robot;
+                    int r = 0;
+                    if (dyn_a) r = __shfl_sync(FULL, last, a);
+                    if (dyn_b) {
+                        const int lb = __shfl_sync(FULL, last, b);
+                        r = r > lb ? r : lb;
+                    }
+                    r += 1;
+                    if ((dyn_a && lane == a) || (dyn_b && lane == b)) {
+                        last = r;
+                        const bool solo = !(dyn_a && dyn_b);  // the only lane that solves this manifold
+                        const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) | (solo ? 0x4000u : 0u) |
+                                           ((unsigned)(stc ? lane : (lane == a ? b : a)) << 8) | (unsigned)m;
+                        e3 = ne == 3 ? e : e3;
+                        e2 = ne == 2 ? e : e2;
+                        e1 = ne == 1 ? e : e1;
+                        e0 = ne == 0 ? e : e0;
+                        ++ne;
+                    }
                 }
-                r += 1;
-                if (lane == a || (!stc && lane == b)) {
-                    last = r;
-                    const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) |
-                                       ((unsigned)(stc ? lane : (lane == a ? b : a)) << 8) | (unsigned)m;
-                    if (ne == 0) ent[0] = e;
-                    else if (ne == 1) ent[1] = e;
-                    else if (ne == 2) ent[2] = e;
-                    else ent[3] = e;
-                    ++ne;
-                }
+                cache.ent[0] = e0;
+                cache.ent[1] = e1;
+                cache.ent[2] = e2;
+                cache.ent[3] = e3;
+                cache.rounds = __reduce_max_sync(FULL, last);
+                cache.nm = dr.nm;
+                cache.sig0 = sig0;
+                cache.sig1 = sig1;
             }
-            const int rounds = __reduce_max_sync(FULL, last);
+            const int rounds = cache.rounds;
             st.colour_passes += (unsigned)(rounds * sc.vel_iters);
             PH_T(t2);
             PH_ADD(2, t1, t2);
@@ -757,10 +837,10 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     unsigned e = 0u;
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        if ((int)(ent[c] >> 16) == r) e = ent[c];
+                        if ((int)(cache.ent[c] >> 16) == r) e = cache.ent[c];
                     const int slr = e ? (int)(e & 0xffu) : 0xff;
-                    const int jr = e ? (int)((e >> 8) & 0x7fu) : lane;
-                    solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
+                    const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
+                    solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u, (e & 0x4000u) != 0u);
                 }
             }
             PH_T(t3);
@@ -818,12 +898,13 @@ __device__ __forceinline__ bool body_in_bounds(const DevScene& sc, float xf, flo
 
 // isValid(state) with the state already in the lanes (sx, sy, sth = the float state values)
 __device__ __forceinline__ uint32_t state_validity_flags(const DevScene& sc, const WarpMem& W, Body& bd, int lane,
-                                                         float sx, float sy, float sth, StepStats* st)
+                                                         float sx, float sy, float sth, StepStats* st,
+                                                         StepCache& cache)
 {
     bool oob = bd.live && !body_in_bounds(sc, sx, sy, sth);
     if (__any_sync(FULL, oob)) return MPS_F_BOUNDS;
     set_state(W, bd, lane, sx, sy, sth);
-    DetectResult dr = detect(sc, W, lane, false);
+    DetectResult dr = detect(sc, W, lane, false, cache);
     (void)st;
     uint32_t f = 0;
     if (dr.max_pen > sc.pen_max) f |= MPS_F_INFEASIBLE;
@@ -899,6 +980,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     bd.vx = bd.vy = bd.w = 0.0f;
 
     StepStats st = {0u, 0u, 0u, 0u};
+    StepCache cache;
+    cache.reset();
     const int L = p.L;
 
     for (;;) {
@@ -909,6 +992,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         int n = p.n_ctrl ? p.n_ctrl[k] : L;
         if (n > L) n = L;
         const long long t_begin = clock64();
+        cache.reset();
 #ifdef MPS_PHASE_PROF
         for (int i = 0; i < 6; ++i) st.ph[i] = 0;
 #endif
@@ -987,7 +1071,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 }
                 bool bad, over;
                 float pen;
-                physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, pen, st);
+                physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, pen, st, cache);
                 time += sc.dt;
                 if (over) {
                     flags |= MPS_F_OVERFLOW;
@@ -1006,7 +1090,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 while (rest <= sc.t_max && !resting && ok) {
                     bool bad, over;
                     float pen;
-                    physics_step(sc, W, bd, lane, 0.0f, 0.0f, 0.0f, bad, over, pen, st);
+                    physics_step(sc, W, bd, lane, 0.0f, 0.0f, 0.0f, bad, over, pen, st, cache);
                     ok = !bad;
                     rest += sc.dt;
                     if (bad) flags |= MPS_F_REST_CONTACT;
@@ -1028,7 +1112,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             // extractState: theta normalised in double, read back as float
             float rx = bd.x, ry = bd.y;
             float rth = (float)mps_normalize_orientation((double)bd.th);
-            uint32_t vf = state_validity_flags(sc, W, bd, lane, rx, ry, rth, &st);
+            uint32_t vf = state_validity_flags(sc, W, bd, lane, rx, ry, rth, &st, cache);
             flags |= vf;
             ok = ok && vf == 0u;
             if (ok) {
@@ -1282,7 +1366,9 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
             sy = p.states[(size_t)i * 3 * B + 3 * lane + 1];
             sth = p.states[(size_t)i * 3 * B + 3 * lane + 2];
         }
-        uint32_t f = state_validity_flags(sc, W, bd, lane, sx, sy, sth, nullptr);
+        StepCache cache;
+        cache.reset();
+        uint32_t f = state_validity_flags(sc, W, bd, lane, sx, sy, sth, nullptr, cache);
         if (lane == 0) {
             p.flags[i] = f;
             p.valid[i] = f == 0u ? 1 : 0;
