@@ -37,9 +37,8 @@ namespace {
 //   [3 + 3k] ia*rna, ib*rnb, ia*rta, ib*rtb
 //   [4 + 3k] normal mass, tangent mass, bias, -
 //   [8] acc_n0, acc_t0, acc_n1, acc_t1   (accumulated impulses)
-#define MF_VEC4 9
+#define MF_VEC4 8
 #define MF_FIELDS (4 * MF_VEC4)
-#define MF_HAS_BIAS (1 << 24)
 
 struct Shape {
     int shape;
@@ -480,29 +479,51 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                     } else {
                         mub = sc.s_mu[b - B];
                     }
-                    mf[1] = make_float4(ma * m.nx, ma * m.ny, mb * m.nx, mb * m.ny);
+                    // rows of the manifold (layout: 0 meta|n|friction, 1 / 3 lever arms of point 0 / 1,
+                    // 2 / 4 inverse effective masses, bias term and the t-t / n-n coupling, 5 t-n couplings,
+                    // 6 / 7 accumulated impulses, one private copy per owner lane); the rows of a missing
+                    // second point are all zero and run through the same arithmetic
                     float tx = m.ny, ty = -m.nx;
+                    float iarna[2] = {0.0f, 0.0f}, ibrnb[2] = {0.0f, 0.0f}, iarta[2] = {0.0f, 0.0f}, ibrtb[2] = {0.0f, 0.0f};
+                    float rna[2] = {0.0f, 0.0f}, rnb[2] = {0.0f, 0.0f}, rta[2] = {0.0f, 0.0f}, rtb[2] = {0.0f, 0.0f};
+                    float nmass[2] = {0.0f, 0.0f}, tmass[2] = {0.0f, 0.0f}, kb[2] = {0.0f, 0.0f};
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         if (k < cnt) {
                             float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
-                            float rna = rax * m.ny - ray * m.nx;
-                            float rnb = rbx * m.ny - rby * m.nx;
-                            float rta = rax * ty - ray * tx;
-                            float rtb = rbx * ty - rby * tx;
-                            float iarna = ia * rna, ibrnb = ib * rnb, iarta = ia * rta, ibrtb = ib * rtb;
-                            float kn = ((ma + mb) + iarna * rna) + ibrnb * rnb;
-                            float kt = ((ma + mb) + iarta * rta) + ibrtb * rtb;
+                            rna[k] = rax * m.ny - ray * m.nx;
+                            rnb[k] = rbx * m.ny - rby * m.nx;
+                            rta[k] = rax * ty - ray * tx;
+                            rtb[k] = rbx * ty - rby * tx;
+                            iarna[k] = ia * rna[k];
+                            ibrnb[k] = ib * rnb[k];
+                            iarta[k] = ia * rta[k];
+                            ibrtb[k] = ib * rtb[k];
+                            float kn = ((ma + mb) + iarna[k] * rna[k]) + ibrnb[k] * rnb[k];
+                            float kt = ((ma + mb) + iarta[k] * rta[k]) + ibrtb[k] * rtb[k];
                             float pen_k = -m.sep[k] - sc.slop;
                             float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
-                            if (bias != 0.0f) meta |= MF_HAS_BIAS;
-                            mf[2 + 3 * k] = make_float4(rna, rnb, rta, rtb);
-                            mf[3 + 3 * k] = make_float4(iarna, ibrnb, iarta, ibrtb);
-                            mf[4 + 3 * k] = make_float4(kn > 0.0f ? 1.0f / kn : 0.0f, kt > 0.0f ? 1.0f / kt : 0.0f, bias,
-                                                        0.0f);
+                            nmass[k] = kn > 0.0f ? 1.0f / kn : 0.0f;
+                            tmass[k] = kt > 0.0f ? 1.0f / kt : 0.0f;
+                            kb[k] = nmass[k] * bias;
                         }
                     }
-                    mf[8] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    float ktt = 0.0f, knn = 0.0f, ktn01 = 0.0f, ktn10 = 0.0f, ktn11 = 0.0f;
+                    const float ktn00 = iarta[0] * rna[0] + ibrtb[0] * rnb[0];
+                    if (cnt > 1) {
+                        ktt = ((ma + mb) + iarta[0] * rta[1]) + ibrtb[0] * rtb[1];
+                        knn = ((ma + mb) + iarna[0] * rna[1]) + ibrnb[0] * rnb[1];
+                        ktn01 = iarta[0] * rna[1] + ibrtb[0] * rnb[1];
+                        ktn10 = iarta[1] * rna[0] + ibrtb[1] * rnb[0];
+                        ktn11 = iarta[1] * rna[1] + ibrtb[1] * rnb[1];
+                    }
+                    mf[1] = make_float4(rna[0], rnb[0], rta[0], rtb[0]);
+                    mf[2] = make_float4(nmass[0], tmass[0], kb[0], ktt);
+                    mf[3] = make_float4(rna[1], rnb[1], rta[1], rtb[1]);
+                    mf[4] = make_float4(nmass[1], tmass[1], kb[1], knn);
+                    mf[5] = make_float4(ktn00, ktn01, ktn10, ktn11);
+                    mf[6] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    mf[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, sqrtf(sc.mu_c[a] * mub));
                     W.slot[a * sc.slot_stride + b] = (uint8_t)idx;
                     int col;
@@ -607,122 +628,85 @@ struct StepStats {
 
 // One pass of the Gauss-Seidel sweep: every lane that owns a body with a manifold scheduled in this pass
 // solves it (both owners of a body pair do, redundantly and identically; the partner's twist arrives by
-// shuffle).  Per lane: sl = manifold slot or 0xff, j = partner lane (self when none or static),
-// stat = the partner is a static.
-__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat,
-                                           bool solo = false)
+// shuffle) and updates its own body.  Per lane: sl = manifold slot or 0xff, j = partner lane (self when none
+// or static), stat = the partner is a static.
+// The pass has no data-dependent branch and no barrier: lanes without a manifold run the arithmetic on slot 0
+// and drop the result, a one-point manifold carries zero rows for the second point, and each owner lane keeps
+// its own copy of the accumulated impulses, so no lane reads what another lane writes during the sweep.
+__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat)
 {
     float ovx = __shfl_sync(FULL, bd.vx, j);
     float ovy = __shfl_sync(FULL, bd.vy, j);
     float ow_ = __shfl_sync(FULL, bd.w, j);
+    const bool act = sl != 0xff;
+    const bool is_a = stat || lane < j;
+    float4* mf = W.man + (act ? sl : 0) * MF_VEC4;
+    const float4 m0 = mf[0], r0 = mf[1], g0 = mf[2], r1 = mf[3], g1 = mf[4], kc = mf[5];
+    float4* accp = mf + (is_a ? 6 : 7);
+    float4 acc = *accp;
     if (stat) {
         ovx = 0.0f;
         ovy = 0.0f;
         ow_ = 0.0f;
     }
-    const bool act = sl != 0xff;
-    const unsigned amask = __ballot_sync(FULL, act);
-    if (act) {
-        const bool is_a = stat || lane < j;
-        float4* mf = W.man + sl * MF_VEC4;
-        // everything the pass reads is loaded before anything is written back: the two owner lanes of a
-        // pair must see the same accumulated impulses
-        const float4 m0 = mf[0];
-        const float4 mm = mf[1];
-        const int cnt = (__float_as_int(m0.x) >> 16) & 0xff;
-        const float4 r0 = mf[2], i0 = mf[3], k0 = mf[4];
-        float4 r1 = r0, i1 = i0, k1 = k0;
-        if (cnt > 1) {
-            r1 = mf[5];
-            i1 = mf[6];
-            k1 = mf[7];
-        }
-        float4 acc = mf[8];
-        __syncwarp(amask);
-        const float nx = m0.y, ny = m0.z, fr = m0.w;
-        const float tx = ny, ty = -nx;
-        const float manx = mm.x, many = mm.y, mbnx = mm.z, mbny = mm.w;
-        float vax, vay, wa, vbx, vby, wb;
-        if (is_a) {
-            vax = bd.vx; vay = bd.vy; wa = bd.w;
-            vbx = ovx; vby = ovy; wb = ow_;  // zero for a static partner
-        } else {
-            vax = ovx; vay = ovy; wa = ow_;
-            vbx = bd.vx; vby = bd.vy; wb = bd.w;
-        }
-        // friction first (Box2D order), point 0 then point 1
-        {
-            float dvx = vbx - vax;
-            float dvy = vby - vay;
-            float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r0.w, -(wa * r0.z))));
-            float lambda = k0.y * -vt;
-            float max_f = fr * acc.x;
-            float new_imp = fminf(fmaxf(acc.y + lambda, -max_f), max_f);
-            lambda = new_imp - acc.y;
-            acc.y = new_imp;
-            vax = fmaf(-many, lambda, vax);
-            vay = fmaf(manx, lambda, vay);
-            wa = fmaf(-i0.z, lambda, wa);
-            vbx = fmaf(mbny, lambda, vbx);
-            vby = fmaf(-mbnx, lambda, vby);
-            wb = fmaf(i0.w, lambda, wb);
-        }
-        if (cnt > 1) {
-            float dvx = vbx - vax;
-            float dvy = vby - vay;
-            float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
-            float lambda = k1.y * -vt;
-            float max_f = fr * acc.z;
-            float new_imp = fminf(fmaxf(acc.w + lambda, -max_f), max_f);
-            lambda = new_imp - acc.w;
-            acc.w = new_imp;
-            vax = fmaf(-many, lambda, vax);
-            vay = fmaf(manx, lambda, vay);
-            wa = fmaf(-i1.z, lambda, wa);
-            vbx = fmaf(mbny, lambda, vbx);
-            vby = fmaf(-mbnx, lambda, vby);
-            wb = fmaf(i1.w, lambda, wb);
-        }
-        // then non-penetration
-        {
-            float dvx = vbx - vax;
-            float dvy = vby - vay;
-            float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r0.y, -(wa * r0.x))));
-            float lambda = k0.x * (k0.z - vn);
-            float new_imp = fmaxf(acc.x + lambda, 0.0f);
-            lambda = new_imp - acc.x;
-            acc.x = new_imp;
-            vax = fmaf(-manx, lambda, vax);
-            vay = fmaf(-many, lambda, vay);
-            wa = fmaf(-i0.x, lambda, wa);
-            vbx = fmaf(mbnx, lambda, vbx);
-            vby = fmaf(mbny, lambda, vby);
-            wb = fmaf(i0.y, lambda, wb);
-        }
-        if (cnt > 1) {
-            float dvx = vbx - vax;
-            float dvy = vby - vay;
-            float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
-            float lambda = k1.x * (k1.z - vn);
-            float new_imp = fmaxf(acc.z + lambda, 0.0f);
-            lambda = new_imp - acc.z;
-            acc.z = new_imp;
-            vax = fmaf(-manx, lambda, vax);
-            vay = fmaf(-many, lambda, vay);
-            wa = fmaf(-i1.x, lambda, wa);
-            vbx = fmaf(mbnx, lambda, vbx);
-            vby = fmaf(mbny, lambda, vby);
-            wb = fmaf(i1.y, lambda, wb);
-        }
-        if (is_a) {
-            bd.vx = vax; bd.vy = vay; bd.w = wa;
-        } else {
-            bd.vx = vbx; bd.vy = vby; bd.w = wb;
-        }
-        // the accumulated impulses are written by body a's lane, or by the only lane there is
-        if (is_a || solo) mf[8] = acc;
+    const float nx = m0.y, ny = m0.z, fr = m0.w;
+    const float tx = ny, ty = -nx;
+    // lever arms of this lane's own body
+    const float on0 = is_a ? r0.x : r0.y, ot0 = is_a ? r0.z : r0.w;
+    const float on1 = is_a ? r1.x : r1.y, ot1 = is_a ? r1.z : r1.w;
+    const float sm = is_a ? -bd.inv_m : bd.inv_m;
+    const float si = is_a ? -bd.inv_i : bd.inv_i;
+    const float vax = is_a ? bd.vx : ovx, vay = is_a ? bd.vy : ovy, wa = is_a ? bd.w : ow_;
+    const float vbx = is_a ? ovx : bd.vx, vby = is_a ? ovy : bd.vy, wb = is_a ? ow_ : bd.w;
+    // relative velocity along every row, from the twists at the start of the visit
+    const float dvx = vbx - vax;
+    const float dvy = vby - vay;
+    const float ut0 = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r0.w, -(wa * r0.z))));
+    const float ut1 = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
+    const float un0 = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r0.y, -(wa * r0.x))));
+    const float un1 = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
+    // friction first (Box2D order), point 0 then point 1, then non-penetration; an impulse on an earlier
+    // row reaches a later row through the coupling coefficient
+    float dt0, dt1, dn0, dn1;
+    {
+        const float lim = fr * acc.x;
+        const float dl = g0.y * -ut0;
+        dt0 = fminf(fmaxf(dl, -lim - acc.y), lim - acc.y);
+        acc.y = acc.y + dt0;
     }
-    __syncwarp();
+    {
+        const float u = fmaf(g0.w, dt0, ut1);
+        const float lim = fr * acc.z;
+        const float dl = g1.y * -u;
+        dt1 = fminf(fmaxf(dl, -lim - acc.w), lim - acc.w);
+        acc.w = acc.w + dt1;
+    }
+    {
+        const float u = fmaf(kc.z, dt1, fmaf(kc.x, dt0, un0));
+        const float dl = fmaf(-g0.x, u, g0.z);
+        dn0 = fmaxf(dl, -acc.x);
+        acc.x = acc.x + dn0;
+    }
+    {
+        const float u = fmaf(g1.w, dn0, fmaf(kc.w, dt1, fmaf(kc.y, dt0, un1)));
+        const float dl = fmaf(-g1.x, u, g1.z);
+        dn1 = fmaxf(dl, -acc.z);
+        acc.z = acc.z + dn1;
+    }
+    // total impulse on b (a receives the opposite); each lane updates its own body only
+    const float st = dt0 + dt1;
+    const float rr = fmaf(on1, dn1, fmaf(ot1, dt1, fmaf(on0, dn0, ot0 * dt0)));
+    const float px = fmaf(nx, dn1, fmaf(nx, dn0, tx * st));
+    const float py = fmaf(ny, dn1, fmaf(ny, dn0, ty * st));
+    const float nvx = fmaf(sm, px, bd.vx);
+    const float nvy = fmaf(sm, py, bd.vy);
+    const float nw = fmaf(si, rr, bd.w);
+    if (act) {
+        bd.vx = nvx;
+        bd.vy = nvy;
+        bd.w = nw;
+        *accp = acc;
+    }
 }
 
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
@@ -780,7 +764,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             // Any schedule that keeps the relative order of manifolds sharing a body produces the bits of
             // the canonical sweep; independent contacts (different islands) now solve concurrently.
             // Each lane packs its <= 4 entries (one per colour at most) as
-            // round << 16 | static << 15 | solo << 14 | partner << 8 | slot.
+            // round << 16 | static << 15 | partner << 8 | slot.
             // The schedule depends only on which pair sits in which manifold slot: reuse the last one while
             // that list is unchanged (contact sets persist over many steps).
             const unsigned sig0 =
@@ -809,8 +793,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     r += 1;
                     if ((dyn_a && lane == a) || (dyn_b && lane == b)) {
                         last = r;
-                        const bool solo = !(dyn_a && dyn_b);  // the only lane that solves this manifold
-                        const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) | (solo ? 0x4000u : 0u) |
+                        const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) |
                                            ((unsigned)(stc ? lane : (lane == a ? b : a)) << 8) | (unsigned)m;
                         e3 = ne == 3 ? e : e3;
                         e2 = ne == 2 ? e : e2;
@@ -832,7 +815,8 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             st.colour_passes += (unsigned)(rounds * sc.vel_iters);
             PH_T(t2);
             PH_ADD(2, t1, t2);
-            for (int it = 0; it < sc.vel_iters; ++it) {
+            const int iters = sc.vel_iters;
+            for (int it = 0; it < iters; ++it) {
                 for (int r = 1; r <= rounds; ++r) {
                     unsigned e = 0u;
 #pragma unroll
@@ -840,7 +824,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                         if ((int)(cache.ent[c] >> 16) == r) e = cache.ent[c];
                     const int slr = e ? (int)(e & 0xffu) : 0xff;
                     const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
-                    solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u, (e & 0x4000u) != 0u);
+                    solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
                 }
             }
             PH_T(t3);

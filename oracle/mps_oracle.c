@@ -239,9 +239,9 @@ typedef struct orc_manifold {
     float rax[2], ray[2], rbx[2], rby[2], sep[2];
     /* solver rows (spec §3.4): Jacobian lever arms, effective masses, bias, accumulated impulses */
     float rna[2], rnb[2], rta[2], rtb[2];
-    float iarna[2], ibrnb[2], iarta[2], ibrtb[2];
-    float nmass[2], tmass[2], bias[2], acc_n[2], acc_t[2];
-    float manx, many, mbnx, mbny;
+    float nmass[2], tmass[2], kb[2], acc_n[2], acc_t[2]; /* kb = nmass * bias */
+    float ktt, knn, ktn[2][2]; /* couplings between the rows: K = J M^-1 J^T off the diagonal */
+    float ma, ia, mb, ib;
     float friction;
 } orc_manifold;
 
@@ -599,32 +599,49 @@ static void manifold_prepare(const orc_world* wd, orc_manifold* m)
         mub = sc->s_mu_contact[m->b - B];
     }
     m->friction = sqrtf(sc->mu_contact[m->a] * mub);
-    m->manx = ma * m->nx;
-    m->many = ma * m->ny;
-    m->mbnx = mb * m->nx;
-    m->mbny = mb * m->ny;
-    for (k = 0; k < m->count; ++k) {
-        float rna = m->rax[k] * m->ny - m->ray[k] * m->nx;
-        float rnb = m->rbx[k] * m->ny - m->rby[k] * m->nx;
-        float rta = m->rax[k] * ty - m->ray[k] * tx;
-        float rtb = m->rbx[k] * ty - m->rby[k] * tx;
-        float iarna = ia * rna, ibrnb = ib * rnb, iarta = ia * rta, ibrtb = ib * rtb;
-        float kn = ((ma + mb) + iarna * rna) + ibrnb * rnb;
-        float kt = ((ma + mb) + iarta * rta) + ibrtb * rtb;
-        float pen = -m->sep[k] - sc->slop;
-        m->rna[k] = rna;
-        m->rnb[k] = rnb;
-        m->rta[k] = rta;
-        m->rtb[k] = rtb;
-        m->iarna[k] = iarna;
-        m->ibrnb[k] = ibrnb;
-        m->iarta[k] = iarta;
-        m->ibrtb[k] = ibrtb;
-        m->nmass[k] = kn > 0.0f ? 1.0f / kn : 0.0f;
-        m->tmass[k] = kt > 0.0f ? 1.0f / kt : 0.0f;
-        m->bias[k] = pen > 0.0f ? fminf(wd->beta_dt * pen, sc->max_bias_vel) : 0.0f;
-        m->acc_n[k] = 0.0f;
-        m->acc_t[k] = 0.0f;
+    m->ma = ma;
+    m->ia = ia;
+    m->mb = mb;
+    m->ib = ib;
+    {
+        float iarna[2] = {0.0f, 0.0f}, ibrnb[2] = {0.0f, 0.0f}, iarta[2] = {0.0f, 0.0f}, ibrtb[2] = {0.0f, 0.0f};
+        for (k = 0; k < m->count; ++k) {
+            float rna = m->rax[k] * m->ny - m->ray[k] * m->nx;
+            float rnb = m->rbx[k] * m->ny - m->rby[k] * m->nx;
+            float rta = m->rax[k] * ty - m->ray[k] * tx;
+            float rtb = m->rbx[k] * ty - m->rby[k] * tx;
+            float kn, kt, pen, nmass, bias;
+            iarna[k] = ia * rna;
+            ibrnb[k] = ib * rnb;
+            iarta[k] = ia * rta;
+            ibrtb[k] = ib * rtb;
+            kn = ((ma + mb) + iarna[k] * rna) + ibrnb[k] * rnb;
+            kt = ((ma + mb) + iarta[k] * rta) + ibrtb[k] * rtb;
+            pen = -m->sep[k] - sc->slop;
+            m->rna[k] = rna;
+            m->rnb[k] = rnb;
+            m->rta[k] = rta;
+            m->rtb[k] = rtb;
+            nmass = kn > 0.0f ? 1.0f / kn : 0.0f;
+            bias = pen > 0.0f ? fminf(wd->beta_dt * pen, sc->max_bias_vel) : 0.0f;
+            m->nmass[k] = nmass;
+            m->tmass[k] = kt > 0.0f ? 1.0f / kt : 0.0f;
+            m->kb[k] = nmass * bias;
+            m->acc_n[k] = 0.0f;
+            m->acc_t[k] = 0.0f;
+        }
+        /* how an impulse on one row changes the relative velocity along another (spec §3.4) */
+        m->ktn[0][0] = iarta[0] * m->rna[0] + ibrtb[0] * m->rnb[0];
+        m->ktt = 0.0f;
+        m->knn = 0.0f;
+        m->ktn[0][1] = m->ktn[1][0] = m->ktn[1][1] = 0.0f;
+        if (m->count > 1) {
+            m->ktt = ((ma + mb) + iarta[0] * m->rta[1]) + ibrtb[0] * m->rtb[1];
+            m->knn = ((ma + mb) + iarna[0] * m->rna[1]) + ibrnb[0] * m->rnb[1];
+            m->ktn[0][1] = iarta[0] * m->rna[1] + ibrtb[0] * m->rnb[1];
+            m->ktn[1][0] = iarta[1] * m->rna[0] + ibrtb[1] * m->rnb[0];
+            m->ktn[1][1] = iarta[1] * m->rna[1] + ibrtb[1] * m->rnb[1];
+        }
     }
 }
 
@@ -688,9 +705,12 @@ static void world_detect(orc_world* wd)
     }
 }
 
-/* One Gauss-Seidel visit of a manifold.  The relative velocity along a row is evaluated as a fused
- * multiply-add chain (fmaf = one rounding per step, spec §3.4), the impulse applied with one fmaf per
- * velocity component. */
+/* One Gauss-Seidel visit of a manifold: friction rows (point 0, point 1), then the non-penetration rows.
+ * The relative velocities along all rows are evaluated once from the twists at the start of the visit
+ * (fused multiply-add chains, one rounding per step); an impulse d on an earlier row reaches a later row
+ * through the coupling coefficient, u_s += K_sr d_r, which is what re-evaluating u_s from the updated
+ * twists would give in exact arithmetic.  Impulse increments are clamped directly
+ * (d = clamp(-u / K_ss, lo - acc, hi - acc)) and the twists are updated once at the end (spec §3.4). */
 static void solve_manifold(orc_world* wd, orc_manifold* m)
 {
     int B = wd->B, k;
@@ -698,50 +718,63 @@ static void solve_manifold(orc_world* wd, orc_manifold* m)
     float vax = wd->vx[a], vay = wd->vy[a], wa = wd->w[a];
     float vbx = 0.0f, vby = 0.0f, wb = 0.0f;
     float nx = m->nx, ny = m->ny, tx = m->ny, ty = -m->nx;
+    float ut[2], un[2], dt_[2], dn[2];
+    float dvx, dvy, px, py, ra, rb, st;
     if (b < B) {
         vbx = wd->vx[b];
         vby = wd->vy[b];
         wb = wd->w[b];
     }
-    for (k = 0; k < m->count; ++k) { /* friction first (Box2D order) */
-        float dvx = vbx - vax;
-        float dvy = vby - vay;
-        float vt = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, m->rtb[k], -(wa * m->rta[k]))));
-        float lambda = m->tmass[k] * -vt;
-        float max_f = m->friction * m->acc_n[k];
-        float new_imp = fminf(fmaxf(m->acc_t[k] + lambda, -max_f), max_f);
-        lambda = new_imp - m->acc_t[k];
-        m->acc_t[k] = new_imp;
-        /* P = lambda * t with t = (ny, -nx) */
-        vax = fmaf(-m->many, lambda, vax);
-        vay = fmaf(m->manx, lambda, vay);
-        wa = fmaf(-m->iarta[k], lambda, wa);
-        vbx = fmaf(m->mbny, lambda, vbx);
-        vby = fmaf(-m->mbnx, lambda, vby);
-        wb = fmaf(m->ibrtb[k], lambda, wb);
+    dvx = vbx - vax;
+    dvy = vby - vay;
+    /* A manifold with one point runs the same arithmetic with the second point's coefficients all zero
+     * (manifold_prepare leaves them so): no data-dependent branch on the device, identical bits here. */
+    for (k = 0; k < 2; ++k) {
+        ut[k] = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, m->rtb[k], -(wa * m->rta[k]))));
+        un[k] = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, m->rnb[k], -(wa * m->rna[k]))));
     }
-    for (k = 0; k < m->count; ++k) { /* then non-penetration */
-        float dvx = vbx - vax;
-        float dvy = vby - vay;
-        float vn = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, m->rnb[k], -(wa * m->rna[k]))));
-        float lambda = m->nmass[k] * (m->bias[k] - vn);
-        float new_imp = fmaxf(m->acc_n[k] + lambda, 0.0f);
-        lambda = new_imp - m->acc_n[k];
-        m->acc_n[k] = new_imp;
-        vax = fmaf(-m->manx, lambda, vax);
-        vay = fmaf(-m->many, lambda, vay);
-        wa = fmaf(-m->iarna[k], lambda, wa);
-        vbx = fmaf(m->mbnx, lambda, vbx);
-        vby = fmaf(m->mbny, lambda, vby);
-        wb = fmaf(m->ibrnb[k], lambda, wb);
+    { /* friction, point 0 */
+        float lim = m->friction * m->acc_n[0];
+        float dl = m->tmass[0] * -ut[0];
+        float d = fminf(fmaxf(dl, -lim - m->acc_t[0]), lim - m->acc_t[0]);
+        dt_[0] = d;
+        m->acc_t[0] = m->acc_t[0] + d;
     }
-    wd->vx[a] = vax;
-    wd->vy[a] = vay;
-    wd->w[a] = wa;
+    { /* friction, point 1 */
+        float u = fmaf(m->ktt, dt_[0], ut[1]);
+        float lim = m->friction * m->acc_n[1];
+        float dl = m->tmass[1] * -u;
+        float d = fminf(fmaxf(dl, -lim - m->acc_t[1]), lim - m->acc_t[1]);
+        dt_[1] = d;
+        m->acc_t[1] = m->acc_t[1] + d;
+    }
+    { /* non-penetration, point 0 */
+        float u = fmaf(m->ktn[1][0], dt_[1], fmaf(m->ktn[0][0], dt_[0], un[0]));
+        float dl = fmaf(-m->nmass[0], u, m->kb[0]);
+        float d = fmaxf(dl, -m->acc_n[0]);
+        dn[0] = d;
+        m->acc_n[0] = m->acc_n[0] + d;
+    }
+    { /* non-penetration, point 1 */
+        float u = fmaf(m->knn, dn[0], fmaf(m->ktn[1][1], dt_[1], fmaf(m->ktn[0][1], dt_[0], un[1])));
+        float dl = fmaf(-m->nmass[1], u, m->kb[1]);
+        float d = fmaxf(dl, -m->acc_n[1]);
+        dn[1] = d;
+        m->acc_n[1] = m->acc_n[1] + d;
+    }
+    /* total impulse on b (minus that on a) and the angular parts */
+    st = dt_[0] + dt_[1];
+    ra = fmaf(m->rna[1], dn[1], fmaf(m->rta[1], dt_[1], fmaf(m->rna[0], dn[0], m->rta[0] * dt_[0])));
+    rb = fmaf(m->rnb[1], dn[1], fmaf(m->rtb[1], dt_[1], fmaf(m->rnb[0], dn[0], m->rtb[0] * dt_[0])));
+    px = fmaf(nx, dn[1], fmaf(nx, dn[0], tx * st));
+    py = fmaf(ny, dn[1], fmaf(ny, dn[0], ty * st));
+    wd->vx[a] = fmaf(-m->ma, px, vax);
+    wd->vy[a] = fmaf(-m->ma, py, vay);
+    wd->w[a] = fmaf(-m->ia, ra, wa);
     if (b < B) {
-        wd->vx[b] = vbx;
-        wd->vy[b] = vby;
-        wd->w[b] = wb;
+        wd->vx[b] = fmaf(m->mb, px, vbx);
+        wd->vy[b] = fmaf(m->mb, py, vby);
+        wd->w[b] = fmaf(m->ib, rb, wb);
     }
 }
 
