@@ -275,6 +275,13 @@ __device__ __forceinline__ int collide(const Shape& A, const Shape& Bs, float re
     return collide_disc_disc(A, Bs, m);
 }
 
+__device__ __forceinline__ unsigned char* opaque_shared_base(unsigned char* dyn)
+{
+    unsigned int s32 = (unsigned int)__cvta_generic_to_shared(dyn);
+    asm volatile("" : "+r"(s32));
+    return (unsigned char*)__cvta_shared_to_generic((size_t)s32);
+}
+
 // per-warp working set in shared memory
 struct WarpMem {
     float* px;  // [32] poses mirrored for the pair tests
@@ -924,7 +931,10 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // The base of the dynamic shared memory goes through an opaque register once: otherwise the compiler
+    // rematerialises the symbol's address at every use, each time with a read of a special register.
+    unsigned char* smem_raw = opaque_shared_base(smem_dyn);
     DevScene& sc = *reinterpret_cast<DevScene*>(smem_raw);
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.scene);
@@ -1315,7 +1325,10 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // The base of the dynamic shared memory goes through an opaque register once: otherwise the compiler
+    // rematerialises the symbol's address at every use, each time with a read of a special register.
+    unsigned char* smem_raw = opaque_shared_base(smem_dyn);
     DevScene& sc = *reinterpret_cast<DevScene*>(smem_raw);
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.scene);
