@@ -809,11 +809,30 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                         ++ne;
                     }
                 }
+                const int nr = __reduce_max_sync(FULL, last);
+                if (nr <= 4) {
+                    // few rounds (the usual case): index the entries by round, ent[r - 1] = this lane's
+                    // manifold of round r or 0, so the sweep needs no search
+                    unsigned b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const unsigned e = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
+                        const int er = (int)(e >> 16);
+                        b0 = er == 1 ? e : b0;
+                        b1 = er == 2 ? e : b1;
+                        b2 = er == 3 ? e : b2;
+                        b3 = er == 4 ? e : b3;
+                    }
+                    e0 = b0;
+                    e1 = b1;
+                    e2 = b2;
+                    e3 = b3;
+                }
                 cache.ent[0] = e0;
                 cache.ent[1] = e1;
                 cache.ent[2] = e2;
                 cache.ent[3] = e3;
-                cache.rounds = __reduce_max_sync(FULL, last);
+                cache.rounds = nr;
                 cache.nm = dr.nm;
                 cache.sig0 = sig0;
                 cache.sig1 = sig1;
@@ -823,15 +842,27 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             PH_T(t2);
             PH_ADD(2, t1, t2);
             const int iters = sc.vel_iters;
-            for (int it = 0; it < iters; ++it) {
-                for (int r = 1; r <= rounds; ++r) {
-                    unsigned e = 0u;
+            auto pass = [&](unsigned e) {
+                const int slr = e ? (int)(e & 0xffu) : 0xff;
+                const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
+                solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
+            };
+            if (rounds <= 4) {
+                for (int it = 0; it < iters; ++it) {
+                    pass(cache.ent[0]);
+                    if (rounds > 1) pass(cache.ent[1]);
+                    if (rounds > 2) pass(cache.ent[2]);
+                    if (rounds > 3) pass(cache.ent[3]);
+                }
+            } else {
+                for (int it = 0; it < iters; ++it) {
+                    for (int r = 1; r <= rounds; ++r) {
+                        unsigned e = 0u;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if ((int)(cache.ent[c] >> 16) == r) e = cache.ent[c];
-                    const int slr = e ? (int)(e & 0xffu) : 0xff;
-                    const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
-                    solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
+                        for (int c = 0; c < 4; ++c)
+                            if ((int)(cache.ent[c] >> 16) == r) e = cache.ent[c];
+                        pass(e);
+                    }
                 }
             }
             PH_T(t3);
