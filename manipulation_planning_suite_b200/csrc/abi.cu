@@ -23,7 +23,7 @@ thread_local std::string g_last_error;
 
 // words per chain written by the rollout kernel's cycle counters (8 in the -DMPS_PHASE_PROF profiling build)
 #ifdef MPS_PHASE_PROF
-#define MPS_CYCLE_WORDS 8
+#define MPS_CYCLE_WORDS 12
 #else
 #define MPS_CYCLE_WORDS 1
 #endif

@@ -219,47 +219,48 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
     float s1 = (v1x * nrx + v1y * nry) - hu;
     float s2 = (v2x * nrx + v2y * nry) - hu;
     if ((t1 > ht && t2 > ht) || (t1 < -ht && t2 < -ht)) return 0;
-    float ct0 = t1, cs0 = s1, ct1 = t2, cs1 = s2;
-    if (t1 > ht) {
-        float al = (ht - t1) / (t2 - t1);
-        cs0 = s1 + al * (s2 - s1);
-        ct0 = ht;
-    } else if (t1 < -ht) {
-        float al = (-ht - t1) / (t2 - t1);
-        cs0 = s1 + al * (s2 - s1);
-        ct0 = -ht;
-    }
-    if (t2 > ht) {
-        float al = (ht - t2) / (t1 - t2);
-        cs1 = s2 + al * (s1 - s2);
-        ct1 = ht;
-    } else if (t2 < -ht) {
-        float al = (-ht - t2) / (t1 - t2);
-        cs1 = s2 + al * (s1 - s2);
-        ct1 = -ht;
-    }
-    int n = 0;
+    // clip the incident edge to the side planes, without branches: the clipped values are computed for
+    // both ends (a zero denominator only occurs when nothing is clipped) and selected
+    const bool hi1 = t1 > ht, lo1 = !hi1 && t1 < -ht;
+    const bool hi2 = t2 > ht, lo2 = !hi2 && t2 < -ht;
+    const float lim1 = hi1 ? ht : -ht;
+    const float lim2 = hi2 ? ht : -ht;
+    const float al1 = (lim1 - t1) / (t2 - t1);
+    const float al2 = (lim2 - t2) / (t1 - t2);
+    const float cl1 = s1 + al1 * (s2 - s1);
+    const float cl2 = s2 + al2 * (s1 - s2);
+    const bool c1 = hi1 || lo1, c2 = hi2 || lo2;
+    float ct0 = c1 ? lim1 : t1, cs0 = c1 ? cl1 : s1;
+    float ct1 = c2 ? lim2 : t2, cs1 = c2 ? cl2 : s2;
+    // contact points: the clipped ends that lie behind the reference face, midway between the two surfaces;
+    // both are computed, the second moves to slot 0 when the first is not a contact
+    float qax[2], qay[2], qbx[2], qby[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        float csk = k == 0 ? cs0 : cs1;
-        float ctk = k == 0 ? ct0 : ct1;
-        if (csk <= 0.0f) {
-            float h = hu + 0.5f * csk;
-            float rrx = trx * ctk + nrx * h;
-            float rry = tryy * ctk + nry * h;
-            float rix = rrx - ddx;
-            float riy = rry - ddy;
-            // n is 0 or 1 here; written without dynamic register indexing
-            float ax_ = ref_is_b ? rix : rrx, ay_ = ref_is_b ? riy : rry;
-            float bx_ = ref_is_b ? rrx : rix, by_ = ref_is_b ? rry : riy;
-            if (n == 0) {
-                m.rax[0] = ax_; m.ray[0] = ay_; m.rbx[0] = bx_; m.rby[0] = by_; m.sep[0] = csk;
-            } else {
-                m.rax[1] = ax_; m.ray[1] = ay_; m.rbx[1] = bx_; m.rby[1] = by_; m.sep[1] = csk;
-            }
-            ++n;
-        }
+        const float csk = k == 0 ? cs0 : cs1;
+        const float ctk = k == 0 ? ct0 : ct1;
+        const float h = hu + 0.5f * csk;
+        const float rrx = trx * ctk + nrx * h;
+        const float rry = tryy * ctk + nry * h;
+        const float rix = rrx - ddx;
+        const float riy = rry - ddy;
+        qax[k] = ref_is_b ? rix : rrx;
+        qay[k] = ref_is_b ? riy : rry;
+        qbx[k] = ref_is_b ? rrx : rix;
+        qby[k] = ref_is_b ? rry : riy;
     }
+    const bool v0 = cs0 <= 0.0f, v1 = cs1 <= 0.0f;
+    const int n = (v0 ? 1 : 0) + (v1 ? 1 : 0);
+    m.rax[0] = v0 ? qax[0] : qax[1];
+    m.ray[0] = v0 ? qay[0] : qay[1];
+    m.rbx[0] = v0 ? qbx[0] : qbx[1];
+    m.rby[0] = v0 ? qby[0] : qby[1];
+    m.sep[0] = v0 ? cs0 : cs1;
+    m.rax[1] = qax[1];
+    m.ray[1] = qay[1];
+    m.rbx[1] = qbx[1];
+    m.rby[1] = qby[1];
+    m.sep[1] = cs1;
     if (n == 0) return 0;
     m.count = n;
     m.nx = ref_is_b ? -nrx : nrx;
@@ -357,7 +358,8 @@ __device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpM
 
 // collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
 __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare,
-                                               StepCache& cache, long long* t_mid = nullptr)
+                                               StepCache& cache, long long* t_mid = nullptr,
+                                               long long* sub = nullptr)
 {
     const int B = sc.B;
     const int Mcap = sc.Mcap;
@@ -443,8 +445,11 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
     unsigned long long lane_col = 0ull;
     unsigned n_touch = 0;
     for (int base = 0; base < nlist; base += 32) {
+#ifdef MPS_PHASE_PROF
+        long long tsb = clock64();
+#endif
         int c = base + lane;
-        Manifold m;
+        Manifold m = {};
         int cnt = 0, a = 0, b = 0;
         bool near = false;
         if (c < nlist) {
@@ -454,6 +459,10 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             near = pair_near(pr, 0.0f);
         }
         ncand += __popc(__ballot_sync(FULL, near));
+#ifdef MPS_PHASE_PROF
+        long long ts0 = clock64();
+        if (sub) sub[0] += ts0 - tsb;
+#endif
         if (near) {
             Shape A, Bs;
             load_pair_shapes(sc, W, a, b, A, Bs);
@@ -461,8 +470,18 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         }
         bool touch = cnt > 0;
         unsigned tmask = __ballot_sync(FULL, touch);
+#ifdef MPS_PHASE_PROF
+        long long ts1 = clock64();
+        if (sub) sub[1] += ts1 - ts0;
+#endif
         if (tmask == 0u) continue;
         n_touch += __popc(tmask);
+#ifdef MPS_PHASE_PROF
+        struct RowTimer {
+            long long t0, *dst;
+            __device__ ~RowTimer() { if (dst) dst[2] += clock64() - t0; }
+        } row_timer{ts1, sub};
+#endif
         if (touch) {
             float pen = -m.sep[0];
             if (pen > lane_pen) lane_pen = pen;
@@ -496,24 +515,26 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                     float nmass[2] = {0.0f, 0.0f}, tmass[2] = {0.0f, 0.0f}, kb[2] = {0.0f, 0.0f};
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        if (k < cnt) {
-                            float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
-                            rna[k] = rax * m.ny - ray * m.nx;
-                            rnb[k] = rbx * m.ny - rby * m.nx;
-                            rta[k] = rax * ty - ray * tx;
-                            rtb[k] = rbx * ty - rby * tx;
-                            iarna[k] = ia * rna[k];
-                            ibrnb[k] = ib * rnb[k];
-                            iarta[k] = ia * rta[k];
-                            ibrtb[k] = ib * rtb[k];
-                            float kn = ((ma + mb) + iarna[k] * rna[k]) + ibrnb[k] * rnb[k];
-                            float kt = ((ma + mb) + iarta[k] * rta[k]) + ibrtb[k] * rtb[k];
-                            float pen_k = -m.sep[k] - sc.slop;
-                            float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
-                            nmass[k] = kn > 0.0f ? 1.0f / kn : 0.0f;
-                            tmass[k] = kt > 0.0f ? 1.0f / kt : 0.0f;
-                            kb[k] = nmass[k] * bias;
-                        }
+                        // both points go through the arithmetic; a missing second point is zeroed afterwards
+                        const bool has = k < cnt;
+                        const float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
+                        const float sepk = m.sep[k];
+                        rna[k] = has ? rax * m.ny - ray * m.nx : 0.0f;
+                        rnb[k] = has ? rbx * m.ny - rby * m.nx : 0.0f;
+                        rta[k] = has ? rax * ty - ray * tx : 0.0f;
+                        rtb[k] = has ? rbx * ty - rby * tx : 0.0f;
+                        iarna[k] = ia * rna[k];
+                        ibrnb[k] = ib * rnb[k];
+                        iarta[k] = ia * rta[k];
+                        ibrtb[k] = ib * rtb[k];
+                        const float kn = ((ma + mb) + iarna[k] * rna[k]) + ibrnb[k] * rnb[k];
+                        const float kt = ((ma + mb) + iarta[k] * rta[k]) + ibrtb[k] * rtb[k];
+                        const float pen_k = -sepk - sc.slop;
+                        const float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
+                        const float rn = 1.0f / kn, rt = 1.0f / kt;
+                        nmass[k] = (has && kn > 0.0f) ? rn : 0.0f;
+                        tmass[k] = (has && kt > 0.0f) ? rt : 0.0f;
+                        kb[k] = nmass[k] * bias;
                     }
                     float ktt = 0.0f, knn = 0.0f, ktn01 = 0.0f, ktn10 = 0.0f, ktn11 = 0.0f;
                     const float ktn00 = iarta[0] * rna[0] + ibrtb[0] * rnb[0];
@@ -622,7 +643,8 @@ __device__ __forceinline__ void set_state(const WarpMem& W, Body& b, int lane, f
 struct StepStats {
     unsigned steps, candidates, touching, colour_passes;
 #ifdef MPS_PHASE_PROF
-    long long ph[6];  // broad phase, narrow phase, round scheduling, solver rounds, friction + integration, contact steps
+    long long ph[10];  // broad phase, narrow phase, round scheduling, solver rounds, friction + integration,
+                       // contact steps, narrow: reach test / collide / rows
 #endif
 };
 #ifdef MPS_PHASE_PROF
@@ -730,7 +752,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     PH_T(t0);
 #ifdef MPS_PHASE_PROF
     long long t_mid = t0;
-    DetectResult dr = detect(sc, W, lane, true, cache, &t_mid);
+    DetectResult dr = detect(sc, W, lane, true, cache, &t_mid, &st.ph[6]);
 #else
     DetectResult dr = detect(sc, W, lane, true, cache);
 #endif
@@ -1019,7 +1041,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         const long long t_begin = clock64();
         cache.reset();
 #ifdef MPS_PHASE_PROF
-        for (int i = 0; i < 6; ++i) st.ph[i] = 0;
+        for (int i = 0; i < 10; ++i) st.ph[i] = 0;
 #endif
         // start state of the chain
         float sx = 0.0f, sy = 0.0f, sth = 0.0f;
@@ -1214,9 +1236,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             p.out_goal_step[k] = goal_step;
 #ifdef MPS_PHASE_PROF
             if (p.out_cycles) {
-                p.out_cycles[(size_t)k * 8] = clock64() - t_begin;
-                for (int i = 0; i < 6; ++i) p.out_cycles[(size_t)k * 8 + 1 + i] = st.ph[i];
-                p.out_cycles[(size_t)k * 8 + 7] = 0;
+                p.out_cycles[(size_t)k * 12] = clock64() - t_begin;
+                for (int i = 0; i < 10; ++i) p.out_cycles[(size_t)k * 12 + 1 + i] = st.ph[i];
+                p.out_cycles[(size_t)k * 12 + 11] = 0;
             }
 #else
             if (p.out_cycles) p.out_cycles[k] = clock64() - t_begin;
