@@ -3,7 +3,7 @@
 //
 // Arithmetic contract: the whole library is compiled with
 // -fmad=false, so every +,-,*,/ and sqrtf below is one correctly rounded IEEE
-// operation — the same operation sequence the physics spec mps-planar-v1 writes
+// operation — the same operation sequence the physics spec mps-planar-v2 writes
 // down.  No libm sin/cos on the device path: mps_sincos is the spec's own
 // polynomial.
 #pragma once

@@ -9,7 +9,7 @@
 //   SimEnvValidityChecker::isValid + CollisionPolicy       ompl/state/SimEnvState.cpp:1365-1394,1441-1502
 //   SimEnvWorldStateDistanceMeasure::distance              ompl/state/SimEnvWorldStateDistanceMeasure.cpp:34-51
 //   ObjectsRelocationGoal::distanceGoal / isSatisfied      ompl/state/goal/ObjectsRelocationGoal.cpp:108-123
-// The physics step itself follows the spec mps-planar-v1.
+// The physics step itself follows the spec mps-planar-v2.
 //
 // Mapping to the machine:
 //   * one warp = one rollout chain; lane i owns body i: pose, twist and friction accumulators

@@ -18,7 +18,7 @@
  *   src/mps/planner/ompl/state/goal/ObjectsRelocationGoal.cpp:108-123     goal distance
  *   src/mps/planner/pushing/algorithm/RRT.cpp:449-489,531-565            chains (HybridActionRRT)
  * The physics step (sim_env/Box2D in the reference; absent here) follows the
- * spec "mps-planar-v1" of DESIGN.md §3 — PARITY UNPINNED for that part.
+ * spec "mps-planar-v2" of DESIGN.md §3 — PARITY UNPINNED for that part.
  */
 #include "mps_oracle.h"
 
@@ -190,7 +190,7 @@ int orc_collision_allowed(const mps_scene* sc, int a, int b)
 }
 
 /* ------------------------------------------------------------------------- */
-/* physics spec mps-planar-v1                                                 */
+/* physics spec mps-planar-v2                                                 */
 /* ------------------------------------------------------------------------- */
 
 /* deterministic sincos: Cody-Waite reduction by pi/2, degree-7/6 polynomials */

@@ -1,4 +1,4 @@
-"""Generates tests/golden/physics_golden.npz: rollouts of the physics spec mps-planar-v1 produced by the
+"""Generates tests/golden/physics_golden.npz: rollouts of the physics spec mps-planar-v2 produced by the
 CPU oracle on seeded inputs.  The reference's physics (sim_env / Box2D) is not in /root/reference, so
 these vectors pin OUR spec (regression + CPU/GPU agreement), not the reference: "parity unpinned".
 

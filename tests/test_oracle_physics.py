@@ -1,4 +1,4 @@
-"""CPU tests of the physics spec mps-planar-v1 as implemented by the oracle: mechanics sanity, the
+"""CPU tests of the physics spec mps-planar-v2 as implemented by the oracle: mechanics sanity, the
 propagate contract of the reference (SimEnvStatePropagator.cpp:42-118) and best-of-K semantics
 (NaiveControlSampler.cpp:34-71, RRT.cpp:449-489)."""
 import ctypes as C
