@@ -259,6 +259,8 @@ static void derive_scene(const mps_scene* sc, DevScene* d)
     for (int k = 0; k < S; ++k)
         for (int i = 0; i < B; ++i) d->pairs[P++] = (uint16_t)(i | ((B + k) << 8));
     d->P = P;
+    const char* fg = getenv("MPS_FORCE_GENERAL_SWEEP");
+    d->force_general = (fg && fg[0] == '1') ? 1 : 0;
 }
 
 extern "C" {

@@ -28,6 +28,7 @@ struct DevScene {
     int Mcap;     // manifold capacity per rollout
     int strict;   // strict_active_contacts
     int slot_stride;  // bytes per row of the per-warp slot table (multiple of 4)
+    int force_general;  // test hook (env MPS_FORCE_GENERAL_SWEEP=1 at context creation): always take the general sweep
     int jam_steps, _pad_i;
     float dt, t_max, slop, beta_dt, max_bias, pen_max, v_rest2, w_rest, ref_tol;
     float x_min, x_max, y_min, y_max;

@@ -320,7 +320,6 @@ struct DetectResult {
     bool bad;       // a touching pair the policy forbids
     bool overflow;  // more touching pairs than Mcap
     float max_pen;
-    unsigned long long colours;
     int nm;         // manifolds stored (<= Mcap)
     unsigned candidates, touching;
 };
@@ -442,7 +441,6 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
     int nm = 0;
     bool lane_bad = false, lane_over = false;
     float lane_pen = 0.0f;
-    unsigned long long lane_col = 0ull;
     unsigned n_touch = 0;
     for (int base = 0; base < nlist; base += 32) {
 #ifdef MPS_PHASE_PROF
@@ -553,16 +551,6 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                     mf[6] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     mf[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, sqrtf(sc.mu_c[a] * mub));
-                    W.slot[a * sc.slot_stride + b] = (uint8_t)idx;
-                    int col;
-                    if (b < B) {
-                        W.slot[b * sc.slot_stride + a] = (uint8_t)idx;
-                        col = a + b;
-                        if (col >= B) col -= B;
-                    } else {
-                        col = b;
-                    }
-                    lane_col |= 1ull << col;
                 } else {
                     mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, 0.0f);
                 }
@@ -573,12 +561,10 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         nm += __popc(tmask);
     }
     DetectResult r;
-    r.bad = __any_sync(FULL, lane_bad);
-    r.overflow = __any_sync(FULL, lane_over);
+    const unsigned fl = __reduce_or_sync(FULL, (lane_bad ? 1u : 0u) | (lane_over ? 2u : 0u));
+    r.bad = (fl & 1u) != 0u;
+    r.overflow = (fl & 2u) != 0u;
     r.max_pen = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(lane_pen)));
-    unsigned lo = __reduce_or_sync(FULL, (unsigned)(lane_col & 0xffffffffull));
-    unsigned hi = __reduce_or_sync(FULL, (unsigned)(lane_col >> 32));
-    r.colours = ((unsigned long long)hi << 32) | lo;
     r.nm = nm < Mcap ? nm : Mcap;
     r.candidates = (unsigned)ncand;
     r.touching = n_touch;
@@ -738,6 +724,49 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane,
     }
 }
 
+// General sweep, colour by colour in canonical order, for steps in which some body has more than 4
+// manifolds (rare): the slot table and the set of active colours are built from the manifold list first.
+__device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem& W, Body& bd, int lane, int nm,
+                                              StepStats& st)
+{
+    const int B = sc.B;
+    unsigned long long lane_col = 0ull;
+    for (int m = lane; m < nm; m += 32) {
+        const int meta = __float_as_int(W.man[m * MF_VEC4].x);
+        const int a = meta & 0xff, b = (meta >> 8) & 0xff;
+        W.slot[a * sc.slot_stride + b] = (uint8_t)m;
+        int col;
+        if (b < B) {
+            W.slot[b * sc.slot_stride + a] = (uint8_t)m;
+            col = a + b;
+            if (col >= B) col -= B;
+        } else {
+            col = b;
+        }
+        lane_col |= 1ull << col;
+    }
+    const unsigned lo = __reduce_or_sync(FULL, (unsigned)(lane_col & 0xffffffffull));
+    const unsigned hi = __reduce_or_sync(FULL, (unsigned)(lane_col >> 32));
+    const unsigned long long colours = ((unsigned long long)hi << 32) | lo;
+    __syncwarp();
+    st.colour_passes += (unsigned)(__popcll(colours) * sc.vel_iters);
+    for (int it = 0; it < sc.vel_iters; ++it) {
+        unsigned long long cm = colours;
+        while (cm) {
+            const int col = __ffsll((long long)cm) - 1;
+            cm &= cm - 1ull;
+            const int slot = lookup_slot(sc, W, lane, col, nm);
+            const bool stat = col >= B;
+            int j = lane;
+            if (!stat && bd.live) {
+                j = col - lane;
+                if (j < 0) j += B;
+            }
+            solve_pass(W, bd, lane, slot, j, stat);
+        }
+    }
+}
+
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, int lane, float ux,
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
@@ -783,17 +812,16 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
         bd.vx = bd.vx + bd.inv_m * ix;
         bd.vy = bd.vy + bd.inv_m * iy;
     }
-    if (dr.colours != 0ull) {
-        const int ncol = __popcll(dr.colours);
-        if (ncol <= 4) {
-            // Common case: at most 4 active colours.  The canonical order is colour by colour, but two
+    if (dr.nm > 0) {
+        {
+            // Common case: no body has more than 4 manifolds.  The canonical order is colour by colour, but two
             // manifolds that share no body commute, so each manifold is scheduled in the earliest ROUND
             // after every earlier manifold (in canonical order) that shares a body with it:
             //     round(m) = 1 + max(last round of body a, last round of body b).
             // Any schedule that keeps the relative order of manifolds sharing a body produces the bits of
             // the canonical sweep; independent contacts (different islands) now solve concurrently.
-            // Each lane packs its <= 4 entries (one per colour at most) as
-            // round << 16 | static << 15 | partner << 8 | slot.
+            // Each lane packs its <= 4 entries as round << 16 | static << 15 | partner << 8 | slot; a body
+            // with more manifolds than that sends the step to the general sweep below (rounds = -1).
             // The schedule depends only on which pair sits in which manifold slot: reuse the last one while
             // that list is unchanged (contact sets persist over many steps).
             const unsigned sig0 =
@@ -831,8 +859,9 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                         ++ne;
                     }
                 }
-                const int nr = __reduce_max_sync(FULL, last);
-                if (nr <= 4) {
+                int nr = __reduce_max_sync(FULL, last);
+                if (__any_sync(FULL, ne > 4) || sc.force_general) nr = -1;
+                if (nr >= 0 && nr <= 4) {
                     // few rounds (the usual case): index the entries by round, ent[r - 1] = this lane's
                     // manifold of round r or 0, so the sweep needs no search
                     unsigned b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
@@ -860,7 +889,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 cache.sig1 = sig1;
             }
             const int rounds = cache.rounds;
-            st.colour_passes += (unsigned)(rounds * sc.vel_iters);
+            if (rounds >= 0) st.colour_passes += (unsigned)(rounds * sc.vel_iters);
             PH_T(t2);
             PH_ADD(2, t1, t2);
             const int iters = sc.vel_iters;
@@ -869,7 +898,9 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
                 solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
             };
-            if (rounds <= 4) {
+            if (rounds < 0) {
+                general_sweep(sc, W, bd, lane, dr.nm, st);
+            } else if (rounds <= 4) {
                 for (int it = 0; it < iters; ++it) {
                     pass(cache.ent[0]);
                     if (rounds > 1) pass(cache.ent[1]);
@@ -892,24 +923,6 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
 #ifdef MPS_PHASE_PROF
             st.ph[5] += 1;
 #endif
-        } else {
-            // general case: walk the colour mask; slots looked up per pass
-            st.colour_passes += (unsigned)(ncol * sc.vel_iters);
-            for (int it = 0; it < sc.vel_iters; ++it) {
-                unsigned long long cm = dr.colours;
-                while (cm) {
-                    const int col = __ffsll((long long)cm) - 1;
-                    cm &= cm - 1ull;
-                    const int slot = lookup_slot(sc, W, lane, col, dr.nm);
-                    const bool stat = col >= B;
-                    int j = lane;
-                    if (!stat && bd.live) {
-                        j = col - lane;
-                        if (j < 0) j += B;
-                    }
-                    solve_pass(W, bd, lane, slot, j, stat);
-                }
-            }
         }
     }
     if (bd.live) {

@@ -280,3 +280,17 @@ def test_per_chain_starts_long_chains_and_stop_at_goal(stop_at_goal):
         assert any(ran[k, goal[k].argmax() + 1:].any() for k in range(K) if goal[k].any())
     # chains that share a start state and controls prefix agree; different starts give different results
     assert len({tuple(r["want"]["all_states"][k, 0]) for k in range(K)}) > 7
+
+
+def test_general_sweep_matches_oracle(monkeypatch):
+    """The colour-by-colour sweep used when a body has more than 4 manifolds, forced on through the test hook:
+    same bits as the round schedule and as the oracle."""
+    monkeypatch.setenv("MPS_FORCE_GENERAL_SWEEP", "1")
+    sc, _ = scenes.make_scene(8, seed=3)
+    start = scenes.cluttered_start(sc, 23)
+    rng = np.random.RandomState(4)
+    controls = scenes.sample_controls_towards(rng, sc, start, 64, 2)
+    dest = scenes.sample_state(rng, sc)
+    r = compare_extend(sc, start, controls, dest=dest)
+    assert r["got"].all_steps.sum() > 1000
+    assert ((r["want"]["all_flags"] & abi.MPS_F_OK) != 0).any()
