@@ -305,7 +305,7 @@ def run_ours(args):
             "nn": nn,
             "winner": None if winner is None else {"k": winner.k, "n_ok": winner.n_ok, "distance": winner.distance},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -463,10 +463,28 @@ def run_reference(args):
                          "sample": f"{sample} chains per step x {steps} steps, pthread fan-out (one world per thread)"},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def emit(line: dict):
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
 
 
 def main():
+    # libraries (NCCL, torch) may print banners on stdout: send everything but the JSON line to stderr
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
