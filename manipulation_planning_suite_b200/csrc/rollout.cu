@@ -335,24 +335,17 @@ __device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpM
     A.s = W.ps[a];
     A.hx = sc.hx[a];
     A.hy = sc.hy[a];
-    if (b < B) {
-        Bs.shape = sc.shape[b];
-        Bs.x = W.px[b];
-        Bs.y = W.py[b];
-        Bs.c = W.pc[b];
-        Bs.s = W.ps[b];
-        Bs.hx = sc.hx[b];
-        Bs.hy = sc.hy[b];
-    } else {
-        int k = b - B;
-        Bs.shape = sc.s_shape[k];
-        Bs.x = sc.s_x[k];
-        Bs.y = sc.s_y[k];
-        Bs.c = sc.s_c[k];
-        Bs.s = sc.s_s[k];
-        Bs.hx = sc.s_hx[k];
-        Bs.hy = sc.s_hy[k];
-    }
+    // the second shape is a body (pose mirrored in W) or a static (pose in the scene): the addresses are
+    // selected, not the code path
+    const bool body = b < B;
+    const int k = body ? b : b - B;
+    Bs.shape = *(body ? &sc.shape[k] : &sc.s_shape[k]);
+    Bs.x = *(body ? &W.px[k] : &sc.s_x[k]);
+    Bs.y = *(body ? &W.py[k] : &sc.s_y[k]);
+    Bs.c = *(body ? &W.pc[k] : &sc.s_c[k]);
+    Bs.s = *(body ? &W.ps[k] : &sc.s_s[k]);
+    Bs.hx = *(body ? &sc.hx[k] : &sc.s_hx[k]);
+    Bs.hy = *(body ? &sc.hy[k] : &sc.s_hy[k]);
 }
 
 // collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
@@ -487,22 +480,19 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                 pen = -m.sep[1];
                 if (pen > lane_pen) lane_pen = pen;
             }
-            bool allowed = (b >= B) ? !((sc.static_forbidden >> a) & 1u) : !((sc.pair_forbidden[a] >> b) & 1u);
-            if (!allowed) lane_bad = true;
+            const bool bstat = b >= B;
+            const unsigned forbid = bstat ? (sc.static_forbidden >> a) : (sc.pair_forbidden[a] >> (b & 31));
+            if (forbid & 1u) lane_bad = true;
             int idx = nm + __popc(tmask & ((1u << lane) - 1u));
             if (idx < Mcap) {
                 float4* mf = W.man + idx * MF_VEC4;
                 int meta = a | (b << 8) | (cnt << 16);
                 if (prepare) {
-                    float ma = sc.inv_m[a], ia = sc.inv_i[a];
-                    float mb = 0.0f, ib = 0.0f, mub;
-                    if (b < B) {
-                        mb = sc.inv_m[b];
-                        ib = sc.inv_i[b];
-                        mub = sc.mu_c[b];
-                    } else {
-                        mub = sc.s_mu[b - B];
-                    }
+                    const float ma = sc.inv_m[a], ia = sc.inv_i[a];
+                    const int kb_ = bstat ? b - B : b;
+                    const float mbq = sc.inv_m[bstat ? 0 : b], ibq = sc.inv_i[bstat ? 0 : b];
+                    const float mb = bstat ? 0.0f : mbq, ib = bstat ? 0.0f : ibq;
+                    const float mub = *(bstat ? &sc.s_mu[kb_] : &sc.mu_c[kb_]);
                     // rows of the manifold (layout: 0 meta|n|friction, 1 / 3 lever arms of point 0 / 1,
                     // 2 / 4 inverse effective masses, bias term and the t-t / n-n coupling, 5 t-n couplings,
                     // 6 / 7 accumulated impulses, one private copy per owner lane); the rows of a missing
@@ -534,15 +524,15 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                         tmass[k] = (has && kt > 0.0f) ? rt : 0.0f;
                         kb[k] = nmass[k] * bias;
                     }
-                    float ktt = 0.0f, knn = 0.0f, ktn01 = 0.0f, ktn10 = 0.0f, ktn11 = 0.0f;
+                    const bool two = cnt > 1;
                     const float ktn00 = iarta[0] * rna[0] + ibrtb[0] * rnb[0];
-                    if (cnt > 1) {
-                        ktt = ((ma + mb) + iarta[0] * rta[1]) + ibrtb[0] * rtb[1];
-                        knn = ((ma + mb) + iarna[0] * rna[1]) + ibrnb[0] * rnb[1];
-                        ktn01 = iarta[0] * rna[1] + ibrtb[0] * rnb[1];
-                        ktn10 = iarta[1] * rna[0] + ibrtb[1] * rnb[0];
-                        ktn11 = iarta[1] * rna[1] + ibrtb[1] * rnb[1];
-                    }
+                    const float ktt_ = ((ma + mb) + iarta[0] * rta[1]) + ibrtb[0] * rtb[1];
+                    const float knn_ = ((ma + mb) + iarna[0] * rna[1]) + ibrnb[0] * rnb[1];
+                    const float ktn01_ = iarta[0] * rna[1] + ibrtb[0] * rnb[1];
+                    const float ktn10_ = iarta[1] * rna[0] + ibrtb[1] * rnb[0];
+                    const float ktn11_ = iarta[1] * rna[1] + ibrtb[1] * rnb[1];
+                    const float ktt = two ? ktt_ : 0.0f, knn = two ? knn_ : 0.0f;
+                    const float ktn01 = two ? ktn01_ : 0.0f, ktn10 = two ? ktn10_ : 0.0f, ktn11 = two ? ktn11_ : 0.0f;
                     mf[1] = make_float4(rna[0], rnb[0], rta[0], rtb[0]);
                     mf[2] = make_float4(nmass[0], tmass[0], kb[0], ktt);
                     mf[3] = make_float4(rna[1], rnb[1], rta[1], rtb[1]);
