@@ -1471,9 +1471,19 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
 cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, cudaStream_t stream)
 {
     RolloutParams p = p_in;
-    // few chains (at most ~3 CTAs of 4 warps per SM): latency build; otherwise the occupancy build
-    if ((long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3) return launch_rollout_t<3>(p, num_sms, stream);
-    return launch_rollout_t<4>(p, num_sms, stream);
+    // few chains (at most ~3 CTAs of 4 warps per SM): latency build; otherwise the occupancy builds
+    static int forced = -1;  // tuning aid: MPS_ROLLOUT_MINB=3|4 pins the instantiation (5 and 6 CTAs per SM were
+                             // measured too: they spill and gain nothing, the kernel is not occupancy-bound)
+    if (forced < 0) {
+        const char* e = getenv("MPS_ROLLOUT_MINB");
+        forced = e ? atoi(e) : 0;
+    }
+    int minb = forced;
+    if (minb == 0) minb = (long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3 ? 3 : 4;
+    switch (minb) {
+    case 3: return launch_rollout_t<3>(p, num_sms, stream);
+    default: return launch_rollout_t<4>(p, num_sms, stream);
+    }
 }
 
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
