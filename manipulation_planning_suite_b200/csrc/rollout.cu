@@ -51,13 +51,16 @@ struct Manifold {
     float rax[2], ray[2], rbx[2], rby[2], sep[2];
 };
 
-__device__ __forceinline__ int collide_disc_disc(const Shape& A, const Shape& Bs, Manifold& m)
+__device__ __forceinline__ int collide_disc_disc(const Shape& A, const Shape& Bs, Manifold& m, float& gap)
 {
     float dx = Bs.x - A.x;
     float dy = Bs.y - A.y;
     float d2 = dx * dx + dy * dy;
     float R = A.hx + Bs.hx;
-    if (d2 > R * R) return 0;
+    if (d2 > R * R) {
+        gap = sqrtf(d2) - R;
+        return 0;
+    }
     float d = sqrtf(d2);
     float nx, ny;
     if (d > 1e-9f) {
@@ -81,7 +84,8 @@ __device__ __forceinline__ int collide_disc_disc(const Shape& A, const Shape& Bs
 }
 
 // box X against disc D; a_is_box: body a of the pair is the box
-__device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, bool a_is_box, Manifold& m)
+__device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, bool a_is_box, Manifold& m,
+                                                float& gap)
 {
     float ddx = D.x - X.x;
     float ddy = D.y - X.y;
@@ -111,7 +115,10 @@ __device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, 
         float vx = lx - qx;
         float vy = ly - qy;
         float d2 = vx * vx + vy * vy;
-        if (d2 > r * r) return 0;
+        if (d2 > r * r) {
+            gap = sqrtf(d2) - r;
+            return 0;
+        }
         float d = sqrtf(d2);
         nlx = vx / d;
         nly = vy / d;
@@ -150,7 +157,8 @@ __device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, 
 
 // rectangle-rectangle: 4-axis SAT, reference face = least penetration (A unless B is better by
 // ref_tol), incident edge clipped to the reference face's side planes
-__device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, float ref_tol, Manifold& m)
+__device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, float ref_tol, Manifold& m,
+                                               float& gap)
 {
     float dx = Bs.x - A.x;
     float dy = Bs.y - A.y;
@@ -166,7 +174,10 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
     float sep_ay = fabsf(pay) - A.hy - (Bs.hx * ad01 + Bs.hy * ad00);
     float sep_bx = fabsf(pbx) - Bs.hx - (A.hx * ad00 + A.hy * ad01);
     float sep_by = fabsf(pby) - Bs.hy - (A.hx * ad01 + A.hy * ad00);
-    if (sep_ax > 0.0f || sep_ay > 0.0f || sep_bx > 0.0f || sep_by > 0.0f) return 0;
+    if (sep_ax > 0.0f || sep_ay > 0.0f || sep_bx > 0.0f || sep_by > 0.0f) {
+        gap = fmaxf(fmaxf(sep_ax, sep_ay), fmaxf(sep_bx, sep_by));  // separated by at least this along an axis
+        return 0;
+    }
     bool a_face_y = sep_ay > sep_ax;
     bool b_face_y = sep_by > sep_bx;
     float sep_a = a_face_y ? sep_ay : sep_ax;
@@ -268,12 +279,14 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
     return n;
 }
 
-__device__ __forceinline__ int collide(const Shape& A, const Shape& Bs, float ref_tol, Manifold& m)
+// gap: when the shapes do not touch, a lower bound of their distance (0 when none is known)
+__device__ __forceinline__ int collide(const Shape& A, const Shape& Bs, float ref_tol, Manifold& m, float& gap)
 {
-    if (A.shape == MPS_SHAPE_BOX && Bs.shape == MPS_SHAPE_BOX) return collide_box_box(A, Bs, ref_tol, m);
-    if (A.shape == MPS_SHAPE_BOX && Bs.shape == MPS_SHAPE_DISC) return collide_box_disc(A, Bs, true, m);
-    if (A.shape == MPS_SHAPE_DISC && Bs.shape == MPS_SHAPE_BOX) return collide_box_disc(Bs, A, false, m);
-    return collide_disc_disc(A, Bs, m);
+    gap = 0.0f;
+    if (A.shape == MPS_SHAPE_BOX && Bs.shape == MPS_SHAPE_BOX) return collide_box_box(A, Bs, ref_tol, m, gap);
+    if (A.shape == MPS_SHAPE_BOX && Bs.shape == MPS_SHAPE_DISC) return collide_box_disc(A, Bs, true, m, gap);
+    if (A.shape == MPS_SHAPE_DISC && Bs.shape == MPS_SHAPE_BOX) return collide_box_disc(Bs, A, false, m, gap);
+    return collide_disc_disc(A, Bs, m, gap);
 }
 
 __device__ __forceinline__ unsigned char* opaque_shared_base(unsigned char* dyn)
@@ -289,6 +302,7 @@ struct WarpMem {
     float* py;
     float* pc;
     float* ps;
+    float* mv;        // [32] upper bound of the distance any point of the body has travelled in this chain
     float4* man;      // [Mcap][MF_VEC4]
     uint8_t* slot;    // [B][slot_stride]: manifold slot of pair (row body, column body|static); never
                       // cleared — an entry is trusted only if the manifold it names carries the same pair
@@ -306,6 +320,8 @@ struct WarpMem {
 struct StepCache {
     float rx, ry;  // this lane's body position at the last rebuild
     int n_list;    // pairs in W.cand, < 0: none
+    float clear_until;  // list entry `lane` was found separated by a gap: it cannot touch while the distance
+                        // its two bodies have travelled (W.mv) stays below this; -inf = unknown
     unsigned ent[4];
     int rounds, nm;       // nm < 0: no schedule
     unsigned sig0, sig1;  // pair of manifold slot `lane` / `lane + 32` the schedule was built for
@@ -313,6 +329,7 @@ struct StepCache {
     {
         n_list = -1;
         nm = -1;
+        clear_until = -1.0f;
     }
 };
 
@@ -419,6 +436,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             nl += n0 + __popc(m1);
         }
         cache.n_list = nl;
+        cache.clear_until = -1.0f;
         if (lane < B) {
             cache.rx = W.px[lane];
             cache.ry = W.py[lane];
@@ -454,10 +472,18 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         long long ts0 = clock64();
         if (sub) sub[0] += ts0 - tsb;
 #endif
+        // A pair found separated by a gap g cannot touch before its bodies have travelled g between them:
+        // until then the narrow phase is skipped for it (entries of the first trip only; exact, the skipped
+        // test could only have said "not touching").
         if (near) {
-            Shape A, Bs;
-            load_pair_shapes(sc, W, a, b, A, Bs);
-            cnt = collide(A, Bs, sc.ref_tol, m);
+            const float travelled = W.mv[a] + (b < B ? W.mv[b] : 0.0f);
+            if (base != 0 || !(travelled < cache.clear_until)) {
+                Shape A, Bs;
+                float gap;
+                load_pair_shapes(sc, W, a, b, A, Bs);
+                cnt = collide(A, Bs, sc.ref_tol, m, gap);
+                if (base == 0) cache.clear_until = gap > 4e-5f ? travelled + (0.9f * gap - 2e-5f) : -1.0f;
+            }
         }
         bool touch = cnt > 0;
         unsigned tmask = __ballot_sync(FULL, touch);
@@ -587,6 +613,7 @@ __device__ __forceinline__ int lookup_slot(const DevScene& sc, const WarpMem& W,
 struct Body {
     float x, y, th, c, s, vx, vy, w;
     float inv_m, inv_i, mass, inertia, lin_cap, ang_cap;
+    float mv, brad;  // travelled-distance bound (see WarpMem::mv), bounding radius
     bool dynamic;  // lane < B and not the robot
     bool live;     // lane < B
 };
@@ -598,6 +625,7 @@ __device__ __forceinline__ void publish_pose(const WarpMem& W, const Body& b, in
         W.py[lane] = b.y;
         W.pc[lane] = b.c;
         W.ps[lane] = b.s;
+        W.mv[lane] = b.mv;
     }
     __syncwarp();
 }
@@ -609,6 +637,7 @@ __device__ __forceinline__ void set_state(const WarpMem& W, Body& b, int lane, f
         b.y = y;
         b.th = mps_wrap_angle(th);
         mps_sincos(b.th, &b.s, &b.c);
+        b.mv += 1e-5f;  // the pose handed in may differ from the integrated one by a rounding of theta
     }
     b.vx = 0.0f;
     b.vy = 0.0f;
@@ -916,10 +945,13 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
         }
     }
     if (bd.live) {
+        const float ox = bd.x, oy = bd.y;
         bd.x = bd.x + sc.dt * bd.vx;
         bd.y = bd.y + sc.dt * bd.vy;
         bd.th = mps_wrap_angle(bd.th + sc.dt * bd.w);
         mps_sincos(bd.th, &bd.s, &bd.c);
+        // no point of the body moved further than |dx| + |dy| + R |dtheta| (slack for rounding)
+        bd.mv += (fabsf(bd.x - ox) + fabsf(bd.y - oy) + bd.brad * fabsf(sc.dt * bd.w)) * 1.001f + 1e-7f;
     }
     publish_pose(W, bd, lane);
     PH_T(t4);
@@ -1008,7 +1040,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     W.py = W.px + 32;
     W.pc = W.py + 32;
     W.ps = W.pc + 32;
-    W.man = reinterpret_cast<float4*>(W.ps + 32);
+    W.mv = W.ps + 32;
+    W.man = reinterpret_cast<float4*>(W.mv + 32);
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
 
@@ -1022,6 +1055,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         bd.mass = sc.mass[li];
         bd.inertia = sc.inertia[li];
         bd.lin_cap = sc.lin_cap[li];
+        bd.brad = sc.brad[li];
         bd.ang_cap = sc.ang_cap[li];
     }
     bd.x = bd.y = bd.th = 0.0f;
@@ -1043,6 +1077,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         if (n > L) n = L;
         const long long t_begin = clock64();
         cache.reset();
+        bd.mv = 0.0f;
 #ifdef MPS_PHASE_PROF
         for (int i = 0; i < 10; ++i) st.ph[i] = 0;
 #endif
@@ -1401,13 +1436,16 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
     W.py = W.px + 32;
     W.pc = W.py + 32;
     W.ps = W.pc + 32;
-    W.man = reinterpret_cast<float4*>(W.ps + 32);
+    W.mv = W.ps + 32;
+    W.man = reinterpret_cast<float4*>(W.mv + 32);
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * sc.Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
     Body bd;
     bd.live = lane < B;
     bd.dynamic = false;
     bd.inv_m = bd.inv_i = bd.mass = bd.inertia = bd.lin_cap = bd.ang_cap = 0.0f;
+    bd.mv = 0.0f;
+    bd.brad = 0.0f;
     bd.x = bd.y = bd.th = 0.0f;
     bd.c = 1.0f;
     bd.s = 0.0f;
@@ -1433,7 +1471,7 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
 
 size_t mps_rollout_warp_bytes(const DevScene& sc)
 {
-    size_t b = 4 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) +
+    size_t b = 5 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) +
                (((size_t)sc.B * sc.slot_stride + 3) & ~(size_t)3) + sizeof(uint16_t) * (size_t)sc.P;
     return (b + 15) & ~(size_t)15;
 }
