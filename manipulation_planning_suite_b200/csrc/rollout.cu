@@ -460,30 +460,31 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         int c = base + lane;
         Manifold m = {};
         int cnt = 0, a = 0, b = 0;
-        bool near = false;
+        // A pair found separated by a gap g cannot touch before its bodies have travelled g between them:
+        // until then it is not looked at again (entries of the first trip only).  Exact: the skipped test
+        // could only have said "not touching".  `candidates` counts the pairs that are looked at.
+        bool look = false;
+        float travelled = 0.0f;
         if (c < nlist) {
             unsigned pr = W.cand[c];
             a = pr & 0xff;
             b = pr >> 8;
-            near = pair_near(pr, 0.0f);
+            travelled = W.mv[a] + (b < B ? W.mv[b] : 0.0f);
+            look = base != 0 || !(travelled < cache.clear_until);
         }
+        if (!__any_sync(FULL, look)) continue;
+        const bool near = look && pair_near((unsigned)a | ((unsigned)b << 8), 0.0f);
         ncand += __popc(__ballot_sync(FULL, near));
 #ifdef MPS_PHASE_PROF
         long long ts0 = clock64();
         if (sub) sub[0] += ts0 - tsb;
 #endif
-        // A pair found separated by a gap g cannot touch before its bodies have travelled g between them:
-        // until then the narrow phase is skipped for it (entries of the first trip only; exact, the skipped
-        // test could only have said "not touching").
         if (near) {
-            const float travelled = W.mv[a] + (b < B ? W.mv[b] : 0.0f);
-            if (base != 0 || !(travelled < cache.clear_until)) {
-                Shape A, Bs;
-                float gap;
-                load_pair_shapes(sc, W, a, b, A, Bs);
-                cnt = collide(A, Bs, sc.ref_tol, m, gap);
-                if (base == 0) cache.clear_until = gap > 4e-5f ? travelled + (0.9f * gap - 2e-5f) : -1.0f;
-            }
+            Shape A, Bs;
+            float gap;
+            load_pair_shapes(sc, W, a, b, A, Bs);
+            cnt = collide(A, Bs, sc.ref_tol, m, gap);
+            if (base == 0) cache.clear_until = gap > 4e-5f ? travelled + (0.9f * gap - 2e-5f) : -1.0f;
         }
         bool touch = cnt > 0;
         unsigned tmask = __ballot_sync(FULL, touch);
