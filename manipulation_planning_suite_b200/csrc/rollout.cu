@@ -1134,56 +1134,55 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             const double t_dec_end = 2.0 * (double)t_acc + (double)t_pl;
             float time = 0.0f;
             bool ok = true;
-            // active phase (SimEnvStatePropagator.cpp:75-83)
-            while (time < T && ok) {
-                float ux, uy, uw;
-                if (time < t_acc) {
-                    ux = time * a0;
-                    uy = time * a1;
-                    uw = time * a2;
-                } else if (time < t_ap) {
-                    ux = v0;
-                    uy = v1;
-                    uw = v2;
-                } else if ((double)time < t_dec_end) {
-                    float s = time - t_acc - t_pl;
-                    ux = v0 - s * a0;
-                    uy = v1 - s * a1;
-                    uw = v2 - s * a2;
-                } else {
-                    ux = 0.0f;
-                    uy = 0.0f;
-                    uw = 0.0f;
+            // Active phase (SimEnvStatePropagator.cpp:75-83) and rest phase (:86-105) run through ONE loop with
+            // one call of physics_step: the step is the bulk of the kernel's code, and a second inlined copy
+            // costs more in instruction-cache misses than the phase test costs per step.
+            float rest = 0.0f;
+            bool in_rest = false, resting = false;
+            int jam = 0;
+            for (;;) {
+                if (!in_rest && !(time < T && ok)) {
+                    if (!ok) break;
+                    in_rest = true;
+                    resting = at_rest(sc, bd);
+                }
+                if (in_rest && !(rest <= sc.t_max && !resting && ok)) break;
+                float ux = 0.0f, uy = 0.0f, uw = 0.0f;
+                if (!in_rest) {
+                    if (time < t_acc) {
+                        ux = time * a0;
+                        uy = time * a1;
+                        uw = time * a2;
+                    } else if (time < t_ap) {
+                        ux = v0;
+                        uy = v1;
+                        uw = v2;
+                    } else if ((double)time < t_dec_end) {
+                        float s = time - t_acc - t_pl;
+                        ux = v0 - s * a0;
+                        uy = v1 - s * a1;
+                        uw = v2 - s * a2;
+                    }
                 }
                 bool bad, over;
                 float pen;
                 physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, pen, st, cache);
-                time += sc.dt;
                 if (over) {
                     flags |= MPS_F_OVERFLOW;
                     ok = false;
                 }
-                if (bad && sc.strict) {
-                    flags |= MPS_F_ACTIVE_CONTACT;
-                    ok = false;
-                }
-            }
-            // rest phase (:86-105)
-            float rest = 0.0f;
-            if (ok) {
-                bool resting = at_rest(sc, bd);
-                int jam = 0;
-                while (rest <= sc.t_max && !resting && ok) {
-                    bool bad, over;
-                    float pen;
-                    physics_step(sc, W, bd, lane, 0.0f, 0.0f, 0.0f, bad, over, pen, st, cache);
-                    ok = !bad;
-                    rest += sc.dt;
-                    if (bad) flags |= MPS_F_REST_CONTACT;
-                    if (over) {
-                        flags |= MPS_F_OVERFLOW;
+                if (!in_rest) {
+                    time += sc.dt;
+                    if (bad && sc.strict) {
+                        flags |= MPS_F_ACTIVE_CONTACT;
                         ok = false;
                     }
+                } else {
+                    if (bad) {
+                        flags |= MPS_F_REST_CONTACT;
+                        ok = false;
+                    }
+                    rest += sc.dt;
                     // jam rule: wedged deeper than 2 * slop for jam_steps consecutive rest steps
                     jam = pen > 2.0f * sc.slop ? jam + 1 : 0;
                     if (sc.jam_steps > 0 && jam >= sc.jam_steps) {
@@ -1192,6 +1191,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                     }
                     resting = at_rest(sc, bd);
                 }
+            }
+            if (in_rest) {
                 if (!(rest <= sc.t_max && resting)) flags |= MPS_F_NOT_AT_REST;
                 ok = rest <= sc.t_max && resting && ok;
             }
