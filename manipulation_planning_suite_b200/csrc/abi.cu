@@ -259,6 +259,7 @@ static void derive_scene(const mps_scene* sc, DevScene* d)
     for (int k = 0; k < S; ++k)
         for (int i = 0; i < B; ++i) d->pairs[P++] = (uint16_t)(i | ((B + k) << 8));
     d->P = P;
+    if (d->Mcap > P) d->Mcap = P;  // no more manifolds than pairs: same overflow behaviour, less shared memory
     const char* fg = getenv("MPS_FORCE_GENERAL_SWEEP");
     d->force_general = (fg && fg[0] == '1') ? 1 : 0;
 }
@@ -953,7 +954,7 @@ int mps_extend_launch(mps_ctx* ctx)
     }
     const bool timed = ctx->timing && ctx->ev_count < MPS_EVENT_RING;
     if (timed) MPS_CUDA_CHECK(cudaEventRecord(ctx->ev0[ctx->ev_count], ctx->stream), ctx);
-    MPS_CUDA_CHECK(mps_launch_rollout(ctx->rp, ctx->num_sms, ctx->stream), ctx);
+    MPS_CUDA_CHECK(mps_launch_rollout(ctx->rp, ctx->num_sms, ctx->scene.n_bodies, ctx->stream), ctx);
     if (timed) {
         MPS_CUDA_CHECK(cudaEventRecord(ctx->ev1[ctx->ev_count], ctx->stream), ctx);
         ctx->ev_count++;
@@ -1264,7 +1265,7 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     sp.tree_slice = ctx->forest.slice;
     sp.inst_ids = rp.inst_ids;
     sp.parents = rp.parents;
-    MPS_CUDA_CHECK(mps_launch_rollout(rp, ctx->num_sms, st), ctx);
+    MPS_CUDA_CHECK(mps_launch_rollout(rp, ctx->num_sms, ctx->scene.n_bodies, st), ctx);
     MPS_CUDA_CHECK(mps_launch_select(sp, st), ctx);
     ctx->launches += 2;
     ctx->extend_ready = false;  // the plain extend's cached parameters no longer describe the buffers

@@ -27,6 +27,28 @@
 
 #define FULL 0xffffffffu
 
+// A rollout chain is run by a group of G consecutive lanes of a warp (G = 32: the whole warp; G = 16 / 8: two /
+// four chains per warp for scenes with at most G bodies, so that the lanes a small scene leaves idle carry
+// other chains).  `lane` in the device functions below is the lane WITHIN the group (= body / pair index);
+// every warp collective uses the group's mask, so groups of one warp may be in different places of the code.
+struct Ln {
+    int g;       // lane within the group
+    int base;    // first lane of the group in the warp
+    unsigned m;  // member mask of the group
+    __device__ __forceinline__ int abs_lane(int body) const { return base + body; }
+    __device__ __forceinline__ unsigned below() const { return (1u << (base + g)) - 1u; }  // lanes before this one
+};
+template <int G>
+__device__ __forceinline__ Ln make_ln()
+{
+    Ln ln;
+    const int pl = threadIdx.x & 31;
+    ln.g = pl & (G - 1);
+    ln.base = pl & ~(G - 1);
+    ln.m = G == 32 ? FULL : (((1u << G) - 1u) << ln.base);
+    return ln;
+}
+
 namespace {
 
 
@@ -307,6 +329,7 @@ struct WarpMem {
     uint8_t* slot;    // [B][slot_stride]: manifold slot of pair (row body, column body|static); never
                       // cleared — an entry is trusted only if the manifold it names carries the same pair
     uint16_t* cand;   // [P] broad-phase survivors of the current step
+    uint16_t* sig;    // [Mcap] pair of every manifold slot the round schedule was built for (packed groups)
 };
 
 // State a chain carries from one physics step to the next (registers).
@@ -366,10 +389,12 @@ __device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpM
 }
 
 // collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
-__device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, int lane, bool prepare,
+template <int G>
+__device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, const Ln ln, bool prepare,
                                                StepCache& cache, long long* t_mid = nullptr,
                                                long long* sub = nullptr)
 {
+    const int lane = ln.g;
     const int B = sc.B;
     const int Mcap = sc.Mcap;
     // ---- broad phase: lane = pair, bounding circles, survivors compacted into W.cand ------------
@@ -410,14 +435,14 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             float dy = W.py[lane] - cache.ry;
             moved = dx * dx + dy * dy > MPS_SKIN_MOVE2;
         }
-        rebuild = __any_sync(FULL, moved);
+        rebuild = __any_sync(ln.m, moved);
     }
     if (rebuild) {
         // two chunks of 32 pairs per trip so that their loads and tests overlap
         int nl = 0;
-        const unsigned lt = (1u << lane) - 1u;
-        for (int base = 0; base < sc.P; base += 64) {
-            const int p0 = base + lane, p1 = base + 32 + lane;
+        const unsigned lt = ln.below();
+        for (int base = 0; base < sc.P; base += 2 * G) {
+            const int p0 = base + lane, p1 = base + G + lane;
             unsigned pr0 = 0, pr1 = 0;
             bool c0 = false, c1 = false;
             if (p0 < sc.P) {
@@ -428,8 +453,8 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
                 pr1 = sc.pairs[p1];
                 c1 = pair_near(pr1, MPS_SKIN);
             }
-            const unsigned m0 = __ballot_sync(FULL, c0);
-            const unsigned m1 = __ballot_sync(FULL, c1);
+            const unsigned m0 = __ballot_sync(ln.m, c0);
+            const unsigned m1 = __ballot_sync(ln.m, c1);
             const int n0 = __popc(m0);
             if (c0) W.cand[nl + __popc(m0 & lt)] = (uint16_t)pr0;
             if (c1) W.cand[nl + n0 + __popc(m1 & lt)] = (uint16_t)pr1;
@@ -441,7 +466,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             cache.rx = W.px[lane];
             cache.ry = W.py[lane];
         }
-        __syncwarp();
+        __syncwarp(ln.m);
     }
     const int nlist = cache.n_list;
     int ncand = 0;
@@ -453,7 +478,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
     bool lane_bad = false, lane_over = false;
     float lane_pen = 0.0f;
     unsigned n_touch = 0;
-    for (int base = 0; base < nlist; base += 32) {
+    for (int base = 0; base < nlist; base += G) {
 #ifdef MPS_PHASE_PROF
         long long tsb = clock64();
 #endif
@@ -472,9 +497,9 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             travelled = W.mv[a] + (b < B ? W.mv[b] : 0.0f);
             look = base != 0 || !(travelled < cache.clear_until);
         }
-        if (!__any_sync(FULL, look)) continue;
+        if (!__any_sync(ln.m, look)) continue;
         const bool near = look && pair_near((unsigned)a | ((unsigned)b << 8), 0.0f);
-        ncand += __popc(__ballot_sync(FULL, near));
+        ncand += __popc(__ballot_sync(ln.m, near));
 #ifdef MPS_PHASE_PROF
         long long ts0 = clock64();
         if (sub) sub[0] += ts0 - tsb;
@@ -487,7 +512,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             if (base == 0) cache.clear_until = gap > 4e-5f ? travelled + (0.9f * gap - 2e-5f) : -1.0f;
         }
         bool touch = cnt > 0;
-        unsigned tmask = __ballot_sync(FULL, touch);
+        unsigned tmask = __ballot_sync(ln.m, touch);
 #ifdef MPS_PHASE_PROF
         long long ts1 = clock64();
         if (sub) sub[1] += ts1 - ts0;
@@ -510,7 +535,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             const bool bstat = b >= B;
             const unsigned forbid = bstat ? (sc.static_forbidden >> a) : (sc.pair_forbidden[a] >> (b & 31));
             if (forbid & 1u) lane_bad = true;
-            int idx = nm + __popc(tmask & ((1u << lane) - 1u));
+            int idx = nm + __popc(tmask & ln.below());
             if (idx < Mcap) {
                 float4* mf = W.man + idx * MF_VEC4;
                 int meta = a | (b << 8) | (cnt << 16);
@@ -578,14 +603,14 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         nm += __popc(tmask);
     }
     DetectResult r;
-    const unsigned fl = __reduce_or_sync(FULL, (lane_bad ? 1u : 0u) | (lane_over ? 2u : 0u));
+    const unsigned fl = __reduce_or_sync(ln.m, (lane_bad ? 1u : 0u) | (lane_over ? 2u : 0u));
     r.bad = (fl & 1u) != 0u;
     r.overflow = (fl & 2u) != 0u;
-    r.max_pen = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(lane_pen)));
+    r.max_pen = __uint_as_float(__reduce_max_sync(ln.m, __float_as_uint(lane_pen)));
     r.nm = nm < Mcap ? nm : Mcap;
     r.candidates = (unsigned)ncand;
     r.touching = n_touch;
-    __syncwarp();
+    __syncwarp(ln.m);
     return r;
 }
 
@@ -619,8 +644,9 @@ struct Body {
     bool live;     // lane < B
 };
 
-__device__ __forceinline__ void publish_pose(const WarpMem& W, const Body& b, int lane)
+__device__ __forceinline__ void publish_pose(const WarpMem& W, const Body& b, const Ln ln)
 {
+    const int lane = ln.g;
     if (b.live) {
         W.px[lane] = b.x;
         W.py[lane] = b.y;
@@ -628,10 +654,10 @@ __device__ __forceinline__ void publish_pose(const WarpMem& W, const Body& b, in
         W.ps[lane] = b.s;
         W.mv[lane] = b.mv;
     }
-    __syncwarp();
+    __syncwarp(ln.m);
 }
 
-__device__ __forceinline__ void set_state(const WarpMem& W, Body& b, int lane, float x, float y, float th)
+__device__ __forceinline__ void set_state(const WarpMem& W, Body& b, const Ln ln, float x, float y, float th)
 {
     if (b.live) {
         b.x = x;
@@ -643,7 +669,7 @@ __device__ __forceinline__ void set_state(const WarpMem& W, Body& b, int lane, f
     b.vx = 0.0f;
     b.vy = 0.0f;
     b.w = 0.0f;
-    publish_pose(W, b, lane);
+    publish_pose(W, b, ln);
 }
 
 struct StepStats {
@@ -668,11 +694,12 @@ struct StepStats {
 // The pass has no data-dependent branch and no barrier: lanes without a manifold run the arithmetic on slot 0
 // and drop the result, a one-point manifold carries zero rows for the second point, and each owner lane keeps
 // its own copy of the accumulated impulses, so no lane reads what another lane writes during the sweep.
-__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane, int sl, int j, bool stat)
+__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln ln, int sl, int j, bool stat)
 {
-    float ovx = __shfl_sync(FULL, bd.vx, j);
-    float ovy = __shfl_sync(FULL, bd.vy, j);
-    float ow_ = __shfl_sync(FULL, bd.w, j);
+    const int lane = ln.g;
+    float ovx = __shfl_sync(ln.m, bd.vx, ln.abs_lane(j));
+    float ovy = __shfl_sync(ln.m, bd.vy, ln.abs_lane(j));
+    float ow_ = __shfl_sync(ln.m, bd.w, ln.abs_lane(j));
     const bool act = sl != 0xff;
     const bool is_a = stat || lane < j;
     float4* mf = W.man + (act ? sl : 0) * MF_VEC4;
@@ -746,12 +773,14 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, int lane,
 
 // General sweep, colour by colour in canonical order, for steps in which some body has more than 4
 // manifolds (rare): the slot table and the set of active colours are built from the manifold list first.
-__device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem& W, Body& bd, int lane, int nm,
+template <int G>
+__device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem& W, Body& bd, const Ln ln, int nm,
                                               StepStats& st)
 {
+    const int lane = ln.g;
     const int B = sc.B;
     unsigned long long lane_col = 0ull;
-    for (int m = lane; m < nm; m += 32) {
+    for (int m = lane; m < nm; m += G) {
         const int meta = __float_as_int(W.man[m * MF_VEC4].x);
         const int a = meta & 0xff, b = (meta >> 8) & 0xff;
         W.slot[a * sc.slot_stride + b] = (uint8_t)m;
@@ -765,10 +794,10 @@ __device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem&
         }
         lane_col |= 1ull << col;
     }
-    const unsigned lo = __reduce_or_sync(FULL, (unsigned)(lane_col & 0xffffffffull));
-    const unsigned hi = __reduce_or_sync(FULL, (unsigned)(lane_col >> 32));
+    const unsigned lo = __reduce_or_sync(ln.m, (unsigned)(lane_col & 0xffffffffull));
+    const unsigned hi = __reduce_or_sync(ln.m, (unsigned)(lane_col >> 32));
     const unsigned long long colours = ((unsigned long long)hi << 32) | lo;
-    __syncwarp();
+    __syncwarp(ln.m);
     st.colour_passes += (unsigned)(__popcll(colours) * sc.vel_iters);
     for (int it = 0; it < sc.vel_iters; ++it) {
         unsigned long long cm = colours;
@@ -782,16 +811,18 @@ __device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem&
                 j = col - lane;
                 if (j < 0) j += B;
             }
-            solve_pass(W, bd, lane, slot, j, stat);
+            solve_pass(W, bd, ln, slot, j, stat);
         }
     }
 }
 
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
-__device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, int lane, float ux,
+template <int G>
+__device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, const Ln ln, float ux,
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
                                              StepStats& st, StepCache& cache)
 {
+    const int lane = ln.g;
     const int B = sc.B;
     if (lane == sc.robot) {
         bd.vx = ux;
@@ -801,9 +832,9 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     PH_T(t0);
 #ifdef MPS_PHASE_PROF
     long long t_mid = t0;
-    DetectResult dr = detect(sc, W, lane, true, cache, &t_mid, &st.ph[6]);
+    DetectResult dr = detect<G>(sc, W, ln, true, cache, &t_mid, &st.ph[6]);
 #else
-    DetectResult dr = detect(sc, W, lane, true, cache);
+    DetectResult dr = detect<G>(sc, W, ln, true, cache);
 #endif
     PH_T(t1);
     PH_ADD(0, t0, t_mid);
@@ -844,11 +875,19 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             // with more manifolds than that sends the step to the general sweep below (rounds = -1).
             // The schedule depends only on which pair sits in which manifold slot: reuse the last one while
             // that list is unchanged (contact sets persist over many steps).
-            const unsigned sig0 =
-                lane < dr.nm ? (unsigned)(__float_as_int(W.man[lane * MF_VEC4].x) & 0xffff) : 0xffffffffu;
-            const unsigned sig1 =
-                lane + 32 < dr.nm ? (unsigned)(__float_as_int(W.man[(lane + 32) * MF_VEC4].x) & 0xffff) : 0xffffffffu;
-            const bool same = __all_sync(FULL, cache.nm == dr.nm && sig0 == cache.sig0 && sig1 == cache.sig1);
+            unsigned sig0 = 0xffffffffu, sig1 = 0xffffffffu;
+            bool same;
+            if (G == 32) {
+                if (lane < dr.nm) sig0 = (unsigned)(__float_as_int(W.man[lane * MF_VEC4].x) & 0xffff);
+                if (lane + 32 < dr.nm) sig1 = (unsigned)(__float_as_int(W.man[(lane + 32) * MF_VEC4].x) & 0xffff);
+                same = __all_sync(ln.m, cache.nm == dr.nm && sig0 == cache.sig0 && sig1 == cache.sig1);
+            } else {
+                // packed groups keep the list the schedule was built for in shared memory
+                bool eq = cache.nm == dr.nm;
+                for (int sl = lane; sl < dr.nm; sl += G)
+                    eq = eq && W.sig[sl] == (uint16_t)(__float_as_int(W.man[sl * MF_VEC4].x) & 0xffff);
+                same = __all_sync(ln.m, eq);
+            }
             if (!same) {
                 unsigned e0 = 0u, e1 = 0u, e2 = 0u, e3 = 0u;
                 int last = 0, ne = 0;
@@ -862,9 +901,9 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     const bool dyn_a = a != sc.robot;
                     const bool dyn_b = !stc && b != sc.robot;
                     int r = 0;
-                    if (dyn_a) r = __shfl_sync(FULL, last, a);
+                    if (dyn_a) r = __shfl_sync(ln.m, last, ln.abs_lane(a));
                     if (dyn_b) {
-                        const int lb = __shfl_sync(FULL, last, b);
+                        const int lb = __shfl_sync(ln.m, last, ln.abs_lane(b));
                         r = r > lb ? r : lb;
                     }
                     r += 1;
@@ -879,8 +918,8 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                         ++ne;
                     }
                 }
-                int nr = __reduce_max_sync(FULL, last);
-                if (__any_sync(FULL, ne > 4) || sc.force_general) nr = -1;
+                int nr = __reduce_max_sync(ln.m, last);
+                if (__any_sync(ln.m, ne > 4) || sc.force_general) nr = -1;
                 if (nr >= 0 && nr <= 4) {
                     // few rounds (the usual case): index the entries by round, ent[r - 1] = this lane's
                     // manifold of round r or 0, so the sweep needs no search
@@ -907,6 +946,11 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 cache.nm = dr.nm;
                 cache.sig0 = sig0;
                 cache.sig1 = sig1;
+                if (G != 32) {
+                    for (int sl = lane; sl < dr.nm; sl += G)
+                        W.sig[sl] = (uint16_t)(__float_as_int(W.man[sl * MF_VEC4].x) & 0xffff);
+                    __syncwarp(ln.m);
+                }
             }
             const int rounds = cache.rounds;
             if (rounds >= 0) st.colour_passes += (unsigned)(rounds * sc.vel_iters);
@@ -916,10 +960,10 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             auto pass = [&](unsigned e) {
                 const int slr = e ? (int)(e & 0xffu) : 0xff;
                 const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
-                solve_pass(W, bd, lane, slr, jr, (e & 0x8000u) != 0u);
+                solve_pass(W, bd, ln, slr, jr, (e & 0x8000u) != 0u);
             };
             if (rounds < 0) {
-                general_sweep(sc, W, bd, lane, dr.nm, st);
+                general_sweep<G>(sc, W, bd, ln, dr.nm, st);
             } else if (rounds <= 4) {
                 for (int it = 0; it < iters; ++it) {
                     pass(cache.ent[0]);
@@ -954,16 +998,16 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
         // no point of the body moved further than |dx| + |dy| + R |dtheta| (slack for rounding)
         bd.mv += (fabsf(bd.x - ox) + fabsf(bd.y - oy) + bd.brad * fabsf(sc.dt * bd.w)) * 1.001f + 1e-7f;
     }
-    publish_pose(W, bd, lane);
+    publish_pose(W, bd, ln);
     PH_T(t4);
     PH_ADD(4, t1, t4);  // includes phases 2 and 3
 }
 
-__device__ __forceinline__ bool at_rest(const DevScene& sc, const Body& bd)
+__device__ __forceinline__ bool at_rest(const DevScene& sc, const Body& bd, const Ln ln)
 {
     bool moving = false;
     if (bd.live) moving = (bd.vx * bd.vx + bd.vy * bd.vy > sc.v_rest2) || (fabsf(bd.w) > sc.w_rest);
-    return !__any_sync(FULL, moving);
+    return !__any_sync(ln.m, moving);
 }
 
 // satisfiesBounds of the reference's compound space, per body in double
@@ -977,14 +1021,15 @@ __device__ __forceinline__ bool body_in_bounds(const DevScene& sc, float xf, flo
 }
 
 // isValid(state) with the state already in the lanes (sx, sy, sth = the float state values)
-__device__ __forceinline__ uint32_t state_validity_flags(const DevScene& sc, const WarpMem& W, Body& bd, int lane,
+template <int G>
+__device__ __forceinline__ uint32_t state_validity_flags(const DevScene& sc, const WarpMem& W, Body& bd, const Ln ln,
                                                          float sx, float sy, float sth, StepStats* st,
                                                          StepCache& cache)
 {
     bool oob = bd.live && !body_in_bounds(sc, sx, sy, sth);
-    if (__any_sync(FULL, oob)) return MPS_F_BOUNDS;
-    set_state(W, bd, lane, sx, sy, sth);
-    DetectResult dr = detect(sc, W, lane, false, cache);
+    if (__any_sync(ln.m, oob)) return MPS_F_BOUNDS;
+    set_state(W, bd, ln, sx, sy, sth);
+    DetectResult dr = detect<G>(sc, W, ln, false, cache);
     (void)st;
     uint32_t f = 0;
     if (dr.max_pen > sc.pen_max) f |= MPS_F_INFEASIBLE;
@@ -994,10 +1039,11 @@ __device__ __forceinline__ uint32_t state_validity_flags(const DevScene& sc, con
 }
 
 // sum_i mask_i w_i (pw |dxy_i| + ow arc_i) accumulated in body order, in double
-__device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& bd, int lane, float sx, float sy,
+__device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& bd, const Ln ln, float sx, float sy,
                                                 float sth, const float* __restrict__ other,
                                                 const float* __restrict__ weights, uint32_t mask)
 {
+    const int lane = ln.g;
     double term = 0.0;
     if (bd.live && ((mask >> lane) & 1u)) {
         double cfg = mps_body_distance(sx, sy, sth, other[3 * lane], other[3 * lane + 1], other[3 * lane + 2],
@@ -1007,7 +1053,7 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
     }
     double dist = 0.0;
     for (int i = 0; i < sc.B; ++i) {
-        double t = __shfl_sync(FULL, term, i);
+        double t = __shfl_sync(ln.m, term, ln.abs_lane(i));
         if ((mask >> i) & 1u) dist += t;
     }
     return dist;
@@ -1017,7 +1063,7 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
 // registers, no spills) for launches with few chains, where one warp per scheduler runs alone and only its
 // own dependent-instruction latency matters, and MINB = 4 (128 registers) for launches that fill the machine,
 // where resident warps per SM decide the throughput.
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, int G>
 __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -1031,11 +1077,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         for (int i = threadIdx.x; i < (int)(sizeof(DevScene) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const Ln ln = make_ln<G>();
+    const int lane = ln.g;  // lane within the chain's group = body index
+    const int group = (threadIdx.x >> 5) * (32 / G) + ((threadIdx.x & 31) / G);
     const int B = sc.B;
     const int Mcap = sc.Mcap;
-    unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)warp * p.warp_bytes;
+    unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)group * p.warp_bytes;
     WarpMem W;
     W.px = reinterpret_cast<float*>(wbase);
     W.py = W.px + 32;
@@ -1045,6 +1092,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     W.man = reinterpret_cast<float4*>(W.mv + 32);
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
+    W.sig = W.cand + ((sc.P + 1) & ~1);
 
     Body bd;
     bd.live = lane < B;
@@ -1072,7 +1120,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     for (;;) {
         int k = 0;
         if (lane == 0) k = (int)atomicAdd(p.work_counter, 1u);
-        k = __shfl_sync(FULL, k, 0);
+        k = __shfl_sync(ln.m, k, ln.abs_lane(0));
         if (k >= p.K) break;
         int n = p.n_ctrl ? p.n_ctrl[k] : L;
         if (n > L) n = L;
@@ -1110,7 +1158,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             const float* ctrl = p.controls + kl * MPS_CONTROL_DIM;
             uint32_t flags = MPS_F_RAN;
             unsigned steps0 = st.steps;
-            set_state(W, bd, lane, sx, sy, sth);
+            set_state(W, bd, ln, sx, sy, sth);
             // RampVelocityControl::computeRamp (rest time reset to 0 before propagating)
             float v0 = ctrl[0], v1 = ctrl[1], v2 = ctrl[2], t_pl = ctrl[3];
             float t_acc = fabsf(v0 / sc.accel[0]);
@@ -1144,7 +1192,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 if (!in_rest && !(time < T && ok)) {
                     if (!ok) break;
                     in_rest = true;
-                    resting = at_rest(sc, bd);
+                    resting = at_rest(sc, bd, ln);
                 }
                 if (in_rest && !(rest <= sc.t_max && !resting && ok)) break;
                 float ux = 0.0f, uy = 0.0f, uw = 0.0f;
@@ -1166,7 +1214,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 }
                 bool bad, over;
                 float pen;
-                physics_step(sc, W, bd, lane, ux, uy, uw, bad, over, pen, st, cache);
+                physics_step<G>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
                 if (over) {
                     flags |= MPS_F_OVERFLOW;
                     ok = false;
@@ -1189,7 +1237,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                         flags |= MPS_F_JAMMED;
                         ok = false;
                     }
-                    resting = at_rest(sc, bd);
+                    resting = at_rest(sc, bd, ln);
                 }
             }
             if (in_rest) {
@@ -1199,7 +1247,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             // extractState: theta normalised in double, read back as float
             float rx = bd.x, ry = bd.y;
             float rth = (float)mps_normalize_orientation((double)bd.th);
-            uint32_t vf = state_validity_flags(sc, W, bd, lane, rx, ry, rth, &st, cache);
+            uint32_t vf = state_validity_flags<G>(sc, W, bd, ln, rx, ry, rth, &st, cache);
             flags |= vf;
             ok = ok && vf == 0u;
             if (ok) {
@@ -1209,8 +1257,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                     double gd = 0.0;
                     for (int g = 0; g < p.n_goals; ++g) {
                         int gb = p.goals[g].body;
-                        float gx = __shfl_sync(FULL, rx, gb);
-                        float gy = __shfl_sync(FULL, ry, gb);
+                        float gx = __shfl_sync(ln.m, rx, ln.abs_lane(gb));
+                        float gy = __shfl_sync(ln.m, ry, ln.abs_lane(gb));
                         float fx = p.goals[g].x - gx;
                         float fy = p.goals[g].y - gy;
                         double dc = sqrt((double)fx * (double)fx + (double)fy * (double)fy);
@@ -1225,7 +1273,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 if (p.ball_center) {
                     uint32_t arr_mask = ~(1u << sc.robot);
                     if (B < 32) arr_mask &= (1u << B) - 1u;
-                    double bdist = warp_distance(sc, bd, lane, rx, ry, rth, p.ball_center, p.weights, arr_mask);
+                    double bdist = warp_distance(sc, bd, ln, rx, ry, rth, p.ball_center, p.weights, arr_mask);
                     if (bdist <= (double)p.ball_radius) flags |= MPS_F_IN_BALL;
                 }
             }
@@ -1269,7 +1317,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
             }
         }
         double dist = __longlong_as_double(0x7ff0000000000000ll);  // +inf
-        if (n_ok > 0 && dest) dist = warp_distance(sc, bd, lane, sx, sy, sth, dest, p.weights, dmask);
+        if (n_ok > 0 && dest) dist = warp_distance(sc, bd, ln, sx, sy, sth, dest, p.weights, dmask);
         if (lane == 0) {
             p.out_dist[k] = dist;
             p.out_nok[k] = n_ok;
@@ -1442,6 +1490,8 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
     W.man = reinterpret_cast<float4*>(W.mv + 32);
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * sc.Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
+    W.sig = W.cand + ((sc.P + 1) & ~1);
+    const Ln ln = make_ln<32>();
     Body bd;
     bd.live = lane < B;
     bd.dynamic = false;
@@ -1461,7 +1511,7 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
         }
         StepCache cache;
         cache.reset();
-        uint32_t f = state_validity_flags(sc, W, bd, lane, sx, sy, sth, nullptr, cache);
+        uint32_t f = state_validity_flags<32>(sc, W, bd, ln, sx, sy, sth, nullptr, cache);
         if (lane == 0) {
             p.flags[i] = f;
             p.valid[i] = f == 0u ? 1 : 0;
@@ -1474,7 +1524,8 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
 size_t mps_rollout_warp_bytes(const DevScene& sc)
 {
     size_t b = 5 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) +
-               (((size_t)sc.B * sc.slot_stride + 3) & ~(size_t)3) + sizeof(uint16_t) * (size_t)sc.P;
+               (((size_t)sc.B * sc.slot_stride + 3) & ~(size_t)3) + sizeof(uint16_t) * (size_t)((sc.P + 1) & ~1) +
+               sizeof(uint16_t) * (size_t)sc.Mcap;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1482,48 +1533,64 @@ size_t mps_rollout_scene_bytes() { return (sizeof(DevScene) + 15) & ~(size_t)15;
 
 #define ROLLOUT_WARPS 4
 
-template <int MINB>
+// WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
+template <int WARPS, int MINB, int G>
 static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
 {
-    size_t smem = p.scene_bytes + (size_t)ROLLOUT_WARPS * p.warp_bytes;
+    const int groups = WARPS * (32 / G);  // chains a CTA works on at a time
+    size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<ROLLOUT_WARPS, MINB>,
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WARPS, MINB, G>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     int blocks_per_sm = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<ROLLOUT_WARPS, MINB>,
-                                                                  ROLLOUT_WARPS * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<WARPS, MINB, G>,
+                                                                  WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    int want = (p.K + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS;
+    int want = (p.K + groups - 1) / groups;
     int grid = num_sms * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    rollout_kernel<ROLLOUT_WARPS, MINB><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
+    rollout_kernel<WARPS, MINB, G><<<grid, WARPS * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, cudaStream_t stream)
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bodies, cudaStream_t stream)
 {
     RolloutParams p = p_in;
-    // few chains (at most ~3 CTAs of 4 warps per SM): latency build; otherwise the occupancy builds
-    static int forced = -1;  // tuning aid: MPS_ROLLOUT_MINB=3|4 pins the instantiation (5 and 6 CTAs per SM were
-                             // measured too: they spill and gain nothing, the kernel is not occupancy-bound)
-    if (forced < 0) {
-        const char* e = getenv("MPS_ROLLOUT_MINB");
-        forced = e ? atoi(e) : 0;
+    // Few chains (at most ~3 CTAs of 4 warps per SM): one warp per chain, latency build.  Launches that fill
+    // the machine are bound by instruction issue: scenes with at most 8 / 16 bodies then run four / two chains
+    // per warp (same arithmetic per chain, so the same bits), which divides the instructions per chain.
+    // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build,
+    // MPS_ROLLOUT_GROUP = 8 | 16 | 32 the lanes per chain.
+    static int forced_minb = -1, forced_g = -1;
+    if (forced_minb < 0) {
+        forced_minb = env_int("MPS_ROLLOUT_MINB", 0);
+        forced_g = env_int("MPS_ROLLOUT_GROUP", 0);
     }
-    int minb = forced;
-    if (minb == 0) minb = (long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3 ? 3 : 4;
-    switch (minb) {
-    case 3: return launch_rollout_t<3>(p, num_sms, stream);
-    default: return launch_rollout_t<4>(p, num_sms, stream);
-    }
+    const bool few = (long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3;
+    int g = forced_g;
+    if (g == 0) g = few ? 32 : (n_bodies <= 8 ? 8 : n_bodies <= 16 ? 16 : 32);
+    if (g == 8 && n_bodies > 8) g = 16;
+    if (g == 16 && n_bodies > 16) g = 32;
+    if (g == 8) return launch_rollout_t<2, 4, 8>(p, num_sms, stream);
+    if (g == 16) return launch_rollout_t<ROLLOUT_WARPS, 4, 16>(p, num_sms, stream);
+    int minb = forced_minb;
+    if (minb == 0) minb = few ? 3 : 4;
+    if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream);
+    return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream);
 }
 
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)

@@ -84,6 +84,6 @@ struct ValidityParams {
 
 size_t mps_rollout_warp_bytes(const DevScene& sc);
 size_t mps_rollout_scene_bytes();
-cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, cudaStream_t stream);
+cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, int n_bodies, cudaStream_t stream);
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream);
 cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream);

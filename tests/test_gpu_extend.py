@@ -294,3 +294,21 @@ def test_general_sweep_matches_oracle(monkeypatch):
     r = compare_extend(sc, start, controls, dest=dest)
     assert r["got"].all_steps.sum() > 1000
     assert ((r["want"]["all_flags"] & abi.MPS_F_OK) != 0).any()
+
+
+@pytest.mark.parametrize("group,n_objects", [(8, 3), (8, 6), (8, 7), (16, 8), (16, 12), (16, 15)])
+def test_packed_chains_match_oracle(monkeypatch, group, n_objects):
+    """Two / four chains per warp (scenes with at most 16 / 8 bodies, chosen automatically for launches that fill
+    the machine, forced here through MPS_ROLLOUT_GROUP): same bits as one chain per warp and as the oracle."""
+    monkeypatch.setenv("MPS_ROLLOUT_GROUP", str(group))
+    sc, _ = scenes.make_scene(n_objects, seed=30 + n_objects)
+    start = scenes.cluttered_start(sc, 40 + n_objects)
+    rng = np.random.RandomState(n_objects)
+    K, L = 70, 3   # not a multiple of the chains per CTA: the last groups run out of work at different times
+    controls = scenes.sample_controls_towards(rng, sc, start, K, L)
+    n_ctrl = rng.randint(1, L + 1, size=K).astype(np.int32)
+    dest = scenes.sample_state(rng, sc)
+    goals = [(1, float(start[3]) + 0.1, float(start[4]), 0.15)]
+    r = compare_extend(sc, start, controls, n_ctrl=n_ctrl, dest=dest, goals=goals, ball_center=start, ball_radius=0.3)
+    assert r["got"].all_steps.sum() > 2000
+    assert ((r["want"]["all_flags"] & abi.MPS_F_OK) != 0).any()
