@@ -41,7 +41,8 @@ struct mps_ctx {
     mps_scene scene;
     DevScene hscene;
     DevScene* d_scene = nullptr;
-    size_t scene_bytes = 0, warp_bytes = 0;
+    size_t scene_bytes = 0, warp_bytes = 0, warp_bytes_small = 0;
+    int mcap_small = 0;
     std::string err;
     unsigned long long launches = 0;
 
@@ -49,7 +50,7 @@ struct mps_ctx {
     DevBuf d_start, d_controls, d_nctrl, d_dest, d_weights, d_goals, d_ball;
     DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
     DevBuf d_record;  // packed winner record: best | states | controls | flags
-    DevBuf d_work, d_counters, d_cycles;
+    DevBuf d_work, d_counters, d_cycles, d_redo;
     // pinned staging
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -366,6 +367,12 @@ int mps_ctx_create_on_stream(const mps_scene* scene, int device, void* cuda_stre
         if ((e = cudaMemcpy(ctx->d_scene, &ctx->hscene, sizeof(DevScene), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = mps_fail_cuda(nullptr, e, "cudaMemcpy scene", __LINE__); break; }
         ctx->scene_bytes = mps_rollout_scene_bytes();
         ctx->warp_bytes = mps_rollout_warp_bytes(ctx->hscene);
+        // manifold slots per chain of a packed launch (two / four chains per warp): enough for every contact
+        // pattern seen in practice; a chain that needs more is run again by the one-chain-per-warp kernel
+        ctx->mcap_small = 2 * ctx->hscene.B > 8 ? 2 * ctx->hscene.B : 8;
+        if (const char* e = getenv("MPS_ROLLOUT_SMALL_CAP")) ctx->mcap_small = atoi(e);  // test hook
+        if (ctx->mcap_small >= ctx->hscene.Mcap) ctx->mcap_small = 0;
+        ctx->warp_bytes_small = ctx->mcap_small ? mps_rollout_group_bytes(ctx->hscene, ctx->mcap_small) : ctx->warp_bytes;
         memset(&ctx->tree, 0, sizeof(ctx->tree));
         ctx->tree.B = scene->n_bodies;
         memset(&ctx->forest, 0, sizeof(ctx->forest));
@@ -391,7 +398,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_start, &ctx->d_controls, &ctx->d_nctrl, &ctx->d_dest, &ctx->d_weights, &ctx->d_goals,
                       &ctx->d_ball, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
-                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
+                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_redo, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
                       &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_nn_out, &ctx->d_part_d,
                       &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags, &ctx->d_fsizes,
@@ -845,6 +852,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     if ((rc = ensure(ctx, ctx->d_record, record_bytes(B, L)))) return rc;
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
     if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * (size_t)K * MPS_CYCLE_WORDS))) return rc;
+    if ((rc = ensure(ctx, ctx->d_redo, (size_t)K))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
         MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
@@ -878,6 +886,10 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     rp.scene = ctx->d_scene;
     rp.scene_bytes = ctx->scene_bytes;
     rp.warp_bytes = ctx->warp_bytes;
+    rp.warp_bytes_small = ctx->warp_bytes_small;
+    rp.mcap_small = ctx->mcap_small;
+    rp.redo_only = 0;
+    rp.redo = (uint8_t*)ctx->d_redo.p;
     rp.start = (const float*)ctx->d_start.p;
     rp.start_stride = in->starts ? (size_t)3 * B : 0;
     rp.stop_at_goal = in->stop_at_goal;
@@ -1185,6 +1197,7 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     if ((rc = ensure(ctx, ctx->d_nok, sizeof(int32_t) * KT))) return rc;
     if ((rc = ensure(ctx, ctx->d_goal_step, sizeof(int32_t) * KT))) return rc;
     if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * KT * MPS_CYCLE_WORDS))) return rc;
+    if ((rc = ensure(ctx, ctx->d_redo, (size_t)KT))) return rc;
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
@@ -1209,6 +1222,10 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     rp.scene = ctx->d_scene;
     rp.scene_bytes = ctx->scene_bytes;
     rp.warp_bytes = ctx->warp_bytes;
+    rp.warp_bytes_small = ctx->warp_bytes_small;
+    rp.mcap_small = ctx->mcap_small;
+    rp.redo_only = 0;
+    rp.redo = (uint8_t*)ctx->d_redo.p;
     rp.controls = (const float*)ctx->d_controls.p;
     rp.n_ctrl = in->n_ctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
     rp.K = (int)KT;

@@ -330,6 +330,7 @@ struct WarpMem {
                       // cleared — an entry is trusted only if the manifold it names carries the same pair
     uint16_t* cand;   // [P] broad-phase survivors of the current step
     uint16_t* sig;    // [Mcap] pair of every manifold slot the round schedule was built for (packed groups)
+    int mcap;         // manifold slots of this group (sc.Mcap, or the small capacity of a packed launch)
 };
 
 // State a chain carries from one physics step to the next (registers).
@@ -396,7 +397,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
 {
     const int lane = ln.g;
     const int B = sc.B;
-    const int Mcap = sc.Mcap;
+    const int Mcap = W.mcap;
     // ---- broad phase: lane = pair, bounding circles, survivors compacted into W.cand ------------
     // reach test of one pair; skin = 0 is the exact test of the physics spec
     auto pair_near = [&](unsigned pr, float skin) -> bool {
@@ -1081,7 +1082,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     const int lane = ln.g;  // lane within the chain's group = body index
     const int group = (threadIdx.x >> 5) * (32 / G) + ((threadIdx.x & 31) / G);
     const int B = sc.B;
-    const int Mcap = sc.Mcap;
+    // a packed launch may give every group fewer manifold slots than the scene allows: a chain that needs more
+    // is left to the one-chain-per-warp kernel that follows (p.redo)
+    const bool small_cap = G < 32 && p.mcap_small > 0;
+    const int Mcap = small_cap ? p.mcap_small : sc.Mcap;
     unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)group * p.warp_bytes;
     WarpMem W;
     W.px = reinterpret_cast<float*>(wbase);
@@ -1093,6 +1097,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
     W.sig = W.cand + ((sc.P + 1) & ~1);
+    W.mcap = Mcap;
 
     Body bd;
     bd.live = lane < B;
@@ -1122,6 +1127,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         if (lane == 0) k = (int)atomicAdd(p.work_counter, 1u);
         k = __shfl_sync(ln.m, k, ln.abs_lane(0));
         if (k >= p.K) break;
+        if (p.redo_only && !p.redo[k]) continue;
+        bool redo = false;
         int n = p.n_ctrl ? p.n_ctrl[k] : L;
         if (n > L) n = L;
         const long long t_begin = clock64();
@@ -1215,6 +1222,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 bool bad, over;
                 float pen;
                 physics_step<G>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
+                if (over && small_cap) {
+                    redo = true;
+                    break;
+                }
                 if (over) {
                     flags |= MPS_F_OVERFLOW;
                     ok = false;
@@ -1244,10 +1255,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 if (!(rest <= sc.t_max && resting)) flags |= MPS_F_NOT_AT_REST;
                 ok = rest <= sc.t_max && resting && ok;
             }
+            if (redo) break;
             // extractState: theta normalised in double, read back as float
             float rx = bd.x, ry = bd.y;
             float rth = (float)mps_normalize_orientation((double)bd.th);
             uint32_t vf = state_validity_flags<G>(sc, W, bd, ln, rx, ry, rth, &st, cache);
+            if ((vf & MPS_F_OVERFLOW) && small_cap) {
+                redo = true;
+                break;
+            }
             flags |= vf;
             ok = ok && vf == 0u;
             if (ok) {
@@ -1300,6 +1316,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 ++l;
                 break;
             }
+        }
+        if (redo) {
+            if (lane == 0) p.redo[k] = 1;
+            continue;
         }
         // controls of the chain that were never propagated
         for (; l < L; ++l) {
@@ -1491,6 +1511,7 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
     W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * sc.Mcap);
     W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
     W.sig = W.cand + ((sc.P + 1) & ~1);
+    W.mcap = sc.Mcap;
     const Ln ln = make_ln<32>();
     Body bd;
     bd.live = lane < B;
@@ -1521,11 +1542,14 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
 
 }  // namespace
 
-size_t mps_rollout_warp_bytes(const DevScene& sc)
+size_t mps_rollout_warp_bytes(const DevScene& sc) { return mps_rollout_group_bytes(sc, sc.Mcap); }
+
+// shared memory of one chain (one lane group) with `mcap` manifold slots
+size_t mps_rollout_group_bytes(const DevScene& sc, int mcap)
 {
-    size_t b = 5 * 32 * sizeof(float) + (size_t)MF_FIELDS * sc.Mcap * sizeof(float) +
+    size_t b = 5 * 32 * sizeof(float) + (size_t)MF_FIELDS * mcap * sizeof(float) +
                (((size_t)sc.B * sc.slot_stride + 3) & ~(size_t)3) + sizeof(uint16_t) * (size_t)((sc.P + 1) & ~1) +
-               sizeof(uint16_t) * (size_t)sc.Mcap;
+               sizeof(uint16_t) * (size_t)mcap;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1538,6 +1562,7 @@ template <int WARPS, int MINB, int G>
 static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
 {
     const int groups = WARPS * (32 / G);  // chains a CTA works on at a time
+    if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1571,8 +1596,8 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
 {
     RolloutParams p = p_in;
     // Few chains (at most ~3 CTAs of 4 warps per SM): one warp per chain, latency build.  Launches that fill
-    // the machine are bound by instruction issue: scenes with at most 8 / 16 bodies then run four / two chains
-    // per warp (same arithmetic per chain, so the same bits), which divides the instructions per chain.
+    // the machine are bound by instruction issue: scenes with at most 8 bodies then run four chains per warp
+    // (same arithmetic per chain, so the same bits), which divides the instructions per chain.
     // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build,
     // MPS_ROLLOUT_GROUP = 8 | 16 | 32 the lanes per chain.
     static int forced_minb = -1, forced_g = -1;
@@ -1582,11 +1607,27 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     }
     const bool few = (long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3;
     int g = forced_g;
-    if (g == 0) g = few ? 32 : (n_bodies <= 8 ? 8 : n_bodies <= 16 ? 16 : 32);
+    // measured on B200 (profiles/tools/throughput_probe.py): four chains per warp gain 20-60 % for scenes with
+    // at most 8 bodies; two chains per warp (9..16 bodies) gain nothing on contact-rich scenes and stay opt-in
+    if (g == 0) g = few ? 32 : (n_bodies <= 8 ? 8 : 32);
     if (g == 8 && n_bodies > 8) g = 16;
     if (g == 16 && n_bodies > 16) g = 32;
-    if (g == 8) return launch_rollout_t<2, 4, 8>(p, num_sms, stream);
-    if (g == 16) return launch_rollout_t<ROLLOUT_WARPS, 4, 16>(p, num_sms, stream);
+    if (g != 32) {
+        // packed launch with the small manifold capacity, then the chains it could not hold (normally none)
+        // once more, one per warp with the full capacity
+        cudaError_t e = cudaMemsetAsync(p.redo, 0, (size_t)p.K, stream);
+        if (e != cudaSuccess) return e;
+        RolloutParams q = p;
+        q.redo_only = 0;
+        e = g == 8 ? launch_rollout_t<4, 4, 8>(q, num_sms, stream) : launch_rollout_t<ROLLOUT_WARPS, 4, 16>(q, num_sms, stream);
+        if (e != cudaSuccess) return e;
+        if (p.mcap_small <= 0) return cudaSuccess;
+        p.redo_only = 1;
+        p.mcap_small = 0;
+        return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream);
+    }
+    p.redo_only = 0;
+    p.mcap_small = 0;
     int minb = forced_minb;
     if (minb == 0) minb = few ? 3 : 4;
     if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream);

@@ -11,7 +11,11 @@ struct DevScene;
 struct RolloutParams {
     const DevScene* scene;  // device copy
     size_t scene_bytes;     // shared-memory bytes reserved for the scene copy
-    size_t warp_bytes;      // shared-memory bytes per warp
+    size_t warp_bytes;      // shared-memory bytes per chain (lane group) with the scene's manifold capacity
+    size_t warp_bytes_small;  // the same with mcap_small slots
+    int mcap_small;         // manifold slots per chain of a packed launch (0: the scene's capacity)
+    int redo_only;          // set by the launcher: only the chains flagged in `redo` are run
+    uint8_t* redo;          // [K] chains a packed launch left to the one-chain-per-warp kernel
     const float* start;     // [3B], or [K][3B] when start_stride != 0
     size_t start_stride;    // 0 or 3B
     const float* controls;  // [K][L][5]
@@ -83,6 +87,7 @@ struct ValidityParams {
 };
 
 size_t mps_rollout_warp_bytes(const DevScene& sc);
+size_t mps_rollout_group_bytes(const DevScene& sc, int mcap);
 size_t mps_rollout_scene_bytes();
 cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, int n_bodies, cudaStream_t stream);
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream);

@@ -312,3 +312,18 @@ def test_packed_chains_match_oracle(monkeypatch, group, n_objects):
     r = compare_extend(sc, start, controls, n_ctrl=n_ctrl, dest=dest, goals=goals, ball_center=start, ball_radius=0.3)
     assert r["got"].all_steps.sum() > 2000
     assert ((r["want"]["all_flags"] & abi.MPS_F_OK) != 0).any()
+
+
+@pytest.mark.parametrize("group", [8, 16])
+def test_packed_chains_redo_pass(monkeypatch, group):
+    """A packed launch gives each chain few manifold slots; chains that need more are run again one per warp.
+    With the capacity forced down to 1 almost every contact-rich chain takes that path: same bits."""
+    monkeypatch.setenv("MPS_ROLLOUT_GROUP", str(group))
+    monkeypatch.setenv("MPS_ROLLOUT_SMALL_CAP", "1")
+    sc, _ = scenes.make_scene(6, seed=36)
+    start = scenes.cluttered_start(sc, 46)
+    rng = np.random.RandomState(8)
+    controls = scenes.sample_controls_towards(rng, sc, start, 90, 2)
+    dest = scenes.sample_state(rng, sc)
+    r = compare_extend(sc, start, controls, dest=dest)
+    assert (r["got"].all_steps.sum(axis=1) > 0).all()
