@@ -30,10 +30,22 @@ class SweepResult:
     goal_nodes: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # [n] node index of the goal state
 
 
-def _rng_for(seed: int, instance_ids: np.ndarray, iteration: int) -> np.random.RandomState:
+def _rng_for(seed: int, instance_ids: np.ndarray, iteration: int) -> np.random.Generator:
     # one stream per (seed, iteration); instance-specific draws are taken from fixed positions of it,
     # so an instance's randomness does not depend on which other instances are still active
-    return np.random.RandomState((seed * 1000003 + iteration) % (2**31 - 1))
+    return np.random.Generator(np.random.SFC64([int(seed), int(iteration)]))
+
+
+def _sample_controls(rng: np.random.Generator, n: int) -> np.ndarray:
+    """scenes.sample_controls (RampVelocityControlSampler::sample) in float32 on a Generator: [n][5]"""
+    g = rng.standard_normal((n, 2), dtype=np.float32)
+    g /= np.maximum(np.linalg.norm(g, axis=1, keepdims=True), 1e-12)
+    u = rng.random((n, 3), dtype=np.float32)
+    c = np.zeros((n, 5), np.float32)
+    c[:, 0:2] = g * (scenes.V_LIMIT * np.sqrt(u[:, 0:1]))
+    c[:, 2] = (2.0 * u[:, 1] - 1.0) * scenes.W_LIMIT
+    c[:, 3] = scenes.DURATION_LIMITS[0] + (scenes.DURATION_LIMITS[1] - scenes.DURATION_LIMITS[0]) * u[:, 2]
+    return c
 
 
 def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int, num_control_samples: int = 10,
@@ -51,37 +63,39 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
     goal_nodes = np.full(n_instances, -1, np.int64)
     active = np.arange(n_instances, dtype=np.int32)
     rollouts = 0
+    timing = {"sample_host": 0.0, "is_valid": 0.0, "nearest": 0.0, "controls_host": 0.0, "extend": 0.0}
     t0 = time.perf_counter()
     it = 0
     C = candidates_per_sample
     for it in range(max_iterations):
         if len(active) == 0 or time.perf_counter() - t0 > wall_timeout:
             break
+        ta = time.perf_counter()
         rng = _rng_for(seed, active, it)
         # per-instance draws are indexed by the GLOBAL instance id so that sharding does not change them
         gid = active.astype(np.int64) + instance_offset
         n_glob = int(gid.max()) + 1
-        u_goal = rng.rand(n_glob)[gid]
-        u_obj = rng.rand(n_glob)[gid]
-        obj_uniform = rng.randint(0, B, size=n_glob)[gid]
-        tgt_pick = np.minimum(rng.randint(0, len(targets) + 1, size=n_glob), len(targets) - 1)[gid]  # :133-136 quirk
+        u_goal = rng.random(n_glob)[gid]
+        u_obj = rng.random(n_glob)[gid]
+        obj_uniform = rng.integers(0, B, size=n_glob)[gid]
+        tgt_pick = np.minimum(rng.integers(0, len(targets) + 1, size=n_glob), len(targets) - 1)[gid]  # :133-136 quirk
         M = len(active)
         # ---- sample(): goal-biased or uniform VALID state; C candidates each, one validity launch ----
-        cand = np.zeros((n_glob, C, 3 * B), np.float32)
-        cand[:, :, 0::3] = rng.uniform(sc.x_min, sc.x_max, size=(n_glob, C, B))
-        cand[:, :, 1::3] = rng.uniform(sc.y_min, sc.y_max, size=(n_glob, C, B))
-        cand[:, :, 2::3] = rng.uniform(-np.pi, np.pi, size=(n_glob, C, B))
-        ball = rng.normal(size=(n_glob, C, len(targets), 2))
+        lo = np.array([sc.x_min, sc.y_min, -np.pi], np.float32)
+        span = np.array([sc.x_max - sc.x_min, sc.y_max - sc.y_min, 2 * np.pi], np.float32)
+        cand = (lo + span * rng.random((n_glob, C, B, 3), dtype=np.float32))[gid].reshape(M, C, 3 * B)
+        ball = rng.standard_normal((n_glob, C, len(targets), 2), dtype=np.float32)
         ball /= np.maximum(np.linalg.norm(ball, axis=-1, keepdims=True), 1e-12)
-        ball *= np.sqrt(rng.uniform(size=(n_glob, C, len(targets), 1)))
-        cand = cand[gid]
+        ball *= np.sqrt(rng.random((n_glob, C, len(targets), 1), dtype=np.float32))
         ball = ball[gid]
         is_goal = u_goal < goal_bias
         for gi, g in enumerate(goals):  # ObjectsRelocationGoal::sampleGoal: targets inside their goal discs
             b = int(g[0])
             cand[is_goal, :, 3 * b] = g[1] + g[3] * ball[is_goal, :, gi, 0]
             cand[is_goal, :, 3 * b + 1] = g[2] + g[3] * ball[is_goal, :, gi, 1]
+        tb = time.perf_counter()
         valid, _ = ctx.is_valid(cand.reshape(M * C, 3 * B))
+        tc = time.perf_counter()
         valid = valid.reshape(M, C)
         first = np.where(valid.any(axis=1), valid.argmax(axis=1), C - 1)
         samples = cand[np.arange(M), first]
@@ -90,11 +104,20 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
                        np.where(u_obj < target_bias + robot_bias, sc.robot_id, obj_uniform))
         obj = np.where(is_goal, np.asarray(targets)[tgt_pick], obj).astype(np.int64)
         # ---- selectTreeNode(): nearest node under the full metric (RRT.cpp:192-204) ----
+        td = time.perf_counter()
         near, _ = forest.nearest(active, samples)
+        te = time.perf_counter()
         # ---- extend(): K random controls, best by the active object's distance, appended (:358-390) ----
-        controls = scenes.sample_controls(rng, n_glob * K, 1).reshape(n_glob, K, 1, 5)[gid]
+        controls = _sample_controls(rng, n_glob * K).reshape(n_glob, K, 1, 5)[gid]
+        tf = time.perf_counter()
         res = forest.extend(active, near, controls, dests=samples, masks=(1 << obj).astype(np.uint32), goals=goals,
                             append=True)
+        tg = time.perf_counter()
+        timing["sample_host"] += (tb - ta) + (td - tc)
+        timing["is_valid"] += tc - tb
+        timing["nearest"] += te - td
+        timing["controls_host"] += tf - te
+        timing["extend"] += tg - tf
         rollouts += M * K
         reached = (res["flags"][:, 0] & abi.MPS_F_GOAL) != 0
         reached &= res["k"] >= 0
@@ -106,7 +129,9 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
             goal_nodes[ids] = res["tree_index"][reached]
             active = active[~reached]
     wall = time.perf_counter() - t0
-    return SweepResult(solved_it, solved_t, forest.sizes(), it + 1, rollouts, wall, goal_nodes), forest
+    res_ = SweepResult(solved_it, solved_t, forest.sizes(), it + 1, rollouts, wall, goal_nodes)
+    res_.timing = {k: round(v, 4) for k, v in timing.items()}
+    return res_, forest
 
 
 def extract_path(forest: api.Forest, inst: int, goal_node: int):

@@ -14,4 +14,5 @@ res, forest = multi_seed.naive_rrt_sweep(ctx, start, goals, n_instances=n, num_c
 solved = (res.solved_iteration >= 0)
 print(json.dumps({"instances": n, "iterations": res.iterations, "wall_s": round(res.wall_s, 3), "rollouts": res.rollouts,
                   "rollouts_per_s": round(res.rollouts / res.wall_s, 1), "solved_fraction": round(float(solved.mean()), 4),
-                  "median_time_to_solution_s": None if not solved.any() else round(float(np.nanmedian(res.solved_time)), 3)}))
+                  "median_time_to_solution_s": None if not solved.any() else round(float(np.nanmedian(res.solved_time)), 3),
+                  "seconds_in": getattr(res, "timing", None)}))
