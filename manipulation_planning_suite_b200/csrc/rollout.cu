@@ -1,5 +1,5 @@
 // rollout.cu — K push rollouts of the planar robot/object contact simulation with the
-// validity / goal / slice-ball tests fused in, one warp per rollout chain (sm_100a).
+// validity / goal / slice-ball tests fused in, one lane group per rollout chain (sm_100a).
 //
 // What it replaces in the reference (paths relative to the reference root):
 //   the K-sample loop of NaiveControlSampler::sampleTo      ompl/control/NaiveControlSampler.cpp:46-64
@@ -12,16 +12,19 @@
 // The physics step itself follows the spec mps-planar-v2.
 //
 // Mapping to the machine:
-//   * one warp = one rollout chain; lane i owns body i: pose, twist and friction accumulators
-//     live in that lane's registers, poses are mirrored to shared memory for the pair tests;
-//   * broad phase: lane = pair index, 32 pairs per pass, ballot-compacted;
-//   * narrow phase: lane = candidate pair, manifolds written SoA into the warp's shared slice;
-//   * solver: Gauss-Seidel in colour order.  Colour r < B holds the body pairs with
-//     (i + j) mod B == r, colour B + s the pairs (i, static s); a colour touches every body at most
-//     once, so its manifolds are solved by their two owner lanes at the same time, the partner's
-//     twist arriving by warp shuffle.  A sequential CPU sweep in the same order gives the same bits;
-//   * rest test / policy test: warp votes;
-//   * warps pull chain indices from an atomic counter (rollout lengths vary by 10x).
+//   * one lane group (a whole warp, or 8 / 16 lanes for small scenes in launches that fill the machine) = one
+//     rollout chain; lane i of the group owns body i: pose and twist live in that lane's registers, poses are
+//     mirrored to shared memory for the pair tests;
+//   * broad phase: lane = pair index, ballot-compacted into a candidate list that carries a skin and is reused
+//     until a body has moved too far; narrow phase: lane = listed pair (exact reach test, then SAT / clipping),
+//     touching pairs compacted into manifold records of 8 float4 in the group's shared slice;
+//   * solver: Gauss-Seidel sweeps in the spec's canonical order (colour r < B holds the body pairs with
+//     (i + j) mod B == r, colour B + s the pairs (i, static s)); manifolds that share no dynamic body commute, so
+//     every manifold is put in the earliest round after the manifolds it depends on and a round's manifolds are
+//     visited at the same time by their owner lanes, the partner's twist arriving by shuffle.  A sequential CPU
+//     sweep in canonical order gives the same bits;
+//   * rest test / policy test: group votes;
+//   * groups pull chain indices from an atomic counter (rollout lengths vary by 10x).
 #include "mps_device.cuh"
 #include "rollout.h"
 
@@ -1060,10 +1063,10 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
     return dist;
 }
 
-// MINB = CTAs per SM the register allocation is held to.  Two instantiations are built: MINB = 3 (up to 168
-// registers, no spills) for launches with few chains, where one warp per scheduler runs alone and only its
-// own dependent-instruction latency matters, and MINB = 4 (128 registers) for launches that fill the machine,
-// where resident warps per SM decide the throughput.
+// MINB = CTAs per SM the register allocation is held to, G = lanes per chain.  Built: <4, 3, 32> (up to 168
+// registers) for launches with few chains, where one warp per scheduler runs alone and only its own
+// dependent-instruction latency matters; <4, 4, 32> (128 registers) for launches that fill the machine;
+// <4, 4, 8> and <4, 4, 16> with four / two chains per warp (see mps_launch_rollout).  None spills.
 template <int WARPS, int MINB, int G>
 __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams p)
 {
