@@ -88,3 +88,32 @@ def test_data_triplet_csv_round_trip(tmp_path):
     assert notes == ["box, 0.35"] * 7
     dg.write_triplets(str(f), starts[:2], results[:2], controls[:2])   # no annotation: no trailing field
     assert len(f.read_text().splitlines()[0].split(", ")) == 2 * 3 * B + 5
+
+
+def test_host_library_exports_and_struct_layouts():
+    """libmps_host.so exports every entry point of host/mps_host_c.h and the ctypes structures match the C ones
+    (checked against a C program compiled with gcc)."""
+    import ctypes as C
+    import os
+    import re
+    import subprocess
+    import tempfile
+
+    L = host_api.load_host_library()
+    hdr = os.path.join(os.path.dirname(host_api.HOST_LIB_PATH), "mps_host_c.h")
+    names = re.findall(r"\b(mps_host_\w+)\s*\(", open(hdr).read())
+    assert {"mps_host_plan", "mps_host_shortcut", "mps_host_default_params", "mps_host_ramp_steer",
+            "mps_host_max_pushing_distance"} <= set(names)
+    for n in names:
+        assert hasattr(L, n), f"{n} not exported"
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu %%zu\\n", sizeof(mps_host_params), sizeof(mps_host_result), offsetof(mps_host_params, shortcut_type), offsetof(mps_host_result, shortcut_accepted));return 0;}\n' % hdr
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-o", exe, c], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(host_api.HostParams), C.sizeof(host_api.HostResult),
+                   host_api.HostParams.shortcut_type.offset, host_api.HostResult.shortcut_accepted.offset]
+    p = host_api.default_params()
+    assert p.shortcut_type == host_api.SHORTCUT_TYPES["LocalShortcut"] and p.max_shortcut_time == 5.0  # reference defaults
