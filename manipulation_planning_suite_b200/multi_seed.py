@@ -12,6 +12,7 @@ instances are batched with them or on how many GPUs the sweep is split over.
 from __future__ import annotations
 
 import time
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -67,27 +68,43 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
     t0 = time.perf_counter()
     it = 0
     C = candidates_per_sample
+    n_glob = instance_offset + n_instances
+    T = len(targets)
+
+    def draw(iteration: int) -> dict:
+        """All random numbers of one iteration for instances 0 .. n_glob - 1 (position = global instance id, so an
+        instance's draws do not depend on which other instances are still active).  Runs one iteration ahead on
+        a worker thread while the device works (numpy and ctypes release the GIL)."""
+        rng = _rng_for(seed, None, iteration)
+        d = {"u_goal": rng.random(n_glob), "u_obj": rng.random(n_glob), "obj_uniform": rng.integers(0, B, size=n_glob),
+             "tgt_pick": np.minimum(rng.integers(0, T + 1, size=n_glob), T - 1),  # :133-136 quirk
+             "cand": rng.random((n_glob, C, B, 3), dtype=np.float32)}
+        ball = rng.standard_normal((n_glob, C, T, 2), dtype=np.float32)
+        ball /= np.maximum(np.linalg.norm(ball, axis=-1, keepdims=True), 1e-12)
+        ball *= np.sqrt(rng.random((n_glob, C, T, 1), dtype=np.float32))
+        d["ball"] = ball
+        d["controls"] = _sample_controls(rng, n_glob * K).reshape(n_glob, K, 1, 5)
+        return d
+
+    pool = ThreadPoolExecutor(max_workers=1)
+    ahead = pool.submit(draw, 0)
+    lo = np.array([sc.x_min, sc.y_min, -np.pi], np.float32)
+    span = np.array([sc.x_max - sc.x_min, sc.y_max - sc.y_min, 2 * np.pi], np.float32)
     for it in range(max_iterations):
         if len(active) == 0 or time.perf_counter() - t0 > wall_timeout:
             break
         ta = time.perf_counter()
-        rng = _rng_for(seed, active, it)
-        # per-instance draws are indexed by the GLOBAL instance id so that sharding does not change them
+        rnd = ahead.result()
+        ahead = pool.submit(draw, it + 1)
         gid = active.astype(np.int64) + instance_offset
-        n_glob = int(gid.max()) + 1
-        u_goal = rng.random(n_glob)[gid]
-        u_obj = rng.random(n_glob)[gid]
-        obj_uniform = rng.integers(0, B, size=n_glob)[gid]
-        tgt_pick = np.minimum(rng.integers(0, len(targets) + 1, size=n_glob), len(targets) - 1)[gid]  # :133-136 quirk
+        u_goal = rnd["u_goal"][gid]
+        u_obj = rnd["u_obj"][gid]
+        obj_uniform = rnd["obj_uniform"][gid]
+        tgt_pick = rnd["tgt_pick"][gid]
         M = len(active)
         # ---- sample(): goal-biased or uniform VALID state; C candidates each, one validity launch ----
-        lo = np.array([sc.x_min, sc.y_min, -np.pi], np.float32)
-        span = np.array([sc.x_max - sc.x_min, sc.y_max - sc.y_min, 2 * np.pi], np.float32)
-        cand = (lo + span * rng.random((n_glob, C, B, 3), dtype=np.float32))[gid].reshape(M, C, 3 * B)
-        ball = rng.standard_normal((n_glob, C, len(targets), 2), dtype=np.float32)
-        ball /= np.maximum(np.linalg.norm(ball, axis=-1, keepdims=True), 1e-12)
-        ball *= np.sqrt(rng.random((n_glob, C, len(targets), 1), dtype=np.float32))
-        ball = ball[gid]
+        cand = (lo + span * rnd["cand"][gid]).reshape(M, C, 3 * B)
+        ball = rnd["ball"][gid]
         is_goal = u_goal < goal_bias
         for gi, g in enumerate(goals):  # ObjectsRelocationGoal::sampleGoal: targets inside their goal discs
             b = int(g[0])
@@ -108,7 +125,7 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
         near, _ = forest.nearest(active, samples)
         te = time.perf_counter()
         # ---- extend(): K random controls, best by the active object's distance, appended (:358-390) ----
-        controls = _sample_controls(rng, n_glob * K).reshape(n_glob, K, 1, 5)[gid]
+        controls = rnd["controls"][gid]
         tf = time.perf_counter()
         res = forest.extend(active, near, controls, dests=samples, masks=(1 << obj).astype(np.uint32), goals=goals,
                             append=True)
@@ -129,6 +146,8 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
             goal_nodes[ids] = res["tree_index"][reached]
             active = active[~reached]
     wall = time.perf_counter() - t0
+    ahead.cancel()
+    pool.shutdown(wait=True)
     res_ = SweepResult(solved_it, solved_t, forest.sizes(), it + 1, rollouts, wall, goal_nodes)
     res_.timing = {k: round(v, 4) for k, v in timing.items()}
     return res_, forest
