@@ -33,7 +33,9 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(n_objects=6, K=1024, L=4, tree_nodes=100_000, scene_seed=1002)
 NN_CFG = dict(n_objects=10, nodes=1_000_000, seed=1003)
-METRIC = "push rollouts/sec"
+# BASELINE.json's metric names two figures; `value` is the first (push rollouts/sec), the second (weighted-NN
+# queries/sec) is reported under "nn" of the same line
+METRIC = "push rollouts/sec + weighted-NN queries/sec at 1/2/4/8 B200 vs host CPU"
 UNIT = "rollouts/s"
 
 
@@ -292,6 +294,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg2 HybridActionRRT extend: B=7 (robot+6 objects), 4 wall boxes, "
                                    f"K={K} chains/GPU, L<=4 controls, tree {CFG['tree_nodes']} nodes, 1 NN query/extend",
+                       "value_is": "push rollouts/sec (propagated controls per second); weighted-NN queries/sec is under nn",
                        "rollouts_per_step": rollouts_per_step, "l2": "flushed before every timed step (256 MB write)",
                        "sharding": f"K={K}x{world} chains sharded contiguously, winner records all-gathered (NCCL)"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
