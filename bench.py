@@ -69,6 +69,20 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        # NVML polled every few ms (the timed region is tens of ms long); nvidia-smi -lms as the fallback
+        self.nv = None
+        self.samples = []
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -78,11 +92,39 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, int(r)))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nv is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            nv = self.nv
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted({k for _, _, r in self.samples for k, b in bits.items() if r & b})
+            sm = [s_[0] for s_ in self.samples]
+            mx = [s_[1] for s_ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -285,7 +327,7 @@ def run_ours(args):
     # ---- CPU baseline (oracle, 1 thread, bounded sample) on rank 0 at N = 1 -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_baseline(sc, start, batches[0], goals, threads=1, max_seconds=12.0)
+        cpu = cpu_baseline(sc, start, batches[warmup:], goals, threads=1, max_seconds=12.0)
 
     if rank == 0:
         line = {
@@ -403,26 +445,22 @@ def load_oracle():
     return ob
 
 
-def cpu_baseline(sc, start, batch, goals, threads: int, max_seconds: float):
+def cpu_baseline(sc, start, batches, goals, threads: int, max_seconds: float):
     """The CPU oracle (port of the path) timed on the host cores on a bounded sample of
-    the same workload.  This is the only place bench.py executes oracle/ in the default arm."""
+    the same workload: whole batches of the timed steps, one after the other, until `max_seconds` of CPU
+    work are done.  This is the only place bench.py executes oracle/ in the default arm."""
     ob = load_oracle()
-    controls, n_ctrl, dest = batch
-    K = CFG["K"]
-    sample = min(K, 256 if threads == 1 else K)
     t0 = time.perf_counter()
     done = 0
-    reps = 0
-    while True:
-        r = ob.extend(sc, start, controls[:sample], n_ctrl=n_ctrl[:sample], dest=dest, compare_f32=True, goals=goals,
-                      threads=threads)
+    n = 0
+    while time.perf_counter() - t0 < max_seconds:
+        controls, n_ctrl, dest = batches[n % len(batches)]
+        r = ob.extend(sc, start, controls, n_ctrl=n_ctrl, dest=dest, compare_f32=True, goals=goals, threads=threads)
         done += int(((r["all_flags"] & 1) != 0).sum())
-        reps += 1
-        if time.perf_counter() - t0 > max_seconds or reps >= 8:
-            break
+        n += 1
     dt = time.perf_counter() - t0
     return {"value": round(done / dt, 1), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{reps} x the first {sample} chains of the step's batch ({done} propagated controls, {dt:.1f} s)"}
+            "sample": f"{n} whole batches of {CFG['K']} chains from the timed steps ({done} propagated controls, {dt:.1f} s)"}
 
 
 def run_reference(args):
