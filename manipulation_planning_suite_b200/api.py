@@ -376,6 +376,12 @@ class NearestNeighbors:
         return out
 
 
+# struct mps_extend_best as a numpy record (same layout as abi.ExtendBest)
+_BEST_DTYPE = np.dtype([("k", np.int32), ("n_ok", np.int32), ("goal_step", np.int32), ("tree_index", np.int32),
+                        ("distance", np.float64)])
+assert _BEST_DTYPE.itemsize == C.sizeof(abi.ExtendBest)
+
+
 class Forest:
     """Many independent planner instances in one context (mps_forest_*): one tree per instance in a shared
     dimension-major SoA, batches of M instances per launch (BASELINE config 5)."""
@@ -447,11 +453,10 @@ class Forest:
         bc = np.zeros((M, L, 5), np.float32)
         bf = np.zeros((M, L), np.uint32)
         self.ctx._check(self.lib.mps_forest_extend(self.ctx.h, C.byref(fin), best, _fp(bs), _fp(bc), _fp(bf, C.c_uint32)))
-        return dict(
-            k=np.array([b.k for b in best], np.int32), n_ok=np.array([b.n_ok for b in best], np.int32),
-            goal_step=np.array([b.goal_step for b in best], np.int32),
-            tree_index=np.array([b.tree_index for b in best], np.int32),
-            distance=np.array([b.distance for b in best], np.float64), states=bs, controls=bc, flags=bf)
+        rec = np.frombuffer(best, dtype=_BEST_DTYPE, count=M)  # one structured view instead of M attribute reads
+        return dict(k=rec["k"].copy(), n_ok=rec["n_ok"].copy(), goal_step=rec["goal_step"].copy(),
+                    tree_index=rec["tree_index"].copy(), distance=rec["distance"].copy(), states=bs, controls=bc,
+                    flags=bf)
 
     def read(self, inst: int, first: int, n: int):
         B = self.ctx.B
