@@ -31,12 +31,6 @@ class SweepResult:
     goal_nodes: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # [n] node index of the goal state
 
 
-def _rng_for(seed: int, instance_ids: np.ndarray, iteration: int) -> np.random.Generator:
-    # one stream per (seed, iteration); instance-specific draws are taken from fixed positions of it,
-    # so an instance's randomness does not depend on which other instances are still active
-    return np.random.Generator(np.random.SFC64([int(seed), int(iteration)]))
-
-
 def _sample_controls(rng: np.random.Generator, n: int) -> np.ndarray:
     """scenes.sample_controls (RampVelocityControlSampler::sample) in float32 on a Generator: [n][5]"""
     g = rng.standard_normal((n, 2), dtype=np.float32)
@@ -68,22 +62,37 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
     t0 = time.perf_counter()
     it = 0
     C = candidates_per_sample
-    n_glob = instance_offset + n_instances
     T = len(targets)
+    # Random numbers are drawn per BLOCK of 256 consecutive global instance ids from a generator seeded with
+    # (seed, iteration, block): an instance's draws depend neither on which other instances are still active nor
+    # on how the instances are split over GPUs (as long as the split is aligned to blocks), and a rank only
+    # draws for its own instances.
+    BLK = 256
+    first_blk = instance_offset // BLK
+    last_blk = (instance_offset + n_instances - 1) // BLK
+    base_id = first_blk * BLK                      # global id of row 0 of the drawn arrays
+    n_rows = (last_blk - first_blk + 1) * BLK
 
     def draw(iteration: int) -> dict:
-        """All random numbers of one iteration for instances 0 .. n_glob - 1 (position = global instance id, so an
-        instance's draws do not depend on which other instances are still active).  Runs one iteration ahead on
-        a worker thread while the device works (numpy and ctypes release the GIL)."""
-        rng = _rng_for(seed, None, iteration)
-        d = {"u_goal": rng.random(n_glob), "u_obj": rng.random(n_glob), "obj_uniform": rng.integers(0, B, size=n_glob),
-             "tgt_pick": np.minimum(rng.integers(0, T + 1, size=n_glob), T - 1),  # :133-136 quirk
-             "cand": rng.random((n_glob, C, B, 3), dtype=np.float32)}
-        ball = rng.standard_normal((n_glob, C, T, 2), dtype=np.float32)
-        ball /= np.maximum(np.linalg.norm(ball, axis=-1, keepdims=True), 1e-12)
-        ball *= np.sqrt(rng.random((n_glob, C, T, 1), dtype=np.float32))
-        d["ball"] = ball
-        d["controls"] = _sample_controls(rng, n_glob * K).reshape(n_glob, K, 1, 5)
+        """All random numbers of one iteration for this rank's blocks.  Runs one iteration ahead on a worker
+        thread while the device works (numpy and ctypes release the GIL)."""
+        d = {"u_goal": np.empty(n_rows), "u_obj": np.empty(n_rows), "obj_uniform": np.empty(n_rows, np.int64),
+             "tgt_pick": np.empty(n_rows, np.int64), "cand": np.empty((n_rows, C, B, 3), np.float32),
+             "ball": np.empty((n_rows, C, T, 2), np.float32), "controls": np.empty((n_rows, K, 1, 5), np.float32)}
+        for blk in range(first_blk, last_blk + 1):
+            rng = np.random.Generator(np.random.SFC64([int(seed), int(iteration), int(blk)]))
+            r0 = (blk - first_blk) * BLK
+            sl = slice(r0, r0 + BLK)
+            d["u_goal"][sl] = rng.random(BLK)
+            d["u_obj"][sl] = rng.random(BLK)
+            d["obj_uniform"][sl] = rng.integers(0, B, size=BLK)
+            d["tgt_pick"][sl] = np.minimum(rng.integers(0, T + 1, size=BLK), T - 1)  # :133-136 quirk
+            d["cand"][sl] = rng.random((BLK, C, B, 3), dtype=np.float32)
+            ball = rng.standard_normal((BLK, C, T, 2), dtype=np.float32)
+            ball /= np.maximum(np.linalg.norm(ball, axis=-1, keepdims=True), 1e-12)
+            ball *= np.sqrt(rng.random((BLK, C, T, 1), dtype=np.float32))
+            d["ball"][sl] = ball
+            d["controls"][sl] = _sample_controls(rng, BLK * K).reshape(BLK, K, 1, 5)
         return d
 
     pool = ThreadPoolExecutor(max_workers=1)
@@ -96,7 +105,7 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
         ta = time.perf_counter()
         rnd = ahead.result()
         ahead = pool.submit(draw, it + 1)
-        gid = active.astype(np.int64) + instance_offset
+        gid = active.astype(np.int64) + (instance_offset - base_id)  # row of each active instance in the drawn arrays
         u_goal = rnd["u_goal"][gid]
         u_obj = rnd["u_obj"][gid]
         obj_uniform = rnd["obj_uniform"][gid]
