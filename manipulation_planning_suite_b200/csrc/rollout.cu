@@ -1567,12 +1567,14 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
     const int groups = WARPS * (32 / G);  // chains a CTA works on at a time
     if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // the attribute is per device: a process may hold contexts on several
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WARPS, MINB, G>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int blocks_per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<WARPS, MINB, G>,
@@ -1648,12 +1650,14 @@ cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
 cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream)
 {
     size_t smem = p.scene_bytes + (size_t)ROLLOUT_WARPS * p.warp_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(validity_kernel<ROLLOUT_WARPS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int want = (p.n + ROLLOUT_WARPS - 1) / ROLLOUT_WARPS;
     int grid = num_sms * 4;
