@@ -327,3 +327,49 @@ def test_packed_chains_redo_pass(monkeypatch, group):
     dest = scenes.sample_state(rng, sc)
     r = compare_extend(sc, start, controls, dest=dest)
     assert (r["got"].all_steps.sum(axis=1) > 0).all()
+
+
+def test_baseline_config2_whole_batch_matches_oracle():
+    """BASELINE config 2 at full size (the bench workload: B = 7, K = 1024 chains of up to 4 controls): every
+    chain of one batch against the oracle (pthread fan-out, a fraction of a second)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    sc, start, batches, goals = bench.make_workload(0, 1, 2)
+    controls, n_ctrl, dest = batches[1]
+    ctx = api.Context(sc)
+    got = ctx.extend(start, controls, dump=True, n_ctrl=n_ctrl, dest=dest, compare_f32=True, goals=goals)
+    want = ob.extend(sc, start, controls, n_ctrl=n_ctrl, dest=dest, compare_f32=True, goals=goals, threads=os.cpu_count() or 1)
+    assert np.array_equal(got.all_flags, want["all_flags"]) and np.array_equal(got.all_steps, want["all_steps"])
+    assert np.array_equal(got.all_rest, want["all_rest"]) and np.array_equal(got.all_dist, want["all_dist"])
+    _, _, exact, n = assert_states_close(got.all_states, want["all_states"], want["all_flags"])
+    assert exact == n and n > 2000
+    assert got.k == want["k"] and got.distance == want["distance"]
+    ctx.close()
+
+
+def test_baseline_config4_shape_determinism_and_sampled_parity():
+    """BASELINE config 4's shape (B = 17, 65 536 single-control rollouts in one launch): run-to-run identical,
+    a checksum over all outputs, and 256 sampled chains against the oracle."""
+    sc, _ = scenes.make_scene(16, seed=1004)
+    start = scenes.cluttered_start(sc, 1004)
+    rng = np.random.RandomState(16)
+    K = 65536
+    controls = scenes.sample_controls_towards(rng, sc, start, K, 1)
+    dest = scenes.sample_state(rng, sc)
+    ctx = api.Context(sc)
+    a = ctx.extend(start, controls, dump=True, dest=dest)
+    b = ctx.extend(start, controls, dump=True, dest=dest)
+    assert a.k == b.k and a.distance == b.distance
+    assert np.array_equal(a.all_states, b.all_states) and np.array_equal(a.all_flags, b.all_flags)
+    ok = (a.all_flags[:, 0] & abi.MPS_F_OK) != 0
+    assert 0.05 < ok.mean() <= 1.0
+    # the winner is the first chain with the smallest distance among the valid ones
+    d = np.where(ok, a.all_dist, np.inf)
+    assert a.k == int(np.argmin(d)) and a.distance == d.min()
+    idx = rng.choice(K, 256, replace=False)
+    want = ob.extend(sc, start, controls[idx], dest=dest, threads=8)
+    assert np.array_equal(a.all_flags[idx], want["all_flags"]) and np.array_equal(a.all_dist[idx], want["all_dist"])
+    assert_states_close(a.all_states[idx], want["all_states"], want["all_flags"])
+    ctx.close()
