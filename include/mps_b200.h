@@ -288,6 +288,29 @@ int mps_forest_nearest(mps_ctx* ctx, int32_t M, const int32_t* inst_ids, const f
 /* best [M], best_states [M][L][3B], best_controls [M][L][5], best_flags [M][L]; any may be NULL */
 int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_best* best, float* best_states,
                       float* best_controls, uint32_t* best_flags);
+/* One whole NaiveRRT iteration for M instances without host random numbers or per-iteration uploads: on the
+ * device, every instance draws its sample (goal-biased or uniform, the first valid of C candidate states:
+ * RearrangementRRT::sample RRT.cpp:171-190, ObjectsRelocationGoal::sampleGoal :67-102), its active object
+ * (sampleActiveObject RRT.cpp:246-257), finds the nearest node of its own tree, draws K controls
+ * (RampVelocityControlSampler::sample RampVelocityControl.cpp:353-394), propagates them, appends the best.
+ * Random numbers are a hash of (seed, iteration, instance_offset + instance id, purpose, index): they do not
+ * depend on the other instances nor on how the instances are split over devices. */
+typedef struct mps_forest_naive_in {
+    int32_t M;                 /* active instances of this iteration */
+    int32_t iteration;
+    const int32_t* inst_ids;   /* [M] which tree */
+    int64_t instance_offset;   /* global instance id = instance_offset + inst_ids[m] */
+    uint64_t seed;
+    int32_t K;                 /* num_control_samples */
+    int32_t C;                 /* candidate states per sample */
+    float goal_bias, target_bias, robot_bias;
+    int32_t n_goals;
+    const mps_goal* goals;     /* relocation goals shared by all instances */
+    const float* weights;      /* [B] or NULL */
+    float velocity_limit, omega_limit, duration_min, duration_max;  /* control limits */
+} mps_forest_naive_in;
+/* best [M] (k, n_ok, goal_step, tree_index, distance), flags [M] (MPS_F_* of the appended state); may be NULL */
+int mps_forest_naive_step(mps_ctx* ctx, const mps_forest_naive_in* in, mps_extend_best* best, uint32_t* flags);
 /* nodes [first, first + n) of one tree: states [n][3B], parents [n], controls [n][5]; any may be NULL */
 int mps_forest_read(mps_ctx* ctx, int32_t inst, int64_t first, int64_t n, float* states, int32_t* parents,
                     float* controls);

@@ -136,6 +136,23 @@ class ExtendBest(C.Structure):
     ]
 
 
+class ForestNaiveIn(C.Structure):
+    """struct mps_forest_naive_in"""
+
+    _fields_ = [
+        ("M", _i32), ("iteration", _i32),
+        ("inst_ids", C.POINTER(_i32)),
+        ("instance_offset", C.c_int64),
+        ("seed", C.c_uint64),
+        ("K", _i32), ("C", _i32),
+        ("goal_bias", _f32), ("target_bias", _f32), ("robot_bias", _f32),
+        ("n_goals", _i32),
+        ("goals", C.POINTER(Goal)),
+        ("weights", C.POINTER(_f32)),
+        ("velocity_limit", _f32), ("omega_limit", _f32), ("duration_min", _f32), ("duration_max", _f32),
+    ]
+
+
 class ForestExtendIn(C.Structure):
     """struct mps_forest_extend_in"""
 
@@ -223,6 +240,7 @@ SYMBOLS = {
     "mps_forest_sizes": (C.c_int, [_ctx, _P(C.c_int64)]),
     "mps_forest_nearest": (C.c_int, [_ctx, _i32, _P(_i32), _P(_f32), _P(_f32), _P(_u32), _P(C.c_int64), _P(C.c_double)]),
     "mps_forest_extend": (C.c_int, [_ctx, _P(ForestExtendIn), _P(ExtendBest), _P(_f32), _P(_f32), _P(_u32)]),
+    "mps_forest_naive_step": (C.c_int, [_ctx, _P(ForestNaiveIn), _P(ExtendBest), _P(_u32)]),
     "mps_forest_read": (C.c_int, [_ctx, _i32, C.c_int64, C.c_int64, _P(_f32), _P(_i32), _P(_f32)]),
     "mps_extend_record_size": (C.c_int, [_ctx, _P(C.c_int64)]),
     "mps_extend_record_to": (C.c_int, [_ctx, C.c_void_p]),

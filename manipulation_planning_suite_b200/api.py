@@ -458,6 +458,36 @@ class Forest:
                     tree_index=rec["tree_index"].copy(), distance=rec["distance"].copy(), states=bs, controls=bc,
                     flags=bf)
 
+    def naive_step(self, inst_ids, iteration: int, seed: int, goals, K: int = 10, C_: int = 8, goal_bias: float = 0.2,
+                   target_bias: float = 0.25, robot_bias: float = 0.0, instance_offset: int = 0, weights=None,
+                   velocity_limit: float = 0.6, omega_limit: float = 1.5, duration_limits=(0.1, 1.0)):
+        """One NaiveRRT iteration of the given instances entirely on the device (mps_forest_naive_step).
+        Returns dict(k, n_ok, goal_step, tree_index, distance, flags), one entry per instance."""
+        ids = np.ascontiguousarray(inst_ids, np.int32)
+        M = len(ids)
+        garr = (abi.Goal * len(goals))()
+        for i, g in enumerate(goals):
+            garr[i].body, garr[i].x, garr[i].y, garr[i].tol = int(g[0]), float(g[1]), float(g[2]), float(g[3])
+        w = None if weights is None else _f32(weights, (self.ctx.B,))
+        fin = abi.ForestNaiveIn()
+        fin.M, fin.iteration = M, int(iteration)
+        fin.inst_ids = _fp(ids, C.c_int32)
+        fin.instance_offset = int(instance_offset)
+        fin.seed = int(seed)
+        fin.K, fin.C = int(K), int(C_)
+        fin.goal_bias, fin.target_bias, fin.robot_bias = float(goal_bias), float(target_bias), float(robot_bias)
+        fin.n_goals = len(goals)
+        fin.goals = garr
+        fin.weights = _fp(w)
+        fin.velocity_limit, fin.omega_limit = float(velocity_limit), float(omega_limit)
+        fin.duration_min, fin.duration_max = float(duration_limits[0]), float(duration_limits[1])
+        best = (abi.ExtendBest * M)()
+        fl = np.zeros(M, np.uint32)
+        self.ctx._check(self.lib.mps_forest_naive_step(self.ctx.h, C.byref(fin), best, _fp(fl, C.c_uint32)))
+        rec = np.frombuffer(best, dtype=_BEST_DTYPE, count=M)
+        return dict(k=rec["k"].copy(), n_ok=rec["n_ok"].copy(), goal_step=rec["goal_step"].copy(),
+                    tree_index=rec["tree_index"].copy(), distance=rec["distance"].copy(), flags=fl)
+
     def read(self, inst: int, first: int, n: int):
         B = self.ctx.B
         st = np.zeros((n, 3 * B), np.float32)

@@ -14,6 +14,7 @@
 
 #include "mps_device.cuh"
 #include "nn_scan.h"
+#include "forest_step.h"
 #include "peak.h"
 #include "rollout.h"
 
@@ -1166,18 +1167,11 @@ int mps_forest_nearest(mps_ctx* ctx, int32_t M, const int32_t* inst_ids, const f
     return mps_tree_nearest_fetch(ctx, indices, distances);
 }
 
-int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_best* best, float* best_states,
-                      float* best_controls, uint32_t* best_flags)
+// device buffers of a forest extend of M instances x K chains x L controls
+static int forest_ensure_buffers(mps_ctx* ctx, int M, int K, int L)
 {
-    if (!ctx || !in || !in->inst_ids || !in->parents || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_forest_extend");
-    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
-    const int B = ctx->scene.n_bodies, M = in->M, K = in->K, L = in->L;
-    if (M < 1 || K < 1 || L < 1 || L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "M, K >= 1 and L in [1, 64]");
-    if ((long long)M * K > (1ll << 24)) return mps_fail(ctx, MPS_ERR_ARG, "M * K too large");
-    if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS || (in->n_goals > 0 && !in->goals)) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
-    int rc = check_inst_ids(ctx, in->inst_ids, M);
-    if (rc) return rc;
-    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    const int B = ctx->scene.n_bodies;
+    int rc;
     const size_t KT = (size_t)M * K, KL = KT * L;
     const size_t cb = sizeof(float) * MPS_CONTROL_DIM * KL, nb = sizeof(int32_t) * KT, db = sizeof(float) * 3 * B * (size_t)M,
                  mb = sizeof(int32_t) * (size_t)M, wb = sizeof(float) * B;
@@ -1207,16 +1201,17 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     if ((rc = ensure(ctx, ctx->d_fbest_states, sizeof(float) * 3 * B * L * (size_t)M))) return rc;
     if ((rc = ensure(ctx, ctx->d_fbest_controls, sizeof(float) * MPS_CONTROL_DIM * L * (size_t)M))) return rc;
     if ((rc = ensure(ctx, ctx->d_fbest_flags, sizeof(uint32_t) * L * (size_t)M))) return rc;
-    cudaStream_t st = ctx->stream;
-    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_controls.p, in->controls, cb, cudaMemcpyHostToDevice, st), ctx);
-    if (in->n_ctrl) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nctrl.p, in->n_ctrl, nb, cudaMemcpyHostToDevice, st), ctx);
-    if (in->dests) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_dest.p, in->dests, db, cudaMemcpyHostToDevice, st), ctx);
-    if (in->weights) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_weights.p, in->weights, wb, cudaMemcpyHostToDevice, st), ctx);
-    if (in->n_goals > 0) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_goals.p, in->goals, sizeof(mps_goal) * in->n_goals, cudaMemcpyHostToDevice, st), ctx);
-    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_finst.p, in->inst_ids, mb, cudaMemcpyHostToDevice, st), ctx);
-    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_fparents.p, in->parents, mb, cudaMemcpyHostToDevice, st), ctx);
-    if (in->masks) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_fmasks.p, in->masks, mb, cudaMemcpyHostToDevice, st), ctx);
+    return MPS_OK;
+}
 
+// rollout + select (+ append) of a forest extend whose inputs are already in the device buffers
+static int forest_extend_launch(mps_ctx* ctx, int M, int K, int L, bool has_nctrl, bool has_dests, bool has_weights,
+                                bool has_masks, int compare_f32, int n_goals, int append, mps_extend_best* best,
+                                float* best_states, float* best_controls, uint32_t* best_flags)
+{
+    const int B = ctx->scene.n_bodies;
+    const size_t KT = (size_t)M * K;
+    cudaStream_t st = ctx->stream;
     RolloutParams rp;
     memset(&rp, 0, sizeof(rp));
     rp.scene = ctx->d_scene;
@@ -1227,14 +1222,14 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     rp.redo_only = 0;
     rp.redo = (uint8_t*)ctx->d_redo.p;
     rp.controls = (const float*)ctx->d_controls.p;
-    rp.n_ctrl = in->n_ctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
+    rp.n_ctrl = has_nctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
     rp.K = (int)KT;
     rp.L = L;
-    rp.dest = in->dests ? (const float*)ctx->d_dest.p : nullptr;
-    rp.weights = in->weights ? (const float*)ctx->d_weights.p : nullptr;
+    rp.dest = has_dests ? (const float*)ctx->d_dest.p : nullptr;
+    rp.weights = has_weights ? (const float*)ctx->d_weights.p : nullptr;
     rp.mask = B < 32 ? (1u << B) - 1u : 0xffffffffu;
     rp.goals = (const mps_goal*)ctx->d_goals.p;
-    rp.n_goals = in->n_goals;
+    rp.n_goals = n_goals;
     rp.out_states = (float*)ctx->d_states.p;
     rp.out_rest = (float*)ctx->d_rest.p;
     rp.out_flags = (uint32_t*)ctx->d_flags.p;
@@ -1251,7 +1246,7 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     rp.f_states = ctx->forest.states;
     rp.f_cols = ctx->forest.cap;
     rp.f_seg = ctx->f_seg;
-    rp.masks = in->masks ? (const uint32_t*)ctx->d_fmasks.p : nullptr;
+    rp.masks = has_masks ? (const uint32_t*)ctx->d_fmasks.p : nullptr;
 
     SelectParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -1259,8 +1254,8 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     sp.L = L;
     sp.B = B;
     sp.M = M;
-    sp.has_dest = in->dests ? 1 : 0;
-    sp.compare_f32 = in->compare_f32;
+    sp.has_dest = has_dests ? 1 : 0;
+    sp.compare_f32 = compare_f32;
     sp.dist = rp.out_dist;
     sp.nok = rp.out_nok;
     sp.goal_step = rp.out_goal_step;
@@ -1272,7 +1267,7 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     sp.best_states = (float*)ctx->d_fbest_states.p;
     sp.best_controls = (float*)ctx->d_fbest_controls.p;
     sp.best_flags = (uint32_t*)ctx->d_fbest_flags.p;
-    sp.append = in->append_to_tree;
+    sp.append = append;
     sp.tree_size = (long long*)ctx->d_fsizes.p;
     sp.tree_cap = ctx->forest.cap;
     sp.tree_seg = ctx->f_seg;
@@ -1291,6 +1286,148 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     if (best_controls) MPS_CUDA_CHECK(cudaMemcpyAsync(best_controls, sp.best_controls, sizeof(float) * MPS_CONTROL_DIM * L * (size_t)M, cudaMemcpyDeviceToHost, st), ctx);
     if (best_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(best_flags, sp.best_flags, sizeof(uint32_t) * L * (size_t)M, cudaMemcpyDeviceToHost, st), ctx);
     MPS_CUDA_CHECK(cudaStreamSynchronize(st), ctx);
+    return MPS_OK;
+}
+
+
+int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_best* best, float* best_states,
+                      float* best_controls, uint32_t* best_flags)
+{
+    if (!ctx || !in || !in->inst_ids || !in->parents || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_forest_extend");
+    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    const int B = ctx->scene.n_bodies, M = in->M, K = in->K, L = in->L;
+    if (M < 1 || K < 1 || L < 1 || L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "M, K >= 1 and L in [1, 64]");
+    if ((long long)M * K > (1ll << 24)) return mps_fail(ctx, MPS_ERR_ARG, "M * K too large");
+    if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS || (in->n_goals > 0 && !in->goals)) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
+    int rc = check_inst_ids(ctx, in->inst_ids, M);
+    if (rc) return rc;
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    if ((rc = forest_ensure_buffers(ctx, M, K, L))) return rc;
+    const size_t KT = (size_t)M * K, KL = KT * L;
+    const size_t cb = sizeof(float) * MPS_CONTROL_DIM * KL, nb = sizeof(int32_t) * KT, db = sizeof(float) * 3 * B * (size_t)M,
+                 mb = sizeof(int32_t) * (size_t)M, wb = sizeof(float) * B;
+    cudaStream_t st = ctx->stream;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_controls.p, in->controls, cb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->n_ctrl) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_nctrl.p, in->n_ctrl, nb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->dests) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_dest.p, in->dests, db, cudaMemcpyHostToDevice, st), ctx);
+    if (in->weights) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_weights.p, in->weights, wb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->n_goals > 0) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_goals.p, in->goals, sizeof(mps_goal) * in->n_goals, cudaMemcpyHostToDevice, st), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_finst.p, in->inst_ids, mb, cudaMemcpyHostToDevice, st), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_fparents.p, in->parents, mb, cudaMemcpyHostToDevice, st), ctx);
+    if (in->masks) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_fmasks.p, in->masks, mb, cudaMemcpyHostToDevice, st), ctx);
+
+    return forest_extend_launch(ctx, M, K, L, in->n_ctrl != nullptr, in->dests != nullptr, in->weights != nullptr,
+                                in->masks != nullptr, in->compare_f32, in->n_goals, in->append_to_tree, best, best_states,
+                                best_controls, best_flags);
+}
+
+int mps_forest_naive_step(mps_ctx* ctx, const mps_forest_naive_in* in, mps_extend_best* best, uint32_t* flags)
+{
+    if (!ctx || !in || !in->inst_ids) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_forest_naive_step");
+    if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    const int B = ctx->scene.n_bodies, M = in->M, K = in->K, C = in->C, L = 1;
+    if (M < 1 || M > 65535 || K < 1 || C < 1) return mps_fail(ctx, MPS_ERR_ARG, "M in [1, 65535], K, C >= 1");
+    if ((long long)M * K > (1ll << 24)) return mps_fail(ctx, MPS_ERR_ARG, "M * K too large");
+    if (in->n_goals < 1 || in->n_goals > MPS_MAX_GOALS || !in->goals) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
+    for (int g = 0; g < in->n_goals; ++g)
+        if (in->goals[g].body < 0 || in->goals[g].body >= B) return mps_fail(ctx, MPS_ERR_ARG, "goal body out of range");
+    int rc = check_inst_ids(ctx, in->inst_ids, M);
+    if (rc) return rc;
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    if ((rc = forest_ensure_buffers(ctx, M, K, L))) return rc;
+    const size_t MC = (size_t)M * C;
+    if ((rc = ensure(ctx, ctx->d_vstates, sizeof(float) * 3 * B * MC))) return rc;
+    if ((rc = ensure(ctx, ctx->d_valid, MC))) return rc;
+    if ((rc = ensure(ctx, ctx->d_vflags, sizeof(uint32_t) * MC))) return rc;
+    // buffers of the nearest-neighbour query (as mps_tree_nearest_upload sets them up)
+    if ((rc = ensure(ctx, ctx->d_nn_out, 16 * (size_t)M))) return rc;
+    const int max_grid = ctx->num_sms * 16;
+    if ((rc = ensure(ctx, ctx->d_part_d, sizeof(double) * (size_t)M * max_grid))) return rc;
+    if ((rc = ensure(ctx, ctx->d_part_i, sizeof(long long) * (size_t)M * max_grid))) return rc;
+    if (ctx->d_tickets.bytes < sizeof(unsigned) * (size_t)M) {
+        if ((rc = ensure(ctx, ctx->d_tickets, sizeof(unsigned) * (size_t)M))) return rc;
+        MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.bytes, ctx->stream), ctx);
+    }
+    cudaStream_t st = ctx->stream;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_finst.p, in->inst_ids, sizeof(int32_t) * (size_t)M, cudaMemcpyHostToDevice, st), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_goals.p, in->goals, sizeof(mps_goal) * in->n_goals, cudaMemcpyHostToDevice, st), ctx);
+    if (in->weights) MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_weights.p, in->weights, sizeof(float) * B, cudaMemcpyHostToDevice, st), ctx);
+
+    // 1. candidate states, active objects and controls
+    NaiveSampleParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.M = M;
+    sp.C = C;
+    sp.K = K;
+    sp.B = B;
+    sp.inst_ids = (const int32_t*)ctx->d_finst.p;
+    sp.instance_offset = in->instance_offset;
+    sp.seed = in->seed;
+    sp.iteration = in->iteration;
+    sp.x_min = ctx->scene.x_min;
+    sp.x_max = ctx->scene.x_max;
+    sp.y_min = ctx->scene.y_min;
+    sp.y_max = ctx->scene.y_max;
+    sp.goal_bias = in->goal_bias;
+    sp.target_bias = in->target_bias;
+    sp.robot_bias = in->robot_bias;
+    sp.robot = ctx->scene.robot_id;
+    sp.goals = (const mps_goal*)ctx->d_goals.p;
+    sp.n_goals = in->n_goals;
+    sp.v_limit = in->velocity_limit;
+    sp.w_limit = in->omega_limit;
+    sp.dur_min = in->duration_min;
+    sp.dur_max = in->duration_max;
+    sp.cand = (float*)ctx->d_vstates.p;
+    sp.masks = (uint32_t*)ctx->d_fmasks.p;
+    sp.controls = (float*)ctx->d_controls.p;
+    MPS_CUDA_CHECK(mps_launch_naive_sample(sp, st), ctx);
+    // 2. validity of the candidates, first valid one becomes the sample (= dest of the extend, query of the NN)
+    ValidityParams vp;
+    vp.scene = ctx->d_scene;
+    vp.scene_bytes = ctx->scene_bytes;
+    vp.warp_bytes = ctx->warp_bytes;
+    vp.states = (const float*)ctx->d_vstates.p;
+    vp.n = (int)MC;
+    vp.valid = (uint8_t*)ctx->d_valid.p;
+    vp.flags = (uint32_t*)ctx->d_vflags.p;
+    MPS_CUDA_CHECK(mps_launch_validity(vp, ctx->num_sms, st), ctx);
+    MPS_CUDA_CHECK(mps_launch_naive_pick(M, C, B, (const float*)ctx->d_vstates.p, (const uint8_t*)ctx->d_valid.p,
+                                         (float*)ctx->d_dest.p, st),
+                   ctx);
+    // 3. selectTreeNode: nearest node of the instance's own tree under the full metric
+    NNParams np;
+    memset(&np, 0, sizeof(np));
+    np.tree = ctx->forest;
+    np.n = (long long)ctx->f_seg;
+    np.queries = (const float*)ctx->d_dest.p;
+    np.weights = in->weights ? (const float*)ctx->d_weights.p : nullptr;
+    np.pw = ctx->scene.position_weight;
+    np.ow = ctx->scene.orientation_weight;
+    np.Q = M;
+    np.out_idx = (long long*)ctx->d_nn_out.p;
+    np.out_dist = (double*)((char*)ctx->d_nn_out.p + 8 * (size_t)M);
+    np.part_d = (double*)ctx->d_part_d.p;
+    np.part_i = (long long*)ctx->d_part_i.p;
+    np.tickets = (unsigned*)ctx->d_tickets.p;
+    np.inst_ids = (const int32_t*)ctx->d_finst.p;
+    np.seg_sizes = (const long long*)ctx->d_fsizes.p;
+    np.seg = ctx->f_seg;
+    np.grid_x = mps_nn_grid_x((long long)ctx->f_seg, ctx->num_sms);
+    int cap_grid = ctx->num_sms * 16 / M;
+    if (cap_grid < 1) cap_grid = 1;
+    if (np.grid_x > cap_grid) np.grid_x = cap_grid;
+    MPS_CUDA_CHECK(mps_launch_nn_scan(np, st), ctx);
+    MPS_CUDA_CHECK(mps_launch_idx_to_parent(M, np.out_idx, (int32_t*)ctx->d_fparents.p, st), ctx);
+    ctx->launches += 5;
+    ctx->nn_ready = false;
+    // 4. extend: K rollouts per instance, best by the active object's distance, appended to the tree
+    std::vector<uint32_t> bf;
+    if (flags) bf.resize((size_t)M);
+    rc = forest_extend_launch(ctx, M, K, L, false, true, in->weights != nullptr, true, 0, in->n_goals, 1, best, nullptr,
+                              nullptr, flags ? bf.data() : nullptr);
+    if (rc) return rc;
+    if (flags) memcpy(flags, bf.data(), sizeof(uint32_t) * (size_t)M);
     return MPS_OK;
 }
 

@@ -46,7 +46,7 @@ def _sample_controls(rng: np.random.Generator, n: int) -> np.ndarray:
 def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int, num_control_samples: int = 10,
                     max_iterations: int = 500, seed: int = 1, goal_bias: float = 0.2, target_bias: float = 0.25,
                     robot_bias: float = 0.0, wall_timeout: float = 1e9, instance_offset: int = 0,
-                    candidates_per_sample: int = 8) -> SweepResult:
+                    candidates_per_sample: int = 8, device_sampling: bool = False) -> SweepResult:
     sc = ctx.scene
     B = sc.n_bodies
     K = int(num_control_samples)
@@ -95,6 +95,28 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
             d["controls"][sl] = _sample_controls(rng, BLK * K).reshape(BLK, K, 1, 5)
         return d
 
+    if device_sampling:
+        # the whole iteration runs on the device (mps_forest_naive_step): no host random numbers, no uploads
+        # but the ids of the instances still running; draws are a hash of (seed, iteration, global instance id)
+        for it in range(max_iterations):
+            if len(active) == 0 or time.perf_counter() - t0 > wall_timeout:
+                break
+            ta = time.perf_counter()
+            res = forest.naive_step(active, it, seed, goals, K=K, C_=C, goal_bias=goal_bias, target_bias=target_bias,
+                                    robot_bias=robot_bias, instance_offset=instance_offset)
+            timing["extend"] += time.perf_counter() - ta
+            rollouts += len(active) * K
+            reached = ((res["flags"] & abi.MPS_F_GOAL) != 0) & (res["k"] >= 0)
+            if reached.any():
+                ids = active[reached]
+                solved_it[ids] = it
+                solved_t[ids] = time.perf_counter() - t0
+                goal_nodes[ids] = res["tree_index"][reached]
+                active = active[~reached]
+        wall = time.perf_counter() - t0
+        res_ = SweepResult(solved_it, solved_t, forest.sizes(), it + 1, rollouts, wall, goal_nodes)
+        res_.timing = {"device_step": round(timing["extend"], 4)}
+        return res_, forest
     pool = ThreadPoolExecutor(max_workers=1)
     ahead = pool.submit(draw, 0)
     lo = np.array([sc.x_min, sc.y_min, -np.pi], np.float32)

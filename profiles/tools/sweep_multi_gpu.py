@@ -27,13 +27,16 @@ sc, start = scenes.make_scene(8, seed=1005)
 goals = [(1, float(start[3]) + 0.25, float(start[4]) + 0.1, 0.1)]
 ctx = api.Context(sc, device=local)
 # warm-up (context, kernels, allocator), then the timed sweep between barriers
-multi_seed.naive_rrt_sweep(ctx, start, goals, n_instances=min(n, 64), num_control_samples=10, max_iterations=3, seed=5)
+DEVICE = os.environ.get("SWEEP_DEVICE", "0") == "1"
+multi_seed.naive_rrt_sweep(ctx, start, goals, n_instances=n, num_control_samples=10, max_iterations=3, seed=99,
+                           device_sampling=DEVICE)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
 res, forest = multi_seed.naive_rrt_sweep(ctx, start, goals, n_instances=n, num_control_samples=10, max_iterations=iters,
-                                         seed=5, goal_bias=0.2, target_bias=0.4, instance_offset=rank * n)
+                                         seed=5, goal_bias=0.2, target_bias=0.4, instance_offset=rank * n,
+                                         device_sampling=DEVICE)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 v = torch.tensor([dt, float(res.rollouts), float((res.solved_iteration >= 0).sum())], dtype=torch.float64, device="cuda")

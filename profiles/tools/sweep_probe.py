@@ -10,7 +10,8 @@ sc, start = scenes.make_scene(8, seed=1005)
 goals = [(1, float(start[3]) + 0.25, float(start[4]) + 0.1, 0.1)]
 ctx = api.Context(sc)
 res, forest = multi_seed.naive_rrt_sweep(ctx, start, goals, n_instances=n, num_control_samples=10, max_iterations=iters,
-                                         seed=5, goal_bias=0.2, target_bias=0.4)
+                                         seed=5, goal_bias=0.2, target_bias=0.4,
+                                         device_sampling=os.environ.get("SWEEP_DEVICE", "0") == "1")
 solved = (res.solved_iteration >= 0)
 print(json.dumps({"instances": n, "iterations": res.iterations, "wall_s": round(res.wall_s, 3), "rollouts": res.rollouts,
                   "rollouts_per_s": round(res.rollouts / res.wall_s, 1), "solved_fraction": round(float(solved.mean()), 4),

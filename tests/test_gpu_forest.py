@@ -62,12 +62,16 @@ def test_forest_extend_and_nearest_match_oracle_per_instance():
     ctx.close()
 
 
-def test_multi_seed_naive_rrt_sweep_solutions_replay():
+@pytest.mark.parametrize("device_sampling", [False, True])
+def test_multi_seed_naive_rrt_sweep_solutions_replay(device_sampling):
+    """Lockstep multi-seed NaiveRRT (BASELINE config 5), with the random draws on the host or the whole iteration
+    on the device (mps_forest_naive_step): solutions replay on the oracle, the split over devices is invisible."""
     sc, start = scenes.make_scene(3, seed=1001)
     goals = [(1, float(start[3]) + 0.2, float(start[4]) + 0.1, 0.12)]
     ctx = api.Context(sc)
     res, forest = multi_seed.naive_rrt_sweep(ctx, start, goals, n_instances=64, num_control_samples=10,
-                                             max_iterations=150, seed=7, goal_bias=0.2, target_bias=0.4)
+                                             max_iterations=150, seed=7, goal_bias=0.2, target_bias=0.4,
+                                             device_sampling=device_sampling)
     assert res.rollouts > 0 and res.iterations >= 1
     solved = np.flatnonzero(res.solved_iteration >= 0)
     assert len(solved) >= 4, f"only {len(solved)} of 64 instances solved"
@@ -84,7 +88,8 @@ def test_multi_seed_naive_rrt_sweep_solutions_replay():
     # sharding invariance: instances [32, 64) run alone give the same outcome as inside the full sweep
     ctx2 = api.Context(sc)
     res2, _ = multi_seed.naive_rrt_sweep(ctx2, start, goals, n_instances=32, num_control_samples=10, max_iterations=150,
-                                         seed=7, goal_bias=0.2, target_bias=0.4, instance_offset=32)
+                                         seed=7, goal_bias=0.2, target_bias=0.4, instance_offset=32,
+                                         device_sampling=device_sampling)
     assert np.array_equal(res2.solved_iteration, res.solved_iteration[32:])
     ctx.close()
     ctx2.close()
