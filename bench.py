@@ -324,6 +324,10 @@ def run_ours(args):
         if world == 1 and not args.skip_cpu:
             nn["cpu_baseline"] = nn_cpu_baseline(scenes)
 
+    throughput = None
+    if rank == 0 and world == 1 and not args.skip_nn:
+        throughput = bench_throughput(api, scenes, local_rank, fp32_peak)
+
     # ---- CPU baseline (oracle, 1 thread, bounded sample) on rank 0 at N = 1 -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -348,6 +352,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "nn": nn,
+            "throughput": throughput,
             "winner": None if winner is None else {"k": winner.k, "n_ok": winner.n_ok, "distance": winner.distance},
         }
         emit(line)
@@ -398,6 +403,35 @@ def bench_nn(api, scenes, device):
             "roofline": {"kernel": "nn_scan_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm,
                          "unit": "GB/s", "frac": round(gbs / hbm, 4), "traffic": ncu_traffic("nn_scan_kernel"), "peak_source": src,
                          "algorithmic_bytes_per_launch": bytes_alg}}
+
+
+def bench_throughput(api, scenes, device, fp32_peak):
+    """The rollout kernel when the launch fills the machine (not the headline: BASELINE config 4's shape and
+    the same with 7 bodies, single-control rollouts from a contact-rich start)."""
+    import torch
+
+    out = {}
+    for name, n_objects, K in (("cfg4_shape_B17_K65536", 16, 65536), ("B7_K65536", 6, 65536)):
+        sc, _ = scenes.make_scene(n_objects, seed=1000 + n_objects)
+        start = scenes.cluttered_start(sc, 1000 + n_objects)
+        rng = np.random.RandomState(n_objects)
+        controls = scenes.sample_controls_towards(rng, sc, start, K, 1)
+        ctx = api.Context(sc, device=device)
+        ctx.extend_upload(start, controls, dest=scenes.sample_state(rng, sc))
+        ctx.extend_launch()
+        ctx.synchronize()
+        ctx.counters()
+        iters = 3
+        ms = ctx.time_launches(0, iters) / iters
+        cnt = ctx.counters()
+        flops = flop_model(sc.n_bodies, sc.n_statics, sc.vel_iters, cnt) / iters
+        tf = flops / (ms * 1e-3) / 1e12
+        out[name] = {"rollouts_per_s": round(K / ms * 1e3, 1), "ms_per_launch": round(ms, 3),
+                     "physics_steps_per_launch": cnt["steps"] / iters,
+                     "fp32": {"achieved_tflops": round(tf, 3), "peak_tflops": round(fp32_peak, 2),
+                              "frac": round(tf / fp32_peak, 5)}}
+        ctx.close()
+    return out
 
 
 def nn_cpu_baseline(scenes):
