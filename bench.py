@@ -389,10 +389,13 @@ def bench_nn(api, scenes, device):
         ms = e0.elapsed_time(e1) / iters
         idx, dist_ = tree.nearest_fetch()
         # end to end: host query in, (index, distance) out
+        qs = [scenes.sample_state(rng, sc) for _ in range(53)]  # drawing the sample is not part of the query
+        for i in range(3):
+            tree.nearest(qs[i])
         t0 = time.perf_counter()
-        for i in range(20):
-            tree.nearest(scenes.sample_state(rng, sc))
-        e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+        for i in range(3, 53):
+            tree.nearest(qs[i])
+        e2e_ms = (time.perf_counter() - t0) / 50 * 1e3
         ctx.close()
     hbm, src = peaks()
     bytes_alg = N * 3 * B * 4

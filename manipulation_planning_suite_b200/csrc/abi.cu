@@ -73,6 +73,7 @@ struct mps_ctx {
     size_t h_nn_out_bytes = 0;
     NNParams np;
     bool nn_ready = false;
+    bool nn_direct = false;  // the pending query's result lands in h_nn_out without a copy
     int nn_Q = 0;
 
     // forest (multi-instance batches)
@@ -728,7 +729,9 @@ int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const
         if ((rc = ensure(ctx, ctx->d_tickets, sizeof(unsigned) * (size_t)Q))) return rc;
         MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.bytes, ctx->stream), ctx);
     }
-    if (qb + 2 * mb + wb <= 65536) {
+    if (Q == 1) {
+        // one query: it travels in the kernel parameters (filled below), nothing to copy
+    } else if (qb + 2 * mb + wb <= 65536) {
         // small payloads: copy straight from the caller's memory (the driver stages pageable memory before
         // cudaMemcpyAsync returns), no staging buffer and no synchronise on the query path
         MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_queries.p, queries, qb, cudaMemcpyHostToDevice, ctx->stream), ctx);
@@ -771,8 +774,17 @@ int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const
     np.part_d = (double*)ctx->d_part_d.p;
     np.part_i = (long long*)ctx->d_part_i.p;
     np.tickets = (unsigned*)ctx->d_tickets.p;
+    if (Q == 1) {
+        np.inline_q = 1;
+        np.inline_has_w = weights ? 1 : 0;
+        np.inline_mask = masks ? masks[0] : 0xffffffffu;
+        np.inline_filter = slice_filters ? slice_filters[0] : -1;
+        memcpy(np.q_inline, queries, qb);
+        if (weights) memcpy(np.w_inline, weights, wb);
+    }
     ctx->nn_Q = Q;
     ctx->nn_ready = true;
+    ctx->nn_direct = false;
     return MPS_OK;
 }
 
@@ -796,8 +808,10 @@ int mps_tree_nearest_fetch(mps_ctx* ctx, int64_t* indices, double* distances)
     if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
     if (!ctx->nn_ready) return mps_fail(ctx, MPS_ERR_STATE, "nothing to fetch");
     const int Q = ctx->nn_Q;
-    // one D2H of idx[Q] | dist[Q] into pinned memory, one synchronise
-    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nn_out, ctx->d_nn_out.p, 16 * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    // one D2H of idx[Q] | dist[Q] into pinned memory, one synchronise (the one-shot single query had the
+    // kernel write the pinned block itself: synchronise only)
+    if (!ctx->nn_direct)
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nn_out, ctx->d_nn_out.p, 16 * (size_t)Q, cudaMemcpyDeviceToHost, ctx->stream), ctx);
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     if (indices) memcpy(indices, ctx->h_nn_out, 8 * (size_t)Q);
     if (distances) memcpy(distances, (char*)ctx->h_nn_out + 8 * (size_t)Q, 8 * (size_t)Q);
@@ -816,7 +830,15 @@ int mps_tree_nearest_batch(mps_ctx* ctx, const float* queries, int32_t Q, const 
 int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
                      int64_t* index, double* distance)
 {
-    return mps_tree_nearest_batch(ctx, query, 1, weights, &mask, &slice_filter, index, distance);
+    // One query, one launch, one synchronise: the query rides in the kernel parameters and the last CTA writes
+    // (index, distance) straight into pinned host memory (device-visible under unified addressing).
+    int rc = mps_tree_nearest_upload(ctx, query, 1, weights, &mask, &slice_filter);
+    if (rc) return rc;
+    ctx->np.out_idx = (long long*)ctx->h_nn_out;
+    ctx->np.out_dist = (double*)((char*)ctx->h_nn_out + 8);
+    ctx->nn_direct = true;
+    if ((rc = mps_tree_nearest_launch(ctx))) return rc;
+    return mps_tree_nearest_fetch(ctx, index, distance);
 }
 
 // ---- extend -----------------------------------------------------------------------------------

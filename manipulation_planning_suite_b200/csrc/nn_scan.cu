@@ -106,10 +106,11 @@ __device__ __forceinline__ double warp_exact_distance(const TreeView& t, long lo
 // scanned rows are about the size of L2 (1 M nodes x 132 B: 29.2 us vs 32.9 us), slower when they are several
 // times larger (4 M nodes: 96 us vs 88 us) - the host picks per launch (mps_launch_nn_scan).
 template <bool STREAM>
-__global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNParams p)
+__global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(const __grid_constant__ NNParams p)
 {
     __shared__ float s_q[3 * MPS_MAX_BODIES];
-    __shared__ float s_w[MPS_MAX_BODIES];
+    __shared__ float s_w[MPS_MAX_BODIES];   // weight of the a-th active body
+    __shared__ float s_wb[MPS_MAX_BODIES];  // weight of body i (1 when the call has none)
     __shared__ int s_act[MPS_MAX_BODIES];
     __shared__ int s_nact;
     __shared__ unsigned int s_bound;
@@ -125,16 +126,22 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
     const int warp = tid >> 5;
     const int q = blockIdx.y;
     const int B = p.tree.B;
-    uint32_t mask = p.masks ? p.masks[q] : 0xffffffffu;
+    // the query, its mask / slice filter and the weights come from device buffers, or (single query through
+    // mps_tree_nearest) from the kernel parameters themselves
+    const bool inl = p.inline_q != 0;
+    uint32_t mask = inl ? p.inline_mask : (p.masks ? p.masks[q] : 0xffffffffu);
     if (B < 32) mask &= (1u << B) - 1u;
-    const int filter = p.filters ? p.filters[q] : -1;
-    const float* qg = p.queries + (size_t)q * 3 * B;
-    if (tid < 3 * B) s_q[tid] = qg[tid];
-    // active-body list, built in parallel: body i goes to position popc(mask below bit i)
-    if (tid < B && ((mask >> tid) & 1u)) {
-        const int a = __popc(mask & ((1u << tid) - 1u));
-        s_act[a] = tid;
-        s_w[a] = p.weights ? p.weights[tid] : 1.0f;
+    const int filter = inl ? p.inline_filter : (p.filters ? p.filters[q] : -1);
+    if (tid < 3 * B) s_q[tid] = inl ? p.q_inline[tid] : p.queries[(size_t)q * 3 * B + tid];
+    if (tid < B) {
+        const float w = inl ? (p.inline_has_w ? p.w_inline[tid] : 1.0f) : (p.weights ? p.weights[tid] : 1.0f);
+        s_wb[tid] = w;
+        // active-body list, built in parallel: body i goes to position popc(mask below bit i)
+        if ((mask >> tid) & 1u) {
+            const int a = __popc(mask & ((1u << tid) - 1u));
+            s_act[a] = tid;
+            s_w[a] = w;
+        }
     }
     if (tid == 0) {
         s_nact = __popc(mask);
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
                         s_cand_i[slot] = n0 + j;
                     } else {
                         // list full (adversarial orderings): evaluate on the spot
-                        const double e = exact_distance(p.tree, (long long)col0 + n0 + j, s_q, p.weights, mask, p.pw, p.ow);
+                        const double e = exact_distance(p.tree, (long long)col0 + n0 + j, s_q, s_wb, mask, p.pw, p.ow);
                         take_min(best_d, best_i, e, n0 + j);
                     }
                 }
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(NNPa
         for (int c = warp; c < ncand; c += NN_THREADS / 32) {
             if (__uint_as_float(s_cand_d[c]) <= thr) {
                 const long long n = s_cand_i[c];
-                const double e = warp_exact_distance(p.tree, (long long)col0 + n, s_q, p.weights, mask, p.pw, p.ow, lane);
+                const double e = warp_exact_distance(p.tree, (long long)col0 + n, s_q, s_wb, mask, p.pw, p.ow, lane);
                 if (lane == 0) take_min(best_d, best_i, e, n);
             }
         }

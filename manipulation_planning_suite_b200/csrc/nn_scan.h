@@ -35,6 +35,14 @@ struct NNParams {
     const long long* seg_sizes;   // [segments]
     size_t seg;
     int grid_x;
+    // single query carried in the kernel parameters (no host -> device copy on the query path): used when
+    // inline_q != 0, Q == 1; queries / masks / filters / weights above are then ignored
+    int inline_q;
+    int inline_has_w;
+    uint32_t inline_mask;
+    int32_t inline_filter;
+    float q_inline[3 * 32];
+    float w_inline[32];
 };
 
 int mps_nn_grid_x(long long n, int num_sms);
