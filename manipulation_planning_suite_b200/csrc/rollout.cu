@@ -63,6 +63,12 @@ namespace {
 //   [4 + 3k] normal mass, tangent mass, bias, -
 //   [8] acc_n0, acc_t0, acc_n1, acc_t1   (accumulated impulses)
 #define MF_VEC4 8
+// sweeps of at most this many rounds keep the manifold rows in registers (see physics_step): two in the build
+// with the large register budget, MPS_REG_ROUNDS in the packed 128-register builds, none in the unpacked
+// 128-register build (measured on B200: +6 % on cfg2, +8 % packed at B = 7, -5 % unpacked at B = 17)
+#ifndef MPS_REG_ROUNDS
+#define MPS_REG_ROUNDS 1
+#endif
 #define MF_FIELDS (4 * MF_VEC4)
 
 struct Shape {
@@ -698,18 +704,31 @@ struct StepStats {
 // The pass has no data-dependent branch and no barrier: lanes without a manifold run the arithmetic on slot 0
 // and drop the result, a one-point manifold carries zero rows for the second point, and each owner lane keeps
 // its own copy of the accumulated impulses, so no lane reads what another lane writes during the sweep.
-__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln ln, int sl, int j, bool stat)
+// rows of one manifold as the sweep reads them (WarpMem::man layout)
+struct MRows {
+    float4 m0, r0, g0, r1, g1, kc;
+};
+
+__device__ __forceinline__ MRows load_rows(const float4* mf)
 {
-    const int lane = ln.g;
+    MRows R;
+    R.m0 = mf[0];
+    R.r0 = mf[1];
+    R.g0 = mf[2];
+    R.r1 = mf[3];
+    R.g1 = mf[4];
+    R.kc = mf[5];
+    return R;
+}
+
+// the arithmetic of one visit; acc = this owner lane's copy of the accumulated impulses
+__device__ __forceinline__ void solve_core(const MRows& R, float4& acc, Body& bd, const Ln ln, bool act, int j,
+                                           bool stat, bool is_a)
+{
     float ovx = __shfl_sync(ln.m, bd.vx, ln.abs_lane(j));
     float ovy = __shfl_sync(ln.m, bd.vy, ln.abs_lane(j));
     float ow_ = __shfl_sync(ln.m, bd.w, ln.abs_lane(j));
-    const bool act = sl != 0xff;
-    const bool is_a = stat || lane < j;
-    float4* mf = W.man + (act ? sl : 0) * MF_VEC4;
-    const float4 m0 = mf[0], r0 = mf[1], g0 = mf[2], r1 = mf[3], g1 = mf[4], kc = mf[5];
-    float4* accp = mf + (is_a ? 6 : 7);
-    float4 acc = *accp;
+    const float4 m0 = R.m0, r0 = R.r0, g0 = R.g0, r1 = R.r1, g1 = R.g1, kc = R.kc;
     if (stat) {
         ovx = 0.0f;
         ovy = 0.0f;
@@ -771,8 +790,20 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln 
         bd.vx = nvx;
         bd.vy = nvy;
         bd.w = nw;
-        *accp = acc;
     }
+}
+
+__device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln ln, int sl, int j, bool stat)
+{
+    const int lane = ln.g;
+    const bool act = sl != 0xff;
+    const bool is_a = stat || lane < j;
+    float4* mf = W.man + (act ? sl : 0) * MF_VEC4;
+    const MRows R = load_rows(mf);
+    float4* accp = mf + (is_a ? 6 : 7);
+    float4 acc = *accp;
+    solve_core(R, acc, bd, ln, act, j, stat, is_a);
+    if (act) *accp = acc;
 }
 
 // General sweep, colour by colour in canonical order, for steps in which some body has more than 4
@@ -821,7 +852,7 @@ __device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem&
 }
 
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
-template <int G>
+template <int G, int RR>
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, const Ln ln, float ux,
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
                                              StepStats& st, StepCache& cache)
@@ -968,6 +999,27 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             };
             if (rounds < 0) {
                 general_sweep<G>(sc, W, bd, ln, dr.nm, st);
+            } else if (RR > 0 && rounds <= RR) {
+                // One or two rounds (most contact steps): the rows of this lane's manifolds stay in registers
+                // for the whole sweep and so do the accumulated impulses, which start at zero every step and
+                // are not read after the sweep - a pass is three shuffles and arithmetic, no shared memory.
+                const unsigned ea = cache.ent[0], eb = (RR > 1 && rounds > 1) ? cache.ent[1] : 0u;
+                const bool act_a = ea != 0u, act_b = eb != 0u;
+                const bool st_a = (ea & 0x8000u) != 0u, st_b = (eb & 0x8000u) != 0u;
+                const int j_a = act_a ? (int)((ea >> 8) & 0x3fu) : lane, j_b = act_b ? (int)((eb >> 8) & 0x3fu) : lane;
+                const bool isa_a = st_a || lane < j_a, isa_b = st_b || lane < j_b;
+                const MRows Ra = load_rows(W.man + (act_a ? (int)(ea & 0xffu) : 0) * MF_VEC4);
+                float4 acc_a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (RR < 2 || rounds == 1) {
+                    for (int it = 0; it < iters; ++it) solve_core(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                } else {
+                    const MRows Rb = load_rows(W.man + (act_b ? (int)(eb & 0xffu) : 0) * MF_VEC4);
+                    float4 acc_b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int it = 0; it < iters; ++it) {
+                        solve_core(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                        solve_core(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
+                    }
+                }
             } else if (rounds <= 4) {
                 for (int it = 0; it < iters; ++it) {
                     pass(cache.ent[0]);
@@ -990,6 +1042,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             PH_ADD(3, t2, t3);
 #ifdef MPS_PHASE_PROF
             st.ph[5] += 1;
+            st.ph[9] += rounds < 0 ? 0 : rounds * iters;  // solver passes of the step
 #endif
         }
     }
@@ -1224,7 +1277,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 }
                 bool bad, over;
                 float pen;
-                physics_step<G>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
+                physics_step<G, (MINB <= 3 ? 2 : (G < 32 ? MPS_REG_ROUNDS : 0))>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
                 if (over && small_cap) {
                     redo = true;
                     break;
@@ -1582,6 +1635,12 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int want = (p.K + groups - 1) / groups;
+    static int cap_per_sm = -1;  // tuning aid: MPS_ROLLOUT_CTAS_PER_SM caps the resident CTAs per SM
+    if (cap_per_sm < 0) {
+        const char* e_ = getenv("MPS_ROLLOUT_CTAS_PER_SM");
+        cap_per_sm = e_ ? atoi(e_) : 0;
+    }
+    if (cap_per_sm > 0 && blocks_per_sm > cap_per_sm) blocks_per_sm = cap_per_sm;
     int grid = num_sms * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
