@@ -685,7 +685,7 @@ __device__ __forceinline__ void set_state(const WarpMem& W, Body& b, const Ln ln
 struct StepStats {
     unsigned steps, candidates, touching, colour_passes;
 #ifdef MPS_PHASE_PROF
-    long long ph[10];  // broad phase, narrow phase, round scheduling, solver rounds, friction + integration,
+    long long ph[11];  // broad phase, narrow phase, round scheduling, solver rounds, friction + integration,
                        // contact steps, narrow: reach test / collide / rows
 #endif
 };
@@ -1011,7 +1011,10 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 const MRows Ra = load_rows(W.man + (act_a ? (int)(ea & 0xffu) : 0) * MF_VEC4);
                 float4 acc_a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 if (RR < 2 || rounds == 1) {
+                    PH_T(tl0);
                     for (int it = 0; it < iters; ++it) solve_core(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                    PH_T(tl1);
+                    PH_ADD(10, tl0, tl1);  // the passes alone of one-round sweeps
                 } else {
                     const MRows Rb = load_rows(W.man + (act_b ? (int)(eb & 0xffu) : 0) * MF_VEC4);
                     float4 acc_b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1191,7 +1194,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         cache.reset();
         bd.mv = 0.0f;
 #ifdef MPS_PHASE_PROF
-        for (int i = 0; i < 10; ++i) st.ph[i] = 0;
+        for (int i = 0; i < 11; ++i) st.ph[i] = 0;
 #endif
         // start state of the chain
         float sx = 0.0f, sy = 0.0f, sth = 0.0f;
@@ -1401,8 +1404,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
 #ifdef MPS_PHASE_PROF
             if (p.out_cycles) {
                 p.out_cycles[(size_t)k * 12] = clock64() - t_begin;
-                for (int i = 0; i < 10; ++i) p.out_cycles[(size_t)k * 12 + 1 + i] = st.ph[i];
-                p.out_cycles[(size_t)k * 12 + 11] = 0;
+                for (int i = 0; i < 11; ++i) p.out_cycles[(size_t)k * 12 + 1 + i] = st.ph[i];
             }
 #else
             if (p.out_cycles) p.out_cycles[k] = clock64() - t_begin;

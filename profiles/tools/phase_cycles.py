@@ -32,7 +32,7 @@ for bi in range(3):
         print(f"  chain {k}: {tot} cyc ({tot/1.965e3:.0f} us) {steps[k]} steps ({ph[5]} with contacts), cyc/step {tot/max(steps[k],1):.0f} | "
               f"broad {ph[0]/tot:.1%} narrow {ph[1]/tot:.1%} sched {ph[2]/tot:.1%} solve {ph[3]/tot:.1%} "
               f"friction+integrate {other/tot:.1%} outside step {1-(ph[0]+ph[1]+ph[4])/tot:.1%}"
-              f" | per contact step: solve {ph[3]/max(ph[5],1):.0f} ({out[k,10]/max(ph[5],1):.1f} passes of {ph[3]/max(out[k,10],1):.0f} cyc) sched {ph[2]/max(ph[5],1):.0f}; per step: broad {ph[0]/steps[k]:.0f} narrow {ph[1]/steps[k]:.0f} = reach {out[k,7]/steps[k]:.0f} + collide {out[k,8]/steps[k]:.0f} + rows {out[k,9]/steps[k]:.0f}")
+              f" | per contact step: solve {ph[3]/max(ph[5],1):.0f} ({out[k,10]/max(ph[5],1):.1f} passes of {ph[3]/max(out[k,10],1):.0f} cyc) sched {ph[2]/max(ph[5],1):.0f}; per step: broad {ph[0]/steps[k]:.0f} narrow {ph[1]/steps[k]:.0f} = reach {out[k,7]/steps[k]:.0f} + collide {out[k,8]/steps[k]:.0f} + rows {out[k,9]/steps[k]:.0f}; loops of one-round sweeps {out[k,11]} cyc")
     tot = out[:, 0].sum()
     ph = out[:, 1:7].sum(axis=0)
     print(f"  all chains: broad {ph[0]/tot:.1%} narrow {ph[1]/tot:.1%} sched {ph[2]/tot:.1%} solve {ph[3]/tot:.1%} "
