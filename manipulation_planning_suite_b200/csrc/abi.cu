@@ -49,6 +49,7 @@ struct mps_ctx {
 
     // extend: device buffers
     DevBuf d_start, d_controls, d_nctrl, d_dest, d_weights, d_goals, d_ball;
+    DevBuf d_inpack;  // all inputs of one mps_extend call, one host -> device copy
     DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
     DevBuf d_record;  // packed winner record: best | states | controls | flags
     DevBuf d_work, d_counters, d_cycles, d_redo;
@@ -399,7 +400,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_start, &ctx->d_controls, &ctx->d_nctrl, &ctx->d_dest, &ctx->d_weights, &ctx->d_goals,
-                      &ctx->d_ball, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
+                      &ctx->d_ball, &ctx->d_inpack, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
                       &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_redo, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
                       &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_nn_out, &ctx->d_part_d,
@@ -883,26 +884,29 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     if (in->append_to_tree) {
         if ((rc = tree_ensure(ctx, ctx->tree_upper + L))) return rc;
     }
-    // host -> pinned staging -> device
-    if ((rc = ensure_stage(ctx, 3 * sb + cb + nb + wb + gb + (in->starts ? sb * (size_t)K + 64 : 0) + 256))) return rc;
+    // host -> pinned staging -> device: every input of the call is packed into one block (16-byte aligned
+    // pieces) and travels in ONE copy; the kernels read the pieces where they land in the device block
+    const size_t pack_bytes = 3 * sb + cb + nb + wb + gb + (in->starts ? sb * (size_t)K + 64 : 0) + 256;
+    // (the staging block also receives the winner record in mps_extend_fetch)
+    if ((rc = ensure_stage(ctx, pack_bytes > record_bytes(B, L) ? pack_bytes : record_bytes(B, L)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_inpack, pack_bytes))) return rc;
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
-    char* h = (char*)ctx->h_stage;
-    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
+    char* const h0 = (char*)ctx->h_stage;
+    char* h = h0;
+    auto up = [&](const void* src, size_t bytes) -> const void* {
         memcpy(h, src, bytes);
-        cudaError_t e = cudaMemcpyAsync(d.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        const void* d = (const char*)ctx->d_inpack.p + (h - h0);
         h += align_up(bytes, 16);
-        return e;
+        return d;
     };
-    if (in->starts)
-        MPS_CUDA_CHECK(up(ctx->d_start, in->starts, sb * (size_t)K), ctx);
-    else
-        MPS_CUDA_CHECK(up(ctx->d_start, in->start, sb), ctx);
-    MPS_CUDA_CHECK(up(ctx->d_controls, in->controls, cb), ctx);
-    if (in->n_ctrl) MPS_CUDA_CHECK(up(ctx->d_nctrl, in->n_ctrl, nb), ctx);
-    if (in->dest) MPS_CUDA_CHECK(up(ctx->d_dest, in->dest, sb), ctx);
-    if (in->weights) MPS_CUDA_CHECK(up(ctx->d_weights, in->weights, wb), ctx);
-    if (in->n_goals > 0) MPS_CUDA_CHECK(up(ctx->d_goals, in->goals, sizeof(mps_goal) * in->n_goals), ctx);
-    if (in->ball_center) MPS_CUDA_CHECK(up(ctx->d_ball, in->ball_center, sb), ctx);
+    const void* dp_start = in->starts ? up(in->starts, sb * (size_t)K) : up(in->start, sb);
+    const void* dp_controls = up(in->controls, cb);
+    const void* dp_nctrl = in->n_ctrl ? up(in->n_ctrl, nb) : nullptr;
+    const void* dp_dest = in->dest ? up(in->dest, sb) : nullptr;
+    const void* dp_weights = in->weights ? up(in->weights, wb) : nullptr;
+    const void* dp_goals = in->n_goals > 0 ? up(in->goals, sizeof(mps_goal) * in->n_goals) : ctx->d_goals.p;
+    const void* dp_ball = in->ball_center ? up(in->ball_center, sb) : nullptr;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_inpack.p, h0, (size_t)(h - h0), cudaMemcpyHostToDevice, ctx->stream), ctx);
 
     RolloutParams& rp = ctx->rp;
     memset(&rp, 0, sizeof(rp));
@@ -913,19 +917,19 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     rp.mcap_small = ctx->mcap_small;
     rp.redo_only = 0;
     rp.redo = (uint8_t*)ctx->d_redo.p;
-    rp.start = (const float*)ctx->d_start.p;
+    rp.start = (const float*)dp_start;
     rp.start_stride = in->starts ? (size_t)3 * B : 0;
     rp.stop_at_goal = in->stop_at_goal;
-    rp.controls = (const float*)ctx->d_controls.p;
-    rp.n_ctrl = in->n_ctrl ? (const int32_t*)ctx->d_nctrl.p : nullptr;
+    rp.controls = (const float*)dp_controls;
+    rp.n_ctrl = (const int32_t*)dp_nctrl;
     rp.K = K;
     rp.L = L;
-    rp.dest = in->dest ? (const float*)ctx->d_dest.p : nullptr;
-    rp.weights = in->weights ? (const float*)ctx->d_weights.p : nullptr;
+    rp.dest = (const float*)dp_dest;
+    rp.weights = (const float*)dp_weights;
     rp.mask = in->mask;
-    rp.goals = (const mps_goal*)ctx->d_goals.p;
+    rp.goals = (const mps_goal*)dp_goals;
     rp.n_goals = in->n_goals;
-    rp.ball_center = in->ball_center ? (const float*)ctx->d_ball.p : nullptr;
+    rp.ball_center = (const float*)dp_ball;
     rp.ball_radius = in->ball_radius;
     rp.out_states = (float*)ctx->d_states.p;
     rp.out_rest = (float*)ctx->d_rest.p;
@@ -1006,16 +1010,25 @@ int mps_extend_fetch(mps_ctx* ctx, const mps_extend_out* out)
     const int B = ctx->scene.n_bodies, K = ctx->ext_K, L = ctx->ext_L;
     const size_t KL = (size_t)K * L;
     cudaStream_t s = ctx->stream;
-    if (out->best) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best, ctx->sp.best, sizeof(mps_extend_best), cudaMemcpyDeviceToHost, s), ctx);
-    if (out->best_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_states, ctx->sp.best_states, sizeof(float) * 3 * B * L, cudaMemcpyDeviceToHost, s), ctx);
-    if (out->best_controls) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_controls, ctx->sp.best_controls, sizeof(float) * MPS_CONTROL_DIM * L, cudaMemcpyDeviceToHost, s), ctx);
-    if (out->best_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->best_flags, ctx->sp.best_flags, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost, s), ctx);
+    // the winner record (best | states | controls | flags, contiguous on the device) comes back in one copy
+    const bool want_rec = out->best || out->best_states || out->best_controls || out->best_flags;
+    if (want_rec)
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_stage, ctx->d_record.p, record_bytes(B, L), cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_states) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_states, ctx->d_states.p, sizeof(float) * 3 * B * KL, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_rest) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_rest, ctx->d_rest.p, sizeof(float) * KL, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_flags) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_flags, ctx->d_flags.p, sizeof(uint32_t) * KL, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_dist) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_dist, ctx->d_dist.p, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, s), ctx);
     if (out->all_steps) MPS_CUDA_CHECK(cudaMemcpyAsync(out->all_steps, ctx->d_steps.p, sizeof(int32_t) * KL, cudaMemcpyDeviceToHost, s), ctx);
     MPS_CUDA_CHECK(cudaStreamSynchronize(s), ctx);
+    if (want_rec) {
+        const char* rec = (const char*)ctx->h_stage;
+        const size_t o_states = sizeof(mps_extend_best), o_ctrl = o_states + sizeof(float) * 3 * B * L,
+                     o_flags = o_ctrl + sizeof(float) * MPS_CONTROL_DIM * L;
+        if (out->best) memcpy(out->best, rec, sizeof(mps_extend_best));
+        if (out->best_states) memcpy(out->best_states, rec + o_states, sizeof(float) * 3 * B * L);
+        if (out->best_controls) memcpy(out->best_controls, rec + o_ctrl, sizeof(float) * MPS_CONTROL_DIM * L);
+        if (out->best_flags) memcpy(out->best_flags, rec + o_flags, sizeof(uint32_t) * L);
+    }
     if (ctx->sp.append) return tree_sync_size(ctx);
     return MPS_OK;
 }
