@@ -143,3 +143,36 @@ def test_million_node_properties():
         wi, wd = ob.nn_linear(sc, states, q, mask=mask)
         assert gi == wi and gd == wd
     ctx.close()
+
+
+def test_single_query_paths_agree():
+    """One query can travel three ways: in the kernel parameters with the result written to pinned host memory
+    (mps_tree_nearest), in the kernel parameters with the result fetched by a copy (upload / launch / fetch with
+    Q = 1), and through the device query buffers (a batch).  Same index and the same double every time."""
+    sc, _ = scenes.make_scene(8, seed=77)
+    B = sc.n_bodies
+    rng = np.random.RandomState(77)
+    N = 30011
+    states = np.stack([scenes.sample_state(rng, sc) for _ in range(N)])
+    slices = rng.randint(0, 7, size=N).astype(np.int32)
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.add_batch(states, parents=np.arange(-1, N - 1), slice_ids=slices)
+    weights = rng.uniform(0.5, 2.0, size=B).astype(np.float32)
+    for mask in _masks(B):
+        for w in (None, weights):
+            for filt in (-1, 3):
+                q = scenes.sample_state(rng, sc)
+                wi, wd = ob.nn_linear(sc, states, q, weights=w, mask=mask, slice_ids=slices, slice_filter=filt)
+                i1, d1 = tree.nearest(q, weights=w, mask=mask, slice_filter=filt)
+                tree.nearest_upload(q[None, :], weights=w, masks=np.array([mask], np.uint32),
+                                    slice_filters=np.array([filt], np.int32))
+                tree.nearest_launch()
+                tree.nearest_launch()  # relaunching a staged query is allowed
+                i2, d2 = tree.nearest_fetch()
+                q2 = np.stack([q, scenes.sample_state(rng, sc)])
+                i3, d3 = tree.nearest_batch(q2, weights=w, masks=np.array([mask, mask], np.uint32),
+                                            slice_filters=np.array([filt, filt], np.int32))
+                assert i1 == wi and int(i2[0]) == wi and int(i3[0]) == wi
+                assert d1 == wd and float(d2[0]) == wd and float(d3[0]) == wd
+    ctx.close()
