@@ -55,13 +55,15 @@ __device__ __forceinline__ Ln make_ln()
 namespace {
 
 
-// One manifold = 9 float4 (144 B) in the warp's shared slice, read and written with 128-bit accesses:
-//   [0] meta (a | b << 8 | count << 16 | has_bias << 24), nx, ny, friction
-//   [1] ma*nx, ma*ny, mb*nx, mb*ny
-//   [2 + 3k] rna, rnb, rta, rtb          (point k = 0, 1: Jacobian lever arms)
-//   [3 + 3k] ia*rna, ib*rnb, ia*rta, ib*rtb
-//   [4 + 3k] normal mass, tangent mass, bias, -
-//   [8] acc_n0, acc_t0, acc_n1, acc_t1   (accumulated impulses)
+// One manifold = 8 float4 (128 B) in the group's shared slice, read and written with 128-bit accesses:
+//   [0] meta (a | b << 8 | count << 16), nx, ny, friction coefficient sqrt(mu_a mu_b)
+//   [1] point 0: rna, rnb, rta, rtb        (lever arms r x n, r x t of the two bodies)
+//   [2] point 0: normal mass, tangent mass, normal mass * bias, coupling t0-t1
+//   [3] point 1: rna, rnb, rta, rtb
+//   [4] point 1: normal mass, tangent mass, normal mass * bias, coupling n0-n1
+//   [5] couplings t0-n0, t0-n1, t1-n0, t1-n1
+//   [6] accumulated impulses (n0, t0, n1, t1) of owner lane a   [7] the same, owner lane b's private copy
+// A missing second point carries zero rows.
 #define MF_VEC4 8
 // sweeps of at most this many rounds keep the manifold rows in registers (see physics_step): two in the build
 // with the large register budget, MPS_REG_ROUNDS in the packed 128-register builds, none in the unpacked
