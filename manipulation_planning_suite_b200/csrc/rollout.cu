@@ -525,6 +525,8 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         }
         bool touch = cnt > 0;
         unsigned tmask = __ballot_sync(ln.m, touch);
+        // no manifold of this trip has a second point (most trips): its rows stay zero without the arithmetic
+        const bool any_two = G < 32 || __any_sync(ln.m, cnt > 1);
 #ifdef MPS_PHASE_PROF
         long long ts1 = clock64();
         if (sub) sub[1] += ts1 - ts0;
@@ -568,6 +570,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         // both points go through the arithmetic; a missing second point is zeroed afterwards
+                        if (k == 1 && !any_two) break;
                         const bool has = k < cnt;
                         const float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
                         const float sepk = m.sep[k];
@@ -723,7 +726,12 @@ __device__ __forceinline__ MRows load_rows(const float4* mf)
     return R;
 }
 
-// the arithmetic of one visit; acc = this owner lane's copy of the accumulated impulses
+// the arithmetic of one visit; acc = this owner lane's copy of the accumulated impulses.
+// TWO = false: every manifold visited in this pass has a single point.  The rows of the missing second point are
+// all zero, so its impulses are zeros and every term they enter adds a zero: leaving that arithmetic out gives
+// the same values (only the sign of a result that is exactly zero may differ, which no later operation can
+// turn into a different value: the step uses +, -, *, fma, min, max and comparisons only).
+template <bool TWO>
 __device__ __forceinline__ void solve_core(const MRows& R, float4& acc, Body& bd, const Ln ln, bool act, int j,
                                            bool stat, bool is_a)
 {
@@ -749,19 +757,18 @@ __device__ __forceinline__ void solve_core(const MRows& R, float4& acc, Body& bd
     const float dvx = vbx - vax;
     const float dvy = vby - vay;
     const float ut0 = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r0.w, -(wa * r0.z))));
-    const float ut1 = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
     const float un0 = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r0.y, -(wa * r0.x))));
-    const float un1 = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
     // friction first (Box2D order), point 0 then point 1, then non-penetration; an impulse on an earlier
     // row reaches a later row through the coupling coefficient
-    float dt0, dt1, dn0, dn1;
+    float dt0, dt1 = 0.0f, dn0, dn1 = 0.0f;
     {
         const float lim = fr * acc.x;
         const float dl = g0.y * -ut0;
         dt0 = fminf(fmaxf(dl, -lim - acc.y), lim - acc.y);
         acc.y = acc.y + dt0;
     }
-    {
+    if (TWO) {
+        const float ut1 = fmaf(dvx, tx, fmaf(dvy, ty, fmaf(wb, r1.w, -(wa * r1.z))));
         const float u = fmaf(g0.w, dt0, ut1);
         const float lim = fr * acc.z;
         const float dl = g1.y * -u;
@@ -769,22 +776,26 @@ __device__ __forceinline__ void solve_core(const MRows& R, float4& acc, Body& bd
         acc.w = acc.w + dt1;
     }
     {
-        const float u = fmaf(kc.z, dt1, fmaf(kc.x, dt0, un0));
+        const float u = TWO ? fmaf(kc.z, dt1, fmaf(kc.x, dt0, un0)) : fmaf(kc.x, dt0, un0);
         const float dl = fmaf(-g0.x, u, g0.z);
         dn0 = fmaxf(dl, -acc.x);
         acc.x = acc.x + dn0;
     }
-    {
+    if (TWO) {
+        const float un1 = fmaf(dvx, nx, fmaf(dvy, ny, fmaf(wb, r1.y, -(wa * r1.x))));
         const float u = fmaf(g1.w, dn0, fmaf(kc.w, dt1, fmaf(kc.y, dt0, un1)));
         const float dl = fmaf(-g1.x, u, g1.z);
         dn1 = fmaxf(dl, -acc.z);
         acc.z = acc.z + dn1;
     }
     // total impulse on b (a receives the opposite); each lane updates its own body only
-    const float st = dt0 + dt1;
-    const float rr = fmaf(on1, dn1, fmaf(ot1, dt1, fmaf(on0, dn0, ot0 * dt0)));
-    const float px = fmaf(nx, dn1, fmaf(nx, dn0, tx * st));
-    const float py = fmaf(ny, dn1, fmaf(ny, dn0, ty * st));
+    const float st = TWO ? dt0 + dt1 : dt0;
+    const float rr0 = fmaf(on0, dn0, ot0 * dt0);
+    const float rr = TWO ? fmaf(on1, dn1, fmaf(ot1, dt1, rr0)) : rr0;
+    const float px0 = fmaf(nx, dn0, tx * st);
+    const float py0 = fmaf(ny, dn0, ty * st);
+    const float px = TWO ? fmaf(nx, dn1, px0) : px0;
+    const float py = TWO ? fmaf(ny, dn1, py0) : py0;
     const float nvx = fmaf(sm, px, bd.vx);
     const float nvy = fmaf(sm, py, bd.vy);
     const float nw = fmaf(si, rr, bd.w);
@@ -804,7 +815,7 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln 
     const MRows R = load_rows(mf);
     float4* accp = mf + (is_a ? 6 : 7);
     float4 acc = *accp;
-    solve_core(R, acc, bd, ln, act, j, stat, is_a);
+    solve_core<true>(R, acc, bd, ln, act, j, stat, is_a);
     if (act) *accp = acc;
 }
 
@@ -1012,17 +1023,35 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 const bool isa_a = st_a || lane < j_a, isa_b = st_b || lane < j_b;
                 const MRows Ra = load_rows(W.man + (act_a ? (int)(ea & 0xffu) : 0) * MF_VEC4);
                 float4 acc_a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                // sweeps whose manifolds all have a single point (84 % of the contact steps of cfg2) leave the second
+                // point's rows out; not in packed launches, where the groups of a warp would take different variants
+                // and the warp would run both (measured: -10 % at B = 7, K = 65536)
+                const bool two_a = act_a && ((__float_as_int(Ra.m0.x) >> 16) & 0xff) > 1;
                 if (RR < 2 || rounds == 1) {
+                    const bool two = G < 32 || __any_sync(ln.m, two_a);
                     PH_T(tl0);
-                    for (int it = 0; it < iters; ++it) solve_core(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                    if (two) {
+                        for (int it = 0; it < iters; ++it) solve_core<true>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                    } else {
+                        for (int it = 0; it < iters; ++it) solve_core<false>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                    }
                     PH_T(tl1);
                     PH_ADD(10, tl0, tl1);  // the passes alone of one-round sweeps
                 } else {
                     const MRows Rb = load_rows(W.man + (act_b ? (int)(eb & 0xffu) : 0) * MF_VEC4);
                     float4 acc_b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    for (int it = 0; it < iters; ++it) {
-                        solve_core(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
-                        solve_core(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
+                    const bool two_b = act_b && ((__float_as_int(Rb.m0.x) >> 16) & 0xff) > 1;
+                    const bool two = G < 32 || __any_sync(ln.m, two_a || two_b);
+                    if (two) {
+                        for (int it = 0; it < iters; ++it) {
+                            solve_core<true>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                            solve_core<true>(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
+                        }
+                    } else {
+                        for (int it = 0; it < iters; ++it) {
+                            solve_core<false>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
+                            solve_core<false>(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
+                        }
                     }
                 }
             } else if (rounds <= 4) {

@@ -34,10 +34,10 @@ __global__ void probe(float* out, long long* cyc, int passes, int partner_xor)
     long long t0 = clock64();
     for (int i = 0; i < passes; ++i) {
         if (MODE == 0) {
-            solve_core(R, acc, bd, ln, true, j, false, is_a);
+            solve_core<true>(R, acc, bd, ln, true, j, false, is_a);
         } else if (MODE == 1) {
             // no exchange: the partner's twist is a constant (pure arithmetic chain)
-            solve_core(R, acc, bd, ln, true, lane, true, true);
+            solve_core<true>(R, acc, bd, ln, true, lane, true, true);
         }
     }
     long long t1 = clock64();
