@@ -806,6 +806,7 @@ __device__ __forceinline__ void solve_core(const MRows& R, float4& acc, Body& bd
     }
 }
 
+template <bool TWO = true>
 __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln ln, int sl, int j, bool stat)
 {
     const int lane = ln.g;
@@ -815,7 +816,7 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln 
     const MRows R = load_rows(mf);
     float4* accp = mf + (is_a ? 6 : 7);
     float4 acc = *accp;
-    solve_core<true>(R, acc, bd, ln, act, j, stat, is_a);
+    solve_core<TWO>(R, acc, bd, ln, act, j, stat, is_a);
     if (act) *accp = acc;
 }
 
@@ -925,10 +926,20 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             // that list is unchanged (contact sets persist over many steps).
             unsigned sig0 = 0xffffffffu, sig1 = 0xffffffffu;
             bool same;
+            bool two_step = true;  // some manifold of the step has a second point (unpacked 128-register build)
             if (G == 32) {
                 if (lane < dr.nm) sig0 = (unsigned)(__float_as_int(W.man[lane * MF_VEC4].x) & 0xffff);
                 if (lane + 32 < dr.nm) sig1 = (unsigned)(__float_as_int(W.man[(lane + 32) * MF_VEC4].x) & 0xffff);
                 same = __all_sync(ln.m, cache.nm == dr.nm && sig0 == cache.sig0 && sig1 == cache.sig1);
+                if (RR < 2) {
+                    // does any manifold of the step have a second point?  (the build that keeps two rounds in
+                    // registers asks the rows it has loaded instead; slots beyond 64 are not looked at: such a
+                    // step takes the two-point code)
+                    int cnt2 = 0;
+                    if (lane < dr.nm) cnt2 = (__float_as_int(W.man[lane * MF_VEC4].x) >> 16) & 0xff;
+                    if (lane + 32 < dr.nm) cnt2 = max(cnt2, (__float_as_int(W.man[(lane + 32) * MF_VEC4].x) >> 16) & 0xff);
+                    two_step = dr.nm > 64 || __any_sync(ln.m, cnt2 > 1);
+                }
             } else {
                 // packed groups keep the list the schedule was built for in shared memory
                 bool eq = cache.nm == dr.nm;
@@ -1008,7 +1019,12 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             auto pass = [&](unsigned e) {
                 const int slr = e ? (int)(e & 0xffu) : 0xff;
                 const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
-                solve_pass(W, bd, ln, slr, jr, (e & 0x8000u) != 0u);
+                solve_pass<true>(W, bd, ln, slr, jr, (e & 0x8000u) != 0u);
+            };
+            auto pass1 = [&](unsigned e) {  // no manifold of the step has a second point
+                const int slr = e ? (int)(e & 0xffu) : 0xff;
+                const int jr = e ? (int)((e >> 8) & 0x3fu) : lane;
+                solve_pass<false>(W, bd, ln, slr, jr, (e & 0x8000u) != 0u);
             };
             if (rounds < 0) {
                 general_sweep<G>(sc, W, bd, ln, dr.nm, st);
@@ -1053,6 +1069,15 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                             solve_core<false>(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
                         }
                     }
+                }
+            } else if (RR < 2 && rounds <= 4 && !two_step) {
+                // (not in the build that keeps two rounds in registers: there this path only serves three and four
+                // rounds, and a second copy of it cost more in instruction fetch than it saved - cfg2 2.05 -> 2.09 ms)
+                for (int it = 0; it < iters; ++it) {
+                    pass1(cache.ent[0]);
+                    if (rounds > 1) pass1(cache.ent[1]);
+                    if (rounds > 2) pass1(cache.ent[2]);
+                    if (rounds > 3) pass1(cache.ent[3]);
                 }
             } else if (rounds <= 4) {
                 for (int it = 0; it < iters; ++it) {
