@@ -3,7 +3,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from manipulation_planning_suite_b200 import api, scenes
-n_objects, K = 16, 16384
+n_objects, K = 16, int(os.environ.get("PROF_K", "65536"))
 sc, _ = scenes.make_scene(n_objects, seed=1000 + n_objects)
 start = scenes.cluttered_start(sc, 1000 + n_objects)
 rng = np.random.RandomState(n_objects)
