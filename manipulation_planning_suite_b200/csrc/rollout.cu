@@ -28,6 +28,9 @@
 #include "mps_device.cuh"
 #include "rollout.h"
 
+#include <atomic>
+#include <cstdlib>
+
 #define FULL 0xffffffffu
 
 // A rollout chain is run by a group of G consecutive lanes of a warp (G = 32: the whole warp; G = 16 / 8: two /
@@ -1671,6 +1674,13 @@ size_t mps_rollout_scene_bytes() { return (sizeof(DevScene) + 15) & ~(size_t)15;
 
 #define ROLLOUT_WARPS 4
 
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+
 // WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
 template <int WARPS, int MINB, int G>
 static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
@@ -1678,7 +1688,7 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
     const int groups = WARPS * (32 / G);  // chains a CTA works on at a time
     if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
-    static bool attr_set[64] = {};  // the attribute is per device: a process may hold contexts on several
+    static std::atomic<bool> attr_set[64];  // the attribute is per device: a process may hold contexts on several
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
@@ -1693,11 +1703,9 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int want = (p.K + groups - 1) / groups;
-    static int cap_per_sm = -1;  // tuning aid: MPS_ROLLOUT_CTAS_PER_SM caps the resident CTAs per SM
-    if (cap_per_sm < 0) {
-        const char* e_ = getenv("MPS_ROLLOUT_CTAS_PER_SM");
-        cap_per_sm = e_ ? atoi(e_) : 0;
-    }
+    // tuning aid: MPS_ROLLOUT_CTAS_PER_SM caps the resident CTAs per SM (read once; initialisation of a local
+    // static is thread-safe, contexts of different host threads may launch at the same time)
+    static const int cap_per_sm = env_int("MPS_ROLLOUT_CTAS_PER_SM", 0);
     if (cap_per_sm > 0 && blocks_per_sm > cap_per_sm) blocks_per_sm = cap_per_sm;
     int grid = num_sms * blocks_per_sm;
     if (grid > want) grid = want;
@@ -1708,12 +1716,6 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
     return cudaGetLastError();
 }
 
-static int env_int(const char* name, int dflt)
-{
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bodies, cudaStream_t stream)
 {
     RolloutParams p = p_in;
@@ -1722,11 +1724,8 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     // (same arithmetic per chain, so the same bits), which divides the instructions per chain.
     // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build,
     // MPS_ROLLOUT_GROUP = 8 | 16 | 32 the lanes per chain.
-    static int forced_minb = -1, forced_g = -1;
-    if (forced_minb < 0) {
-        forced_minb = env_int("MPS_ROLLOUT_MINB", 0);
-        forced_g = env_int("MPS_ROLLOUT_GROUP", 0);
-    }
+    static const int forced_minb = env_int("MPS_ROLLOUT_MINB", 0);
+    static const int forced_g = env_int("MPS_ROLLOUT_GROUP", 0);
     const bool few = (long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3;
     int g = forced_g;
     // measured on B200 (profiles/tools/throughput_probe.py): four chains per warp gain 20-60 % for scenes with
@@ -1767,7 +1766,7 @@ cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
 cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream)
 {
     size_t smem = p.scene_bytes + (size_t)ROLLOUT_WARPS * p.warp_bytes;
-    static bool attr_set[64] = {};
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
