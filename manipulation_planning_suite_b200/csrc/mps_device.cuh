@@ -13,6 +13,13 @@
 
 #include "../../include/mps_b200.h"
 
+// dynamic shared memory of a kernel (the test-side SIMT emulator, tests/emu, substitutes a host buffer)
+#ifdef MPS_CPU_EMU
+#define MPS_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#else
+#define MPS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 #define MPS_PI_D 3.14159265358979323846
 #define MPS_PI_F 3.14159265358979323846f
 #define MPS_TWO_PI_F (2.0f * 3.14159265358979323846f)

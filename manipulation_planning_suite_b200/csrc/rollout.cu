@@ -327,9 +327,13 @@ __device__ __forceinline__ int collide(const Shape& A, const Shape& Bs, float re
 
 __device__ __forceinline__ unsigned char* opaque_shared_base(unsigned char* dyn)
 {
+#ifdef MPS_CPU_EMU
+    return dyn;
+#else
     unsigned int s32 = (unsigned int)__cvta_generic_to_shared(dyn);
     asm volatile("" : "+r"(s32));
     return (unsigned char*)__cvta_shared_to_generic((size_t)s32);
+#endif
 }
 
 // per-warp working set in shared memory
@@ -1185,7 +1189,7 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
 template <int WARPS, int MINB, int G>
 __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    MPS_DYN_SMEM(smem_dyn);
     // The base of the dynamic shared memory goes through an opaque register once: otherwise the compiler
     // rematerialises the symbol's address at every use, each time with a read of a special register.
     unsigned char* smem_raw = opaque_shared_base(smem_dyn);
@@ -1603,7 +1607,7 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    MPS_DYN_SMEM(smem_dyn);
     // The base of the dynamic shared memory goes through an opaque register once: otherwise the compiler
     // rematerialises the symbol's address at every use, each time with a read of a special register.
     unsigned char* smem_raw = opaque_shared_base(smem_dyn);
@@ -1672,6 +1676,7 @@ size_t mps_rollout_group_bytes(const DevScene& sc, int mcap)
 
 size_t mps_rollout_scene_bytes() { return (sizeof(DevScene) + 15) & ~(size_t)15; }
 
+#ifndef MPS_CPU_EMU  // the launchers need the CUDA runtime; the test-side emulator (tests/emu) drives the kernels itself
 #define ROLLOUT_WARPS 4
 
 static int env_int(const char* name, int dflt)
@@ -1782,3 +1787,4 @@ cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream
     validity_kernel<ROLLOUT_WARPS><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
+#endif  // MPS_CPU_EMU

@@ -1,0 +1,52 @@
+"""ctypes binding of tests/emu/libmps_emu.so — TEST INFRASTRUCTURE (see tests/emu/cuda_emu.h): the repo's CUDA
+kernel sources compiled for the host through a SIMT emulator, so that the kernels' source can be checked
+against the oracle on a machine without a GPU.  Never imported by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle_binding as ob
+from manipulation_planning_suite_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        d = os.path.join(ROOT, "tests", "emu")
+        subprocess.check_call(["make", "-s", "-C", d])
+        L = C.CDLL(os.path.join(d, "libmps_emu.so"))
+        L.emu_extend.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.ExtendIn), C.POINTER(abi.ExtendOut), C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+        L.emu_is_valid_batch.argtypes = [C.POINTER(abi.Scene), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint8),
+                                         C.POINTER(C.c_uint32)]
+        _lib = L
+    return _lib
+
+
+def extend(sc, start, controls, group=32, minb=3, mcap_small=0, ctas=2, counters=None, **kw):
+    """rollout_kernel<., minb, group> + select_kernel through the emulator; same result dict as ob.extend"""
+    cnt = (C.c_uint64 * 8)()
+
+    def call(sc_, ein, eout):
+        return lib().emu_extend(C.byref(sc_), C.byref(ein), C.byref(eout), group, minb, mcap_small, ctas, cnt)
+
+    r = ob.extend(sc, start, controls, _call=call, **kw)
+    r["counters"] = dict(steps=cnt[0], candidates=cnt[1], touching=cnt[2], colour_passes=cnt[3])
+    return r
+
+
+def is_valid_batch(sc, states):
+    st = ob.f32(states).reshape(-1, 3 * sc.n_bodies)
+    n = st.shape[0]
+    valid = np.zeros(n, np.uint8)
+    flags = np.zeros(n, np.uint32)
+    lib().emu_is_valid_batch(C.byref(sc), ob.fp(st), n, valid.ctypes.data_as(C.POINTER(C.c_uint8)),
+                             flags.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return valid.astype(bool), flags

@@ -154,8 +154,9 @@ def contacts(sc, state, max_m=64):
 
 
 def extend(sc, start, controls, n_ctrl=None, dest=None, weights=None, mask=None, compare_f32=False, goals=None,
-           k_offset=0, ball_center=None, ball_radius=0.0, threads=0, starts=None, stop_at_goal=False):
-    """Same inputs / outputs as manipulation_planning_suite_b200.api.Context.extend(dump=True)."""
+           k_offset=0, ball_center=None, ball_radius=0.0, threads=0, starts=None, stop_at_goal=False, _call=None):
+    """Same inputs / outputs as manipulation_planning_suite_b200.api.Context.extend(dump=True).
+    _call(sc, ein, eout) -> rc: another implementation taking the same structs (tests/emu_binding.py)."""
     B = sc.n_bodies
     controls = f32(controls)
     if controls.ndim == 2:
@@ -213,7 +214,9 @@ def extend(sc, start, controls, n_ctrl=None, dest=None, weights=None, mask=None,
     eout.all_flags = fp(res["all_flags"], C.c_uint32)
     eout.all_dist = fp(res["all_dist"], C.c_double)
     eout.all_steps = fp(res["all_steps"], C.c_int32)
-    if threads and threads > 1:
+    if _call is not None:
+        rc = _call(sc, ein, eout)
+    elif threads and threads > 1:
         rc = lib().orc_extend_mt(C.byref(sc), C.byref(ein), C.byref(eout), threads)
     else:
         rc = lib().orc_extend(C.byref(sc), C.byref(ein), C.byref(eout))
