@@ -53,7 +53,7 @@ struct mps_ctx {
     DevBuf d_inpack;  // all inputs of one mps_extend call, one host -> device copy
     DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
     DevBuf d_record;  // packed winner record: best | states | controls | flags
-    DevBuf d_work, d_counters, d_cycles, d_redo;
+    DevBuf d_work, d_counters, d_cycles, d_redo, d_order;
     // pinned staging
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -315,7 +315,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_start, &ctx->d_controls, &ctx->d_nctrl, &ctx->d_dest, &ctx->d_weights, &ctx->d_goals,
                       &ctx->d_ball, &ctx->d_inpack, &ctx->d_states, &ctx->d_rest, &ctx->d_flags, &ctx->d_steps, &ctx->d_dist,
-                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_redo, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
+                      &ctx->d_nok, &ctx->d_goal_step, &ctx->d_record, &ctx->d_work, &ctx->d_cycles, &ctx->d_redo, &ctx->d_order, &ctx->d_counters, &ctx->d_tree_size, &ctx->d_tstage_states,
                       &ctx->d_tstage_parents, &ctx->d_tstage_controls, &ctx->d_tstage_slices, &ctx->d_queries,
                       &ctx->d_masks, &ctx->d_filters, &ctx->d_nnw, &ctx->d_nn_out, &ctx->d_part_d,
                       &ctx->d_part_i, &ctx->d_tickets, &ctx->d_vstates, &ctx->d_valid, &ctx->d_vflags, &ctx->d_fsizes,
@@ -791,6 +791,7 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     if ((rc = ensure(ctx, ctx->d_work, sizeof(unsigned)))) return rc;
     if ((rc = ensure(ctx, ctx->d_cycles, sizeof(long long) * (size_t)K * MPS_CYCLE_WORDS))) return rc;
     if ((rc = ensure(ctx, ctx->d_redo, (size_t)K))) return rc;
+    if ((rc = ensure(ctx, ctx->d_order, sizeof(int32_t) * (size_t)K))) return rc;
     if (!ctx->d_counters.p) {
         if ((rc = ensure(ctx, ctx->d_counters, sizeof(unsigned long long) * 8))) return rc;
         MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long) * 8, ctx->stream), ctx);
@@ -855,6 +856,10 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     rp.work_counter = (unsigned*)ctx->d_work.p;
     rp.counters = (unsigned long long*)ctx->d_counters.p;
     rp.out_cycles = (long long*)ctx->d_cycles.p;
+    // longest chains first when the launch has more chains than one wave of warps can hide (tuning aid:
+    // MPS_ROLLOUT_LPT=0 keeps the input order)
+    static const bool lpt = !(getenv("MPS_ROLLOUT_LPT") && getenv("MPS_ROLLOUT_LPT")[0] == '0');
+    rp.order = (lpt && K >= 64) ? (const int32_t*)ctx->d_order.p : nullptr;
 
     SelectParams& sp = ctx->sp;
     memset(&sp, 0, sizeof(sp));
@@ -904,6 +909,11 @@ int mps_extend_launch(mps_ctx* ctx)
         sp.tree_parent = ctx->tree.parent;
         sp.tree_slice = ctx->tree.slice;
         ctx->tree_upper += ctx->ext_L;
+    }
+    if (ctx->rp.order) {
+        MPS_CUDA_CHECK(mps_launch_chain_order(ctx->rp.controls, ctx->rp.n_ctrl, ctx->rp.K, ctx->rp.L, ctx->hscene.accel,
+                                              ctx->hscene.dt, (int32_t*)ctx->d_order.p, ctx->stream), ctx);
+        ctx->launches += 1;
     }
     const bool timed = ctx->timing && ctx->ev_count < MPS_EVENT_RING;
     if (timed) MPS_CUDA_CHECK(cudaEventRecord(ctx->ev0[ctx->ev_count], ctx->stream), ctx);

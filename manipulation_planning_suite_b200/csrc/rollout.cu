@@ -336,13 +336,11 @@ __device__ __forceinline__ unsigned char* opaque_shared_base(unsigned char* dyn)
 #endif
 }
 
-// per-warp working set in shared memory
+// per-chain working set in shared memory
 struct WarpMem {
-    float* px;  // [32] poses mirrored for the pair tests
-    float* py;
-    float* pc;
-    float* ps;
-    float* mv;        // [32] upper bound of the distance any point of the body has travelled in this chain
+    float4* pose;     // [B + S] (x, y, cos, sin): the bodies' poses mirrored for the pair tests, then the statics'
+    float* mv;        // [B + S] upper bound of the distance any point of the body has travelled in this chain
+                      // (statics: 0)
     float4* man;      // [Mcap][MF_VEC4]
     uint8_t* slot;    // [B][slot_stride]: manifold slot of pair (row body, column body|static); never
                       // cleared — an entry is trusted only if the manifold it names carries the same pair
@@ -350,6 +348,33 @@ struct WarpMem {
     uint16_t* sig;    // [Mcap] pair of every manifold slot the round schedule was built for (packed groups)
     int mcap;         // manifold slots of this group (sc.Mcap, or the small capacity of a packed launch)
 };
+
+// poses / travelled distances of bodies and statics share one index space (a static is B + k)
+__host__ __device__ __forceinline__ int mps_pose_slots(int B, int S) { return (B + S + 3) & ~3; }
+
+__device__ __forceinline__ WarpMem carve_warp_mem(const DevScene& sc, unsigned char* wbase, int Mcap)
+{
+    WarpMem W;
+    const int np = mps_pose_slots(sc.B, sc.S);
+    W.pose = reinterpret_cast<float4*>(wbase);
+    W.mv = reinterpret_cast<float*>(W.pose + np);
+    W.man = reinterpret_cast<float4*>(W.mv + np);
+    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * Mcap);
+    W.cand = reinterpret_cast<uint16_t*>(W.slot + ((sc.B * sc.slot_stride + 3) & ~3));
+    W.sig = W.cand + ((sc.P + 1) & ~1);
+    W.mcap = Mcap;
+    return W;
+}
+
+// the statics' entries of the pose table (once per chain group; the bodies' entries follow every step)
+__device__ __forceinline__ void publish_statics(const DevScene& sc, const WarpMem& W, const Ln ln, int G)
+{
+    for (int k = ln.g; k < sc.S; k += G) {
+        W.pose[sc.B + k] = make_float4(sc.s_x[k], sc.s_y[k], sc.s_c[k], sc.s_s[k]);
+        W.mv[sc.B + k] = 0.0f;
+    }
+    __syncwarp(ln.m);
+}
 
 // State a chain carries from one physics step to the next (registers).
 //  * Candidate list with a skin: the broad phase keeps every pair within reach + MPS_SKIN and is rebuilt only
@@ -387,27 +412,165 @@ __device__ __forceinline__ void load_pair_shapes(const DevScene& sc, const WarpM
                                                  Shape& Bs)
 {
     const int B = sc.B;
+    const float4 pa = W.pose[a], pb = W.pose[b];
     A.shape = sc.shape[a];
-    A.x = W.px[a];
-    A.y = W.py[a];
-    A.c = W.pc[a];
-    A.s = W.ps[a];
+    A.x = pa.x;
+    A.y = pa.y;
+    A.c = pa.z;
+    A.s = pa.w;
     A.hx = sc.hx[a];
     A.hy = sc.hy[a];
-    // the second shape is a body (pose mirrored in W) or a static (pose in the scene): the addresses are
-    // selected, not the code path
+    // the second shape is a body or a static (pose table index B + k): the addresses are selected, not the
+    // code path
     const bool body = b < B;
     const int k = body ? b : b - B;
     Bs.shape = *(body ? &sc.shape[k] : &sc.s_shape[k]);
-    Bs.x = *(body ? &W.px[k] : &sc.s_x[k]);
-    Bs.y = *(body ? &W.py[k] : &sc.s_y[k]);
-    Bs.c = *(body ? &W.pc[k] : &sc.s_c[k]);
-    Bs.s = *(body ? &W.ps[k] : &sc.s_s[k]);
+    Bs.x = pb.x;
+    Bs.y = pb.y;
+    Bs.c = pb.z;
+    Bs.s = pb.w;
     Bs.hx = *(body ? &sc.hx[k] : &sc.s_hx[k]);
     Bs.hy = *(body ? &sc.hy[k] : &sc.s_hy[k]);
 }
 
-// collision detection at the poses in W.px/py/pc/ps.  prepare: also build the solver rows.
+// reach test of one pair (bounding circles; body circle against the static's own box / disc - walls are long,
+// their bounding circle would make every body a candidate).  skin = 0 is the exact test of the narrow phase's
+// entry; conservative with a small margin for statics; only a filter.
+__device__ __forceinline__ bool pair_in_reach(const DevScene& sc, const WarpMem& W, unsigned pr, float skin)
+{
+    const int B = sc.B;
+    const int a = pr & 0xff, b = pr >> 8;
+    const float4 pa = W.pose[a], pb = W.pose[b];
+    if (b < B) {
+        float rr = sc.brad[a] + sc.brad[b];
+        rr = rr + skin;
+        float dx = pb.x - pa.x;
+        float dy = pb.y - pa.y;
+        return !(dx * dx + dy * dy > rr * rr);
+    }
+    const int k = b - B;
+    float dx = pa.x - pb.x;
+    float dy = pa.y - pb.y;
+    float rr = sc.brad[a] * 1.001f + 1e-5f;
+    if (sc.s_shape[k] == MPS_SHAPE_BOX) {
+        rr = rr + skin;
+        float lx = dx * pb.z + dy * pb.w;
+        float ly = dy * pb.z - dx * pb.w;
+        float ex = fmaxf(fabsf(lx) - sc.s_hx[k], 0.0f);
+        float ey = fmaxf(fabsf(ly) - sc.s_hy[k], 0.0f);
+        return !(ex * ex + ey * ey > rr * rr);
+    }
+    rr += sc.s_hx[k];
+    rr = rr + skin;
+    return !(dx * dx + dy * dy > rr * rr);
+}
+
+// broad phase: lane = pair of the scene's table, bounding circles with a skin, survivors compacted into W.cand
+// in table order (= the solver's canonical order)
+template <int G>
+__device__ __forceinline__ void rebuild_list(const DevScene& sc, const WarpMem& W, const Ln ln, StepCache& cache)
+{
+    const int lane = ln.g;
+    // two chunks of G pairs per trip so that their loads and tests overlap
+    int nl = 0;
+    const unsigned lt = ln.below();
+    for (int base = 0; base < sc.P; base += 2 * G) {
+        const int p0 = base + lane, p1 = base + G + lane;
+        unsigned pr0 = 0, pr1 = 0;
+        bool c0 = false, c1 = false;
+        if (p0 < sc.P) {
+            pr0 = sc.pairs[p0];
+            c0 = pair_in_reach(sc, W, pr0, MPS_SKIN);
+        }
+        if (p1 < sc.P) {
+            pr1 = sc.pairs[p1];
+            c1 = pair_in_reach(sc, W, pr1, MPS_SKIN);
+        }
+        const unsigned m0 = __ballot_sync(ln.m, c0);
+        const unsigned m1 = __ballot_sync(ln.m, c1);
+        const int n0 = __popc(m0);
+        if (c0) W.cand[nl + __popc(m0 & lt)] = (uint16_t)pr0;
+        if (c1) W.cand[nl + n0 + __popc(m1 & lt)] = (uint16_t)pr1;
+        nl += n0 + __popc(m1);
+    }
+    cache.n_list = nl;
+    cache.clear_until = -1.0f;
+    if (lane < sc.B) {
+        const float4 me = W.pose[lane];
+        cache.rx = me.x;
+        cache.ry = me.y;
+    }
+    __syncwarp(ln.m);
+}
+
+// manifold record of a touching pair in the chain's shared slice.  prepare: with the solver rows (layout: 0
+// meta|n|friction, 1 / 3 lever arms of point 0 / 1, 2 / 4 inverse effective masses, bias term and the t-t / n-n
+// coupling, 5 t-n couplings, 6 / 7 accumulated impulses, one private copy per owner lane); the rows of a
+// missing second point are all zero and run through the same arithmetic.  any_two: some manifold of this trip
+// has a second point (otherwise its arithmetic is left out: the rows stay zero).
+__device__ __forceinline__ void store_manifold(const DevScene& sc, float4* mf, const Manifold& m, int cnt, int a, int b,
+                                               bool any_two, bool prepare)
+{
+    const int B = sc.B;
+    const bool bstat = b >= B;
+    const int meta = a | (b << 8) | (cnt << 16);
+    if (!prepare) {
+        mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, 0.0f);
+        return;
+    }
+    const float ma = sc.inv_m[a], ia = sc.inv_i[a];
+    const int kb_ = bstat ? b - B : b;
+    const float mbq = sc.inv_m[bstat ? 0 : b], ibq = sc.inv_i[bstat ? 0 : b];
+    const float mb = bstat ? 0.0f : mbq, ib = bstat ? 0.0f : ibq;
+    const float mub = *(bstat ? &sc.s_mu[kb_] : &sc.mu_c[kb_]);
+    float tx = m.ny, ty = -m.nx;
+    float iarna[2] = {0.0f, 0.0f}, ibrnb[2] = {0.0f, 0.0f}, iarta[2] = {0.0f, 0.0f}, ibrtb[2] = {0.0f, 0.0f};
+    float rna[2] = {0.0f, 0.0f}, rnb[2] = {0.0f, 0.0f}, rta[2] = {0.0f, 0.0f}, rtb[2] = {0.0f, 0.0f};
+    float nmass[2] = {0.0f, 0.0f}, tmass[2] = {0.0f, 0.0f}, kb[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        // both points go through the arithmetic; a missing second point is zeroed afterwards
+        if (k == 1 && !any_two) break;
+        const bool has = k < cnt;
+        const float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
+        const float sepk = m.sep[k];
+        rna[k] = has ? rax * m.ny - ray * m.nx : 0.0f;
+        rnb[k] = has ? rbx * m.ny - rby * m.nx : 0.0f;
+        rta[k] = has ? rax * ty - ray * tx : 0.0f;
+        rtb[k] = has ? rbx * ty - rby * tx : 0.0f;
+        iarna[k] = ia * rna[k];
+        ibrnb[k] = ib * rnb[k];
+        iarta[k] = ia * rta[k];
+        ibrtb[k] = ib * rtb[k];
+        const float kn = ((ma + mb) + iarna[k] * rna[k]) + ibrnb[k] * rnb[k];
+        const float kt = ((ma + mb) + iarta[k] * rta[k]) + ibrtb[k] * rtb[k];
+        const float pen_k = -sepk - sc.slop;
+        const float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
+        const float rn = 1.0f / kn, rt = 1.0f / kt;
+        nmass[k] = (has && kn > 0.0f) ? rn : 0.0f;
+        tmass[k] = (has && kt > 0.0f) ? rt : 0.0f;
+        kb[k] = nmass[k] * bias;
+    }
+    const bool two = cnt > 1;
+    const float ktn00 = iarta[0] * rna[0] + ibrtb[0] * rnb[0];
+    const float ktt_ = ((ma + mb) + iarta[0] * rta[1]) + ibrtb[0] * rtb[1];
+    const float knn_ = ((ma + mb) + iarna[0] * rna[1]) + ibrnb[0] * rnb[1];
+    const float ktn01_ = iarta[0] * rna[1] + ibrtb[0] * rnb[1];
+    const float ktn10_ = iarta[1] * rna[0] + ibrtb[1] * rnb[0];
+    const float ktn11_ = iarta[1] * rna[1] + ibrtb[1] * rnb[1];
+    const float ktt = two ? ktt_ : 0.0f, knn = two ? knn_ : 0.0f;
+    const float ktn01 = two ? ktn01_ : 0.0f, ktn10 = two ? ktn10_ : 0.0f, ktn11 = two ? ktn11_ : 0.0f;
+    mf[1] = make_float4(rna[0], rnb[0], rta[0], rtb[0]);
+    mf[2] = make_float4(nmass[0], tmass[0], kb[0], ktt);
+    mf[3] = make_float4(rna[1], rnb[1], rta[1], rtb[1]);
+    mf[4] = make_float4(nmass[1], tmass[1], kb[1], knn);
+    mf[5] = make_float4(ktn00, ktn01, ktn10, ktn11);
+    mf[6] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    mf[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, sqrtf(sc.mu_c[a] * mub));
+}
+
+// collision detection at the poses in W.pose.  prepare: also build the solver rows.
 template <int G>
 __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem& W, const Ln ln, bool prepare,
                                                StepCache& cache, long long* t_mid = nullptr,
@@ -418,75 +581,19 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
     const int Mcap = W.mcap;
     // ---- broad phase: lane = pair, bounding circles, survivors compacted into W.cand ------------
     // reach test of one pair; skin = 0 is the exact test of the physics spec
-    auto pair_near = [&](unsigned pr, float skin) -> bool {
-        const int a = pr & 0xff, b = pr >> 8;
-        if (b < B) {
-            // bounding circles
-            float rr = sc.brad[a] + sc.brad[b];
-            rr = rr + skin;
-            float dx = W.px[b] - W.px[a];
-            float dy = W.py[b] - W.py[a];
-            return !(dx * dx + dy * dy > rr * rr);
-        }
-        // body circle against the static's own box / disc (walls are long: their bounding circle
-        // would make every body a candidate).  Conservative with a small margin; only a filter.
-        const int k = b - B;
-        float dx = W.px[a] - sc.s_x[k];
-        float dy = W.py[a] - sc.s_y[k];
-        float rr = sc.brad[a] * 1.001f + 1e-5f;
-        if (sc.s_shape[k] == MPS_SHAPE_BOX) {
-            rr = rr + skin;
-            float lx = dx * sc.s_c[k] + dy * sc.s_s[k];
-            float ly = dy * sc.s_c[k] - dx * sc.s_s[k];
-            float ex = fmaxf(fabsf(lx) - sc.s_hx[k], 0.0f);
-            float ey = fmaxf(fabsf(ly) - sc.s_hy[k], 0.0f);
-            return !(ex * ex + ey * ey > rr * rr);
-        }
-        rr += sc.s_hx[k];
-        rr = rr + skin;
-        return !(dx * dx + dy * dy > rr * rr);
-    };
+    auto pair_near = [&](unsigned pr, float skin) -> bool { return pair_in_reach(sc, W, pr, skin); };
     bool rebuild = cache.n_list < 0;
     if (!rebuild) {
         bool moved = false;
         if (lane < B) {
-            float dx = W.px[lane] - cache.rx;
-            float dy = W.py[lane] - cache.ry;
+            const float4 me = W.pose[lane];
+            float dx = me.x - cache.rx;
+            float dy = me.y - cache.ry;
             moved = dx * dx + dy * dy > MPS_SKIN_MOVE2;
         }
         rebuild = __any_sync(ln.m, moved);
     }
-    if (rebuild) {
-        // two chunks of 32 pairs per trip so that their loads and tests overlap
-        int nl = 0;
-        const unsigned lt = ln.below();
-        for (int base = 0; base < sc.P; base += 2 * G) {
-            const int p0 = base + lane, p1 = base + G + lane;
-            unsigned pr0 = 0, pr1 = 0;
-            bool c0 = false, c1 = false;
-            if (p0 < sc.P) {
-                pr0 = sc.pairs[p0];
-                c0 = pair_near(pr0, MPS_SKIN);
-            }
-            if (p1 < sc.P) {
-                pr1 = sc.pairs[p1];
-                c1 = pair_near(pr1, MPS_SKIN);
-            }
-            const unsigned m0 = __ballot_sync(ln.m, c0);
-            const unsigned m1 = __ballot_sync(ln.m, c1);
-            const int n0 = __popc(m0);
-            if (c0) W.cand[nl + __popc(m0 & lt)] = (uint16_t)pr0;
-            if (c1) W.cand[nl + n0 + __popc(m1 & lt)] = (uint16_t)pr1;
-            nl += n0 + __popc(m1);
-        }
-        cache.n_list = nl;
-        cache.clear_until = -1.0f;
-        if (lane < B) {
-            cache.rx = W.px[lane];
-            cache.ry = W.py[lane];
-        }
-        __syncwarp(ln.m);
-    }
+    if (rebuild) rebuild_list<G>(sc, W, ln, cache);
     const int nlist = cache.n_list;
     int ncand = 0;
 #ifdef MPS_PHASE_PROF
@@ -513,7 +620,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             unsigned pr = W.cand[c];
             a = pr & 0xff;
             b = pr >> 8;
-            travelled = W.mv[a] + (b < B ? W.mv[b] : 0.0f);
+            travelled = W.mv[a] + W.mv[b];  // a static's entry is 0
             look = base != 0 || !(travelled < cache.clear_until);
         }
         if (!__any_sync(ln.m, look)) continue;
@@ -558,66 +665,7 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
             if (forbid & 1u) lane_bad = true;
             int idx = nm + __popc(tmask & ln.below());
             if (idx < Mcap) {
-                float4* mf = W.man + idx * MF_VEC4;
-                int meta = a | (b << 8) | (cnt << 16);
-                if (prepare) {
-                    const float ma = sc.inv_m[a], ia = sc.inv_i[a];
-                    const int kb_ = bstat ? b - B : b;
-                    const float mbq = sc.inv_m[bstat ? 0 : b], ibq = sc.inv_i[bstat ? 0 : b];
-                    const float mb = bstat ? 0.0f : mbq, ib = bstat ? 0.0f : ibq;
-                    const float mub = *(bstat ? &sc.s_mu[kb_] : &sc.mu_c[kb_]);
-                    // rows of the manifold (layout: 0 meta|n|friction, 1 / 3 lever arms of point 0 / 1,
-                    // 2 / 4 inverse effective masses, bias term and the t-t / n-n coupling, 5 t-n couplings,
-                    // 6 / 7 accumulated impulses, one private copy per owner lane); the rows of a missing
-                    // second point are all zero and run through the same arithmetic
-                    float tx = m.ny, ty = -m.nx;
-                    float iarna[2] = {0.0f, 0.0f}, ibrnb[2] = {0.0f, 0.0f}, iarta[2] = {0.0f, 0.0f}, ibrtb[2] = {0.0f, 0.0f};
-                    float rna[2] = {0.0f, 0.0f}, rnb[2] = {0.0f, 0.0f}, rta[2] = {0.0f, 0.0f}, rtb[2] = {0.0f, 0.0f};
-                    float nmass[2] = {0.0f, 0.0f}, tmass[2] = {0.0f, 0.0f}, kb[2] = {0.0f, 0.0f};
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        // both points go through the arithmetic; a missing second point is zeroed afterwards
-                        if (k == 1 && !any_two) break;
-                        const bool has = k < cnt;
-                        const float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
-                        const float sepk = m.sep[k];
-                        rna[k] = has ? rax * m.ny - ray * m.nx : 0.0f;
-                        rnb[k] = has ? rbx * m.ny - rby * m.nx : 0.0f;
-                        rta[k] = has ? rax * ty - ray * tx : 0.0f;
-                        rtb[k] = has ? rbx * ty - rby * tx : 0.0f;
-                        iarna[k] = ia * rna[k];
-                        ibrnb[k] = ib * rnb[k];
-                        iarta[k] = ia * rta[k];
-                        ibrtb[k] = ib * rtb[k];
-                        const float kn = ((ma + mb) + iarna[k] * rna[k]) + ibrnb[k] * rnb[k];
-                        const float kt = ((ma + mb) + iarta[k] * rta[k]) + ibrtb[k] * rtb[k];
-                        const float pen_k = -sepk - sc.slop;
-                        const float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
-                        const float rn = 1.0f / kn, rt = 1.0f / kt;
-                        nmass[k] = (has && kn > 0.0f) ? rn : 0.0f;
-                        tmass[k] = (has && kt > 0.0f) ? rt : 0.0f;
-                        kb[k] = nmass[k] * bias;
-                    }
-                    const bool two = cnt > 1;
-                    const float ktn00 = iarta[0] * rna[0] + ibrtb[0] * rnb[0];
-                    const float ktt_ = ((ma + mb) + iarta[0] * rta[1]) + ibrtb[0] * rtb[1];
-                    const float knn_ = ((ma + mb) + iarna[0] * rna[1]) + ibrnb[0] * rnb[1];
-                    const float ktn01_ = iarta[0] * rna[1] + ibrtb[0] * rnb[1];
-                    const float ktn10_ = iarta[1] * rna[0] + ibrtb[1] * rnb[0];
-                    const float ktn11_ = iarta[1] * rna[1] + ibrtb[1] * rnb[1];
-                    const float ktt = two ? ktt_ : 0.0f, knn = two ? knn_ : 0.0f;
-                    const float ktn01 = two ? ktn01_ : 0.0f, ktn10 = two ? ktn10_ : 0.0f, ktn11 = two ? ktn11_ : 0.0f;
-                    mf[1] = make_float4(rna[0], rnb[0], rta[0], rtb[0]);
-                    mf[2] = make_float4(nmass[0], tmass[0], kb[0], ktt);
-                    mf[3] = make_float4(rna[1], rnb[1], rta[1], rtb[1]);
-                    mf[4] = make_float4(nmass[1], tmass[1], kb[1], knn);
-                    mf[5] = make_float4(ktn00, ktn01, ktn10, ktn11);
-                    mf[6] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    mf[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, sqrtf(sc.mu_c[a] * mub));
-                } else {
-                    mf[0] = make_float4(__int_as_float(meta), m.nx, m.ny, 0.0f);
-                }
+                store_manifold(sc, W.man + idx * MF_VEC4, m, cnt, a, b, any_two, prepare);
             } else {
                 lane_over = true;
             }
@@ -670,10 +718,7 @@ __device__ __forceinline__ void publish_pose(const WarpMem& W, const Body& b, co
 {
     const int lane = ln.g;
     if (b.live) {
-        W.px[lane] = b.x;
-        W.py[lane] = b.y;
-        W.pc[lane] = b.c;
-        W.ps[lane] = b.s;
+        W.pose[lane] = make_float4(b.x, b.y, b.c, b.s);
         W.mv[lane] = b.mv;
     }
     __syncwarp(ln.m);
@@ -745,12 +790,12 @@ __device__ __forceinline__ void solve_core(const MRows& R, float4& acc, Body& bd
     float ovx = __shfl_sync(ln.m, bd.vx, ln.abs_lane(j));
     float ovy = __shfl_sync(ln.m, bd.vy, ln.abs_lane(j));
     float ow_ = __shfl_sync(ln.m, bd.w, ln.abs_lane(j));
-    const float4 m0 = R.m0, r0 = R.r0, g0 = R.g0, r1 = R.r1, g1 = R.g1, kc = R.kc;
     if (stat) {
         ovx = 0.0f;
         ovy = 0.0f;
         ow_ = 0.0f;
     }
+    const float4 m0 = R.m0, r0 = R.r0, g0 = R.g0, r1 = R.r1, g1 = R.g1, kc = R.kc;
     const float nx = m0.y, ny = m0.z, fr = m0.w;
     const float tx = ny, ty = -nx;
     // lever arms of this lane's own body
@@ -825,6 +870,72 @@ __device__ __forceinline__ void solve_pass(const WarpMem& W, Body& bd, const Ln 
     float4 acc = *accp;
     solve_core<TWO>(R, acc, bd, ln, act, j, stat, is_a);
     if (act) *accp = acc;
+}
+
+// Round schedule of the solver for the manifold list in W.man[0 .. nm) (canonical order): every manifold goes
+// to the earliest round after the earlier manifolds that share a dynamic body with it,
+//     round(m) = 1 + max(last round of body a, last round of body b);
+// each lane packs its <= 4 entries as round << 16 | static << 15 | partner << 8 | slot (a body with more sends
+// the step to the general sweep: rounds = -1).  With at most 4 rounds the entries are indexed by round.
+__device__ __forceinline__ void build_schedule(const DevScene& sc, const WarpMem& W, const Ln ln, int nm,
+                                               StepCache& cache)
+{
+    const int lane = ln.g;
+    const int B = sc.B;
+    unsigned e0 = 0u, e1 = 0u, e2 = 0u, e3 = 0u;
+    int last = 0, ne = 0;
+    // the manifold list is in canonical order (the pair table is): walk it once
+    for (int m = 0; m < nm; ++m) {
+        const int meta = __float_as_int(W.man[m * MF_VEC4].x);
+        const int a = meta & 0xff, b = (meta >> 8) & 0xff;
+        const bool stc = b >= B;
+        // the robot is kinematic: its twist is only read, so manifolds that share nothing but the
+        // robot commute and the robot neither waits nor is waited for
+        const bool dyn_a = a != sc.robot;
+        const bool dyn_b = !stc && b != sc.robot;
+        int r = 0;
+        if (dyn_a) r = __shfl_sync(ln.m, last, ln.abs_lane(a));
+        if (dyn_b) {
+            const int lb = __shfl_sync(ln.m, last, ln.abs_lane(b));
+            r = r > lb ? r : lb;
+        }
+        r += 1;
+        if ((dyn_a && lane == a) || (dyn_b && lane == b)) {
+            last = r;
+            const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) |
+                               ((unsigned)(stc ? lane : (lane == a ? b : a)) << 8) | (unsigned)m;
+            e3 = ne == 3 ? e : e3;
+            e2 = ne == 2 ? e : e2;
+            e1 = ne == 1 ? e : e1;
+            e0 = ne == 0 ? e : e0;
+            ++ne;
+        }
+    }
+    int nr = __reduce_max_sync(ln.m, last);
+    if (__any_sync(ln.m, ne > 4) || sc.force_general) nr = -1;
+    if (nr >= 0 && nr <= 4) {
+        // few rounds (the usual case): index the entries by round, ent[r - 1] = this lane's
+        // manifold of round r or 0, so the sweep needs no search
+        unsigned b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned e = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
+            const int er = (int)(e >> 16);
+            b0 = er == 1 ? e : b0;
+            b1 = er == 2 ? e : b1;
+            b2 = er == 3 ? e : b2;
+            b3 = er == 4 ? e : b3;
+        }
+        e0 = b0;
+        e1 = b1;
+        e2 = b2;
+        e3 = b3;
+    }
+    cache.ent[0] = e0;
+    cache.ent[1] = e1;
+    cache.ent[2] = e2;
+    cache.ent[3] = e3;
+    cache.rounds = nr;
 }
 
 // General sweep, colour by colour in canonical order, for steps in which some body has more than 4
@@ -955,60 +1066,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                 same = __all_sync(ln.m, eq);
             }
             if (!same) {
-                unsigned e0 = 0u, e1 = 0u, e2 = 0u, e3 = 0u;
-                int last = 0, ne = 0;
-                // the manifold list is in canonical order (the pair table is): walk it once
-                for (int m = 0; m < dr.nm; ++m) {
-                    const int meta = __float_as_int(W.man[m * MF_VEC4].x);
-                    const int a = meta & 0xff, b = (meta >> 8) & 0xff;
-                    const bool stc = b >= B;
-                    // the robot is kinematic: its twist is only read, so manifolds that share nothing but the
-                    // robot commute and the robot neither waits nor is waited for
-                    const bool dyn_a = a != sc.robot;
-                    const bool dyn_b = !stc && b != sc.robot;
-                    int r = 0;
-                    if (dyn_a) r = __shfl_sync(ln.m, last, ln.abs_lane(a));
-                    if (dyn_b) {
-                        const int lb = __shfl_sync(ln.m, last, ln.abs_lane(b));
-                        r = r > lb ? r : lb;
-                    }
-                    r += 1;
-                    if ((dyn_a && lane == a) || (dyn_b && lane == b)) {
-                        last = r;
-                        const unsigned e = ((unsigned)r << 16) | (stc ? 0x8000u : 0u) |
-                                           ((unsigned)(stc ? lane : (lane == a ? b : a)) << 8) | (unsigned)m;
-                        e3 = ne == 3 ? e : e3;
-                        e2 = ne == 2 ? e : e2;
-                        e1 = ne == 1 ? e : e1;
-                        e0 = ne == 0 ? e : e0;
-                        ++ne;
-                    }
-                }
-                int nr = __reduce_max_sync(ln.m, last);
-                if (__any_sync(ln.m, ne > 4) || sc.force_general) nr = -1;
-                if (nr >= 0 && nr <= 4) {
-                    // few rounds (the usual case): index the entries by round, ent[r - 1] = this lane's
-                    // manifold of round r or 0, so the sweep needs no search
-                    unsigned b0 = 0u, b1 = 0u, b2 = 0u, b3 = 0u;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const unsigned e = c == 0 ? e0 : c == 1 ? e1 : c == 2 ? e2 : e3;
-                        const int er = (int)(e >> 16);
-                        b0 = er == 1 ? e : b0;
-                        b1 = er == 2 ? e : b1;
-                        b2 = er == 3 ? e : b2;
-                        b3 = er == 4 ? e : b3;
-                    }
-                    e0 = b0;
-                    e1 = b1;
-                    e2 = b2;
-                    e3 = b3;
-                }
-                cache.ent[0] = e0;
-                cache.ent[1] = e1;
-                cache.ent[2] = e2;
-                cache.ent[3] = e3;
-                cache.rounds = nr;
+                build_schedule(sc, W, ln, dr.nm, cache);
                 cache.nm = dr.nm;
                 cache.sig0 = sig0;
                 cache.sig1 = sig1;
@@ -1209,17 +1267,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     const bool small_cap = G < 32 && p.mcap_small > 0;
     const int Mcap = small_cap ? p.mcap_small : sc.Mcap;
     unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)group * p.warp_bytes;
-    WarpMem W;
-    W.px = reinterpret_cast<float*>(wbase);
-    W.py = W.px + 32;
-    W.pc = W.py + 32;
-    W.ps = W.pc + 32;
-    W.mv = W.ps + 32;
-    W.man = reinterpret_cast<float4*>(W.mv + 32);
-    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * Mcap);
-    W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
-    W.sig = W.cand + ((sc.P + 1) & ~1);
-    W.mcap = Mcap;
+    const WarpMem W = carve_warp_mem(sc, wbase, Mcap);
+    publish_statics(sc, W, ln, G);
 
     Body bd;
     bd.live = lane < B;
@@ -1249,6 +1298,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         if (lane == 0) k = (int)atomicAdd(p.work_counter, 1u);
         k = __shfl_sync(ln.m, k, ln.abs_lane(0));
         if (k >= p.K) break;
+        if (p.order) k = p.order[k];  // longest chains first (mps_launch_chain_order)
         if (p.redo_only && !p.redo[k]) continue;
         bool redo = false;
         int n = p.n_ctrl ? p.n_ctrl[k] : L;
@@ -1483,6 +1533,55 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
     }
 }
 
+// Order in which the warps pull the chains: longest expected first.  A launch lasts as long as its last chain, and
+// chain lengths vary by 10x; the number of active-phase steps of a chain is known from its controls (ramp
+// durations), the rest phase adds a few dozen per control.  Chains are bucketed by that estimate (8 steps per
+// bucket, counting sort by one CTA); the order inside a bucket is arbitrary - no result depends on the order.
+__global__ void __launch_bounds__(1024) chain_order_kernel(const float* __restrict__ controls,
+                                                           const int32_t* __restrict__ n_ctrl, int K, int L, float inv_ax,
+                                                           float inv_ay, float inv_aw, float inv_dt, int32_t* __restrict__ order)
+{
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int offs[256];
+    const int tid = threadIdx.x;
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    auto bucket_of = [&](int k) -> int {
+        int n = n_ctrl ? n_ctrl[k] : L;
+        n = n > L ? L : n;
+        float steps = 0.0f;
+        for (int l = 0; l < n; ++l) {
+            const float* c = controls + ((size_t)k * L + l) * MPS_CONTROL_DIM;
+            const float t_acc = fmaxf(fmaxf(fabsf(c[0] * inv_ax), fabsf(c[1] * inv_ay)), fabsf(c[2] * inv_aw));
+            steps += (2.0f * t_acc + c[3]) * inv_dt + 32.0f;
+        }
+        int bkt = (int)(steps * 0.125f);
+        bkt = bkt < 0 ? 0 : (bkt > 255 ? 255 : bkt);
+        return 255 - bkt;  // bucket 0 = the longest chains
+    };
+    for (int k = tid; k < K; k += blockDim.x) atomicAdd(&hist[bucket_of(k)], 1u);
+    __syncthreads();
+    if (tid < 32) {
+        // exclusive scan of the 256 counts by one warp, 8 per lane
+        unsigned int loc[8], sum = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            loc[i] = sum;
+            sum += hist[tid * 8 + i];
+        }
+        unsigned int inc = sum;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int o = __shfl_up_sync(FULL, inc, off);
+            if (tid >= off) inc += o;
+        }
+        const unsigned int base = inc - sum;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) offs[tid * 8 + i] = base + loc[i];
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += blockDim.x) order[atomicAdd(&offs[bucket_of(k)], 1u)] = k;
+}
+
 // argmin over the K chains: strict <, first index wins (NaiveControlSampler.cpp:55, RRT.cpp:467);
 // copies the winner chain into the best buffers and optionally appends it to the tree.
 __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
@@ -1622,18 +1721,9 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
     const int warp = threadIdx.x >> 5;
     const int B = sc.B;
     unsigned char* wbase = smem_raw + p.scene_bytes + (size_t)warp * p.warp_bytes;
-    WarpMem W;
-    W.px = reinterpret_cast<float*>(wbase);
-    W.py = W.px + 32;
-    W.pc = W.py + 32;
-    W.ps = W.pc + 32;
-    W.mv = W.ps + 32;
-    W.man = reinterpret_cast<float4*>(W.mv + 32);
-    W.slot = reinterpret_cast<uint8_t*>(W.man + MF_VEC4 * sc.Mcap);
-    W.cand = reinterpret_cast<uint16_t*>(W.slot + ((B * sc.slot_stride + 3) & ~3));
-    W.sig = W.cand + ((sc.P + 1) & ~1);
-    W.mcap = sc.Mcap;
+    const WarpMem W = carve_warp_mem(sc, wbase, sc.Mcap);
     const Ln ln = make_ln<32>();
+    publish_statics(sc, W, ln, 32);
     Body bd;
     bd.live = lane < B;
     bd.dynamic = false;
@@ -1668,7 +1758,7 @@ size_t mps_rollout_warp_bytes(const DevScene& sc) { return mps_rollout_group_byt
 // shared memory of one chain (one lane group) with `mcap` manifold slots
 size_t mps_rollout_group_bytes(const DevScene& sc, int mcap)
 {
-    size_t b = 5 * 32 * sizeof(float) + (size_t)MF_FIELDS * mcap * sizeof(float) +
+    size_t b = 5 * sizeof(float) * (size_t)mps_pose_slots(sc.B, sc.S) + (size_t)MF_FIELDS * mcap * sizeof(float) +
                (((size_t)sc.B * sc.slot_stride + 3) & ~(size_t)3) + sizeof(uint16_t) * (size_t)((sc.P + 1) & ~1) +
                sizeof(uint16_t) * (size_t)mcap;
     return (b + 15) & ~(size_t)15;
@@ -1686,25 +1776,21 @@ static int env_int(const char* name, int dflt)
 }
 
 
-// WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
-template <int WARPS, int MINB, int G>
-static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
+// grid of a rollout launch: as many CTAs as fit the machine, at most one group of lanes per chain
+template <class Kernel>
+static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_set, RolloutParams& p, int threads,
+                                         int groups, int num_sms, cudaStream_t stream)
 {
-    const int groups = WARPS * (32 / G);  // chains a CTA works on at a time
-    if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
-    static std::atomic<bool> attr_set[64];  // the attribute is per device: a process may hold contexts on several
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<WARPS, MINB, G>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {  // the attribute is per device: a process may hold contexts on several
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int blocks_per_sm = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, rollout_kernel<WARPS, MINB, G>,
-                                                                  WARPS * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, threads, smem);
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int want = (p.K + groups - 1) / groups;
@@ -1717,8 +1803,17 @@ static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t 
     if (grid < 1) grid = 1;
     e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    rollout_kernel<WARPS, MINB, G><<<grid, WARPS * 32, smem, stream>>>(p);
+    kernel<<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+// WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
+template <int WARPS, int MINB, int G>
+static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
+{
+    if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
+    static std::atomic<bool> attr_set[64];
+    return launch_rollout_kernel(rollout_kernel<WARPS, MINB, G>, attr_set, p, WARPS * 32, WARPS * (32 / G), num_sms, stream);
 }
 
 cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bodies, cudaStream_t stream)
@@ -1758,6 +1853,14 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     if (minb == 0) minb = few ? 3 : 4;
     if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream);
     return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream);
+}
+
+cudaError_t mps_launch_chain_order(const float* controls, const int32_t* n_ctrl, int K, int L, const float accel[3],
+                                   float dt, int32_t* order, cudaStream_t stream)
+{
+    chain_order_kernel<<<1, 1024, 0, stream>>>(controls, n_ctrl, K, L, 1.0f / accel[0], 1.0f / accel[1], 1.0f / accel[2],
+                                               1.0f / dt, order);
+    return cudaGetLastError();
 }
 
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)

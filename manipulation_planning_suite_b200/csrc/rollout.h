@@ -37,6 +37,7 @@ struct RolloutParams {
     int32_t* out_nok;     // [K]
     int32_t* out_goal_step;  // [K]
     unsigned int* work_counter;
+    const int32_t* order;   // [K] order in which the chains are pulled (longest first) or nullptr (0, 1, 2, ...)
     unsigned long long* counters;  // [4] or nullptr
     long long* out_cycles;         // [K] SM clock cycles spent on each chain (profiling aid) or nullptr
     // multi-instance batches (BASELINE cfg 5): K = M * K_per chains, instance m = k / K_per starts from node
@@ -90,5 +91,7 @@ size_t mps_rollout_warp_bytes(const DevScene& sc);
 size_t mps_rollout_group_bytes(const DevScene& sc, int mcap);
 size_t mps_rollout_scene_bytes();
 cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, int n_bodies, cudaStream_t stream);
+cudaError_t mps_launch_chain_order(const float* controls, const int32_t* n_ctrl, int K, int L, const float accel[3],
+                                   float dt, int32_t* order, cudaStream_t stream);
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream);
 cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream);

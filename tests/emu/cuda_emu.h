@@ -128,6 +128,16 @@ inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
     return emu::from_bits<T>(out[src]);
 }
 template <class T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+    (void)width;
+    uint64_t out[32];
+    emu::gather(mask, emu::to_bits(v), out);
+    const int src = emu::cur->lane - (int)delta;
+    if (src < 0 || !((mask >> src) & 1u)) return v;
+    return emu::from_bits<T>(out[src]);
+}
+template <class T>
 inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask, int width = 32)
 {
     (void)width;

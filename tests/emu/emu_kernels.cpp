@@ -24,17 +24,22 @@ struct Buffers {
     unsigned long long counters[8] = {0};
 };
 
-template <int WARPS, int MINB, int G>
-void run_rollout(RolloutParams p, int ctas)
+template <int WARPS, class Body>
+void run_grid(RolloutParams& p, int groups, int ctas, Body body)
 {
-    const int groups = WARPS * (32 / G);
-    if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     const size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
     *p.work_counter = 0u;
     int want = (p.K + groups - 1) / groups;
     int grid = ctas < want ? ctas : want;
     if (grid < 1) grid = 1;
-    emu::launch(dim3(grid), dim3(WARPS * 32), smem, [&]() { rollout_kernel<WARPS, MINB, G>(p); });
+    emu::launch(dim3(grid), dim3(WARPS * 32), smem, body);
+}
+
+template <int WARPS, int MINB, int G>
+void run_rollout(RolloutParams p, int ctas)
+{
+    if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
+    run_grid<WARPS>(p, WARPS * (32 / G), ctas, [&]() { rollout_kernel<WARPS, MINB, G>(p); });
 }
 
 }  // namespace
