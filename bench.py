@@ -150,7 +150,7 @@ class ClockSampler:
 
 
 def flop_model(B: int, S: int, vel_iters: int, counters: dict) -> float:
-    """Algorithmic flops of the rollouts (SURVEY.md §8d counting model, I_p = 0 in mps-planar-v2):
+    """Algorithmic flops of the rollouts (SURVEY.md §8d counting model, I_p = 0 in mps-planar-v3):
     per step 10 (ramp) + 20 (B-1) (support friction) + 8 P (broad phase) + 30 B (integrate + pose),
     + 250 per candidate pair (narrow phase) + 2 * 55 * I_v per touching manifold (solver)."""
     P = B * (B - 1) // 2 + B * S

@@ -72,7 +72,7 @@ extern "C" {
 /*
  * Scene = everything that is fixed for a planning problem: bodies, statics,
  * collision policy, workspace bounds, control acceleration limits, distance
- * sub-weights and the constants of the planar push physics ("mps-planar-v2",
+ * sub-weights and the constants of the planar push physics ("mps-planar-v3",
  * DESIGN.md §3).  Body order is the order of the reference's
  * SimEnvWorldStateSpace sub-spaces (SimEnvState.cpp:1027-1050).
  */

@@ -2,9 +2,9 @@
 // translation units of libmps_b200.so (sm_100a only).
 //
 // Arithmetic contract: the whole library is compiled with
-// -fmad=false, so every +,-,*,/ and sqrtf below is one correctly rounded IEEE
-// operation — the same operation sequence the physics spec mps-planar-v2 writes
-// down.  No libm sin/cos on the device path: mps_sincos is the spec's own
+// -fmad=false, so every +,-,*,/, sqrtf and every explicit fmaf below is one
+// correctly rounded IEEE operation — the same operation sequence the physics
+// spec mps-planar-v3 writes down (the spec says where a multiply-add is fused).  No libm sin/cos on the device path: mps_sincos is the spec's own
 // polynomial.
 #pragma once
 
@@ -62,20 +62,18 @@ __host__ __device__ __forceinline__ void mps_sincos(float a, float* s_out, float
     const float p_lo = 7.54978995489188216e-8f;
     float kf = rintf(a * two_over_pi);
     int k = (int)kf;
-    float r = a - kf * p_hi;
-    r = r - kf * p_mid;
-    r = r - kf * p_lo;
+    float r = fmaf(-kf, p_hi, a);
+    r = fmaf(-kf, p_mid, r);
+    r = fmaf(-kf, p_lo, r);
     float z = r * r;
-    float sp = -1.9515295891e-4f * z + 8.3321608736e-3f;
-    sp = sp * z + -1.6666654611e-1f;
+    float sp = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    sp = fmaf(sp, z, -1.6666654611e-1f);
     sp = sp * z;
-    sp = sp * r + r;
-    float cp = 2.443315711809948e-5f * z + -1.388731625493765e-3f;
-    cp = cp * z + 4.166664568298827e-2f;
+    sp = fmaf(sp, r, r);
+    float cp = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    cp = fmaf(cp, z, 4.166664568298827e-2f);
     cp = cp * z;
-    cp = cp * z;
-    cp = cp - 0.5f * z;
-    cp = cp + 1.0f;
+    cp = fmaf(cp, z, fmaf(-0.5f, z, 1.0f));
     int q = k & 3;
     float sn = (q == 0) ? sp : (q == 1) ? cp : (q == 2) ? -sp : -cp;
     float cs = (q == 0) ? cp : (q == 1) ? -sp : (q == 2) ? -cp : sp;

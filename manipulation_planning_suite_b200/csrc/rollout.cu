@@ -9,7 +9,7 @@
 //   SimEnvValidityChecker::isValid + CollisionPolicy       ompl/state/SimEnvState.cpp:1365-1394,1441-1502
 //   SimEnvWorldStateDistanceMeasure::distance              ompl/state/SimEnvWorldStateDistanceMeasure.cpp:34-51
 //   ObjectsRelocationGoal::distanceGoal / isSatisfied      ompl/state/goal/ObjectsRelocationGoal.cpp:108-123
-// The physics step itself follows the spec mps-planar-v2.
+// The physics step itself follows the spec mps-planar-v3.
 //
 // Mapping to the machine:
 //   * one lane group (a whole warp, or 8 / 16 lanes for small scenes in launches that fill the machine) = one
@@ -91,7 +91,7 @@ __device__ __forceinline__ int collide_disc_disc(const Shape& A, const Shape& Bs
 {
     float dx = Bs.x - A.x;
     float dy = Bs.y - A.y;
-    float d2 = dx * dx + dy * dy;
+    float d2 = fmaf(dx, dx, dy * dy);
     float R = A.hx + Bs.hx;
     if (d2 > R * R) {
         gap = sqrtf(d2) - R;
@@ -107,7 +107,7 @@ __device__ __forceinline__ int collide_disc_disc(const Shape& A, const Shape& Bs
         ny = 0.0f;
     }
     float sep = d - R;
-    float h = A.hx + 0.5f * sep;
+    float h = fmaf(0.5f, sep, A.hx);
     m.nx = nx;
     m.ny = ny;
     m.count = 1;
@@ -125,8 +125,8 @@ __device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, 
 {
     float ddx = D.x - X.x;
     float ddy = D.y - X.y;
-    float lx = ddx * X.c + ddy * X.s;
-    float ly = ddy * X.c - ddx * X.s;
+    float lx = fmaf(ddx, X.c, ddy * X.s);
+    float ly = fmaf(ddy, X.c, -(ddx * X.s));
     float qx = fminf(fmaxf(lx, -X.hx), X.hx);
     float qy = fminf(fmaxf(ly, -X.hy), X.hy);
     float r = D.hx;
@@ -150,7 +150,7 @@ __device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, 
     } else {
         float vx = lx - qx;
         float vy = ly - qy;
-        float d2 = vx * vx + vy * vy;
+        float d2 = fmaf(vx, vx, vy * vy);
         if (d2 > r * r) {
             gap = sqrtf(d2) - r;
             return 0;
@@ -163,12 +163,12 @@ __device__ __forceinline__ int collide_box_disc(const Shape& X, const Shape& D, 
         spy = qy;
     }
     float hs = 0.5f * sep;
-    float cplx = spx + nlx * hs;
-    float cply = spy + nly * hs;
-    float rxx = X.c * cplx - X.s * cply;
-    float rxy = X.s * cplx + X.c * cply;
-    float nx = X.c * nlx - X.s * nly;
-    float ny = X.s * nlx + X.c * nly;
+    float cplx = fmaf(nlx, hs, spx);
+    float cply = fmaf(nly, hs, spy);
+    float rxx = fmaf(X.c, cplx, -(X.s * cply));
+    float rxy = fmaf(X.s, cplx, X.c * cply);
+    float nx = fmaf(X.c, nlx, -(X.s * nly));
+    float ny = fmaf(X.s, nlx, X.c * nly);
     float rdx = rxx - ddx;
     float rdy = rxy - ddy;
     m.count = 1;
@@ -198,18 +198,18 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
 {
     float dx = Bs.x - A.x;
     float dy = Bs.y - A.y;
-    float d00 = A.c * Bs.c + A.s * Bs.s;
-    float d01 = A.s * Bs.c - A.c * Bs.s;
+    float d00 = fmaf(A.c, Bs.c, A.s * Bs.s);
+    float d01 = fmaf(A.s, Bs.c, -(A.c * Bs.s));
     float ad00 = fabsf(d00);
     float ad01 = fabsf(d01);
-    float pax = dx * A.c + dy * A.s;
-    float pay = dy * A.c - dx * A.s;
-    float pbx = dx * Bs.c + dy * Bs.s;
-    float pby = dy * Bs.c - dx * Bs.s;
-    float sep_ax = fabsf(pax) - A.hx - (Bs.hx * ad00 + Bs.hy * ad01);
-    float sep_ay = fabsf(pay) - A.hy - (Bs.hx * ad01 + Bs.hy * ad00);
-    float sep_bx = fabsf(pbx) - Bs.hx - (A.hx * ad00 + A.hy * ad01);
-    float sep_by = fabsf(pby) - Bs.hy - (A.hx * ad01 + A.hy * ad00);
+    float pax = fmaf(dx, A.c, dy * A.s);
+    float pay = fmaf(dy, A.c, -(dx * A.s));
+    float pbx = fmaf(dx, Bs.c, dy * Bs.s);
+    float pby = fmaf(dy, Bs.c, -(dx * Bs.s));
+    float sep_ax = fabsf(pax) - A.hx - fmaf(Bs.hx, ad00, Bs.hy * ad01);
+    float sep_ay = fabsf(pay) - A.hy - fmaf(Bs.hx, ad01, Bs.hy * ad00);
+    float sep_bx = fabsf(pbx) - Bs.hx - fmaf(A.hx, ad00, A.hy * ad01);
+    float sep_by = fabsf(pby) - Bs.hy - fmaf(A.hx, ad01, A.hy * ad00);
     if (sep_ax > 0.0f || sep_ay > 0.0f || sep_bx > 0.0f || sep_by > 0.0f) {
         gap = fmaxf(fmaxf(sep_ax, sep_ay), fmaxf(sep_bx, sep_by));  // separated by at least this along an axis
         return 0;
@@ -230,14 +230,14 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
     float uy = face_y ? Rc : Rs;
     float hu = face_y ? Rhy : Rhx;
     float ht = face_y ? Rhx : Rhy;
-    float proj = ddx * ux + ddy * uy;
+    float proj = fmaf(ddx, ux, ddy * uy);
     float sgn = proj >= 0.0f ? 1.0f : -1.0f;
     float nrx = sgn * ux;
     float nry = sgn * uy;
     float trx = -nry;
     float tryy = nrx;
-    float e0 = nrx * Ic + nry * Is;
-    float e1 = nry * Ic - nrx * Is;
+    float e0 = fmaf(nrx, Ic, nry * Is);
+    float e1 = fmaf(nry, Ic, -(nrx * Is));
     bool inc_y = !(fabsf(e0) >= fabsf(e1));
     float sm, mx, my, hm, he;
     if (!inc_y) {
@@ -253,18 +253,18 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
         hm = Ihy;
         he = Ihx;
     }
-    float cx = ddx + mx * hm;
-    float cy = ddy + my * hm;
+    float cx = fmaf(mx, hm, ddx);
+    float cy = fmaf(my, hm, ddy);
     float ex = -my;
     float ey = mx;
-    float v1x = cx + ex * he;
-    float v1y = cy + ey * he;
-    float v2x = cx - ex * he;
-    float v2y = cy - ey * he;
-    float t1 = v1x * trx + v1y * tryy;
-    float t2 = v2x * trx + v2y * tryy;
-    float s1 = (v1x * nrx + v1y * nry) - hu;
-    float s2 = (v2x * nrx + v2y * nry) - hu;
+    float v1x = fmaf(ex, he, cx);
+    float v1y = fmaf(ey, he, cy);
+    float v2x = fmaf(-ex, he, cx);
+    float v2y = fmaf(-ey, he, cy);
+    float t1 = fmaf(v1x, trx, v1y * tryy);
+    float t2 = fmaf(v2x, trx, v2y * tryy);
+    float s1 = fmaf(v1x, nrx, v1y * nry) - hu;
+    float s2 = fmaf(v2x, nrx, v2y * nry) - hu;
     if ((t1 > ht && t2 > ht) || (t1 < -ht && t2 < -ht)) return 0;
     // clip the incident edge to the side planes, without branches: the clipped values are computed for
     // both ends (a zero denominator only occurs when nothing is clipped) and selected
@@ -274,8 +274,8 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
     const float lim2 = hi2 ? ht : -ht;
     const float al1 = (lim1 - t1) / (t2 - t1);
     const float al2 = (lim2 - t2) / (t1 - t2);
-    const float cl1 = s1 + al1 * (s2 - s1);
-    const float cl2 = s2 + al2 * (s1 - s2);
+    const float cl1 = fmaf(al1, s2 - s1, s1);
+    const float cl2 = fmaf(al2, s1 - s2, s2);
     const bool c1 = hi1 || lo1, c2 = hi2 || lo2;
     float ct0 = c1 ? lim1 : t1, cs0 = c1 ? cl1 : s1;
     float ct1 = c2 ? lim2 : t2, cs1 = c2 ? cl2 : s2;
@@ -286,9 +286,9 @@ __device__ __forceinline__ int collide_box_box(const Shape& A, const Shape& Bs, 
     for (int k = 0; k < 2; ++k) {
         const float csk = k == 0 ? cs0 : cs1;
         const float ctk = k == 0 ? ct0 : ct1;
-        const float h = hu + 0.5f * csk;
-        const float rrx = trx * ctk + nrx * h;
-        const float rry = tryy * ctk + nry * h;
+        const float h = fmaf(0.5f, csk, hu);
+        const float rrx = fmaf(trx, ctk, nrx * h);
+        const float rry = fmaf(tryy, ctk, nry * h);
         const float rix = rrx - ddx;
         const float riy = rry - ddy;
         qax[k] = ref_is_b ? rix : rrx;
@@ -534,16 +534,16 @@ __device__ __forceinline__ void store_manifold(const DevScene& sc, float4* mf, c
         const bool has = k < cnt;
         const float rax = m.rax[k], ray = m.ray[k], rbx = m.rbx[k], rby = m.rby[k];
         const float sepk = m.sep[k];
-        rna[k] = has ? rax * m.ny - ray * m.nx : 0.0f;
-        rnb[k] = has ? rbx * m.ny - rby * m.nx : 0.0f;
-        rta[k] = has ? rax * ty - ray * tx : 0.0f;
-        rtb[k] = has ? rbx * ty - rby * tx : 0.0f;
+        rna[k] = has ? fmaf(rax, m.ny, -(ray * m.nx)) : 0.0f;
+        rnb[k] = has ? fmaf(rbx, m.ny, -(rby * m.nx)) : 0.0f;
+        rta[k] = has ? fmaf(rax, ty, -(ray * tx)) : 0.0f;
+        rtb[k] = has ? fmaf(rbx, ty, -(rby * tx)) : 0.0f;
         iarna[k] = ia * rna[k];
         ibrnb[k] = ib * rnb[k];
         iarta[k] = ia * rta[k];
         ibrtb[k] = ib * rtb[k];
-        const float kn = ((ma + mb) + iarna[k] * rna[k]) + ibrnb[k] * rnb[k];
-        const float kt = ((ma + mb) + iarta[k] * rta[k]) + ibrtb[k] * rtb[k];
+        const float kn = fmaf(ibrnb[k], rnb[k], fmaf(iarna[k], rna[k], ma + mb));
+        const float kt = fmaf(ibrtb[k], rtb[k], fmaf(iarta[k], rta[k], ma + mb));
         const float pen_k = -sepk - sc.slop;
         const float bias = pen_k > 0.0f ? fminf(sc.beta_dt * pen_k, sc.max_bias) : 0.0f;
         const float rn = 1.0f / kn, rt = 1.0f / kt;
@@ -552,12 +552,12 @@ __device__ __forceinline__ void store_manifold(const DevScene& sc, float4* mf, c
         kb[k] = nmass[k] * bias;
     }
     const bool two = cnt > 1;
-    const float ktn00 = iarta[0] * rna[0] + ibrtb[0] * rnb[0];
-    const float ktt_ = ((ma + mb) + iarta[0] * rta[1]) + ibrtb[0] * rtb[1];
-    const float knn_ = ((ma + mb) + iarna[0] * rna[1]) + ibrnb[0] * rnb[1];
-    const float ktn01_ = iarta[0] * rna[1] + ibrtb[0] * rnb[1];
-    const float ktn10_ = iarta[1] * rna[0] + ibrtb[1] * rnb[0];
-    const float ktn11_ = iarta[1] * rna[1] + ibrtb[1] * rnb[1];
+    const float ktn00 = fmaf(iarta[0], rna[0], ibrtb[0] * rnb[0]);
+    const float ktt_ = fmaf(ibrtb[0], rtb[1], fmaf(iarta[0], rta[1], ma + mb));
+    const float knn_ = fmaf(ibrnb[0], rnb[1], fmaf(iarna[0], rna[1], ma + mb));
+    const float ktn01_ = fmaf(iarta[0], rna[1], ibrtb[0] * rnb[1]);
+    const float ktn10_ = fmaf(iarta[1], rna[0], ibrtb[1] * rnb[0]);
+    const float ktn11_ = fmaf(iarta[1], rna[1], ibrtb[1] * rnb[1]);
     const float ktt = two ? ktt_ : 0.0f, knn = two ? knn_ : 0.0f;
     const float ktn01 = two ? ktn01_ : 0.0f, ktn10 = two ? ktn10_ : 0.0f, ktn11 = two ? ktn11_ : 0.0f;
     mf[1] = make_float4(rna[0], rnb[0], rta[0], rtb[0]);
@@ -1015,20 +1015,22 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     if (overflow) return;
     // support-plane friction, once per step before the contact iterations
     if (bd.dynamic) {
-        float imp = -bd.inertia * bd.w;
-        imp = fminf(fmaxf(imp, -bd.ang_cap), bd.ang_cap);
-        bd.w = bd.w + bd.inv_i * imp;
-        float ix = -bd.mass * bd.vx;
-        float iy = -bd.mass * bd.vy;
-        float n2 = ix * ix + iy * iy;
-        float cap = bd.lin_cap;
+        // an impulse within the cap brings the body to rest exactly (spec v3 §3.2 step 3)
+        const float imp = -bd.inertia * bd.w;
+        const float impc = fminf(fmaxf(imp, -bd.ang_cap), bd.ang_cap);
+        bd.w = impc == imp ? 0.0f : fmaf(bd.inv_i, impc, bd.w);
+        const float ix = -bd.mass * bd.vx;
+        const float iy = -bd.mass * bd.vy;
+        const float n2 = fmaf(ix, ix, iy * iy);
+        const float cap = bd.lin_cap;
         if (n2 > cap * cap) {
-            float sc_ = cap / sqrtf(n2);
-            ix = ix * sc_;
-            iy = iy * sc_;
+            const float sc_ = cap / sqrtf(n2);
+            bd.vx = fmaf(bd.inv_m, ix * sc_, bd.vx);
+            bd.vy = fmaf(bd.inv_m, iy * sc_, bd.vy);
+        } else {
+            bd.vx = 0.0f;
+            bd.vy = 0.0f;
         }
-        bd.vx = bd.vx + bd.inv_m * ix;
-        bd.vy = bd.vy + bd.inv_m * iy;
     }
     if (dr.nm > 0) {
         {
@@ -1172,9 +1174,9 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
     }
     if (bd.live) {
         const float ox = bd.x, oy = bd.y;
-        bd.x = bd.x + sc.dt * bd.vx;
-        bd.y = bd.y + sc.dt * bd.vy;
-        bd.th = mps_wrap_angle(bd.th + sc.dt * bd.w);
+        bd.x = fmaf(sc.dt, bd.vx, bd.x);
+        bd.y = fmaf(sc.dt, bd.vy, bd.y);
+        bd.th = mps_wrap_angle(fmaf(sc.dt, bd.w, bd.th));
         mps_sincos(bd.th, &bd.s, &bd.c);
         // no point of the body moved further than |dx| + |dy| + R |dtheta| (slack for rounding)
         bd.mv += (fabsf(bd.x - ox) + fabsf(bd.y - oy) + bd.brad * fabsf(sc.dt * bd.w)) * 1.001f + 1e-7f;
@@ -1187,7 +1189,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
 __device__ __forceinline__ bool at_rest(const DevScene& sc, const Body& bd, const Ln ln)
 {
     bool moving = false;
-    if (bd.live) moving = (bd.vx * bd.vx + bd.vy * bd.vy > sc.v_rest2) || (fabsf(bd.w) > sc.w_rest);
+    if (bd.live) moving = (fmaf(bd.vx, bd.vx, bd.vy * bd.vy) > sc.v_rest2) || (fabsf(bd.w) > sc.w_rest);
     return !__any_sync(ln.m, moving);
 }
 

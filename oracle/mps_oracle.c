@@ -4,9 +4,10 @@
  *
  * TEST INFRASTRUCTURE — see mps_oracle.h.  Never linked into the product.
  *
- * Build: gcc -O3 -ffp-contract=off (no FMA contraction: every +,-,*,/ and sqrtf
- * below is one correctly rounded IEEE-754 binary32/binary64 operation, which is
- * what makes a bit-level comparison against the CUDA path meaningful).
+ * Build: gcc -O3 -ffp-contract=off -mfma (no implicit FMA contraction: every +,-,*,/,
+ * sqrtf and every explicit fmaf below is one correctly rounded IEEE-754 operation,
+ * which is what makes a bit-level comparison against the CUDA path meaningful; the
+ * spec says where a fused multiply-add is used).
  *
  * Reference files restated here (relative to the reference root):
  *   src/mps/planner/util/Math.cpp:8-44                        normalize_orientation, shortest_direction_so2
@@ -18,7 +19,7 @@
  *   src/mps/planner/ompl/state/goal/ObjectsRelocationGoal.cpp:108-123     goal distance
  *   src/mps/planner/pushing/algorithm/RRT.cpp:449-489,531-565            chains (HybridActionRRT)
  * The physics step (sim_env/Box2D in the reference; absent here) follows the
- * spec "mps-planar-v2" of DESIGN.md §3 — PARITY UNPINNED for that part.
+ * spec "mps-planar-v3" of DESIGN.md §3 — PARITY UNPINNED for that part.
  */
 #include "mps_oracle.h"
 
@@ -190,7 +191,7 @@ int orc_collision_allowed(const mps_scene* sc, int a, int b)
 }
 
 /* ------------------------------------------------------------------------- */
-/* physics spec mps-planar-v2                                                 */
+/* physics spec mps-planar-v3                                                 */
 /* ------------------------------------------------------------------------- */
 
 /* deterministic sincos: Cody-Waite reduction by pi/2, degree-7/6 polynomials */
@@ -202,21 +203,19 @@ void orc_sincos(float a, float* s_out, float* c_out)
     const float p_lo = 7.54978995489188216e-8f;
     float kf = rintf(a * two_over_pi);
     int k = (int)kf;
-    float r = a - kf * p_hi;
+    float r = fmaf(-kf, p_hi, a);
     float z, sp, cp, sn, cs;
-    r = r - kf * p_mid;
-    r = r - kf * p_lo;
+    r = fmaf(-kf, p_mid, r);
+    r = fmaf(-kf, p_lo, r);
     z = r * r;
-    sp = -1.9515295891e-4f * z + 8.3321608736e-3f;
-    sp = sp * z + -1.6666654611e-1f;
+    sp = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    sp = fmaf(sp, z, -1.6666654611e-1f);
     sp = sp * z;
-    sp = sp * r + r;
-    cp = 2.443315711809948e-5f * z + -1.388731625493765e-3f;
-    cp = cp * z + 4.166664568298827e-2f;
+    sp = fmaf(sp, r, r);
+    cp = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    cp = fmaf(cp, z, 4.166664568298827e-2f);
     cp = cp * z;
-    cp = cp * z;
-    cp = cp - 0.5f * z;
-    cp = cp + 1.0f;
+    cp = fmaf(cp, z, fmaf(-0.5f, z, 1.0f));
     switch (k & 3) {
     case 0: sn = sp; cs = cp; break;
     case 1: sn = cp; cs = -sp; break;
@@ -356,7 +355,7 @@ static int collide_disc_disc(const orc_shape* A, const orc_shape* Bs, orc_manifo
 {
     float dx = Bs->x - A->x;
     float dy = Bs->y - A->y;
-    float d2 = dx * dx + dy * dy;
+    float d2 = fmaf(dx, dx, dy * dy);
     float R = A->hx + Bs->hx;
     float d, nx, ny, sep, h;
     if (d2 > R * R) return 0;
@@ -369,7 +368,7 @@ static int collide_disc_disc(const orc_shape* A, const orc_shape* Bs, orc_manifo
         ny = 0.0f;
     }
     sep = d - R;
-    h = A->hx + 0.5f * sep;
+    h = fmaf(0.5f, sep, A->hx);
     m->nx = nx;
     m->ny = ny;
     m->count = 1;
@@ -386,8 +385,8 @@ static int collide_box_disc(const orc_shape* X, const orc_shape* D, int a_is_box
 {
     float ddx = D->x - X->x;
     float ddy = D->y - X->y;
-    float lx = ddx * X->c + ddy * X->s;
-    float ly = ddy * X->c - ddx * X->s;
+    float lx = fmaf(ddx, X->c, ddy * X->s);
+    float ly = fmaf(ddy, X->c, -(ddx * X->s));
     float qx = fminf(fmaxf(lx, -X->hx), X->hx);
     float qy = fminf(fmaxf(ly, -X->hy), X->hy);
     float r = D->hx;
@@ -411,7 +410,7 @@ static int collide_box_disc(const orc_shape* X, const orc_shape* D, int a_is_box
     } else {
         float vx = lx - qx;
         float vy = ly - qy;
-        float d2 = vx * vx + vy * vy;
+        float d2 = fmaf(vx, vx, vy * vy);
         float d;
         if (d2 > r * r) return 0;
         d = sqrtf(d2);
@@ -422,12 +421,12 @@ static int collide_box_disc(const orc_shape* X, const orc_shape* D, int a_is_box
         spy = qy;
     }
     hs = 0.5f * sep;
-    cplx = spx + nlx * hs;
-    cply = spy + nly * hs;
-    rxx = X->c * cplx - X->s * cply;
-    rxy = X->s * cplx + X->c * cply;
-    nx = X->c * nlx - X->s * nly;
-    ny = X->s * nlx + X->c * nly;
+    cplx = fmaf(nlx, hs, spx);
+    cply = fmaf(nly, hs, spy);
+    rxx = fmaf(X->c, cplx, -(X->s * cply));
+    rxy = fmaf(X->s, cplx, X->c * cply);
+    nx = fmaf(X->c, nlx, -(X->s * nly));
+    ny = fmaf(X->s, nlx, X->c * nly);
     rdx = rxx - ddx;
     rdy = rxy - ddy;
     m->count = 1;
@@ -454,18 +453,18 @@ static int collide_box_box(const orc_shape* A, const orc_shape* Bs, float ref_to
 {
     float dx = Bs->x - A->x;
     float dy = Bs->y - A->y;
-    float d00 = A->c * Bs->c + A->s * Bs->s;
-    float d01 = A->s * Bs->c - A->c * Bs->s;
+    float d00 = fmaf(A->c, Bs->c, A->s * Bs->s);
+    float d01 = fmaf(A->s, Bs->c, -(A->c * Bs->s));
     float ad00 = fabsf(d00);
     float ad01 = fabsf(d01);
-    float pax = dx * A->c + dy * A->s;
-    float pay = dy * A->c - dx * A->s;
-    float pbx = dx * Bs->c + dy * Bs->s;
-    float pby = dy * Bs->c - dx * Bs->s;
-    float sep_ax = fabsf(pax) - A->hx - (Bs->hx * ad00 + Bs->hy * ad01);
-    float sep_ay = fabsf(pay) - A->hy - (Bs->hx * ad01 + Bs->hy * ad00);
-    float sep_bx = fabsf(pbx) - Bs->hx - (A->hx * ad00 + A->hy * ad01);
-    float sep_by = fabsf(pby) - Bs->hy - (A->hx * ad01 + A->hy * ad00);
+    float pax = fmaf(dx, A->c, dy * A->s);
+    float pay = fmaf(dy, A->c, -(dx * A->s));
+    float pbx = fmaf(dx, Bs->c, dy * Bs->s);
+    float pby = fmaf(dy, Bs->c, -(dx * Bs->s));
+    float sep_ax = fabsf(pax) - A->hx - fmaf(Bs->hx, ad00, Bs->hy * ad01);
+    float sep_ay = fabsf(pay) - A->hy - fmaf(Bs->hx, ad01, Bs->hy * ad00);
+    float sep_bx = fabsf(pbx) - Bs->hx - fmaf(A->hx, ad00, A->hy * ad01);
+    float sep_by = fabsf(pby) - Bs->hy - fmaf(A->hx, ad01, A->hy * ad00);
     int a_face_y, b_face_y, ref_is_b, face_y, inc_y, n, k;
     float sep_a, sep_b;
     const orc_shape *R, *I;
@@ -486,15 +485,15 @@ static int collide_box_box(const orc_shape* A, const orc_shape* Bs, float ref_to
     uy = face_y ? R->c : R->s;
     hu = face_y ? R->hy : R->hx;
     ht = face_y ? R->hx : R->hy;
-    proj = ddx * ux + ddy * uy;
+    proj = fmaf(ddx, ux, ddy * uy);
     sgn = proj >= 0.0f ? 1.0f : -1.0f;
     nrx = sgn * ux;
     nry = sgn * uy;
     trx = -nry;
     tryy = nrx;
     /* incident face of I: the face normal most opposed to the reference normal */
-    e0 = nrx * I->c + nry * I->s;
-    e1 = nry * I->c - nrx * I->s;
+    e0 = fmaf(nrx, I->c, nry * I->s);
+    e1 = fmaf(nry, I->c, -(nrx * I->s));
     inc_y = !(fabsf(e0) >= fabsf(e1));
     if (!inc_y) {
         sm = e0 > 0.0f ? -1.0f : 1.0f;
@@ -509,18 +508,18 @@ static int collide_box_box(const orc_shape* A, const orc_shape* Bs, float ref_to
         hm = I->hy;
         he = I->hx;
     }
-    cx = ddx + mx * hm;
-    cy = ddy + my * hm;
+    cx = fmaf(mx, hm, ddx);
+    cy = fmaf(my, hm, ddy);
     ex = -my;
     ey = mx;
-    v1x = cx + ex * he;
-    v1y = cy + ey * he;
-    v2x = cx - ex * he;
-    v2y = cy - ey * he;
-    t1 = v1x * trx + v1y * tryy;
-    t2 = v2x * trx + v2y * tryy;
-    s1 = (v1x * nrx + v1y * nry) - hu;
-    s2 = (v2x * nrx + v2y * nry) - hu;
+    v1x = fmaf(ex, he, cx);
+    v1y = fmaf(ey, he, cy);
+    v2x = fmaf(-ex, he, cx);
+    v2y = fmaf(-ey, he, cy);
+    t1 = fmaf(v1x, trx, v1y * tryy);
+    t2 = fmaf(v2x, trx, v2y * tryy);
+    s1 = fmaf(v1x, nrx, v1y * nry) - hu;
+    s2 = fmaf(v2x, nrx, v2y * nry) - hu;
     if ((t1 > ht && t2 > ht) || (t1 < -ht && t2 < -ht)) return 0;
     /* clip both end points of the incident edge to the side planes |t| <= ht */
     ct[0] = t1;
@@ -529,28 +528,28 @@ static int collide_box_box(const orc_shape* A, const orc_shape* Bs, float ref_to
     cs[1] = s2;
     if (t1 > ht) {
         float al = (ht - t1) / (t2 - t1);
-        cs[0] = s1 + al * (s2 - s1);
+        cs[0] = fmaf(al, s2 - s1, s1);
         ct[0] = ht;
     } else if (t1 < -ht) {
         float al = (-ht - t1) / (t2 - t1);
-        cs[0] = s1 + al * (s2 - s1);
+        cs[0] = fmaf(al, s2 - s1, s1);
         ct[0] = -ht;
     }
     if (t2 > ht) {
         float al = (ht - t2) / (t1 - t2);
-        cs[1] = s2 + al * (s1 - s2);
+        cs[1] = fmaf(al, s1 - s2, s2);
         ct[1] = ht;
     } else if (t2 < -ht) {
         float al = (-ht - t2) / (t1 - t2);
-        cs[1] = s2 + al * (s1 - s2);
+        cs[1] = fmaf(al, s1 - s2, s2);
         ct[1] = -ht;
     }
     n = 0;
     for (k = 0; k < 2; ++k) {
         if (cs[k] <= 0.0f) {
-            float h = hu + 0.5f * cs[k];
-            float rrx = trx * ct[k] + nrx * h;
-            float rry = tryy * ct[k] + nry * h;
+            float h = fmaf(0.5f, cs[k], hu);
+            float rrx = fmaf(trx, ct[k], nrx * h);
+            float rry = fmaf(tryy, ct[k], nry * h);
             float rix = rrx - ddx;
             float riy = rry - ddy;
             if (ref_is_b) {
@@ -606,17 +605,17 @@ static void manifold_prepare(const orc_world* wd, orc_manifold* m)
     {
         float iarna[2] = {0.0f, 0.0f}, ibrnb[2] = {0.0f, 0.0f}, iarta[2] = {0.0f, 0.0f}, ibrtb[2] = {0.0f, 0.0f};
         for (k = 0; k < m->count; ++k) {
-            float rna = m->rax[k] * m->ny - m->ray[k] * m->nx;
-            float rnb = m->rbx[k] * m->ny - m->rby[k] * m->nx;
-            float rta = m->rax[k] * ty - m->ray[k] * tx;
-            float rtb = m->rbx[k] * ty - m->rby[k] * tx;
+            float rna = fmaf(m->rax[k], m->ny, -(m->ray[k] * m->nx));
+            float rnb = fmaf(m->rbx[k], m->ny, -(m->rby[k] * m->nx));
+            float rta = fmaf(m->rax[k], ty, -(m->ray[k] * tx));
+            float rtb = fmaf(m->rbx[k], ty, -(m->rby[k] * tx));
             float kn, kt, pen, nmass, bias;
             iarna[k] = ia * rna;
             ibrnb[k] = ib * rnb;
             iarta[k] = ia * rta;
             ibrtb[k] = ib * rtb;
-            kn = ((ma + mb) + iarna[k] * rna) + ibrnb[k] * rnb;
-            kt = ((ma + mb) + iarta[k] * rta) + ibrtb[k] * rtb;
+            kn = fmaf(ibrnb[k], rnb, fmaf(iarna[k], rna, ma + mb));
+            kt = fmaf(ibrtb[k], rtb, fmaf(iarta[k], rta, ma + mb));
             pen = -m->sep[k] - sc->slop;
             m->rna[k] = rna;
             m->rnb[k] = rnb;
@@ -631,16 +630,16 @@ static void manifold_prepare(const orc_world* wd, orc_manifold* m)
             m->acc_t[k] = 0.0f;
         }
         /* how an impulse on one row changes the relative velocity along another (spec §3.4) */
-        m->ktn[0][0] = iarta[0] * m->rna[0] + ibrtb[0] * m->rnb[0];
+        m->ktn[0][0] = fmaf(iarta[0], m->rna[0], ibrtb[0] * m->rnb[0]);
         m->ktt = 0.0f;
         m->knn = 0.0f;
         m->ktn[0][1] = m->ktn[1][0] = m->ktn[1][1] = 0.0f;
         if (m->count > 1) {
-            m->ktt = ((ma + mb) + iarta[0] * m->rta[1]) + ibrtb[0] * m->rtb[1];
-            m->knn = ((ma + mb) + iarna[0] * m->rna[1]) + ibrnb[0] * m->rnb[1];
-            m->ktn[0][1] = iarta[0] * m->rna[1] + ibrtb[0] * m->rnb[1];
-            m->ktn[1][0] = iarta[1] * m->rna[0] + ibrtb[1] * m->rnb[0];
-            m->ktn[1][1] = iarta[1] * m->rna[1] + ibrtb[1] * m->rnb[1];
+            m->ktt = fmaf(ibrtb[0], m->rtb[1], fmaf(iarta[0], m->rta[1], ma + mb));
+            m->knn = fmaf(ibrnb[0], m->rnb[1], fmaf(iarna[0], m->rna[1], ma + mb));
+            m->ktn[0][1] = fmaf(iarta[0], m->rna[1], ibrtb[0] * m->rnb[1]);
+            m->ktn[1][0] = fmaf(iarta[1], m->rna[0], ibrtb[1] * m->rnb[0]);
+            m->ktn[1][1] = fmaf(iarta[1], m->rna[1], ibrtb[1] * m->rnb[1]);
         }
     }
 }
@@ -792,22 +791,24 @@ static int world_step(orc_world* wd, const float u[3])
     /* support-plane friction, once per step before the contact iterations: the impulse that brings
      * the body to rest, capped at dt * mu * m * g (linear, vector norm) and dt * mu * m * g * r (angular) */
     for (i = 0; i < B; ++i) {
-        float imp, ix, iy, n2, cap;
+        float imp, impc, ix, iy, n2, cap;
         if (i == wd->robot) continue;
         imp = -sc->inertia[i] * wd->w[i];
-        imp = fminf(fmaxf(imp, -wd->ang_cap[i]), wd->ang_cap[i]);
-        wd->w[i] = wd->w[i] + wd->inv_i[i] * imp;
+        impc = fminf(fmaxf(imp, -wd->ang_cap[i]), wd->ang_cap[i]);
+        /* an impulse within the cap stops the body exactly */
+        wd->w[i] = impc == imp ? 0.0f : fmaf(wd->inv_i[i], impc, wd->w[i]);
         ix = -sc->mass[i] * wd->vx[i];
         iy = -sc->mass[i] * wd->vy[i];
-        n2 = ix * ix + iy * iy;
+        n2 = fmaf(ix, ix, iy * iy);
         cap = wd->lin_cap[i];
         if (n2 > cap * cap) {
             float sc_ = cap / sqrtf(n2);
-            ix = ix * sc_;
-            iy = iy * sc_;
+            wd->vx[i] = fmaf(wd->inv_m[i], ix * sc_, wd->vx[i]);
+            wd->vy[i] = fmaf(wd->inv_m[i], iy * sc_, wd->vy[i]);
+        } else {
+            wd->vx[i] = 0.0f;
+            wd->vy[i] = 0.0f;
         }
-        wd->vx[i] = wd->vx[i] + wd->inv_m[i] * ix;
-        wd->vy[i] = wd->vy[i] + wd->inv_m[i] * iy;
     }
     for (it = 0; it < sc->vel_iters && wd->nm > 0; ++it) {
         /* contacts in colour order: colour r < B holds the body pairs with (i + j) mod B == r,
@@ -831,9 +832,9 @@ static int world_step(orc_world* wd, const float u[3])
         }
     }
     for (i = 0; i < B; ++i) {
-        wd->x[i] = wd->x[i] + sc->dt * wd->vx[i];
-        wd->y[i] = wd->y[i] + sc->dt * wd->vy[i];
-        wd->th[i] = wrap_angle(wd->th[i] + sc->dt * wd->w[i]);
+        wd->x[i] = fmaf(sc->dt, wd->vx[i], wd->x[i]);
+        wd->y[i] = fmaf(sc->dt, wd->vy[i], wd->y[i]);
+        wd->th[i] = wrap_angle(fmaf(sc->dt, wd->w[i], wd->th[i]));
         orc_sincos(wd->th[i], &wd->s[i], &wd->c[i]);
     }
     return wd->bad_contact;
@@ -845,7 +846,7 @@ static int world_at_rest(const orc_world* wd)
     float v2max = sc->v_rest * sc->v_rest;
     int i;
     for (i = 0; i < wd->B; ++i) {
-        if (wd->vx[i] * wd->vx[i] + wd->vy[i] * wd->vy[i] > v2max) return 0;
+        if (fmaf(wd->vx[i], wd->vx[i], wd->vy[i] * wd->vy[i]) > v2max) return 0;
         if (fabsf(wd->w[i]) > sc->w_rest) return 0;
     }
     return 1;

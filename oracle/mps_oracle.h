@@ -12,7 +12,7 @@
  *     (tests/golden/).
  *   * the physics step itself (sim_env / Box2D in the reference, absent from
  *     /root/reference, un-vendored, un-pinned): "PARITY UNPINNED".  The
- *     oracle implements the spec "mps-planar-v2" written for this repo.
+ *     oracle implements the spec "mps-planar-v3" written for this repo.
  */
 #ifndef MPS_ORACLE_H
 #define MPS_ORACLE_H

@@ -15,7 +15,12 @@ import json
 import math
 import os
 
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from spec_np import fma32  # noqa: E402  exact binary32 fused multiply-add (checked against libm in the tests)
 
 f32 = np.float32
 
@@ -124,7 +129,7 @@ def main():
         while time < T:
             u = ramp_velocity(v, a, t_acc, t_pl, time)
             for i in range(3):
-                disp[i] = f32(disp[i] + f32(f32(0.01) * u[i]))
+                disp[i] = fma32(f32(0.01), u[i], disp[i])  # spec v3 §3.2 step 5: x := fma(dt, v, x)
             time = f32(time + f32(0.01))
             n += 1
         out["steps"].append({"params": [float(x) for x in params], "alim": [float(f32(x)) for x in alim], "n_active": n,

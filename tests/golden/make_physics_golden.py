@@ -1,6 +1,9 @@
-"""Generates tests/golden/physics_golden.npz: rollouts of the physics spec mps-planar-v2 produced by the
+"""Generates tests/golden/physics_golden_v3.npz: rollouts of the physics spec mps-planar-v3 produced by the
 CPU oracle on seeded inputs.  The reference's physics (sim_env / Box2D) is not in /root/reference, so
 these vectors pin OUR spec (regression + CPU/GPU agreement), not the reference: "parity unpinned".
+They are a REGRESSION file (the oracle wrote them); the independent pin of the spec is physics_kat_v3.json
+(make_physics_kat.py, from the numpy restatement spec_np.py).  One file per spec version: an existing file is
+never regenerated - a spec change gets a new version and a new file.
 
 Run: python tests/golden/make_physics_golden.py
 """
@@ -37,8 +40,11 @@ def main():
         out[f"c{i}_dest"] = dest
         for k in ("all_states", "all_rest", "all_flags", "all_dist", "all_steps", "best_states"):
             out[f"c{i}_{k}"] = r[k]
-    np.savez_compressed(os.path.join(HERE, "physics_golden.npz"), **out)
-    print("wrote physics_golden.npz", sum(v.nbytes for v in out.values()), "bytes raw")
+    path = os.path.join(HERE, "physics_golden_v3.npz")
+    if os.path.exists(path):
+        raise SystemExit(path + " exists: a committed spec version is never regenerated")
+    np.savez_compressed(path, **out)
+    print("wrote", path, sum(v.nbytes for v in out.values()), "bytes raw")
 
 
 if __name__ == "__main__":

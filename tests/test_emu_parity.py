@@ -59,3 +59,22 @@ def test_validity_kernel_matches_oracle():
     for i in range(len(states)):
         ok, f = ob.is_valid(sc, states[i])
         assert (bool(valid[i]), int(flags[i])) == (ok, f)
+
+
+@pytest.mark.parametrize("group", [32, 8])
+def test_kernel_source_reproduces_the_independent_physics_answers(group):
+    """tests/golden/physics_kat_v3.json (from the numpy restatement of the spec, tests/golden/spec_np.py) against the
+    rollout / validity kernels' source run through the emulator."""
+    import physics_kat as pk
+
+    kat = pk.load()
+    for case in kat["propagate"]:
+        sc = pk.build_scene(case["scene"])
+        r = eb.extend(sc, pk.arr(case["start"]), pk.arr(case["control"]).reshape(1, 1, 5), group=group, minb=4)
+        assert int(r["all_flags"][0, 0]) == case["flags"] and int(r["all_steps"][0, 0]) == case["steps"], case["name"]
+        assert r["all_rest"][0, 0] == np.float32(case["rest"]), case["name"]
+        assert np.array_equal(r["all_states"][0, 0], pk.arr(case["out"])), case["name"]
+    sc = pk.build_scene(kat["valid"]["scene"])
+    valid, flags = eb.is_valid_batch(sc, np.stack([pk.arr(c["state"]) for c in kat["valid"]["cases"]]))
+    for i, case in enumerate(kat["valid"]["cases"]):
+        assert int(flags[i]) == case["flags"] and bool(valid[i]) == (case["flags"] == 0), case["name"]

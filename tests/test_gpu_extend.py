@@ -237,7 +237,7 @@ def test_gpu_reproduces_committed_physics_golden():
     """The CUDA path against the committed fixtures (no oracle involved at run time)."""
     import os
 
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "physics_golden.npz"))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "physics_golden_v3.npz"))
     i = 0
     while f"c{i}_meta" in g:
         n_objects, seed, k, n_ok = [int(x) for x in g[f"c{i}_meta"]]
@@ -253,6 +253,31 @@ def test_gpu_reproduces_committed_physics_golden():
         ctx.close()
         i += 1
     assert i == 4
+
+
+def test_gpu_reproduces_the_independent_physics_answers():
+    """tests/golden/physics_kat_v3.json: known answers of the physics spec computed by the independent numpy
+    restatement (tests/golden/spec_np.py) - neither the oracle nor any kernel wrote them.  The CUDA path must give
+    the same bits: final state, flags, rest time, step count; and the same validity flags."""
+    import physics_kat as pk
+
+    kat = pk.load()
+    for case in kat["propagate"]:
+        sc = pk.build_scene(case["scene"])
+        ctx = api.Context(sc)
+        ok, out, c, fl = ctx.propagate(pk.arr(case["start"]), pk.arr(case["control"]))
+        assert ok == case["ok"] and fl == case["flags"], case["name"]
+        assert c[4] == np.float32(case["rest"]), case["name"]
+        assert np.array_equal(out, pk.arr(case["out"])), (case["name"], out, case["out"])
+        r = ctx.extend(pk.arr(case["start"]), pk.arr(case["control"]).reshape(1, 1, 5), dump=True)
+        assert int(r.all_steps[0, 0]) == case["steps"], case["name"]
+        ctx.close()
+    sc = pk.build_scene(kat["valid"]["scene"])
+    ctx = api.Context(sc)
+    valid, flags = ctx.is_valid(np.stack([pk.arr(c["state"]) for c in kat["valid"]["cases"]]))
+    for i, case in enumerate(kat["valid"]["cases"]):
+        assert int(flags[i]) == case["flags"] and bool(valid[i]) == (case["flags"] == 0), case["name"]
+    ctx.close()
 
 
 @pytest.mark.parametrize("stop_at_goal", [False, True])

@@ -1,4 +1,4 @@
-"""CPU tests of the physics spec mps-planar-v2 as implemented by the oracle: mechanics sanity, the
+"""CPU tests of the physics spec mps-planar-v3 as implemented by the oracle: mechanics sanity, the
 propagate contract of the reference (SimEnvStatePropagator.cpp:42-118) and best-of-K semantics
 (NaiveControlSampler.cpp:34-71, RRT.cpp:449-489)."""
 import ctypes as C
@@ -198,11 +198,11 @@ def test_nn_linear_matches_numpy_bruteforce():
 
 
 def test_oracle_reproduces_committed_physics_golden():
-    """Regression pin of the spec: the committed vectors (tests/golden/make_physics_golden.py) must be
-    reproduced bit for bit by the oracle built from source on this machine."""
+    """Regression pin of the spec version: the committed vectors (tests/golden/make_physics_golden.py, frozen per
+    spec version) must be reproduced bit for bit by the oracle built from source on this machine."""
     import os
 
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "physics_golden.npz"))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "physics_golden_v3.npz"))
     i = 0
     while f"c{i}_meta" in g:
         n_objects, seed, k, n_ok = [int(x) for x in g[f"c{i}_meta"]]
@@ -213,6 +213,114 @@ def test_oracle_reproduces_committed_physics_golden():
             assert np.array_equal(r[key], g[f"c{i}_{key}"]), (i, key)
         i += 1
     assert i == 4
+
+
+# ---- the independent pin of the physics spec -------------------------------------------------------------------
+# tests/golden/physics_kat_v3.json comes from tests/golden/spec_np.py, a numpy-float32 restatement of DESIGN.md §3
+# that shares no code with the oracle.  The oracle has to reproduce every number of it bit for bit.
+
+def test_fma32_of_the_restatement_is_the_ieee_fused_multiply_add():
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import spec_np as sp
+
+    libm = C.CDLL("libm.so.6")
+    libm.fmaf.restype = C.c_float
+    libm.fmaf.argtypes = [C.c_float] * 3
+    rng = np.random.RandomState(0)
+    for i in range(30000):
+        a, b = rng.standard_normal(2).astype(np.float32)
+        if i % 3 == 0:
+            c = np.float32(-(float(a) * float(b)))          # cancellation
+        elif i % 3 == 1:
+            c = np.float32(rng.standard_normal() * 10.0 ** rng.randint(-8, 8))
+        else:
+            c = np.float32(rng.standard_normal())           # the product close to half an ulp of c
+            b = np.float32(float(np.spacing(c)) * 0.5 / float(a))
+        assert sp.fma32(a, b, c) == np.float32(libm.fmaf(a, b, c)), (a, b, c)
+    # exact ties of the double sum that the remainder has to break
+    one, eps = np.float32(1.0), np.float32(2.0 ** -24)
+    for a, b, c in [(one + np.float32(2.0 ** -23), eps, one), (eps, eps, one), (np.float32(3.0), eps, one),
+                    (np.float32(-3.0), eps, one), (eps, -eps, one + np.float32(2.0 ** -23))]:
+        assert sp.fma32(a, b, c) == np.float32(libm.fmaf(a, b, c)), (a, b, c)
+
+
+def _kat():
+    import physics_kat as pk
+
+    return pk, pk.load()
+
+
+def test_oracle_reproduces_the_independent_propagate_answers():
+    pk, kat = _kat()
+    assert kat["spec"] == "mps-planar-v3"
+    names = set()
+    for case in kat["propagate"]:
+        sc = pk.build_scene(case["scene"])
+        ok, out, c, fl, steps = ob.propagate(sc, pk.arr(case["start"]), pk.arr(case["control"]))
+        assert bool(ok) == case["ok"] and fl == case["flags"] and steps == case["steps"], case["name"]
+        assert c[4] == np.float32(case["rest"]), case["name"]
+        assert np.array_equal(out, pk.arr(case["out"])), (case["name"], out, case["out"])
+        names.add(case["name"])
+    assert {"disc_disc_central_push", "box_box_face_two_points", "box_disc_corner", "push_release_slide", "jam_rule",
+            "train_box_disc_box", "box_slides_along_wall"} <= names
+
+
+def test_oracle_reproduces_the_independent_single_step_answers():
+    """pose and twist of every body after each of the first steps, through the oracle's single-step entry"""
+    pk, kat = _kat()
+    n_steps = 0
+    for case in kat["propagate"]:
+        sc = pk.build_scene(case["scene"])
+        pose = pk.arr(case["start"]).copy()
+        for i in range(sc.n_bodies):  # set_state wraps theta; the starts are inside [-pi, pi)
+            assert -np.pi <= pose[3 * i + 2] < np.pi
+        vel = np.zeros_like(pose)
+        nm = C.c_int32()
+        for t in case["trace"]:
+            u = pk.arr(t["u"])
+            ob.lib().orc_step_once(C.byref(sc), ob.fp(pose), ob.fp(vel), ob.fp(u), C.byref(nm))
+            assert nm.value == t["n_manifolds"], case["name"]
+            assert np.array_equal(pose, pk.arr(t["pose"])), (case["name"], n_steps)
+            assert np.array_equal(vel, pk.arr(t["twist"])), (case["name"], n_steps)
+            n_steps += 1
+    assert n_steps > 900
+
+
+def test_oracle_reproduces_the_independent_validity_and_sincos_answers():
+    pk, kat = _kat()
+    sc = pk.build_scene(kat["valid"]["scene"])
+    for case in kat["valid"]["cases"]:
+        valid, f = ob.is_valid(sc, pk.arr(case["state"]))
+        assert f == case["flags"] and bool(valid) == (case["flags"] == 0), case["name"]
+    s = C.c_float()
+    c = C.c_float()
+    for case in kat["sincos"]:
+        ob.lib().orc_sincos(C.c_float(case["a"]), C.byref(s), C.byref(c))
+        assert np.float32(s.value) == np.float32(case["s"]) and np.float32(c.value) == np.float32(case["c"])
+
+
+def test_restatement_run_live_agrees_with_the_oracle_on_a_fresh_case():
+    """the committed file is what spec_np.py computes today, and a case outside the file agrees as well"""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import spec_np as sp
+
+    pk, kat = _kat()
+    case = kat["propagate"][2]
+    sc = pk.build_scene(case["scene"])
+    ok, out, rest, fl, steps = sp.propagate(sc, pk.arr(case["start"]), pk.arr(case["control"]))
+    assert np.array_equal(out, pk.arr(case["out"])) and fl == case["flags"] and steps == case["steps"]
+    sc, _ = scenes.make_scene(5, seed=77)
+    start = scenes.cluttered_start(sc, 77)
+    rng = np.random.RandomState(77)
+    controls = scenes.sample_controls_towards(rng, sc, start, 3, 1)
+    for k in range(3):
+        ok, out, c, fl, steps = ob.propagate(sc, start, controls[k, 0])
+        ok2, out2, rest2, fl2, steps2 = sp.propagate(sc, start, controls[k, 0])
+        assert (bool(ok), fl, steps, c[4]) == (ok2, fl2, steps2, rest2) and np.array_equal(out, out2)
 
 
 def test_gnat_restatement_is_exact():
