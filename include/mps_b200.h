@@ -322,6 +322,18 @@ int mps_forest_read(mps_ctx* ctx, int32_t inst, int64_t first, int64_t n, float*
  * all-gather. */
 int mps_extend_record_size(mps_ctx* ctx, int64_t* bytes);
 int mps_extend_record_to(mps_ctx* ctx, void* dst_device);
+/* Exchange step of the K-sharded extend, on the device (replaces the tail of the reference's sample loop,
+ * NaiveControlSampler.cpp:53-70 / RRT.cpp:466-488, for chains that were propagated on other GPUs).
+ * `gathered_device` = `world` packed records in rank order (the all-gather of every rank's record).  Enqueued on
+ * the ctx stream: the global winner is picked by the reference's rule (strict <; equal keys -> lowest global
+ * chain index), its record becomes this ctx's record (mps_extend_fetch / mps_extend_record_to see it), and when
+ * append_to_tree is set - on the GPU that owns the tree - its chain is appended below `parent` (up to the first
+ * goal state).  best_out != NULL: synchronises and returns the 24-byte head; NULL: asynchronous, read the head
+ * later with mps_extend_head. */
+int mps_extend_merge_records(mps_ctx* ctx, const void* gathered_device, int32_t world, int32_t has_dest,
+                             int32_t compare_f32, int32_t append_to_tree, int32_t parent, mps_extend_best* best_out);
+/* the 24-byte head of the ctx's current winner record (synchronises); nothing else crosses PCIe */
+int mps_extend_head(mps_ctx* ctx, mps_extend_best* best_out);
 
 /* ---- timing helper ---------------------------------------------------- */
 /* Runs `iters` back-to-back launches of the uploaded extend (what=0) or NN batch (what=1)

@@ -244,6 +244,8 @@ SYMBOLS = {
     "mps_forest_read": (C.c_int, [_ctx, _i32, C.c_int64, C.c_int64, _P(_f32), _P(_i32), _P(_f32)]),
     "mps_extend_record_size": (C.c_int, [_ctx, _P(C.c_int64)]),
     "mps_extend_record_to": (C.c_int, [_ctx, C.c_void_p]),
+    "mps_extend_merge_records": (C.c_int, [_ctx, C.c_void_p, _i32, _i32, _i32, _i32, _i32, _P(ExtendBest)]),
+    "mps_extend_head": (C.c_int, [_ctx, _P(ExtendBest)]),
     "mps_ctx_set_kernel_timing": (C.c_int, [_ctx, _i32]),
     "mps_extend_kernel_times": (C.c_int, [_ctx, _P(_f32), _i32, _P(_i32)]),
     "mps_measure_fp32_peak": (C.c_int, [_ctx, _P(_f32)]),

@@ -74,6 +74,7 @@ class Context:
         if rc != abi.MPS_OK:
             raise MpsError(rc, (self.lib.mps_last_error(None) or b"").decode())
         self.h = h
+        self.device = int(device)
         self._keep = None  # arrays referenced by an uploaded extend
 
     def close(self):
@@ -246,6 +247,25 @@ class Context:
 
     def record_to(self, device_ptr: int):
         self._check(self.lib.mps_extend_record_to(self.h, C.c_void_p(device_ptr)))
+
+    def merge_records(self, gathered_ptr: int, world: int, has_dest: bool, compare_f32: bool, append_to_tree: bool = False,
+                      parent: int = -1, wait: bool = False):
+        """Exchange step of the K-sharded extend on the device (mps_extend_merge_records).  wait=True returns the
+        24-byte head (abi.ExtendBest), else the call is asynchronous on the ctx stream."""
+        best = abi.ExtendBest() if wait else None
+        self._check(self.lib.mps_extend_merge_records(self.h, C.c_void_p(gathered_ptr), world, int(has_dest), int(compare_f32),
+                                                      int(append_to_tree), parent, C.byref(best) if wait else None))
+        return best
+
+    def extend_head(self) -> abi.ExtendBest:
+        best = abi.ExtendBest()
+        self._check(self.lib.mps_extend_head(self.h, C.byref(best)))
+        return best
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.mps_ctx_stream(self.h, C.byref(p)))
+        return int(p.value or 0)
 
     # ---- validity -------------------------------------------------------
     def is_valid(self, states):

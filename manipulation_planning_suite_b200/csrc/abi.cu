@@ -82,6 +82,7 @@ struct mps_ctx {
     TreeView forest;
     int f_ninst = 0;
     size_t f_seg = 0;
+    bool f_reset = false;  // mps_forest_reset has run since the last reserve (every tree has its root)
     DevBuf d_fsizes, d_finst, d_fparents, d_fmasks, d_fbest, d_fbest_states, d_fbest_controls, d_fbest_flags, d_froots;
 
     // validity
@@ -1062,6 +1063,7 @@ int mps_forest_reserve(mps_ctx* ctx, int32_t n_instances, int32_t cap_per_instan
     if (rc) return rc;
     ctx->f_ninst = n_instances;
     ctx->f_seg = seg;
+    ctx->f_reset = false;
     if ((rc = ensure(ctx, ctx->d_fsizes, sizeof(long long) * (size_t)n_instances))) return rc;
     MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_fsizes.p, 0, sizeof(long long) * (size_t)n_instances, ctx->stream), ctx);
     return MPS_OK;
@@ -1081,6 +1083,7 @@ int mps_forest_reset(mps_ctx* ctx, const float* roots)
                    ctx);
     ctx->launches++;
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    ctx->f_reset = true;
     return MPS_OK;
 }
 
@@ -1105,6 +1108,7 @@ int mps_forest_nearest(mps_ctx* ctx, int32_t M, const int32_t* inst_ids, const f
 {
     if (!ctx || M < 1 || M > 65535 || !inst_ids || !queries) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_forest_nearest");
     if (!ctx->forest.states) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reserve first");
+    if (!ctx->f_reset) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reset first: the trees have no root yet");
     int rc = check_inst_ids(ctx, inst_ids, M);
     if (rc) return rc;
     // queries / masks / weights go through the plain query path's buffers
@@ -1258,6 +1262,14 @@ int mps_forest_extend(mps_ctx* ctx, const mps_forest_extend_in* in, mps_extend_b
     if (M < 1 || K < 1 || L < 1 || L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "M, K >= 1 and L in [1, 64]");
     if ((long long)M * K > (1ll << 24)) return mps_fail(ctx, MPS_ERR_ARG, "M * K too large");
     if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS || (in->n_goals > 0 && !in->goals)) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
+    if (!ctx->f_reset) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reset first: the trees have no root yet");
+    for (int g = 0; g < in->n_goals; ++g)
+        if (in->goals[g].body < 0 || in->goals[g].body >= B) return mps_fail(ctx, MPS_ERR_ARG, "goal body out of range");
+    // the device reads the start state of instance m at column inst * seg + parents[m]: a parent outside its
+    // segment would be an out-of-bounds read (nodes beyond the tree's size but inside the segment are the
+    // caller's business, like an unknown node id in the reference)
+    for (int m = 0; m < M; ++m)
+        if (in->parents[m] < 0 || (size_t)in->parents[m] >= ctx->f_seg) return mps_fail(ctx, MPS_ERR_ARG, "parent node out of range");
     int rc = check_inst_ids(ctx, in->inst_ids, M);
     if (rc) return rc;
     MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
@@ -1290,6 +1302,13 @@ int mps_forest_naive_step(mps_ctx* ctx, const mps_forest_naive_in* in, mps_exten
     if (in->n_goals < 1 || in->n_goals > MPS_MAX_GOALS || !in->goals) return mps_fail(ctx, MPS_ERR_ARG, "bad goals");
     for (int g = 0; g < in->n_goals; ++g)
         if (in->goals[g].body < 0 || in->goals[g].body >= B) return mps_fail(ctx, MPS_ERR_ARG, "goal body out of range");
+    if (!ctx->f_reset) return mps_fail(ctx, MPS_ERR_STATE, "mps_forest_reset first: the trees have no root yet");
+    {
+        // samples are drawn as min + (max - min) * u: the span must be finite (the scene default is +-FLT_MAX)
+        const float sx = ctx->scene.x_max - ctx->scene.x_min, sy = ctx->scene.y_max - ctx->scene.y_min;
+        if (!std::isfinite(sx) || !std::isfinite(sy) || sx <= 0.0f || sy <= 0.0f)
+            return mps_fail(ctx, MPS_ERR_ARG, "the scene's workspace bounds must span a finite, positive range to sample states");
+    }
     int rc = check_inst_ids(ctx, in->inst_ids, M);
     if (rc) return rc;
     MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
@@ -1440,6 +1459,65 @@ int mps_extend_record_to(mps_ctx* ctx, void* dst_device)
     MPS_CUDA_CHECK(cudaMemcpyAsync(dst_device, ctx->d_record.p, record_bytes(ctx->scene.n_bodies, ctx->ext_L),
                                    cudaMemcpyDeviceToDevice, ctx->stream),
                    ctx);
+    return MPS_OK;
+}
+
+int mps_extend_merge_records(mps_ctx* ctx, const void* gathered_device, int32_t world, int32_t has_dest,
+                             int32_t compare_f32, int32_t append_to_tree, int32_t parent, mps_extend_best* best_out)
+{
+    if (!ctx || !gathered_device) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_merge_records");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "no extend uploaded");
+    if (world < 1 || world > 1024) return mps_fail(ctx, MPS_ERR_ARG, "world must be in [1, 1024]");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    const int B = ctx->scene.n_bodies, L = ctx->ext_L;
+    MergeParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.gathered = (const unsigned char*)gathered_device;
+    mp.world = world;
+    mp.L = L;
+    mp.B = B;
+    mp.rec_bytes = record_bytes(B, L);
+    mp.has_dest = has_dest ? 1 : 0;
+    mp.compare_f32 = compare_f32 ? 1 : 0;
+    mp.record = (unsigned char*)ctx->d_record.p;
+    mp.head_out = nullptr;
+    mp.append = append_to_tree ? 1 : 0;
+    mp.parent = parent;
+    if (mp.append) {
+        int rc = tree_ensure(ctx, ctx->tree_upper + L);
+        if (rc) return rc;
+        mp.tree_size = (long long*)ctx->d_tree_size.p;
+        mp.tree_cap = ctx->tree.cap;
+        mp.tree_states = ctx->tree.states;
+        mp.tree_controls = ctx->tree.controls;
+        mp.tree_parent = ctx->tree.parent;
+        mp.tree_slice = ctx->tree.slice;
+        ctx->tree_upper += L;
+    }
+    MPS_CUDA_CHECK(mps_launch_merge_records(mp, ctx->stream), ctx);
+    ctx->launches += 1;
+    if (best_out) {
+        // only the 24-byte head returns to the host
+        int rc = ensure_stage(ctx, sizeof(mps_extend_best));
+        if (rc) return rc;
+        MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_stage, ctx->d_record.p, sizeof(mps_extend_best), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+        MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+        memcpy(best_out, ctx->h_stage, sizeof(mps_extend_best));
+        if (mp.append) return tree_sync_size(ctx);
+    }
+    return MPS_OK;
+}
+
+int mps_extend_head(mps_ctx* ctx, mps_extend_best* best_out)
+{
+    if (!ctx || !best_out) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_head");
+    if (!ctx->extend_ready) return mps_fail(ctx, MPS_ERR_STATE, "no extend uploaded");
+    int rc = ensure_stage(ctx, sizeof(mps_extend_best));
+    if (rc) return rc;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_stage, ctx->d_record.p, sizeof(mps_extend_best), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    memcpy(best_out, ctx->h_stage, sizeof(mps_extend_best));
+    if (ctx->tree.states && ctx->tree_upper != ctx->tree_n) return tree_sync_size(ctx);
     return MPS_OK;
 }
 

@@ -1704,6 +1704,86 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
     }
 }
 
+// Exchange step of the K-sharded extend: every rank holds the all-gathered winner records in rank
+// order and applies the reference's rule to them - strict <, the first index wins (NaiveControlSampler.cpp:55,
+// RRT.cpp:467; on equal keys the lower global chain index, which for contiguous shards is the lower rank) - so
+// all ranks agree on the winner without another exchange.  The winner's record becomes this ctx's record; the
+// GPU that owns the tree appends the winner chain (RearrangementRRT::addToTree RRT.cpp:234-244, up to the first
+// goal state :479-488).  One CTA.
+__global__ void __launch_bounds__(256) merge_records_kernel(MergeParams p)
+{
+    __shared__ int s_win, s_first;
+    const int tid = threadIdx.x;
+    const int L = p.L, B = p.B;
+    if (tid == 0) {
+        int win = -1;
+        double best = 0.0;
+        int best_k = 0;
+        for (int r = 0; r < p.world; ++r) {
+            const mps_extend_best* h = reinterpret_cast<const mps_extend_best*>(p.gathered + (size_t)r * p.rec_bytes);
+            if (h->k < 0) continue;
+            const double key = !p.has_dest ? 0.0 : (p.compare_f32 ? (double)(float)h->distance : h->distance);
+            if (win < 0 || key < best || (key == best && h->k < best_k)) {
+                win = r;
+                best = key;
+                best_k = h->k;
+            }
+        }
+        s_win = win;
+        int first = -1;
+        if (win >= 0 && p.append) {
+            const mps_extend_best* h = reinterpret_cast<const mps_extend_best*>(p.gathered + (size_t)win * p.rec_bytes);
+            const int n_app = h->goal_step >= 0 ? h->goal_step + 1 : h->n_ok;
+            const long long n0 = p.tree_size[0];
+            if ((size_t)(n0 + n_app) <= p.tree_cap) {
+                first = (int)n0;
+                p.tree_size[0] = n0 + n_app;
+            } else {
+                first = -2;
+            }
+        }
+        s_first = first;
+    }
+    __syncthreads();
+    const int win = s_win, first = s_first;
+    const unsigned char* src = p.gathered + (size_t)(win < 0 ? 0 : win) * p.rec_bytes;
+    // the record travels as 32-bit words (it is 8-byte aligned and a multiple of 8 bytes long)
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(p.record);
+    for (size_t i = tid; i < p.rec_bytes / 4; i += blockDim.x) dw[i] = sw[i];
+    __syncthreads();
+    if (tid == 0) {
+        mps_extend_best* h = reinterpret_cast<mps_extend_best*>(p.record);
+        if (win < 0) {
+            h->k = -1;
+            h->n_ok = 0;
+            h->goal_step = -1;
+            h->distance = __longlong_as_double(0x7ff0000000000000ll);
+        }
+        h->tree_index = (win >= 0 && p.append) ? first : -1;
+        if (p.head_out) *p.head_out = *h;
+    }
+    if (win >= 0 && p.append && first >= 0) {
+        const mps_extend_best* h = reinterpret_cast<const mps_extend_best*>(src);
+        const int n_app = h->goal_step >= 0 ? h->goal_step + 1 : h->n_ok;
+        const float* st = reinterpret_cast<const float*>(src + sizeof(mps_extend_best));
+        const float* ct = st + (size_t)L * 3 * B;
+        const size_t cap = p.tree_cap;
+        for (int i = tid; i < n_app * 3 * B; i += blockDim.x) {
+            const int l = i / (3 * B), r = i % (3 * B);
+            p.tree_states[(size_t)r * cap + first + l] = st[(size_t)l * 3 * B + r];
+        }
+        for (int i = tid; i < n_app * MPS_CONTROL_DIM; i += blockDim.x) {
+            const int l = i / MPS_CONTROL_DIM, c = i % MPS_CONTROL_DIM;
+            p.tree_controls[(size_t)c * cap + first + l] = ct[(size_t)l * MPS_CONTROL_DIM + c];
+        }
+        for (int i = tid; i < n_app; i += blockDim.x) {
+            p.tree_parent[first + i] = i == 0 ? p.parent : first + i - 1;
+            p.tree_slice[first + i] = -1;
+        }
+    }
+}
+
 // isValid for M states, one warp per state
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
@@ -1870,6 +1950,12 @@ cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream)
     int threads = p.K >= 1024 ? 1024 : ((p.K + 31) / 32) * 32;
     if (threads < 32) threads = 32;
     select_kernel<<<p.M, threads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_merge_records(const MergeParams& p, cudaStream_t stream)
+{
+    merge_records_kernel<<<1, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

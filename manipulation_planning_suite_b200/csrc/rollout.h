@@ -78,6 +78,24 @@ struct SelectParams {
     int32_t* tree_slice;
 };
 
+// exchange step of the multi-GPU extend: pick the global winner among the gathered per-rank records
+struct MergeParams {
+    const unsigned char* gathered;  // [world][rec_bytes] packed records in rank order
+    int world, L, B;
+    size_t rec_bytes;
+    int has_dest, compare_f32;
+    unsigned char* record;      // [rec_bytes] this ctx's record buffer: receives the winner's record
+    mps_extend_best* head_out;  // optional second copy of the head (pinned host memory), or nullptr
+    // optional tree append on the GPU that owns the tree
+    int append, parent;
+    long long* tree_size;
+    size_t tree_cap;
+    float* tree_states;
+    float* tree_controls;
+    int32_t* tree_parent;
+    int32_t* tree_slice;
+};
+
 struct ValidityParams {
     const DevScene* scene;
     size_t scene_bytes, warp_bytes;
@@ -94,4 +112,5 @@ cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, int n_bodies
 cudaError_t mps_launch_chain_order(const float* controls, const int32_t* n_ctrl, int K, int L, const float accel[3],
                                    float dt, int32_t* order, cudaStream_t stream);
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream);
+cudaError_t mps_launch_merge_records(const MergeParams& p, cudaStream_t stream);
 cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream_t stream);

@@ -50,6 +50,8 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
     sc = ctx.scene
     B = sc.n_bodies
     K = int(num_control_samples)
+    if not (float(sc.x_max) - float(sc.x_min) < 3.0e38 and float(sc.y_max) - float(sc.y_min) < 3.0e38):
+        raise ValueError("the scene's workspace bounds must span a finite range to sample states (default is +-FLT_MAX)")
     forest = api.Forest(ctx, n_instances, max_iterations + 2)
     forest.reset(np.tile(np.asarray(start, np.float32), (n_instances, 1)))
     targets = [int(g[0]) for g in goals]

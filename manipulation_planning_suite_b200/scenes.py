@@ -34,8 +34,42 @@ DURATION_LIMITS = (0.1, 1.0)
 
 
 def default_scene() -> abi.Scene:
+    """The values of mps_scene_defaults (csrc/abi.cu; DESIGN.md §3 / SURVEY.md Appendix A) without loading the CUDA
+    library, so that the CPU-only arms of bench.py never map the product .so;
+    tests/test_abi_and_host.py checks the two byte for byte."""
     sc = abi.Scene()
-    abi.load_library().mps_scene_defaults(sc)
+    sc.vel_iters = 8
+    for i in range(abi.MPS_MAX_BODIES):
+        sc.shape[i] = abi.MPS_SHAPE_BOX
+        sc.hx[i] = 0.06
+        sc.hy[i] = 0.06
+        sc.mass[i] = 0.35
+        sc.inertia[i] = 0.002
+        sc.mu_ground[i] = 0.19
+        sc.fr_radius[i] = 0.0459
+        sc.mu_contact[i] = 0.3
+    for i in range(abi.MPS_MAX_STATICS):
+        sc.s_shape[i] = abi.MPS_SHAPE_BOX
+        sc.s_hx[i] = 0.05
+        sc.s_hy[i] = 0.05
+        sc.s_mu_contact[i] = 0.3
+    flt_max = 3.4028234663852886e38
+    sc.x_min, sc.x_max, sc.y_min, sc.y_max = -flt_max, flt_max, -flt_max, flt_max
+    sc.accel_limits[0], sc.accel_limits[1], sc.accel_limits[2] = 2.0, 2.0, 4.0
+    sc.position_weight = 1.0
+    sc.orientation_weight = 0.08
+    sc.dt = 0.01
+    sc.t_max = 8.0
+    sc.gravity = 9.81
+    sc.slop = 0.002
+    sc.baumgarte = 0.2
+    sc.max_bias_vel = 0.5
+    sc.pen_max = 0.01
+    sc.v_rest = 0.001
+    sc.w_rest = 0.01
+    sc.max_manifolds = abi.MPS_MAX_MANIFOLDS
+    sc.strict_active_contacts = 0
+    sc.jam_steps = 25
     return sc
 
 

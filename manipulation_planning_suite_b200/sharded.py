@@ -104,9 +104,20 @@ def all_gather_records(local: "torch.Tensor", group=None) -> "torch.Tensor":  # 
 
 
 class ShardedExtend:
-    """One extend over all ranks: local rollouts on this rank's device + the record gather."""
+    """One extend over all ranks: local rollouts on this rank's device, ONE all-gather of the packed winner
+    records, and the merge + tree append on the device (mps_extend_merge_records).  Only the 24-byte head of the
+    winner returns to the host.
 
-    def __init__(self, ctx, group=None):
+    Stream order: the rollout, the record copy, the all-gather and the merge are all enqueued on the ctx's own
+    stream (torch sees it as an ExternalStream; NCCL orders its work against the stream that is current when the
+    collective is called), so nothing reads a record before the select kernel has written it - whichever stream
+    the ctx was created on.
+
+    `owner` = the rank whose ctx holds the tree (north_star: the single-tree NN scan stays on one device); only
+    that rank appends the winner chain.
+    """
+
+    def __init__(self, ctx, group=None, owner: int = 0):
         import torch
         import torch.distributed as dist
 
@@ -116,10 +127,16 @@ class ShardedExtend:
         self.torch = torch
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.owner = owner
+        self.device = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=self.device)
         self._buf = None
+        self._gathered = None
+        self._empty = False
 
     def upload(self, start, controls_all, **kw):
-        """controls_all: the full [K][L][5] batch (same on every rank); this rank keeps its slice."""
+        """controls_all: the full [K][L][5] batch (same on every rank); this rank keeps its slice.
+        append_to_tree / parent: the winner of the WHOLE extend is appended on the owner rank (never the local one)."""
         controls_all = np.asarray(controls_all, np.float32)
         if controls_all.ndim == 2:
             controls_all = controls_all[:, None, :]
@@ -127,28 +144,54 @@ class ShardedExtend:
         k0, k1 = shard_range(K, self.rank, self.world)
         n_ctrl = kw.pop("n_ctrl", None)
         if n_ctrl is not None:
-            n_ctrl = np.asarray(n_ctrl, np.int32)[k0:k1]
+            n_ctrl = np.asarray(n_ctrl, np.int32)
+        self.append = bool(kw.pop("append_to_tree", False))
+        self.parent = int(kw.pop("parent", -1))
         self.has_dest = kw.get("dest") is not None
         self.compare_f32 = bool(kw.get("compare_f32", False))
         self.L = controls_all.shape[1]
-        self.ctx.extend_upload(start, controls_all[k0:k1], n_ctrl=n_ctrl, k_offset=k0, **kw)
+        # a rank whose slice is empty (K < world) still takes part in the gather with a k = -1 record; the ctx is
+        # given chain 0 so that its record buffer has the shape of this extend, but nothing is launched
+        self._empty = k1 <= k0
+        if self._empty:
+            k0, k1 = 0, 1
+        self.ctx.extend_upload(start, controls_all[k0:k1], n_ctrl=None if n_ctrl is None else n_ctrl[k0:k1], k_offset=k0, **kw)
         n = self.ctx.record_size()
         if self._buf is None or self._buf.numel() != n:
-            self._buf = self.torch.empty(n, dtype=self.torch.uint8, device="cuda")
+            self._buf = self.torch.empty(n, dtype=self.torch.uint8, device=self.device)
+            self._gbuf = self.torch.empty((self.world, n), dtype=self.torch.uint8, device=self.device)
+            none = Record(-1, 0, -1, -1, float("inf"), np.zeros((self.L, 3 * self.ctx.B), np.float32),
+                          np.zeros((self.L, 5), np.float32), np.zeros(self.L, np.uint32))
+            self._none = self.torch.from_numpy(pack_record(none, self.ctx.B, self.L)).to(self.device)
 
     def launch(self):
-        """Enqueue rollouts + select + record copy + all-gather on the current stream; no host sync."""
-        self.ctx.extend_launch()
-        self.ctx.record_to(self._buf.data_ptr())
-        if self.world > 1:
-            self._gathered = all_gather_records(self._buf, self.group)
-        else:
-            self._gathered = self._buf.view(1, -1)
-        return self._gathered
+        """Enqueue rollouts + select + record copy + all-gather + merge (+ append on the owner) on the ctx stream;
+        no host synchronisation."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            if self._empty:
+                self._buf.copy_(self._none, non_blocking=True)
+            else:
+                self.ctx.extend_launch()
+                self.ctx.record_to(self._buf.data_ptr())
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self._gbuf.view(-1), self._buf, group=self.group)
+                gathered = self._gbuf
+            else:
+                gathered = self._buf.view(1, -1)
+            self._gathered = gathered
+            self.ctx.merge_records(gathered.data_ptr(), self.world, self.has_dest, self.compare_f32,
+                                   append_to_tree=self.append and self.rank == self.owner, parent=self.parent)
+        return gathered
+
+    def head(self) -> abi.ExtendBest:
+        """The 24-byte head of the merged winner (k is the global chain index; tree_index is set on the owner)."""
+        return self.ctx.extend_head()
 
     def result(self) -> Record | None:
-        """Device -> host read of the gathered records and the rank-independent merge."""
-        host = self._gathered.cpu().numpy()
-        recs = [unpack_record(host[r], self.ctx.B, self.L) for r in range(host.shape[0])]
-        w = merge_records(recs, self.has_dest, self.compare_f32)
-        return None if w < 0 else recs[w]
+        """Head + winner chain of the merged record (device -> host copy of one record)."""
+        K, L = self.ctx._ext_shape
+        r = self.ctx.extend_fetch()
+        if r.k < 0:
+            return None
+        return Record(r.k, r.n_ok, r.goal_step, r.tree_index, r.distance, r.best_states, r.best_controls, r.best_flags)

@@ -57,6 +57,12 @@ def test_scene_defaults_follow_the_reference_defaults():
     assert sc.strict_active_contacts == 0                                 # SimEnvStatePropagator.cpp:79 quirk kept
 
 
+def test_python_scene_defaults_equal_the_library_defaults():
+    lib_sc = abi.Scene()
+    abi.load_library().mps_scene_defaults(lib_sc)
+    assert bytes(lib_sc) == bytes(scenes.default_scene())
+
+
 def test_no_device_is_a_hard_error():
     lib = abi.load_library()
     n = C.c_int(0)

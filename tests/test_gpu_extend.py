@@ -398,3 +398,89 @@ def test_baseline_config4_shape_determinism_and_sampled_parity():
     assert np.array_equal(a.all_flags[idx], want["all_flags"]) and np.array_equal(a.all_dist[idx], want["all_dist"])
     assert_states_close(a.all_states[idx], want["all_states"], want["all_flags"])
     ctx.close()
+
+
+def test_sharded_extend_world_1_equals_ctx_extend_and_appends_on_the_device():
+    """ShardedExtend on one rank: rollouts, record copy, merge kernel and the tree append all on the device, only the
+    24-byte head comes back; same winner, same appended nodes as ctx.extend(append_to_tree=True)."""
+    import torch
+
+    from manipulation_planning_suite_b200 import sharded
+
+    sc, _ = scenes.make_scene(6, seed=21)
+    start = scenes.cluttered_start(sc, 21)
+    rng = np.random.RandomState(21)
+    K, L = 96, 3
+    controls = scenes.sample_controls_towards(rng, sc, start, K, L)
+    n_ctrl = rng.randint(1, L + 1, size=K).astype(np.int32)
+    dest = scenes.sample_state(rng, sc)
+    ref_ctx = api.Context(sc)
+    ref_tree = api.NearestNeighbors(ref_ctx)
+    ref_tree.add(start)
+    want = ref_ctx.extend(start, controls, n_ctrl=n_ctrl, dest=dest, compare_f32=True, append_to_tree=True, parent=0)
+    # the ctx of the sharded extend lives on its own non-blocking stream (not torch's current one): the stream
+    # order must still hold
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.add(start)
+    sh = sharded.ShardedExtend(ctx)
+    for _ in range(2):  # twice: the second run appends below the same parent again
+        sh.upload(start, controls, n_ctrl=n_ctrl, dest=dest, compare_f32=True, append_to_tree=True, parent=0)
+        sh.launch()
+        head = sh.head()
+        assert (head.k, head.n_ok, head.goal_step, head.distance) == (want.k, want.n_ok, want.goal_step, want.distance)
+    assert head.tree_index == 1 + want.n_ok
+    rec = sh.result()
+    assert np.array_equal(rec.states, want.best_states) and np.array_equal(rec.controls, want.best_controls)
+    assert tree.size() == 1 + 2 * want.n_ok and ref_tree.size() == 1 + want.n_ok
+    for i in range(want.n_ok):
+        a, b = tree.get(1 + i), ref_tree.get(1 + i)
+        c = tree.get(1 + want.n_ok + i)
+        for x, y in zip(a, b):          # (state, parent, control, slice id): same node as the fused append made
+            assert np.array_equal(x, y)
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[2], c[2])   # second run: same chain again
+        assert c[1] == (0 if i == 0 else want.n_ok + i)
+    torch.cuda.synchronize()
+    ctx.close()
+    ref_ctx.close()
+
+
+def test_merge_kernel_follows_the_reference_tie_rules():
+    """mps_extend_merge_records on hand-made gathered records: strict <, first rank wins equal keys, float compare
+    when asked, records without a valid chain are skipped, no valid record -> k = -1; equal to the host mirror
+    sharded.merge_records."""
+    import torch
+
+    from manipulation_planning_suite_b200 import sharded
+
+    sc, _ = scenes.make_scene(3, seed=5)
+    B, L = sc.n_bodies, 2
+    start = scenes.cluttered_start(sc, 5)
+    ctx = api.Context(sc)
+    ctx.extend_upload(start, np.zeros((1, L, 5), np.float32), dest=start)   # shapes the ctx's record buffer
+    rng = np.random.RandomState(0)
+
+    def rec(k, d):
+        return sharded.Record(k, 1 if k >= 0 else 0, -1, -1, d, rng.rand(L, 3 * B).astype(np.float32),
+                              rng.rand(L, 5).astype(np.float32), np.array([3, 0], np.uint32))
+
+    d0 = 1.0 + 2.0 ** -30   # equal to 1.0 as a float, larger as a double
+    cases = [([rec(5, 2.0), rec(40, 1.5), rec(70, 1.5)], True, False),
+             ([rec(-1, np.inf), rec(40, 3.0), rec(70, 2.5)], True, False),
+             ([rec(5, d0), rec(40, 1.0), rec(70, 7.0)], True, True),
+             ([rec(5, d0), rec(40, 1.0), rec(70, 7.0)], True, False),
+             ([rec(-1, np.inf), rec(-1, np.inf)], True, False),
+             ([rec(-1, np.inf), rec(33, 9.0), rec(70, 1.0)], False, False)]
+    for recs, has_dest, cf32 in cases:
+        host = np.stack([sharded.pack_record(r, B, L) for r in recs])
+        dev = torch.from_numpy(host).cuda()
+        torch.cuda.synchronize()
+        head = ctx.merge_records(dev.data_ptr(), len(recs), has_dest, cf32, wait=True)
+        w = sharded.merge_records(recs, has_dest, cf32)
+        if w < 0:
+            assert head.k == -1 and head.n_ok == 0 and np.isinf(head.distance)
+        else:
+            assert (head.k, head.distance) == (recs[w].k, recs[w].distance)
+            got = ctx.extend_fetch()
+            assert np.array_equal(got.best_states, recs[w].states) and np.array_equal(got.best_controls, recs[w].controls)
+    ctx.close()

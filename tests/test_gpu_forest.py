@@ -93,3 +93,46 @@ def test_multi_seed_naive_rrt_sweep_solutions_replay(device_sampling):
     assert np.array_equal(res2.solved_iteration, res.solved_iteration[32:])
     ctx.close()
     ctx2.close()
+
+
+def test_forest_calls_validate_what_the_device_would_dereference():
+    """a forest that was reserved but never reset has no roots; parents / goal bodies outside their ranges and a
+    workspace without finite bounds are argument errors, not out-of-bounds reads or NaN samples"""
+    from manipulation_planning_suite_b200 import abi
+
+    sc, start = scenes.make_scene(3, seed=1001)
+    ctx = api.Context(sc)
+    forest = api.Forest(ctx, 4, 16)
+    ids = np.arange(4, dtype=np.int32)
+    controls = np.zeros((4, 2, 1, 5), np.float32)
+    controls[..., 3] = 0.1
+    with pytest.raises(api.MpsError) as e:
+        forest.extend(ids, np.zeros(4, np.int32), controls)
+    assert e.value.code == abi.MPS_ERR_STATE
+    with pytest.raises(api.MpsError) as e:
+        forest.nearest(ids, np.tile(start, (4, 1)))
+    assert e.value.code == abi.MPS_ERR_STATE
+    forest.reset(np.tile(start, (4, 1)))
+    for bad in (-1, 10 ** 6):
+        parents = np.zeros(4, np.int32)
+        parents[2] = bad
+        with pytest.raises(api.MpsError) as e:
+            forest.extend(ids, parents, controls)
+        assert e.value.code == abi.MPS_ERR_ARG
+    with pytest.raises(api.MpsError) as e:
+        forest.extend(ids, np.zeros(4, np.int32), controls, goals=[(17, 0.0, 0.0, 0.1)])
+    assert e.value.code == abi.MPS_ERR_ARG
+    forest.extend(ids, np.zeros(4, np.int32), controls)   # and the valid call still runs
+    ctx.close()
+    # +-FLT_MAX workspace (the scene default): sampling states from it is refused
+    sc2, start2 = scenes.make_scene(3, seed=1001)
+    sc2.x_min, sc2.x_max = -3.4e38, 3.4e38
+    ctx2 = api.Context(sc2)
+    f2 = api.Forest(ctx2, 2, 8)
+    f2.reset(np.tile(start2, (2, 1)))
+    with pytest.raises(api.MpsError) as e:
+        f2.naive_step(np.arange(2, dtype=np.int32), 0, 1, [(1, 0.0, 0.0, 0.1)])
+    assert e.value.code == abi.MPS_ERR_ARG
+    with pytest.raises(ValueError):
+        multi_seed.naive_rrt_sweep(ctx2, start2, [(1, 0.0, 0.0, 0.1)], n_instances=2, max_iterations=2)
+    ctx2.close()
