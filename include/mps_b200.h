@@ -67,7 +67,7 @@ extern "C" {
 #define MPS_F_BAD_CONTACT (1u << 8) /* result has a contact the policy forbids       */
 #define MPS_F_OVERFLOW (1u << 9)    /* more touching pairs than max_manifolds        */
 #define MPS_F_ACTIVE_CONTACT (1u << 10) /* strict_active_contacts only               */
-#define MPS_F_JAMMED (1u << 11)     /* rest phase aborted: penetration > 2 * slop for jam_steps steps */
+#define MPS_F_JAMMED (1u << 11)     /* rest phase aborted: penetration > 1.25 * slop for jam_steps steps */
 
 /*
  * Scene = everything that is fixed for a planning problem: bodies, statics,
@@ -128,7 +128,7 @@ typedef struct mps_scene {
     float w_rest;       /* atRest angular threshold */
     int32_t max_manifolds;          /* touching-pair capacity per rollout, <= MPS_MAX_MANIFOLDS */
     int32_t strict_active_contacts; /* 0 = replicate SimEnvStatePropagator.cpp:79 shadowing quirk */
-    int32_t jam_steps;              /* rest phase gives up after this many consecutive steps deeper than 2 * slop; 0 = never */
+    int32_t jam_steps;              /* rest phase gives up after this many consecutive steps deeper than 1.25 * slop; 0 = never */
 } mps_scene;
 
 /* RelocationGoalSpecification reduced to what distanceGoal reads (ObjectsRelocationGoal.cpp:108-123) */

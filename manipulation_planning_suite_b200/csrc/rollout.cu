@@ -1416,8 +1416,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                         ok = false;
                     }
                     rest += sc.dt;
-                    // jam rule: wedged deeper than 2 * slop for jam_steps consecutive rest steps
-                    jam = pen > 2.0f * sc.slop ? jam + 1 : 0;
+                    // jam rule: wedged deeper than 1.25 * slop for jam_steps consecutive rest steps
+                    jam = pen > 1.25f * sc.slop ? jam + 1 : 0;
                     if (sc.jam_steps > 0 && jam >= sc.jam_steps) {
                         flags |= MPS_F_JAMMED;
                         ok = false;

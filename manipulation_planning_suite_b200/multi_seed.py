@@ -46,7 +46,10 @@ def _sample_controls(rng: np.random.Generator, n: int) -> np.ndarray:
 def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int, num_control_samples: int = 10,
                     max_iterations: int = 500, seed: int = 1, goal_bias: float = 0.2, target_bias: float = 0.25,
                     robot_bias: float = 0.0, wall_timeout: float = 1e9, instance_offset: int = 0,
-                    candidates_per_sample: int = 8, device_sampling: bool = False) -> SweepResult:
+                    candidates_per_sample: int = 8, device_sampling: bool = False,
+                    stop_fraction: float = 0.0) -> SweepResult:
+    """stop_fraction > 0: the sweep ends as soon as that fraction of this call's instances has reached the goal
+    (time-to-solution runs: the stragglers would otherwise run to max_iterations)."""
     sc = ctx.scene
     B = sc.n_bodies
     K = int(num_control_samples)
@@ -103,6 +106,8 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
         for it in range(max_iterations):
             if len(active) == 0 or time.perf_counter() - t0 > wall_timeout:
                 break
+            if stop_fraction > 0.0 and n_instances - len(active) >= stop_fraction * n_instances:
+                break
             ta = time.perf_counter()
             res = forest.naive_step(active, it, seed, goals, K=K, C_=C, goal_bias=goal_bias, target_bias=target_bias,
                                     robot_bias=robot_bias, instance_offset=instance_offset)
@@ -125,6 +130,8 @@ def naive_rrt_sweep(ctx: api.Context, start: np.ndarray, goals, n_instances: int
     span = np.array([sc.x_max - sc.x_min, sc.y_max - sc.y_min, 2 * np.pi], np.float32)
     for it in range(max_iterations):
         if len(active) == 0 or time.perf_counter() - t0 > wall_timeout:
+            break
+        if stop_fraction > 0.0 and n_instances - len(active) >= stop_fraction * n_instances:
             break
         ta = time.perf_counter()
         rnd = ahead.result()

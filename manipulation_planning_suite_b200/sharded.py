@@ -156,6 +156,9 @@ class ShardedExtend:
         if self._empty:
             k0, k1 = 0, 1
         self.ctx.extend_upload(start, controls_all[k0:k1], n_ctrl=None if n_ctrl is None else n_ctrl[k0:k1], k_offset=k0, **kw)
+        self._ensure_buffers()
+
+    def _ensure_buffers(self):
         n = self.ctx.record_size()
         if self._buf is None or self._buf.numel() != n:
             self._buf = self.torch.empty(n, dtype=self.torch.uint8, device=self.device)
@@ -163,6 +166,21 @@ class ShardedExtend:
             none = Record(-1, 0, -1, -1, float("inf"), np.zeros((self.L, 3 * self.ctx.B), np.float32),
                           np.zeros((self.L, 5), np.float32), np.zeros(self.L, np.uint32))
             self._none = self.torch.from_numpy(pack_record(none, self.ctx.B, self.L)).to(self.device)
+
+    def upload_local(self, start, controls_local, k_offset: int, **kw):
+        """This rank's slice only (each rank generated / received just its own chains): controls_local [k][L][5] are
+        the chains [k_offset, k_offset + k) of the extend."""
+        controls_local = np.asarray(controls_local, np.float32)
+        if controls_local.ndim == 2:
+            controls_local = controls_local[:, None, :]
+        self.append = bool(kw.pop("append_to_tree", False))
+        self.parent = int(kw.pop("parent", -1))
+        self.has_dest = kw.get("dest") is not None
+        self.compare_f32 = bool(kw.get("compare_f32", False))
+        self.L = controls_local.shape[1]
+        self._empty = False
+        self.ctx.extend_upload(start, controls_local, k_offset=int(k_offset), **kw)
+        self._ensure_buffers()
 
     def launch(self):
         """Enqueue rollouts + select + record copy + all-gather + merge (+ append on the owner) on the ctx stream;

@@ -972,9 +972,10 @@ static int propagate_impl(const mps_scene* sc, const float* state_in, float* con
                 ok = 0;
             }
             /* jam rule (spec §3.6): the robot has stopped.  A free contact sheds its penetration beyond
-             * the slop by the factor (1 - baumgarte) per step, so a world that stays deeper than 2 * slop
-             * for jam_steps consecutive steps is wedged and will not come to rest */
-            jam = wd.max_pen > 2.0f * sc->slop ? jam + 1 : 0;
+             * the slop by the factor (1 - baumgarte) per step, so even from pen_max it is within 0.25 * slop of the
+             * slop after 13 steps: a world that stays deeper than 1.25 * slop for jam_steps (25) consecutive
+             * steps is wedged between bodies that do not give way and would creep until t_max */
+            jam = wd.max_pen > 1.25f * sc->slop ? jam + 1 : 0;
             if (sc->jam_steps > 0 && jam >= sc->jam_steps) {
                 flags |= MPS_F_JAMMED;
                 ok = 0;

@@ -10,7 +10,7 @@ import bench  # noqa: E402
 from manipulation_planning_suite_b200 import api, scenes  # noqa: E402
 
 K = int(os.environ.get("PROF_K", "1024"))
-sc, start, batches, goals = bench.make_workload(0, 1, 1)
+sc, start, batches, goals = bench.make_workload([0], 1)
 c, n, d = batches[0]
 ctx = api.Context(sc)
 ctx.extend_upload(start, c[:K], n_ctrl=n[:K], dest=d, compare_f32=True, goals=goals)

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import bench
 from manipulation_planning_suite_b200 import api
-sc, start, batches, goals = bench.make_workload(0, 1, 1)
+sc, start, batches, goals = bench.make_workload([0], 1)
 c, n, d = batches[0]
 ctx = api.Context(sc)
 ctx.extend_upload(start, c, n_ctrl=n, dest=d, compare_f32=True, goals=goals)

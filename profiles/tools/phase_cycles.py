@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import bench
 from manipulation_planning_suite_b200 import api
-sc, start, batches, goals = bench.make_workload(0, 1, 3)
+sc, start, batches, goals = bench.make_workload([0], 3)
 names = ["broad phase", "narrow phase", "round scheduling", "solver rounds", "friction+schedule+solve+integrate", "contact steps"]
 for bi in range(3):
     c, n, d = batches[bi]

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 from manipulation_planning_suite_b200 import api, scenes  # noqa: E402
 
 n_batches = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-sc, start, batches, goals = bench.make_workload(0, 1, n_batches)
+sc, start, batches, goals = bench.make_workload([0], n_batches)
 ctx = api.Context(sc)
 for i in range(2):
     c, n, d = batches[i]

@@ -517,7 +517,7 @@ def propagate(sc, state, control):
             if wd.overflow:
                 flags |= F_OVERFLOW
                 ok = False
-            jam = jam + 1 if wd.max_pen > f32(2.0) * f32(sc.slop) else 0
+            jam = jam + 1 if wd.max_pen > f32(1.25) * f32(sc.slop) else 0
             if int(sc.jam_steps) > 0 and jam >= int(sc.jam_steps):
                 flags |= F_JAMMED
                 ok = False

@@ -361,7 +361,7 @@ def test_baseline_config2_whole_batch_matches_oracle():
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
-    sc, start, batches, goals = bench.make_workload(0, 1, 2)
+    sc, start, batches, goals = bench.make_workload([0], 2)
     controls, n_ctrl, dest = batches[1]
     ctx = api.Context(sc)
     got = ctx.extend(start, controls, dump=True, n_ctrl=n_ctrl, dest=dest, compare_f32=True, goals=goals)
