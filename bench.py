@@ -630,7 +630,7 @@ def bench_nn(api, scenes, device, flush):
         if hasattr(tree, "nearest_k"):
             out["top_k"] = bench_nn_topk(tree, qs, flush, stream, torch, N, B)
         if hasattr(tree, "nearest_two_level"):
-            out["slice_two_level"] = bench_nn_two_level(tree, qs, sc, flush, stream, torch)
+            out["slice_two_level"] = bench_nn_two_level(api, tree, qs, sc, flush, stream, torch, device)
         ctx.close()
     hbm, src = peaks()
     bytes_alg = N * 3 * B * 4
@@ -649,6 +649,7 @@ def bench_nn(api, scenes, device, flush):
 
 
 def bench_nn_topk(tree, qs, flush, stream, torch, N, B):
+    """mps_tree_nearest_k: one streaming pass with warp-level top-k lists + exact fix-up (csrc/nn_scan.cu)"""
     res = {}
     for k in (1, 8, 32):
         tree.nearest_k(qs[0], k)
@@ -659,27 +660,48 @@ def bench_nn_topk(tree, qs, flush, stream, torch, N, B):
             t0 = time.perf_counter()
             tree.nearest_k(qs[1 + i], k)
             ts.append(time.perf_counter() - t0)
-        ms = tree.ctx.time_launches(2, 10) / 10 if hasattr(tree.ctx, "time_launches") else float("nan")
+        ms = tree.ctx.time_launches(2, 10) / 10
         res[f"k{k}"] = {"e2e_us_per_query": round(float(np.median(ts)) * 1e6, 1), "kernel_us_back_to_back": round(ms * 1e3, 2),
                         "GBps_algorithmic": round(N * 3 * B * 4 / (ms * 1e-3) / 1e9, 1)}
+    res["fallbacks"] = tree.nearest_k_fallbacks()
     return res
 
 
-def bench_nn_two_level(tree, qs, sc, flush, stream, torch):
-    """SliceBasedOracleRRT's query (RRT.cpp:766-884): nearest slice representative under the robot-only metric, then
-    the nearest member of that slice under the full metric; the second scan takes its slice filter from the first
-    scan's result on the device (two launches, one synchronise)."""
-    ts = []
-    for i in range(3):
-        tree.nearest_two_level(qs[i], rep_mask=1 << sc.robot_id)
-    for i in range(20):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        tree.nearest_two_level(qs[3 + i], rep_mask=1 << sc.robot_id)
-        ts.append(time.perf_counter() - t0)
-    return {"e2e_us_per_query": round(float(np.median(ts)) * 1e6, 1), "n_slices": NN_CFG["n_slices"],
-            "note": "slice representatives = first node of each slice; both scans over the 1 M-node tree"}
+def bench_nn_two_level(api, tree, qs, sc, flush, stream, torch, device):
+    """SliceBasedOracleRRT's query (RRT.cpp:783-827): nearest slice representative under the arrangement metric, then
+    the nearest member of that slice under the robot-only metric.  Chained on the device (the second scan reads its
+    slice filter from the first scan's result; one wait) against two host round trips."""
+    B = sc.n_bodies
+    rng = np.random.RandomState(3)
+    n_slices = NN_CFG["n_slices"]
+    rctx = api.Context(sc, device=device, stream=stream.cuda_stream)
+    rtree = api.NearestNeighbors(rctx)
+    reps = np.empty((n_slices, 3 * B), np.float32)
+    reps[:, 0::3] = rng.uniform(sc.x_min, sc.x_max, size=(n_slices, B))
+    reps[:, 1::3] = rng.uniform(sc.y_min, sc.y_max, size=(n_slices, B))
+    reps[:, 2::3] = rng.uniform(-np.pi, np.pi, size=(n_slices, B))
+    rtree.add_batch(reps)
+    arr_mask, robot_mask = ((1 << B) - 1) & ~(1 << sc.robot_id), 1 << sc.robot_id
+    out = {}
+    for name in ("chained", "two_round_trips"):
+        ts = []
+        for i in range(23):
+            if i >= 3:
+                flush.zero_()
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if name == "chained":
+                r = tree.nearest_two_level(rtree, qs[i], arr_mask, robot_mask)
+            else:
+                ri, rd = rtree.nearest(qs[i], mask=arr_mask)
+                r = ((ri, rd), tree.nearest(qs[i], mask=robot_mask, slice_filter=ri))
+            if i >= 3:
+                ts.append(time.perf_counter() - t0)
+        out[name + "_e2e_us_per_query"] = round(float(np.median(ts)) * 1e6, 1)
+    out["n_slices"] = n_slices
+    out["note"] = "second scan: 1 M nodes, robot sub-state rows only (12 MB) + the slice ids (4 MB)"
+    rctx.close()
+    return out
 
 
 def bench_throughput(api, scenes, device, fp32_peak):

@@ -241,6 +241,22 @@ int mps_tree_add_batch(mps_ctx* ctx, const float* states, const int32_t* parents
  * ties -> lowest index.  slice_filter >= 0 restricts to nodes of that slice; -1 = all. */
 int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask,
                      int32_t slice_filter, int64_t* index, double* distance);
+/* ompl::NearestNeighbors<MotionPtr>::nearestK of the interface the planners hold their tree through
+ * (include/mps/planner/pushing/algorithm/RRT.h:149): the k <= 32 nearest nodes, ascending by (double distance,
+ * node index) - the order a sequential double scan with strict < would produce.  *n_found <= k (fewer nodes in the
+ * tree / the slice).  One streaming pass with warp-level top-k lists; exact (see csrc/nn_scan.cu). */
+int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
+                       int32_t k, int64_t* indices, double* distances, int32_t* n_found);
+/* how many mps_tree_nearest_k calls had to be redone by exact successor scans (diagnostic) */
+int mps_tree_nearest_k_fallbacks(mps_ctx* ctx, int64_t* count);
+/* SliceBasedOracleRRT's two-level search (RRT.cpp:783-827: _slices_nn->nearest, then the slice's own
+ * slice_samples_nn->nearest) as two scans chained on the device: the nearest slice representative in `reps` (a
+ * second context on the same device whose node index is the slice id) under rep_mask, then the nearest node of
+ * this context's tree under member_mask among the nodes of that slice.  No host round trip between the two; valid
+ * when the sample is not adjusted between the levels (active object = robot).  index = -1 when the slice is empty. */
+int mps_tree_nearest_two_level(mps_ctx* ctx, mps_ctx* reps, const float* query, const float* weights, uint32_t rep_mask,
+                               uint32_t member_mask, int64_t* rep_index, double* rep_distance, int64_t* index,
+                               double* distance);
 /* Q queries, one launch per query batch; masks/filters per query may be NULL (= all / -1) */
 int mps_tree_nearest_batch(mps_ctx* ctx, const float* queries, int32_t Q, const float* weights,
                            const uint32_t* masks, const int32_t* slice_filters, int64_t* indices,
@@ -336,7 +352,7 @@ int mps_extend_merge_records(mps_ctx* ctx, const void* gathered_device, int32_t 
 int mps_extend_head(mps_ctx* ctx, mps_extend_best* best_out);
 
 /* ---- timing helper ---------------------------------------------------- */
-/* Runs `iters` back-to-back launches of the uploaded extend (what=0) or NN batch (what=1)
+/* Runs `iters` back-to-back launches of the uploaded extend (what=0), NN batch (what=1) or last top-k query (what=2)
  * on the ctx stream between two CUDA events and returns the elapsed milliseconds. */
 int mps_time_launches(mps_ctx* ctx, int32_t what, int32_t iters, float* elapsed_ms);
 /* Per-launch device time of the rollout kernel: when enabled, every mps_extend_launch brackets the

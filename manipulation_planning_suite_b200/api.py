@@ -340,6 +340,36 @@ class NearestNeighbors:
                                                   slice_filter, C.byref(idx), C.byref(d)))
         return idx.value, d.value
 
+    def nearest_k(self, query, k: int, weights=None, mask=None, slice_filter: int = -1):
+        """ompl nearestK: (indices [n], distances [n]) of the n <= k nearest nodes, ascending (double distance, index)"""
+        B = self.ctx.B
+        q = _f32(query, (3 * B,))
+        w = _f32(weights, (B,))
+        full = (1 << B) - 1 if B < 32 else 0xFFFFFFFF
+        idx = np.zeros(k, np.int64)
+        d = np.zeros(k, np.float64)
+        n = C.c_int32(0)
+        self.ctx._check(self.lib.mps_tree_nearest_k(self.ctx.h, _fp(q), _fp(w), full if mask is None else int(mask),
+                                                    int(slice_filter), int(k), _fp(idx, C.c_int64), _fp(d, C.c_double),
+                                                    C.byref(n)))
+        return idx[: n.value], d[: n.value]
+
+    def nearest_k_fallbacks(self) -> int:
+        n = C.c_int64(0)
+        self.ctx._check(self.lib.mps_tree_nearest_k_fallbacks(self.ctx.h, C.byref(n)))
+        return n.value
+
+    def nearest_two_level(self, reps: "NearestNeighbors", query, rep_mask: int, member_mask: int, weights=None):
+        """chained two-level search: ((rep_index, rep_distance), (index, distance)); reps = the tree of slice
+        representatives (node index = slice id) in a second context on the same device"""
+        B = self.ctx.B
+        q = _f32(query, (3 * B,))
+        w = _f32(weights, (B,))
+        ri, rd, i, d = C.c_int64(-1), C.c_double(0), C.c_int64(-1), C.c_double(0)
+        self.ctx._check(self.lib.mps_tree_nearest_two_level(self.ctx.h, reps.ctx.h, _fp(q), _fp(w), int(rep_mask), int(member_mask),
+                                                            C.byref(ri), C.byref(rd), C.byref(i), C.byref(d)))
+        return (ri.value, rd.value), (i.value, d.value)
+
     def nearest_batch(self, queries, weights=None, masks=None, slice_filters=None):
         B = self.ctx.B
         qs = _f32(queries).reshape(-1, 3 * B)

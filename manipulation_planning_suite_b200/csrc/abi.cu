@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -74,8 +76,13 @@ struct mps_ctx {
     void* h_nn_out = nullptr;  // pinned: idx[Q] | dist[Q]
     size_t h_nn_out_bytes = 0;
     NNParams np;
+    TopKParams topk;
+    bool topk_ready = false;
+    long long topk_fallbacks = 0;
     bool nn_ready = false;
     bool nn_direct = false;  // the pending query's result lands in h_nn_out without a copy
+    unsigned int nn_seq = 0;  // sequence number of the last single query (completion flag in h_nn_out)
+    DevBuf d_topk_keys, d_topk_rej, d_topk_out;  // top-k: per-CTA lists, dropped minima, idx[32] | dist[32] | meta[2]
     int nn_Q = 0;
 
     // forest (multi-instance batches)
@@ -636,7 +643,8 @@ int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const
             ctx->h_nn_out = nullptr;
         }
         ctx->h_nn_out_bytes = 16 * (size_t)(Q < 256 ? 256 : Q);
-        MPS_CUDA_CHECK(cudaMallocHost(&ctx->h_nn_out, ctx->h_nn_out_bytes), ctx);
+        MPS_CUDA_CHECK(cudaMallocHost(&ctx->h_nn_out, ctx->h_nn_out_bytes + 64), ctx);  // + the completion flag
+        memset(ctx->h_nn_out, 0, ctx->h_nn_out_bytes + 64);
     }
     const int max_grid = ctx->num_sms * 16;
     if ((rc = ensure(ctx, ctx->d_part_d, sizeof(double) * (size_t)Q * max_grid))) return rc;
@@ -678,6 +686,14 @@ int mps_tree_nearest_upload(mps_ctx* ctx, const float* queries, int32_t Q, const
     }
     NNParams& np = ctx->np;
     memset(&np, 0, sizeof(np));
+    {
+        // absolute slack of the fp32 candidate filter: the wrapped arc carries a few 1e-7 rad of absolute error
+        // per body whatever the distance (nn_scan.cu); bounded with the largest weight and all B bodies
+        float wmax = 1.0f;
+        if (weights)
+            for (int i = 0; i < B; ++i) wmax = fmaxf(wmax, fabsf(weights[i]));
+        np.abs_eps = 1.0e-15f + 1.5e-6f * (float)ctx->scene.orientation_weight * wmax * (float)B;
+    }
     np.queries = (const float*)ctx->d_queries.p;
     np.masks = masks ? (const uint32_t*)ctx->d_masks.p : nullptr;
     np.filters = slice_filters ? (const int32_t*)ctx->d_filters.p : nullptr;
@@ -743,18 +759,178 @@ int mps_tree_nearest_batch(mps_ctx* ctx, const float* queries, int32_t Q, const 
     return mps_tree_nearest_fetch(ctx, indices, distances);
 }
 
+// waits for the completion flag the scan's last CTA writes behind its result in pinned host memory (a few hundred
+// nanoseconds after the write instead of the microseconds a stream synchronise takes to return); falls back to the
+// synchronise if the flag has not appeared after 20 ms (a failed launch never sets it)
+static int nn_wait_flag(mps_ctx* ctx, unsigned int seq)
+{
+    volatile unsigned int* flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0x3ff) == 0 &&
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
+            MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+            if (*flag != seq) return mps_fail(ctx, MPS_ERR_CUDA, "nearest-neighbour scan finished without a result");
+            break;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return MPS_OK;
+}
+
 int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
                      int64_t* index, double* distance)
 {
-    // One query, one launch, one synchronise: the query rides in the kernel parameters and the last CTA writes
-    // (index, distance) straight into pinned host memory (device-visible under unified addressing).
+    // One query, one launch, no synchronise: the query rides in the kernel parameters, the last CTA writes
+    // (index, distance) and then a sequence number straight into pinned host memory, the host waits for the number.
     int rc = mps_tree_nearest_upload(ctx, query, 1, weights, &mask, &slice_filter);
     if (rc) return rc;
     ctx->np.out_idx = (long long*)ctx->h_nn_out;
     ctx->np.out_dist = (double*)((char*)ctx->h_nn_out + 8);
+    ctx->np.done_flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    ctx->np.done_seq = ++ctx->nn_seq ? ctx->nn_seq : ++ctx->nn_seq;
     ctx->nn_direct = true;
     if ((rc = mps_tree_nearest_launch(ctx))) return rc;
-    return mps_tree_nearest_fetch(ctx, index, distance);
+    if ((rc = nn_wait_flag(ctx, ctx->np.done_seq))) return rc;
+    ctx->np.done_flag = nullptr;  // a re-launch of the cached query (mps_time_launches) does not signal
+    if (index) memcpy(index, ctx->h_nn_out, 8);
+    if (distance) memcpy(distance, (char*)ctx->h_nn_out + 8, 8);
+    return MPS_OK;
+}
+
+// SliceBasedOracleRRT's two-level search without a host round trip between the levels (RRT.cpp:783-827 when the
+// sample needs no oracle adjustment, i.e. the active object is the robot): scan 1 finds the nearest slice
+// representative in `reps` (a second context whose node index is the slice id) under rep_mask, scan 2 - enqueued
+// right behind it on this context's stream - finds the nearest node of the main tree under member_mask among the
+// nodes of that slice, taking its slice filter from scan 1's result in device memory.  One wait for both.
+int mps_tree_nearest_two_level(mps_ctx* ctx, mps_ctx* reps, const float* query, const float* weights, uint32_t rep_mask,
+                               uint32_t member_mask, int64_t* rep_index, double* rep_distance, int64_t* index,
+                               double* distance)
+{
+    if (!ctx || !reps || !query) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_tree_nearest_two_level");
+    if (reps->device != ctx->device || reps->scene.n_bodies != ctx->scene.n_bodies)
+        return mps_fail(ctx, MPS_ERR_ARG, "the two contexts must share the device and the scene");
+    int rc;
+    int32_t none = -1;
+    // scan 1 on the representatives' tree, result in this ctx's device result block (slot 1)
+    if ((rc = tree_sync_size(reps))) return rc;
+    if (reps->stream != ctx->stream) MPS_CUDA_CHECK(cudaStreamSynchronize(reps->stream), ctx);  // its pending appends
+    if ((rc = mps_tree_nearest_upload(ctx, query, 1, weights, &rep_mask, &none))) return rc;
+    if ((rc = ensure(ctx, ctx->d_nn_out, 64))) return rc;
+    NNParams p1 = ctx->np;
+    p1.tree = reps->tree;
+    p1.n = reps->tree_n;
+    p1.grid_x = mps_nn_grid_x(p1.n, ctx->num_sms);
+    p1.out_idx = (long long*)ctx->d_nn_out.p;
+    p1.out_dist = (double*)((char*)ctx->d_nn_out.p + 8);
+    MPS_CUDA_CHECK(mps_launch_nn_scan(p1, ctx->stream), ctx);
+    // scan 2 on the main tree, filter = scan 1's index, result + flag in pinned memory
+    if ((rc = tree_sync_size(ctx))) return rc;
+    NNParams p2 = ctx->np;
+    p2.tree = ctx->tree;
+    p2.n = ctx->tree_n;
+    p2.grid_x = mps_nn_grid_x(p2.n, ctx->num_sms);
+    p2.inline_mask = member_mask;
+    p2.filter_from = p1.out_idx;
+    p2.out_idx = (long long*)ctx->h_nn_out;
+    p2.out_dist = (double*)((char*)ctx->h_nn_out + 8);
+    p2.done_flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    p2.done_seq = ++ctx->nn_seq ? ctx->nn_seq : ++ctx->nn_seq;
+    MPS_CUDA_CHECK(mps_launch_nn_scan(p2, ctx->stream), ctx);
+    // scan 1's result follows to the host behind scan 2 (16 bytes; the wait below covers scan 2 only, so synchronise)
+    MPS_CUDA_CHECK(cudaMemcpyAsync((char*)ctx->h_nn_out + 16, ctx->d_nn_out.p, 16, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    ctx->launches += 2;
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    if (index) memcpy(index, ctx->h_nn_out, 8);
+    if (distance) memcpy(distance, (char*)ctx->h_nn_out + 8, 8);
+    if (rep_index) memcpy(rep_index, (char*)ctx->h_nn_out + 16, 8);
+    if (rep_distance) memcpy(rep_distance, (char*)ctx->h_nn_out + 24, 8);
+    ctx->nn_ready = false;
+    return MPS_OK;
+}
+
+// ompl::NearestNeighbors<MotionPtr>::nearestK for the device tree: the k <= 32 nearest nodes in ascending order of
+// (double distance, node index).  One streaming pass (nn_topk_kernel); the rare launch that reports an ambiguous
+// result (near-equal distances crowding one warp: duplicate nodes) is redone as k successor scans in double.
+int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
+                       int32_t k, int64_t* indices, double* distances, int32_t* n_found)
+{
+    if (!ctx || !query || !indices) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_tree_nearest_k");
+    if (k < 1 || k > NN_TOPK_MAX) return mps_fail(ctx, MPS_ERR_ARG, "k must be in [1, 32]");
+    int rc = mps_tree_nearest_upload(ctx, query, 1, weights, &mask, &slice_filter);
+    if (rc) return rc;
+    if ((rc = tree_sync_size(ctx))) return rc;
+    if (ctx->tree_n >= (1ll << 32)) return mps_fail(ctx, MPS_ERR_CAPACITY, "top-k keys carry 32-bit node indices");
+    const int max_grid = ctx->num_sms * 16;
+    if ((rc = ensure(ctx, ctx->d_topk_keys, sizeof(unsigned long long) * (size_t)max_grid * NN_TOPK_MAX))) return rc;
+    if ((rc = ensure(ctx, ctx->d_topk_rej, sizeof(unsigned int) * (size_t)max_grid))) return rc;
+    if ((rc = ensure(ctx, ctx->d_topk_out, 16 * NN_TOPK_MAX + 16))) return rc;
+    TopKParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.nn = ctx->np;
+    tp.nn.tree = ctx->tree;
+    tp.nn.n = ctx->tree_n;
+    tp.nn.grid_x = mps_nn_grid_x(tp.nn.n, ctx->num_sms);
+    tp.k = k;
+    tp.part_keys = (unsigned long long*)ctx->d_topk_keys.p;
+    tp.part_rej = (unsigned int*)ctx->d_topk_rej.p;
+    tp.out_idx = (long long*)ctx->d_topk_out.p;
+    tp.out_dist = (double*)((char*)ctx->d_topk_out.p + 8 * NN_TOPK_MAX);
+    tp.out_meta = (int*)((char*)ctx->d_topk_out.p + 16 * NN_TOPK_MAX);
+    ctx->topk = tp;
+    ctx->topk_ready = true;
+    MPS_CUDA_CHECK(mps_launch_nn_topk(tp, ctx->stream), ctx);
+    ctx->launches++;
+    char host[16 * NN_TOPK_MAX + 16];
+    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nn_out, ctx->d_topk_out.p, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    memcpy(host, ctx->h_nn_out, sizeof(host));
+    int meta[2];
+    memcpy(meta, host + 16 * NN_TOPK_MAX, sizeof(meta));
+    int found = meta[0];
+    static const bool force_fallback = getenv("MPS_NN_TOPK_FALLBACK") && getenv("MPS_NN_TOPK_FALLBACK")[0] == '1';
+    if (meta[1] == 0 && !force_fallback) {
+        memcpy(indices, host, 8 * (size_t)found);
+        if (distances) memcpy(distances, host + 8 * NN_TOPK_MAX, 8 * (size_t)found);
+    } else {
+        // successor scans: (d, i) strictly above the previous result, k times
+        NextParams nx;
+        memset(&nx, 0, sizeof(nx));
+        nx.nn = tp.nn;
+        nx.nn.out_idx = (long long*)ctx->d_nn_out.p;
+        nx.nn.out_dist = (double*)((char*)ctx->d_nn_out.p + 8);
+        nx.after_d = -1.0;
+        nx.after_i = -1;
+        found = 0;
+        for (int j = 0; j < k; ++j) {
+            MPS_CUDA_CHECK(mps_launch_nn_next(nx, ctx->stream), ctx);
+            ctx->launches++;
+            MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nn_out, ctx->d_nn_out.p, 16, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+            MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+            long long bi;
+            double bd;
+            memcpy(&bi, ctx->h_nn_out, 8);
+            memcpy(&bd, (char*)ctx->h_nn_out + 8, 8);
+            if (bi < 0) break;
+            indices[found] = bi;
+            if (distances) distances[found] = bd;
+            ++found;
+            nx.after_d = bd;
+            nx.after_i = bi;
+        }
+        ctx->topk_fallbacks++;
+    }
+    if (n_found) *n_found = found;
+    ctx->nn_ready = false;
+    return MPS_OK;
+}
+
+int mps_tree_nearest_k_fallbacks(mps_ctx* ctx, int64_t* count)
+{
+    if (!ctx || !count) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument");
+    *count = ctx->topk_fallbacks;
+    return MPS_OK;
 }
 
 // ---- extend -----------------------------------------------------------------------------------
@@ -1576,7 +1752,18 @@ int mps_time_launches(mps_ctx* ctx, int32_t what, int32_t iters, float* elapsed_
     MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     MPS_CUDA_CHECK(cudaEventRecord(e0, ctx->stream), ctx);
     int rc = MPS_OK;
-    for (int i = 0; i < iters && rc == MPS_OK; ++i) rc = what == 0 ? mps_extend_launch(ctx) : mps_tree_nearest_launch(ctx);
+    if (what == 2 && !ctx->topk_ready) rc = mps_fail(ctx, MPS_ERR_STATE, "no top-k query to repeat");
+    for (int i = 0; i < iters && rc == MPS_OK; ++i) {
+        if (what == 0) {
+            rc = mps_extend_launch(ctx);
+        } else if (what == 1) {
+            rc = mps_tree_nearest_launch(ctx);
+        } else {
+            cudaError_t le = mps_launch_nn_topk(ctx->topk, ctx->stream);
+            if (le != cudaSuccess) rc = mps_fail_cuda(ctx, le, "mps_launch_nn_topk", __LINE__);
+            ctx->launches++;
+        }
+    }
     cudaError_t e = cudaEventRecord(e1, ctx->stream);
     if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     float ms = 0.0f;

@@ -29,17 +29,24 @@
 #define NN_BODY_BATCH 6
 #endif
 #define NN_MIN_BLOCKS NN_CTAS_PER_SM
+// Candidate filter of the fp32 pass: relative slack far above the evaluation error of a body term (< 3e-6), plus an
+// absolute slack set per query (NNParams::abs_eps = 1e-15 + 1.5e-6 * ow * sum of the active weights): the arc of a
+// wrapped angle difference, 2 pi - |dtheta|, carries an ABSOLUTE error of a few 1e-7 rad whatever its size, which a
+// relative bound does not cover when the whole distance is tiny (near-duplicate nodes under a one-body mask).
 #define NN_REL_EPS 1.0e-4f
-#define NN_ABS_EPS 1.0e-15f
 #define NN_CAND_CAP 512
 
 namespace {
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {
+#ifdef MPS_CPU_EMU
+    return sqrtf(x);  // the fp32 pass only filters; every reported distance is the double expression
+#else
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 
 __device__ __forceinline__ float body_term_f32(float x, float y, float th, float qx, float qy, float qth, float pwf,
@@ -102,6 +109,58 @@ __device__ __forceinline__ double warp_exact_distance(const TreeView& t, long lo
     return dist;
 }
 
+// fp32 metric of the four nodes n0 .. n0 + 3 (one aligned LDG.128 per body row), +inf for nodes beyond N or outside
+// the slice filter
+template <bool STREAM>
+__device__ __forceinline__ void group_distances(const NNParams& p, const int* s_act, const float* s_q, const float* s_w,
+                                                int nact, size_t cap, size_t col0, long long n0, long long N, int filter,
+                                                float pwf, float owf, float& d0, float& d1, float& d2, float& d3)
+{
+    const float inf = __uint_as_float(0x7f800000u);
+    d0 = 0.0f;
+    d1 = 0.0f;
+    d2 = 0.0f;
+    d3 = 0.0f;
+    for (int a0 = 0; a0 < nact; a0 += NN_BODY_BATCH) {
+        float4 X[NN_BODY_BATCH], Y[NN_BODY_BATCH], T[NN_BODY_BATCH];
+#pragma unroll
+        for (int u = 0; u < NN_BODY_BATCH; ++u) {  // all loads of the batch first: 3 * NN_BODY_BATCH LDG.128 in flight
+            const int a = a0 + u < nact ? a0 + u : nact - 1;
+            const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + col0 + n0;
+            X[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row)) : __ldg(reinterpret_cast<const float4*>(row));
+            Y[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + cap))
+                          : __ldg(reinterpret_cast<const float4*>(row + cap));
+            T[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + 2 * cap))
+                          : __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
+        }
+#pragma unroll
+        for (int u = 0; u < NN_BODY_BATCH; ++u) {
+            if (a0 + u < nact) {
+                const int i = s_act[a0 + u];
+                const float qx = s_q[3 * i], qy = s_q[3 * i + 1], qth = s_q[3 * i + 2];
+                const float w = s_w[a0 + u];
+                d0 += w * body_term_f32(X[u].x, Y[u].x, T[u].x, qx, qy, qth, pwf, owf);
+                d1 += w * body_term_f32(X[u].y, Y[u].y, T[u].y, qx, qy, qth, pwf, owf);
+                d2 += w * body_term_f32(X[u].z, Y[u].z, T[u].z, qx, qy, qth, pwf, owf);
+                d3 += w * body_term_f32(X[u].w, Y[u].w, T[u].w, qx, qy, qth, pwf, owf);
+            }
+        }
+    }
+    if (filter >= 0) {
+        const int4 sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + col0 + n0));
+        if (sl.x != filter) d0 = inf;
+        if (sl.y != filter) d1 = inf;
+        if (sl.z != filter) d2 = inf;
+        if (sl.w != filter) d3 = inf;
+    }
+    if (n0 + 3 >= N) {  // ragged tail
+        if (n0 + 1 >= N) d1 = inf;
+        if (n0 + 2 >= N) d2 = inf;
+        if (n0 + 3 >= N) d3 = inf;
+    }
+}
+
+#ifndef MPS_CPU_EMU
 // STREAM: load the state rows with the evict-first hint (ld.global.cs).  Measured on B200: faster when the
 // scanned rows are about the size of L2 (1 M nodes x 132 B: 29.2 us vs 32.9 us), slower when they are several
 // times larger (4 M nodes: 96 us vs 88 us) - the host picks per launch (mps_launch_nn_scan).
@@ -131,7 +190,22 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     const bool inl = p.inline_q != 0;
     uint32_t mask = inl ? p.inline_mask : (p.masks ? p.masks[q] : 0xffffffffu);
     if (B < 32) mask &= (1u << B) - 1u;
-    const int filter = inl ? p.inline_filter : (p.filters ? p.filters[q] : -1);
+    const int filter = inl ? (p.filter_from ? (int)*p.filter_from : p.inline_filter) : (p.filters ? p.filters[q] : -1);
+    // the rows of this thread's first group are requested before the prologue's barrier (they depend on nothing the
+    // prologue computes): the first LDG.128 of the streaming pass then finds them on their way
+    if (!p.inst_ids && (tid & 7) == 0) {
+        const long long g0 = (long long)blockIdx.x * NN_THREADS + tid;
+        if ((g0 << 2) < p.n) {
+            const float* base = p.tree.states + (g0 << 2);
+            for (int i = 0; i < B; ++i) {
+                if ((mask >> i) & 1u) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(3 * i + r) * p.tree.cap));
+                }
+            }
+        }
+    }
     if (tid < 3 * B) s_q[tid] = inl ? p.q_inline[tid] : p.queries[(size_t)q * 3 * B + tid];
     if (tid < B) {
         const float w = inl ? (p.inline_has_w ? p.w_inline[tid] : 1.0f) : (p.weights ? p.weights[tid] : 1.0f);
@@ -168,44 +242,8 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     // ---- streaming pass: fp32 metric for every node, candidates deferred ------------------------
     for (long long g = (long long)blockIdx.x * NN_THREADS + tid; g < groups; g += (long long)gridDim.x * NN_THREADS) {
         const long long n0 = g << 2;
-        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
-        for (int a0 = 0; a0 < nact; a0 += NN_BODY_BATCH) {
-            float4 X[NN_BODY_BATCH], Y[NN_BODY_BATCH], T[NN_BODY_BATCH];
-#pragma unroll
-            for (int u = 0; u < NN_BODY_BATCH; ++u) {  // all loads of the batch first: 3 * NN_BODY_BATCH LDG.128 in flight
-                const int a = a0 + u < nact ? a0 + u : nact - 1;
-                const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + col0 + n0;
-                X[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row)) : __ldg(reinterpret_cast<const float4*>(row));
-                Y[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + cap))
-                              : __ldg(reinterpret_cast<const float4*>(row + cap));
-                T[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + 2 * cap))
-                              : __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
-            }
-#pragma unroll
-            for (int u = 0; u < NN_BODY_BATCH; ++u) {
-                if (a0 + u < nact) {
-                    const int i = s_act[a0 + u];
-                    const float qx = s_q[3 * i], qy = s_q[3 * i + 1], qth = s_q[3 * i + 2];
-                    const float w = s_w[a0 + u];
-                    d0 += w * body_term_f32(X[u].x, Y[u].x, T[u].x, qx, qy, qth, pwf, owf);
-                    d1 += w * body_term_f32(X[u].y, Y[u].y, T[u].y, qx, qy, qth, pwf, owf);
-                    d2 += w * body_term_f32(X[u].z, Y[u].z, T[u].z, qx, qy, qth, pwf, owf);
-                    d3 += w * body_term_f32(X[u].w, Y[u].w, T[u].w, qx, qy, qth, pwf, owf);
-                }
-            }
-        }
-        if (filter >= 0) {
-            const int4 sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + col0 + n0));
-            if (sl.x != filter) d0 = inf;
-            if (sl.y != filter) d1 = inf;
-            if (sl.z != filter) d2 = inf;
-            if (sl.w != filter) d3 = inf;
-        }
-        if (n0 + 3 >= N) {  // ragged tail
-            if (n0 + 1 >= N) d1 = inf;
-            if (n0 + 2 >= N) d2 = inf;
-            if (n0 + 3 >= N) d3 = inf;
-        }
+        float d0, d1, d2, d3;
+        group_distances<STREAM>(p, s_act, s_q, s_w, nact, cap, col0, n0, N, filter, pwf, owf, d0, d1, d2, d3);
         // Tighten the CTA bound with this warp's fp32 minimum BEFORE testing against it.
         const float dm = fminf(fminf(d0, d1), fminf(d2, d3));
         const unsigned am = __activemask();
@@ -214,7 +252,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
         __syncwarp(am);
         const float b = fminf(__uint_as_float(*reinterpret_cast<volatile unsigned int*>(&s_bound)),
                               __uint_as_float(wmin));
-        const float thr = b * (1.0f + NN_REL_EPS) + NN_ABS_EPS;
+        const float thr = b * (1.0f + NN_REL_EPS) + p.abs_eps;
         if (dm <= thr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -238,7 +276,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     // ---- deferred exact pass: only candidates still within the final CTA bound ---------------------
     {
         const float bf = __uint_as_float(s_bound);
-        const float thr = bf * (1.0f + NN_REL_EPS) + NN_ABS_EPS;
+        const float thr = bf * (1.0f + NN_REL_EPS) + p.abs_eps;
         const int ncand = (int)min(s_ncand, (unsigned)NN_CAND_CAP);
         for (int c = warp; c < ncand; c += NN_THREADS / 32) {
             if (__uint_as_float(s_cand_d[c]) <= thr) {
@@ -272,6 +310,10 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             // small trees: one CTA, no cross-CTA hand-off (saves ~4 dependent global round trips)
             p.out_idx[q] = best_i;
             p.out_dist[q] = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
+            if (p.done_flag) {
+                __threadfence_system();
+                *p.done_flag = p.done_seq;
+            }
             s_last = false;
         } else if (tid == 0) {
             p.part_d[(size_t)q * p.grid_x + blockIdx.x] = best_d;
@@ -300,10 +342,376 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             p.out_idx[q] = fi;
             p.out_dist[q] = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
             p.tickets[q] = 0u;
+            if (p.done_flag) {
+                __threadfence_system();
+                *p.done_flag = p.done_seq;
+            }
         }
     }
 }
 
+
+#endif  // MPS_CPU_EMU
+
+// ------------------------------------------------------------------------------------------------------------
+// Exact k nearest neighbours (k <= 32): ompl::NearestNeighbors<MotionPtr>::nearestK of the interface the reference
+// binds (include/mps/planner/pushing/algorithm/RRT.h:149), under the same metric and tie rule as the 1-NN scan:
+// ascending (double distance, node index).
+//
+// One streaming pass.  Every warp keeps the k smallest keys it has seen, key = fp32 distance bits << 32 | node index,
+// one key per lane in ascending order (a warp-level insertion: ballot for the position, shuffle-up to make room), and
+// the smallest fp32 distance of anything it dropped or never admitted.  The CTA merges its warps' lists by ranking
+// (each thread counts the keys below its own), the last CTA does the same over all CTAs' lists.  fp32 order is not
+// the order of the reference's double metric, so the result is fixed up exactly: every node whose fp32 distance is
+// within the slack of the k-th smallest is re-evaluated with the reference's double expression and the candidates are
+// ranked by (double, index).  That is exact as long as no node that could belong to the answer was dropped before the
+// last stage, which the kernel checks: the smallest dropped distance must lie above the slack (it does unless k + 1
+// near-equal distances meet in one warp, e.g. duplicate nodes); otherwise status = 1 and the host falls back to k
+// successor scans in double (nn_next_kernel).
+#define NN_KEY_SENTINEL 0x7f800000ffffffffull
+
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src)
+{
+    return __shfl_sync(FULL, v, src);
+}
+
+// insert `key` (warp-uniform) into the warp's ascending list (one entry per lane, lanes >= k hold the sentinel);
+// returns the entry that fell off the end (sentinel if the list was not full)
+__device__ __forceinline__ unsigned long long warp_list_insert(unsigned long long& mine, unsigned long long key, int k,
+                                                               int lane)
+{
+    const int pos = __popc(__ballot_sync(FULL, mine < key));
+    const unsigned long long up = __shfl_up_sync(FULL, mine, 1);
+    const unsigned long long dropped = shfl_u64(mine, k - 1);
+    if (lane == pos)
+        mine = key;
+    else if (lane > pos)
+        mine = up;
+    if (lane >= k) mine = NN_KEY_SENTINEL;
+    return dropped;
+}
+
+// the keys a warp holds are offered one by one to the list; rej collects the fp32 bits of what does not stay
+__device__ __forceinline__ void warp_list_offer(unsigned long long& mine, unsigned long long& kth, unsigned int& rej,
+                                                unsigned long long key, bool valid, int k, int lane)
+{
+    unsigned bal = __ballot_sync(FULL, valid && key < kth);
+    if (valid && !(key < kth)) rej = min(rej, (unsigned int)(key >> 32));
+    while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1u;
+        const unsigned long long k64 = shfl_u64(key, src);
+        if (k64 < kth) {
+            const unsigned long long dropped = warp_list_insert(mine, k64, k, lane);
+            if (dropped != NN_KEY_SENTINEL) rej = min(rej, (unsigned int)(dropped >> 32));
+            kth = shfl_u64(mine, k - 1);
+        } else {
+            rej = min(rej, (unsigned int)(k64 >> 32));  // the list tightened since the ballot
+        }
+    }
+}
+
+// the 32 smallest keys of two ascending 32-entry lists (one entry per lane), ascending
+__device__ __forceinline__ unsigned long long warp_merge32(unsigned long long a, unsigned long long b, int lane)
+{
+    const unsigned long long rb = shfl_u64(b, 31 - lane);
+    unsigned long long m = a < rb ? a : rb;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULL, m, s);
+        const bool up = (lane & s) != 0;
+        m = (up == (m < o)) ? o : m;  // lower lane keeps the smaller, upper lane the larger
+    }
+    return m;
+}
+
+// CTA merge of the warps' lists (s_keys[w * 32 + l] = entry l of warp w's ascending list, sentinels at the end):
+// a key's rank is its position in its own list plus, for every other list, the number of entries below it (binary
+// search; keys are unique).  s_out[0 .. k) receives the k smallest in ascending order; the smallest fp32 bits among
+// the valid keys that did not make it goes to *s_rej (atomicMin).
+__device__ __forceinline__ void cta_rank_merge(const unsigned long long* s_keys, unsigned long long* s_out, int k,
+                                               unsigned int* s_rej, int tid)
+{
+    for (int i = tid; i < k; i += NN_THREADS) s_out[i] = NN_KEY_SENTINEL;
+    __syncthreads();
+    const unsigned long long mine = s_keys[tid];
+    if (mine != NN_KEY_SENTINEL) {
+        const int w = tid >> 5;
+        int rank = tid & 31;
+        for (int o = 0; o < NN_THREADS / 32 && rank < k; ++o) {
+            if (o == w) continue;
+            const unsigned long long* L = s_keys + o * 32;
+            int lo = 0, hi = 32;  // first entry of list o that is not below `mine`
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int mid = (lo + hi) >> 1;
+                if (L[mid] < mine)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            if (lo < 32 && L[lo] < mine) ++lo;
+            rank += lo;
+        }
+        if (rank < k)
+            s_out[rank] = mine;
+        else
+            atomicMin(s_rej, (unsigned int)(mine >> 32));
+    }
+    __syncthreads();
+}
+
+template <bool STREAM>
+__global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(const __grid_constant__ TopKParams tp)
+{
+    const NNParams& p = tp.nn;
+    __shared__ float s_q[3 * MPS_MAX_BODIES];
+    __shared__ float s_w[MPS_MAX_BODIES];
+    __shared__ float s_wb[MPS_MAX_BODIES];
+    __shared__ int s_act[MPS_MAX_BODIES];
+    __shared__ int s_nact;
+    __shared__ unsigned long long s_keys[NN_THREADS];  // the warps' lists
+    __shared__ unsigned long long s_out[NN_TOPK_MAX];
+    __shared__ unsigned int s_rej;
+    __shared__ bool s_last;
+    __shared__ unsigned int s_ncand;
+    __shared__ long long s_ci[NN_TOPK_CAND];
+    __shared__ double s_cd[NN_TOPK_CAND];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int B = p.tree.B;
+    const int k = tp.k;
+    uint32_t mask = p.inline_mask;
+    if (B < 32) mask &= (1u << B) - 1u;
+    const int filter = p.filter_from ? (int)*p.filter_from : p.inline_filter;
+    if (tid < 3 * B) s_q[tid] = p.q_inline[tid];
+    if (tid < B) {
+        const float w = p.inline_has_w ? p.w_inline[tid] : 1.0f;
+        s_wb[tid] = w;
+        if ((mask >> tid) & 1u) {
+            const int a = __popc(mask & ((1u << tid) - 1u));
+            s_act[a] = tid;
+            s_w[a] = w;
+        }
+    }
+    if (tid == 0) {
+        s_nact = __popc(mask);
+        s_rej = 0x7f800000u;
+        s_ncand = 0u;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    const float pwf = (float)p.pw, owf = (float)p.ow;
+    const size_t cap = p.tree.cap;
+    const long long N = p.n;
+    const long long groups = (N + 3) >> 2;
+    const float inf = __uint_as_float(0x7f800000u);
+
+    // ---- streaming pass: the whole warp stays in the loop (the list operations are warp collectives) ----------
+    unsigned long long mine = NN_KEY_SENTINEL, kth = NN_KEY_SENTINEL;
+    unsigned int rej = 0x7f800000u;
+    for (long long gw = (long long)blockIdx.x * NN_THREADS + (tid & ~31); gw < groups; gw += (long long)gridDim.x * NN_THREADS) {
+        const long long g = gw + lane;
+        float d0 = inf, d1 = inf, d2 = inf, d3 = inf;
+        const long long n0 = g << 2;
+        if (g < groups) group_distances<STREAM>(p, s_act, s_q, s_w, nact, cap, 0, n0, N, filter, pwf, owf, d0, d1, d2, d3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float dj = j == 0 ? d0 : j == 1 ? d1 : j == 2 ? d2 : d3;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned long long)(unsigned int)(n0 + j);
+#if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 3
+            warp_list_offer(mine, kth, rej, key, dj < inf, k, lane);
+#else
+            rej = min(rej, (unsigned int)(key >> 32));
+#endif
+        }
+    }
+    rej = __reduce_min_sync(FULL, rej);
+    s_keys[tid] = mine;
+    if (lane == 0) atomicMin(&s_rej, rej);
+    __syncthreads();
+#if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 2
+    cta_rank_merge(s_keys, s_out, k, &s_rej, tid);
+#endif
+    if (tid < k) tp.part_keys[(size_t)blockIdx.x * k + tid] = s_out[tid];
+    if (tid == 0) {
+        tp.part_rej[blockIdx.x] = s_rej;
+        __threadfence();
+        const unsigned int t = atomicAdd(&p.tickets[0], 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+#if defined(NN_TOPK_PROBE) && NN_TOPK_PROBE >= 1
+    if (tid == 0) p.tickets[0] = 0u;
+    return;
+#endif
+
+    // ---- last CTA: the k-th smallest fp32 distance of all CTAs' lists, then the exact fix-up -------------------------
+    __threadfence();
+    const int total = (int)gridDim.x * k;
+    const volatile unsigned long long* keys = tp.part_keys;
+    // Every CTA's list is ascending: two lists merge into the 32 smallest of both in six shuffles (the reversed
+    // second list against the first gives a bitonic sequence holding the 32 smallest, five compare-exchange stages
+    // sort it).  Each warp folds its share of the lists into one, two chains at a time; three more merges through
+    // shared memory leave the k smallest fp32 keys of the whole tree in s_out.
+    {
+        const int lists = (int)gridDim.x;
+        auto load_list = [&](int l) -> unsigned long long {
+            return (l < lists && lane < k) ? keys[(size_t)l * k + lane] : NN_KEY_SENTINEL;
+        };
+        // four independent merge chains per warp (the chain is the latency; four of them share the issue slots), the
+        // next four lists already on their way from L2 while the current four are merged
+        unsigned long long acc0 = NN_KEY_SENTINEL, acc1 = NN_KEY_SENTINEL, acc2 = NN_KEY_SENTINEL, acc3 = NN_KEY_SENTINEL;
+        const int step = 4 * (NN_THREADS / 32);
+        int l = warp * 4;
+        unsigned long long n0 = load_list(l), n1 = load_list(l + 1), n2 = load_list(l + 2), n3 = load_list(l + 3);
+        for (; l < lists; l += step) {
+            const unsigned long long b0 = n0, b1 = n1, b2 = n2, b3 = n3;
+            n0 = load_list(l + step);
+            n1 = load_list(l + step + 1);
+            n2 = load_list(l + step + 2);
+            n3 = load_list(l + step + 3);
+            acc0 = warp_merge32(acc0, b0, lane);
+            acc1 = warp_merge32(acc1, b1, lane);
+            acc2 = warp_merge32(acc2, b2, lane);
+            acc3 = warp_merge32(acc3, b3, lane);
+        }
+        acc0 = warp_merge32(acc0, acc1, lane);
+        acc2 = warp_merge32(acc2, acc3, lane);
+        acc0 = warp_merge32(acc0, acc2, lane);
+        s_keys[tid] = acc0;
+        __syncthreads();
+        for (int stride = 1; stride < NN_THREADS / 32; stride <<= 1) {
+            if ((warp & (2 * stride - 1)) == 0) {
+                acc0 = warp_merge32(acc0, s_keys[(warp + stride) * 32 + lane], lane);
+                s_keys[tid] = acc0;
+            }
+            __syncthreads();
+        }
+        if (tid < NN_TOPK_MAX) s_out[tid] = s_keys[tid];
+        if (tid == 0) s_rej = 0x7f800000u;
+        __syncthreads();
+    }
+    int have = 0;
+    for (int i = 0; i < k; ++i) have += s_out[i] != NN_KEY_SENTINEL ? 1 : 0;
+    const unsigned int lo = have > 0 ? (unsigned int)(s_out[have - 1] >> 32) : 0x7f800000u;
+    int status = 0;
+    float thr = inf;
+    if (have > 0) thr = __uint_as_float(lo) * (1.0f + NN_REL_EPS) + p.abs_eps;
+    __syncthreads();
+    // smallest distance any CTA dropped: it must lie beyond the slack
+    unsigned int gr = 0x7f800000u;
+    for (int c = tid; c < (int)gridDim.x; c += NN_THREADS) gr = min(gr, *reinterpret_cast<volatile unsigned int*>(&tp.part_rej[c]));
+    gr = __reduce_min_sync(FULL, gr);
+    if (lane == 0) atomicMin(&s_rej, gr);
+    // candidates: every reported key within the slack
+    for (int i = tid; i < total; i += NN_THREADS) {
+        const unsigned long long key = keys[i];
+        if (key != NN_KEY_SENTINEL && __uint_as_float((unsigned int)(key >> 32)) <= thr) {
+            const unsigned int slot = atomicAdd(&s_ncand, 1u);
+            if (slot < NN_TOPK_CAND) s_ci[slot] = (long long)(unsigned int)(key & 0xffffffffull);
+        }
+    }
+    __syncthreads();
+    if (have == k && __uint_as_float(s_rej) <= thr) status = 1;
+    if (s_ncand > NN_TOPK_CAND) status = 1;
+    const int nc = (int)min(s_ncand, (unsigned int)NN_TOPK_CAND);
+    for (int c = warp; c < nc; c += NN_THREADS / 32) {
+        const double e = warp_exact_distance(p.tree, s_ci[c], s_q, s_wb, mask, p.pw, p.ow, lane);
+        if (lane == 0) s_cd[c] = e;
+    }
+    __syncthreads();
+    if (tid < nc) {
+        const double md = s_cd[tid];
+        const long long mi = s_ci[tid];
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) rank += (s_cd[j] < md || (s_cd[j] == md && s_ci[j] < mi)) ? 1 : 0;
+        if (rank < k) {
+            tp.out_idx[rank] = mi;
+            tp.out_dist[rank] = md;
+        }
+    }
+    if (tid == 0) {
+        tp.out_meta[0] = nc < k ? nc : k;
+        tp.out_meta[1] = status;
+        p.tickets[0] = 0u;
+    }
+}
+
+// successor scan in double: the smallest (distance, index) above (after_d, after_i).  Plain: one thread per node,
+// the reference's expression for every node (a few hundred microseconds per million nodes).
+__global__ void __launch_bounds__(NN_THREADS) nn_next_kernel(const __grid_constant__ NextParams np)
+{
+    const NNParams& p = np.nn;
+    __shared__ float s_q[3 * MPS_MAX_BODIES];
+    __shared__ float s_wb[MPS_MAX_BODIES];
+    __shared__ double s_rd[NN_THREADS / 32];
+    __shared__ long long s_ri[NN_THREADS / 32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int B = p.tree.B;
+    uint32_t mask = p.inline_mask;
+    if (B < 32) mask &= (1u << B) - 1u;
+    const int filter = p.inline_filter;
+    if (tid < 3 * B) s_q[tid] = p.q_inline[tid];
+    if (tid < B) s_wb[tid] = p.inline_has_w ? p.w_inline[tid] : 1.0f;
+    __syncthreads();
+    double best_d = 0.0;
+    long long best_i = -1;
+    for (long long n = (long long)blockIdx.x * NN_THREADS + tid; n < p.n; n += (long long)gridDim.x * NN_THREADS) {
+        if (filter >= 0 && p.tree.slice[n] != filter) continue;
+        const double e = exact_distance(p.tree, n, s_q, s_wb, mask, p.pw, p.ow);
+        if (e > np.after_d || (e == np.after_d && n > np.after_i)) take_min(best_d, best_i, e, n);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        double od = __shfl_down_sync(FULL, best_d, off);
+        long long oi = __shfl_down_sync(FULL, best_i, off);
+        take_min(best_d, best_i, od, oi);
+    }
+    if (lane == 0) {
+        s_rd[warp] = best_d;
+        s_ri[warp] = best_i;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        best_d = tid < NN_THREADS / 32 ? s_rd[tid] : 0.0;
+        best_i = tid < NN_THREADS / 32 ? s_ri[tid] : -1;
+        for (int off = 16; off > 0; off >>= 1) {
+            double od = __shfl_down_sync(FULL, best_d, off);
+            long long oi = __shfl_down_sync(FULL, best_i, off);
+            take_min(best_d, best_i, od, oi);
+        }
+        if (tid == 0) {
+            p.part_d[blockIdx.x] = best_d;
+            p.part_i[blockIdx.x] = best_i;
+            __threadfence();
+            s_last = atomicAdd(&p.tickets[0], 1u) == gridDim.x - 1;
+        }
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();
+        double fd = 0.0;
+        long long fi = -1;
+        for (int c = tid; c < (int)gridDim.x; c += 32)
+            take_min(fd, fi, *reinterpret_cast<volatile double*>(&p.part_d[c]), *reinterpret_cast<volatile long long*>(&p.part_i[c]));
+        for (int off = 16; off > 0; off >>= 1) {
+            double od = __shfl_down_sync(FULL, fd, off);
+            long long oi = __shfl_down_sync(FULL, fi, off);
+            take_min(fd, fi, od, oi);
+        }
+        if (tid == 0) {
+            p.out_idx[0] = fi;
+            p.out_dist[0] = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
+            p.tickets[0] = 0u;
+        }
+    }
+}
+
+#ifndef MPS_CPU_EMU
 // staged node-major rows -> SoA columns [first, first + n)
 __global__ void tree_append_kernel(TreeView t, long long first, long long n, const float* __restrict__ st,
                                    const int32_t* __restrict__ parents, const float* __restrict__ ctrl,
@@ -457,6 +865,23 @@ cudaError_t mps_launch_nn_scan(const NNParams& p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+cudaError_t mps_launch_nn_topk(const TopKParams& p, cudaStream_t stream)
+{
+    dim3 grid((unsigned)p.nn.grid_x, 1, 1);
+    const double scanned = (double)p.nn.n * 12.0 * p.nn.tree.B;
+    if (scanned < 252.0e6)
+        nn_topk_kernel<true><<<grid, NN_THREADS, 0, stream>>>(p);
+    else
+        nn_topk_kernel<false><<<grid, NN_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_nn_next(const NextParams& p, cudaStream_t stream)
+{
+    nn_next_kernel<<<(unsigned)p.nn.grid_x, NN_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t mps_launch_tree_append(const TreeView& t, long long first, long long n, const float* staged_states,
                                    const int32_t* staged_parents, const float* staged_controls,
                                    const int32_t* staged_slices, long long* size_out, cudaStream_t stream)
@@ -498,3 +923,6 @@ cudaError_t mps_launch_forest_roots(const TreeView& forest, size_t seg, int n_in
     forest_roots_kernel<<<blocks, 256, 0, stream>>>(forest, seg, n_inst, roots, sizes);
     return cudaGetLastError();
 }
+#else
+}  // namespace (the launchers above are not part of the emulator build)
+#endif  // MPS_CPU_EMU

@@ -43,10 +43,41 @@ struct NNParams {
     int32_t inline_filter;
     float q_inline[3 * 32];
     float w_inline[32];
+    // chained queries (SliceBasedOracleRRT's two-level search): when set, the slice filter of an inline query is
+    // the node index another scan wrote to device memory (index of the nearest slice representative = slice id)
+    const long long* filter_from;
+    // completion flag for the single-query path: after (index, distance) the last CTA writes `done_seq` here
+    // (pinned host memory) so that the host can wait for the result without a stream synchronise
+    volatile unsigned int* done_flag;
+    unsigned int done_seq;
+    float abs_eps;  // absolute slack of the fp32 candidate filter (covers the rounding of the angle wrap)
+};
+
+// exact k nearest neighbours of one query (k <= 32), see nn_topk_kernel
+#define NN_TOPK_MAX 32
+#define NN_TOPK_CAND 64
+struct TopKParams {
+    NNParams nn;                    // tree, n, the query (inline), pw / ow, grid_x, tickets
+    int k;
+    unsigned long long* part_keys;  // [grid_x][k] per-CTA smallest keys (fp32 distance bits << 32 | node index)
+    unsigned int* part_rej;         // [grid_x] fp32 bits of the smallest distance the CTA dropped
+    long long* out_idx;             // [k] ascending by (double distance, index)
+    double* out_dist;               // [k]
+    int* out_meta;                  // [0] results written (<= k), [1] status: 0 exact, 1 ambiguous (caller falls back)
+};
+
+// lexicographic successor scan in double (rare fallback of the top-k path, and its checker):
+// min over nodes of (distance, index) > (after_d, after_i)
+struct NextParams {
+    NNParams nn;
+    double after_d;
+    long long after_i;
 };
 
 int mps_nn_grid_x(long long n, int num_sms);
 cudaError_t mps_launch_nn_scan(const NNParams& p, cudaStream_t stream);
+cudaError_t mps_launch_nn_topk(const TopKParams& p, cudaStream_t stream);
+cudaError_t mps_launch_nn_next(const NextParams& p, cudaStream_t stream);
 cudaError_t mps_launch_tree_append(const TreeView& t, long long first, long long n, const float* staged_states,
                                    const int32_t* staged_parents, const float* staged_controls,
                                    const int32_t* staged_slices, long long* size_out, cudaStream_t stream);

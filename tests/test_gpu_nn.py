@@ -176,3 +176,130 @@ def test_single_query_paths_agree():
                 assert i1 == wi and int(i2[0]) == wi and int(i3[0]) == wi
                 assert d1 == wd and float(d2[0]) == wd and float(d3[0]) == wd
     ctx.close()
+
+
+def _all_distances(sc, states, q, weights=None, mask=None):
+    """orc_distance (oracle/mps_oracle.c) for every node, vectorised in numpy with the same operations in the same
+    order (double; body order) - checked against the oracle itself on a sample below"""
+    B = sc.n_bodies
+    full = (1 << B) - 1
+    mask = full if mask is None else mask
+    st = states.astype(np.float64)
+    qq = q.astype(np.float64)
+    dist = np.zeros(len(states))
+    for i in range(B):
+        if (mask >> i) & 1:
+            dx = st[:, 3 * i] - qq[3 * i]
+            dy = st[:, 3 * i + 1] - qq[3 * i + 1]
+            dpos = np.sqrt(dx * dx + dy * dy)
+            d = np.abs(st[:, 3 * i + 2] - qq[3 * i + 2])
+            arc = np.where(d > np.pi, 2.0 * np.pi - d, d)
+            cfg = sc.position_weight * dpos + sc.orientation_weight * arc
+            w = 1.0 if weights is None else float(weights[i])
+            dist = dist + w * cfg
+    return dist
+
+
+def _sorted_scan(d, k, keep=None):
+    idx = np.arange(len(d))
+    if keep is not None:
+        d, idx = d[keep], idx[keep]
+    order = np.lexsort((idx, d))[:k]
+    return idx[order], d[order]
+
+
+@pytest.mark.parametrize("n_objects,N", [(3, 7), (6, 5000), (10, 200_000)])
+def test_nearest_k_equals_sorted_double_scan(n_objects, N):
+    """mps_tree_nearest_k (ompl nearestK): ascending (double distance, index), bit-exact"""
+    sc, _ = scenes.make_scene(n_objects, seed=N)
+    B = sc.n_bodies
+    rng = np.random.RandomState(N)
+    states = np.empty((N, 3 * B), np.float32)
+    states[:, 0::3] = rng.uniform(sc.x_min, sc.x_max, size=(N, B))
+    states[:, 1::3] = rng.uniform(sc.y_min, sc.y_max, size=(N, B))
+    states[:, 2::3] = rng.uniform(-np.pi, np.pi, size=(N, B))
+    slices = rng.randint(0, 5, size=N).astype(np.int32)
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.add_batch(states, slice_ids=slices)
+    weights = rng.uniform(0.5, 2.0, size=B).astype(np.float32)
+    for qi in range(4):
+        q = scenes.sample_state(rng, sc)
+        for mask in _masks(B):
+            w = weights if qi % 2 else None
+            d = _all_distances(sc, states, q, weights=w, mask=mask)
+            for j in rng.randint(0, N, size=3):   # the vectorised reference is the oracle's arithmetic
+                assert d[j] == ob.distance(sc, states[j], q, weights=w, mask=mask)
+            for k in (1, 4, 32):
+                gi, gd = tree.nearest_k(q, k, weights=w, mask=mask)
+                wi, wd = _sorted_scan(d, k)
+                assert np.array_equal(gi, wi) and np.array_equal(gd, wd), (qi, mask, k)
+            gi, gd = tree.nearest_k(q, 8, weights=w, mask=mask, slice_filter=3)
+            wi, wd = _sorted_scan(d, 8, keep=slices == 3)
+            assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+            n1, d1 = tree.nearest(q, weights=w, mask=mask)
+            gi, gd = tree.nearest_k(q, 1, weights=w, mask=mask)
+            assert (gi[0], gd[0]) == (n1, d1)
+    ctx.close()
+
+
+def test_nearest_k_at_one_million_nodes_and_with_duplicates():
+    sc, _ = scenes.make_scene(10, seed=1003)
+    B = sc.n_bodies
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    N = 1_000_000
+    tree.fill_random(N, seed=1003, n_slices=64)
+    states = tree.read_states(0, N)
+    rng = np.random.RandomState(5)
+    for _ in range(3):
+        q = scenes.sample_state(rng, sc)
+        d = _all_distances(sc, states, q)
+        gi, gd = tree.nearest_k(q, 32)
+        wi, wd = _sorted_scan(d, 32)
+        assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    assert tree.nearest_k_fallbacks() == 0
+    # duplicates crowd one warp's list: the launch flags it and the successor scans answer exactly
+    small = states[:3000].copy()
+    q = scenes.sample_state(rng, sc)
+    d = _all_distances(sc, small, q)
+    j = int(np.argmin(d))
+    crowded = np.concatenate([small[:64], np.tile(small[j], (40, 1)), small[64:]])
+    tree.clear()
+    tree.add_batch(crowded)
+    gi, gd = tree.nearest_k(q, 6)
+    wi, wd = _sorted_scan(_all_distances(sc, crowded, q), 6)
+    assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    assert tree.nearest_k_fallbacks() == 1
+    gi, gd = tree.nearest_k(q, 32)   # more results asked for than the duplicates: still exact
+    wi, wd = _sorted_scan(_all_distances(sc, crowded, q), 32)
+    assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    ctx.close()
+
+
+def test_two_level_query_equals_two_separate_queries():
+    """mps_tree_nearest_two_level: nearest slice representative, then the nearest member of that slice, chained on the
+    device (SliceBasedOracleRRT::selectTreeNode RRT.cpp:783-827 without the host round trip)"""
+    sc, _ = scenes.make_scene(6, seed=9)
+    B = sc.n_bodies
+    rng = np.random.RandomState(9)
+    n_slices, N = 40, 6000
+    reps = np.stack([scenes.sample_state(rng, sc) for _ in range(n_slices)])
+    states = np.stack([scenes.sample_state(rng, sc) for _ in range(N)])
+    slices = rng.randint(0, n_slices - 1, size=N).astype(np.int32)   # the last slice has no member
+    ctx, rctx = api.Context(sc), api.Context(sc)
+    tree, rtree = api.NearestNeighbors(ctx), api.NearestNeighbors(rctx)
+    tree.add_batch(states, slice_ids=slices)
+    rtree.add_batch(reps)
+    arr_mask, robot_mask = ((1 << B) - 1) & ~1, 1
+    for _ in range(8):
+        q = scenes.sample_state(rng, sc)
+        (ri, rd), (i, d) = tree.nearest_two_level(rtree, q, arr_mask, robot_mask)
+        wri, wrd = rtree.nearest(q, mask=arr_mask)
+        wi, wd = tree.nearest(q, mask=robot_mask, slice_filter=wri)
+        assert (ri, rd, i, d) == (wri, wrd, wi, wd)
+    q = reps[n_slices - 1]   # the empty slice is the nearest: no member
+    (ri, rd), (i, d) = tree.nearest_two_level(rtree, q, arr_mask, robot_mask)
+    assert ri == n_slices - 1 and rd == 0.0 and i == -1
+    ctx.close()
+    rctx.close()
