@@ -212,6 +212,41 @@ int mps_propagate(mps_ctx* ctx, const float* state_in, float* control, float* st
 int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in);
 int mps_extend_launch(mps_ctx* ctx);                       /* asynchronous on the ctx stream */
 int mps_extend_fetch(mps_ctx* ctx, const mps_extend_out* out); /* synchronises */
+/* ---- action sequences generated on the device ---------------------------------------------------------------
+ * HybridActionRRT::sampleActionSequence (pushing/algorithm/RRT.cpp:491-529) for all K chains of an extend in one
+ * kernel: per chain a die (random control with probability action_randomness), the object to move
+ * (sampleActiveObject RRT.cpp:246-257, or fixed_object for OracleRRT), then either the transit primitive -
+ * RampComputer::steer of the robot towards its sampled pose (oracle/RampComputer.cpp:40-92) - or the transfer
+ * primitive - HumanOracle::sampleFeasibleState (oracle/HumanOracle.cpp:136-159), the steer to that pushing pose and
+ * HumanOracle::predictAction from it (:111-134).  Random numbers are a hash of (seed, iteration, k_offset + chain,
+ * purpose, index), so an extend uploads this struct instead of K x L x 20 bytes of controls, and a chain's actions
+ * do not depend on how the chains are split over GPUs. */
+typedef struct mps_hybrid_gen {
+    uint64_t seed;
+    int32_t iteration;
+    int32_t k_offset;          /* global index of chain 0 (multi-GPU sharding; normally = mps_extend_in.k_offset) */
+    int32_t fixed_object;      /* >= 0: every chain acts on this body; -1: sampled per chain */
+    float action_randomness;   /* RRT.cpp:500 */
+    float target_bias, robot_bias;
+    int32_t n_targets;
+    int32_t targets[MPS_MAX_GOALS];
+    float velocity_limits[3];  /* per component (vx, vy, omega); the random control draws (vx, vy) from the disc of
+                                  radius velocity_limits[0] and omega from +-velocity_limits[2] */
+    float duration_min, duration_max;
+    float optimal_push_distance, push_distance_tolerance, push_angle_tolerance; /* HumanOracle.cpp:10-18 */
+    float object_size[MPS_MAX_BODIES]; /* max(width, height) of every body (HumanOracle.cpp:121) */
+} mps_hybrid_gen;
+/* mps_extend_upload with the controls and chain lengths produced on the device: in->controls and in->n_ctrl are
+ * ignored, in->K chains of at most in->L controls are generated (a sequence that needs more is cut at L and
+ * counted).  Then mps_extend_launch / mps_extend_fetch as usual. */
+int mps_extend_upload_generated(mps_ctx* ctx, const mps_extend_in* in, const mps_hybrid_gen* gen);
+/* the generated controls [K][L][5] and chain lengths [K] of the last mps_extend_upload_generated (for replay /
+ * inspection; either may be NULL), and how many chains were cut at L */
+int mps_extend_generated_controls(mps_ctx* ctx, float* controls, int32_t* n_ctrl, int32_t* n_truncated);
+/* n controls of the device's RampVelocityControlSampler::sample (ompl/control/RampVelocityControl.cpp:353-394), the
+ * sampler mps_forest_naive_step and the generator above draw random controls with: hash index gid, draws 0 .. n-1 */
+int mps_sample_controls(mps_ctx* ctx, uint64_t seed, int32_t iteration, int64_t gid, int32_t n, float velocity_limit,
+                        float omega_limit, float duration_min, float duration_max, float* controls);
 /* counters of the last launch: [0] physics steps, [1] candidate pairs, [2] touching manifolds,
  * [3] solver colour passes, [4] kernel launches since ctx creation */
 int mps_extend_counters(mps_ctx* ctx, uint64_t counters[8]);

@@ -136,6 +136,29 @@ class ExtendBest(C.Structure):
     ]
 
 
+class HybridGen(C.Structure):
+    """struct mps_hybrid_gen"""
+
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("iteration", _i32),
+        ("k_offset", _i32),
+        ("fixed_object", _i32),
+        ("action_randomness", _f32),
+        ("target_bias", _f32),
+        ("robot_bias", _f32),
+        ("n_targets", _i32),
+        ("targets", _i32 * MPS_MAX_GOALS),
+        ("velocity_limits", _f32 * 3),
+        ("duration_min", _f32),
+        ("duration_max", _f32),
+        ("optimal_push_distance", _f32),
+        ("push_distance_tolerance", _f32),
+        ("push_angle_tolerance", _f32),
+        ("object_size", _f32 * MPS_MAX_BODIES),
+    ]
+
+
 class ForestNaiveIn(C.Structure):
     """struct mps_forest_naive_in"""
 
@@ -210,6 +233,9 @@ SYMBOLS = {
     "mps_extend": (C.c_int, [_ctx, _P(ExtendIn), _P(ExtendOut)]),
     "mps_propagate": (C.c_int, [_ctx, _P(_f32), _P(_f32), _P(_f32), _P(_i32), _P(_u32)]),
     "mps_extend_upload": (C.c_int, [_ctx, _P(ExtendIn)]),
+    "mps_extend_upload_generated": (C.c_int, [_ctx, _P(ExtendIn), _P(HybridGen)]),
+    "mps_extend_generated_controls": (C.c_int, [_ctx, _P(_f32), _P(_i32), _P(_i32)]),
+    "mps_sample_controls": (C.c_int, [_ctx, C.c_uint64, _i32, C.c_int64, _i32, _f32, _f32, _f32, _f32, _P(_f32)]),
     "mps_extend_launch": (C.c_int, [_ctx]),
     "mps_extend_fetch": (C.c_int, [_ctx, _P(ExtendOut)]),
     "mps_extend_counters": (C.c_int, [_ctx, _P(C.c_uint64)]),

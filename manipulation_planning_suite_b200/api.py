@@ -193,6 +193,59 @@ class Context:
     def extend_launch(self):
         self._check(self.lib.mps_extend_launch(self.h))
 
+    @staticmethod
+    def hybrid_gen(scene: abi.Scene, seed: int, iteration: int = 0, k_offset: int = 0, fixed_object: int = -1,
+                   action_randomness: float = 0.0, target_bias: float = 0.0, robot_bias: float = 0.0, targets=(),
+                   velocity_limits=(0.6, 0.6, 1.5), duration_limits=(0.1, 1.0), optimal_push_distance: float = 0.2,
+                   push_distance_tolerance: float = 0.04, push_angle_tolerance: float = 0.03, object_size=None) -> abi.HybridGen:
+        """struct mps_hybrid_gen with the reference's defaults (HumanOracle.cpp:10-18, OraclePushPlanner.cpp:70-71);
+        object_size defaults to max(width, height) of the scene's bodies"""
+        g = abi.HybridGen()
+        g.seed, g.iteration, g.k_offset, g.fixed_object = int(seed), int(iteration), int(k_offset), int(fixed_object)
+        g.action_randomness, g.target_bias, g.robot_bias = action_randomness, target_bias, robot_bias
+        g.n_targets = len(targets)
+        for i, t in enumerate(targets):
+            g.targets[i] = int(t)
+        for i in range(3):
+            g.velocity_limits[i] = velocity_limits[i]
+        g.duration_min, g.duration_max = duration_limits
+        g.optimal_push_distance, g.push_distance_tolerance = optimal_push_distance, push_distance_tolerance
+        g.push_angle_tolerance = push_angle_tolerance
+        for i in range(int(scene.n_bodies)):
+            if object_size is not None:
+                g.object_size[i] = object_size[i]
+            elif scene.shape[i] == abi.MPS_SHAPE_DISC:
+                g.object_size[i] = 2.0 * scene.hx[i]
+            else:
+                g.object_size[i] = 2.0 * max(scene.hx[i], scene.hy[i])
+        return g
+
+    def extend_upload_generated(self, start, K: int, L: int, gen: abi.HybridGen, **kw):
+        """mps_extend_upload_generated: the K chains' action sequences are produced on the device from `gen`"""
+        dummy = np.zeros((1, 1, 5), np.float32)
+        ein, keep, _, _ = self._extend_in(start, dummy, **kw)
+        ein.controls = None
+        ein.n_ctrl = None
+        ein.K, ein.L = int(K), int(L)
+        self._check(self.lib.mps_extend_upload_generated(self.h, C.byref(ein), C.byref(gen)))
+        self._ext_shape = (int(K), int(L))
+
+    def generated_controls(self):
+        """(controls [K][L][5], n_ctrl [K], n_truncated) of the last extend_upload_generated"""
+        K, L = self._ext_shape
+        c = np.zeros((K, L, 5), np.float32)
+        n = np.zeros(K, np.int32)
+        tr = C.c_int32(0)
+        self._check(self.lib.mps_extend_generated_controls(self.h, _fp(c), _fp(n, C.c_int32), C.byref(tr)))
+        return c, n, tr.value
+
+    def sample_controls(self, seed: int, n: int, iteration: int = 0, gid: int = 0, velocity_limit: float = 0.6,
+                        omega_limit: float = 1.5, duration_limits=(0.1, 1.0)) -> np.ndarray:
+        c = np.zeros((n, 5), np.float32)
+        self._check(self.lib.mps_sample_controls(self.h, int(seed), int(iteration), int(gid), int(n), velocity_limit, omega_limit,
+                                                 duration_limits[0], duration_limits[1], _fp(c)))
+        return c
+
     def extend_fetch(self, dump=False) -> ExtendResult:
         K, L = self._ext_shape
         eout, res = self._extend_out(K, L, dump)

@@ -55,7 +55,8 @@ struct mps_ctx {
     DevBuf d_inpack;  // all inputs of one mps_extend call, one host -> device copy
     DevBuf d_states, d_rest, d_flags, d_steps, d_dist, d_nok, d_goal_step;
     DevBuf d_record;  // packed winner record: best | states | controls | flags
-    DevBuf d_work, d_counters, d_cycles, d_redo, d_order;
+    DevBuf d_work, d_counters, d_cycles, d_redo, d_order, d_gen_trunc;
+    bool gen_ready = false;  // the controls of the uploaded extend were generated on the device
     // pinned staging
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -935,10 +936,30 @@ int mps_tree_nearest_k_fallbacks(mps_ctx* ctx, int64_t* count)
 
 // ---- extend -----------------------------------------------------------------------------------
 
-int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
+static int extend_upload_impl(mps_ctx* ctx, const mps_extend_in* in, const mps_hybrid_gen* gen);
+
+int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in) { return extend_upload_impl(ctx, in, nullptr); }
+
+int mps_extend_upload_generated(mps_ctx* ctx, const mps_extend_in* in, const mps_hybrid_gen* gen)
+{
+    if (!gen) return mps_fail(ctx, MPS_ERR_ARG, "gen is NULL");
+    if (!ctx || !in) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_upload_generated");
+    if (!in->start || in->starts || !in->dest) return mps_fail(ctx, MPS_ERR_ARG, "generated chains start from `start` towards `dest`");
+    const int B = ctx->scene.n_bodies;
+    if (gen->fixed_object >= B || gen->n_targets < 0 || gen->n_targets > MPS_MAX_GOALS)
+        return mps_fail(ctx, MPS_ERR_ARG, "fixed_object / n_targets out of range");
+    for (int i = 0; i < gen->n_targets; ++i)
+        if (gen->targets[i] < 0 || gen->targets[i] >= B) return mps_fail(ctx, MPS_ERR_ARG, "target body out of range");
+    for (int i = 0; i < 3; ++i)
+        if (!(gen->velocity_limits[i] > 0.0f)) return mps_fail(ctx, MPS_ERR_ARG, "velocity limits must be positive");
+    if (!(gen->duration_max > 0.0f)) return mps_fail(ctx, MPS_ERR_ARG, "duration_max must be positive");
+    return extend_upload_impl(ctx, in, gen);
+}
+
+static int extend_upload_impl(mps_ctx* ctx, const mps_extend_in* in, const mps_hybrid_gen* gen)
 {
     if (!ctx || !in) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_extend_upload");
-    if ((!in->start && !in->starts) || !in->controls) return mps_fail(ctx, MPS_ERR_ARG, "start / controls are NULL");
+    if ((!in->start && !in->starts) || (!in->controls && !gen)) return mps_fail(ctx, MPS_ERR_ARG, "start / controls are NULL");
     if (in->K < 1 || in->L < 1 || in->L > MPS_MAX_CHAIN) return mps_fail(ctx, MPS_ERR_ARG, "K must be >= 1 and L in [1, 64]");
     if (in->n_goals < 0 || in->n_goals > MPS_MAX_GOALS) return mps_fail(ctx, MPS_ERR_ARG, "n_goals must be in [0, 8]");
     if (in->n_goals > 0 && !in->goals) return mps_fail(ctx, MPS_ERR_ARG, "goals is NULL");
@@ -992,13 +1013,35 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
         return d;
     };
     const void* dp_start = in->starts ? up(in->starts, sb * (size_t)K) : up(in->start, sb);
-    const void* dp_controls = up(in->controls, cb);
-    const void* dp_nctrl = in->n_ctrl ? up(in->n_ctrl, nb) : nullptr;
+    const void* dp_controls = gen ? ctx->d_controls.p : up(in->controls, cb);
+    const void* dp_nctrl = gen ? ctx->d_nctrl.p : (in->n_ctrl ? up(in->n_ctrl, nb) : nullptr);
     const void* dp_dest = in->dest ? up(in->dest, sb) : nullptr;
     const void* dp_weights = in->weights ? up(in->weights, wb) : nullptr;
     const void* dp_goals = in->n_goals > 0 ? up(in->goals, sizeof(mps_goal) * in->n_goals) : ctx->d_goals.p;
     const void* dp_ball = in->ball_center ? up(in->ball_center, sb) : nullptr;
     MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_inpack.p, h0, (size_t)(h - h0), cudaMemcpyHostToDevice, ctx->stream), ctx);
+    ctx->gen_ready = false;
+    if (gen) {
+        // the chains' controls are produced where they are consumed: one small kernel instead of the K x L x 20 B upload
+        HybridGenParams gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.gen = *gen;
+        gp.K = K;
+        gp.L = L;
+        gp.B = B;
+        gp.robot = ctx->scene.robot_id;
+        for (int i = 0; i < 3; ++i) gp.accel[i] = ctx->scene.accel_limits[i];
+        gp.start = (const float*)dp_start;
+        gp.dest = (const float*)dp_dest;
+        gp.controls = (float*)ctx->d_controls.p;
+        gp.n_ctrl = (int32_t*)ctx->d_nctrl.p;
+        if ((rc = ensure(ctx, ctx->d_gen_trunc, sizeof(unsigned int)))) return rc;
+        MPS_CUDA_CHECK(cudaMemsetAsync(ctx->d_gen_trunc.p, 0, sizeof(unsigned int), ctx->stream), ctx);
+        gp.truncated = (unsigned int*)ctx->d_gen_trunc.p;
+        MPS_CUDA_CHECK(mps_launch_hybrid_controls(gp, ctx->stream), ctx);
+        ctx->launches++;
+        ctx->gen_ready = true;
+    }
 
     RolloutParams& rp = ctx->rp;
     memset(&rp, 0, sizeof(rp));
@@ -1066,6 +1109,35 @@ int mps_extend_upload(mps_ctx* ctx, const mps_extend_in* in)
     ctx->ext_K = K;
     ctx->ext_L = L;
     ctx->extend_ready = true;
+    return MPS_OK;
+}
+
+int mps_extend_generated_controls(mps_ctx* ctx, float* controls, int32_t* n_ctrl, int32_t* n_truncated)
+{
+    if (!ctx) return mps_fail(nullptr, MPS_ERR_ARG, "ctx is NULL");
+    if (!ctx->extend_ready || !ctx->gen_ready) return mps_fail(ctx, MPS_ERR_STATE, "no generated extend uploaded");
+    const size_t KL = (size_t)ctx->ext_K * ctx->ext_L;
+    unsigned int tr = 0;
+    if (controls) MPS_CUDA_CHECK(cudaMemcpyAsync(controls, ctx->d_controls.p, sizeof(float) * MPS_CONTROL_DIM * KL, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    if (n_ctrl) MPS_CUDA_CHECK(cudaMemcpyAsync(n_ctrl, ctx->d_nctrl.p, sizeof(int32_t) * (size_t)ctx->ext_K, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaMemcpyAsync(&tr, ctx->d_gen_trunc.p, sizeof(tr), cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+    if (n_truncated) *n_truncated = (int32_t)tr;
+    return MPS_OK;
+}
+
+int mps_sample_controls(mps_ctx* ctx, uint64_t seed, int32_t iteration, int64_t gid, int32_t n, float velocity_limit,
+                        float omega_limit, float duration_min, float duration_max, float* controls)
+{
+    if (!ctx || !controls || n < 1) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_sample_controls");
+    MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
+    int rc = ensure(ctx, ctx->d_vstates, sizeof(float) * MPS_CONTROL_DIM * (size_t)n);
+    if (rc) return rc;
+    MPS_CUDA_CHECK(mps_launch_sample_controls(seed, iteration, gid, n, velocity_limit, omega_limit, duration_min, duration_max,
+                                              (float*)ctx->d_vstates.p, ctx->stream), ctx);
+    ctx->launches++;
+    MPS_CUDA_CHECK(cudaMemcpyAsync(controls, ctx->d_vstates.p, sizeof(float) * MPS_CONTROL_DIM * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream), ctx);
+    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     return MPS_OK;
 }
 

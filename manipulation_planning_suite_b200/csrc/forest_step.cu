@@ -6,6 +6,7 @@
 // Random numbers are counter-based: u(seed, iteration, global instance id, purpose, index) is a hash, so an
 // instance's draws depend neither on the other instances nor on how the instances are split over GPUs.
 #include "forest_step.h"
+#include "mps_device.cuh"
 
 namespace {
 
@@ -26,6 +27,188 @@ __device__ __forceinline__ float u01(unsigned long long seed, int iteration, lon
     h = mix64(h ^ mix64((unsigned long long)gid));
     h = mix64(h ^ (unsigned long long)idx);
     return (float)(h >> 40) * (1.0f / 16777216.0f);
+}
+
+// RampVelocityControlSampler::sample (ompl/control/RampVelocityControl.cpp:353-394): (vx, vy) uniform in the disc of
+// radius v_limit (the reference normalises a gaussian pair and scales by v_limit * u^(1/2); radius v_limit * sqrt(u)
+// at a uniform angle is the same distribution), omega and the plateau duration uniform, rest time 0
+__device__ __forceinline__ void sample_control(unsigned long long seed, int iteration, long long gid, int tag, int idx,
+                                               float v_limit, float w_limit, float dur_min, float dur_max, float* c)
+{
+    const float two_pi = 6.28318530717958647692f;
+    const float r = v_limit * sqrtf(u01(seed, iteration, gid, tag, idx * 4));
+    float sn, cs;
+    __sincosf(two_pi * u01(seed, iteration, gid, tag, idx * 4 + 1), &sn, &cs);
+    c[0] = r * cs;
+    c[1] = r * sn;
+    c[2] = (2.0f * u01(seed, iteration, gid, tag, idx * 4 + 2) - 1.0f) * w_limit;
+    c[3] = dur_min + (dur_max - dur_min) * u01(seed, iteration, gid, tag, idx * 4 + 3);
+    c[4] = 0.0f;
+}
+
+__global__ void sample_controls_kernel(unsigned long long seed, int iteration, long long gid, int n, float v_limit,
+                                       float w_limit, float dur_min, float dur_max, float* controls)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+        sample_control(seed, iteration, gid, TAG_CTRL, t, v_limit, w_limit, dur_min, dur_max, controls + (size_t)t * MPS_CONTROL_DIM);
+}
+
+// ---- oracle action sequences --------------------------------------------------------------------------------------
+enum { TAG_H_DIE = 11, TAG_H_OBJ = 12, TAG_H_OBJ_UNIFORM = 13, TAG_H_TGT = 14, TAG_H_GAUSS = 15, TAG_H_ZERO = 16, TAG_H_RANDOM = 17 };
+
+__device__ __forceinline__ float shortest_so2(float a, float b)  // util/Math.cpp:33-44
+{
+    float v = b - a;
+    if (fabsf(v) > 3.14159265358979323846f) v = v > 0.0f ? v - 6.28318530717958647692f : v + 6.28318530717958647692f;
+    return v;
+}
+
+// RampVelocityControl::computeRamp's acceleration time for plateau velocities v (RampVelocityControl.cpp:98-118)
+__device__ __forceinline__ float accel_time_of(const float v[3], const float acc[3])
+{
+    float t = fabsf(v[0] / acc[0]);
+    t = fmaxf(t, fabsf(v[1] / acc[1]));
+    t = fmaxf(t, fabsf(v[2] / acc[2]));
+    return t;
+}
+
+// RampComputer::steer (pushing/oracle/RampComputer.cpp:40-92): ramp controls that take the robot from cur to des along
+// the straight line of its configuration space; appends at most `room` controls to out, returns how many the steer
+// consists of (may exceed room)
+__device__ int steer(const float cur[3], const float des[3], const float vlim[3], const float acc[3], float dur_max,
+                     float* out, int room)
+{
+    float dir[3] = {des[0] - cur[0], des[1] - cur[1], shortest_so2(cur[2], des[2])};
+    float distance = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    if (!(distance > 0.0f)) return 0;
+    for (int i = 0; i < 3; ++i) dir[i] /= distance;
+    float vabs = 3.402823466e+38f;
+    for (int i = 0; i < 3; ++i) vabs = fminf(vabs, vlim[i] / fabsf(dir[i]));
+    float vel[3] = {vabs * dir[0], vabs * dir[1], vabs * dir[2]};
+    float ta = accel_time_of(vel, acc);
+    auto norm3 = [](const float v[3], float s) { return sqrtf(s * v[0] * s * v[0] + s * v[1] * s * v[1] + s * v[2] * s * v[2]); };
+    float dist_accel = norm3(vel, ta);
+    int n = 0;
+    while (distance > 0.0f && n < 64) {
+        if (dist_accel > distance) {  // the acceleration phases alone would overshoot: a slower plateau velocity
+            vabs = distance / ta;
+            for (int i = 0; i < 3; ++i) vel[i] = vabs * dir[i];
+            ta = accel_time_of(vel, acc);
+            dist_accel = norm3(vel, ta);
+        }
+        distance = distance - dist_accel;
+        const float max_plateau = fminf(norm3(vel, dur_max), distance);
+        const float duration = max_plateau / vabs;
+        if (n < room) {
+            float* c = out + n * MPS_CONTROL_DIM;
+            c[0] = vel[0];
+            c[1] = vel[1];
+            c[2] = vel[2];
+            c[3] = duration;
+            c[4] = 0.0f;
+        }
+        ++n;
+        distance = distance - max_plateau;
+    }
+    return n;
+}
+
+// standard normal from two uniforms (Box-Muller)
+__device__ __forceinline__ float gauss01(float u1, float u2)
+{
+    return sqrtf(-2.0f * logf(1.0f - u1)) * cosf(6.28318530717958647692f * u2);
+}
+
+// One thread per chain: HybridActionRRT::sampleActionSequence (pushing/algorithm/RRT.cpp:491-529) with
+// OracleControlSampler::{steerRobot, steerPush, sampleFeasibleState, randomControl} (oracle/OracleControlSampler.cpp:
+// 77-207) and HumanOracle::{sampleFeasibleState, predictAction} (oracle/HumanOracle.cpp:111-159) behind them.
+__global__ void hybrid_controls_kernel(HybridGenParams p)
+{
+    const mps_hybrid_gen& g = p.gen;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < p.K; k += gridDim.x * blockDim.x) {
+        float* out = p.controls + (size_t)k * p.L * MPS_CONTROL_DIM;
+        for (int i = 0; i < p.L * MPS_CONTROL_DIM; ++i) out[i] = 0.0f;
+        const long long gid = (long long)g.k_offset + k;
+        int n = 0;
+        const float die = u01(g.seed, g.iteration, gid, TAG_H_DIE, 0);
+        const float cur_r[3] = {p.start[3 * p.robot], p.start[3 * p.robot + 1], p.start[3 * p.robot + 2]};
+        if (die < g.action_randomness) {
+            sample_control(g.seed, g.iteration, gid, TAG_H_RANDOM, 0, g.velocity_limits[0], g.velocity_limits[2], g.duration_min,
+                           g.duration_max, out);
+            n = 1;
+        } else {
+            // which object to move: the caller's (OracleRRT), else sampleActiveObject (RRT.cpp:246-257)
+            int obj = g.fixed_object;
+            if (obj < 0) {
+                const float uo = u01(g.seed, g.iteration, gid, TAG_H_OBJ, 0);
+                obj = (int)(u01(g.seed, g.iteration, gid, TAG_H_OBJ_UNIFORM, 0) * (float)p.B);
+                if (obj > p.B - 1) obj = p.B - 1;
+                if (uo < g.target_bias && g.n_targets > 0) {
+                    int pick = (int)(u01(g.seed, g.iteration, gid, TAG_H_TGT, 0) * (float)g.n_targets);
+                    if (pick > g.n_targets - 1) pick = g.n_targets - 1;
+                    obj = g.targets[pick];
+                } else if (uo < g.target_bias + g.robot_bias) {
+                    obj = p.robot;
+                }
+            }
+            if (obj == p.robot) {  // transit primitive
+                const float des_r[3] = {p.dest[3 * p.robot], p.dest[3 * p.robot + 1], p.dest[3 * p.robot + 2]};
+                n = steer(cur_r, des_r, g.velocity_limits, p.accel, g.duration_max, out, p.L);
+            } else {  // transfer primitive: to a feasible pushing state, then the push (the world is assumed unchanged)
+                const float cur_o[3] = {p.start[3 * obj], p.start[3 * obj + 1], p.start[3 * obj + 2]};
+                const float des_o[3] = {p.dest[3 * obj], p.dest[3 * obj + 1], p.dest[3 * obj + 2]};
+                // HumanOracle::sampleFeasibleState
+                const float pushing_dist = g.optimal_push_distance + g.push_distance_tolerance *
+                    gauss01(u01(g.seed, g.iteration, gid, TAG_H_GAUSS, 0), u01(g.seed, g.iteration, gid, TAG_H_GAUSS, 1));
+                const float angle = g.push_angle_tolerance *
+                    gauss01(u01(g.seed, g.iteration, gid, TAG_H_GAUSS, 2), u01(g.seed, g.iteration, gid, TAG_H_GAUSS, 3));
+                float rel[3] = {des_o[0] - cur_o[0], des_o[1] - cur_o[1], shortest_so2(cur_o[2], des_o[2])};
+                if (sqrtf(rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2]) == 0.0f) {
+                    rel[0] = 0.0001f * (0.5f - u01(g.seed, g.iteration, gid, TAG_H_ZERO, 0));
+                    rel[1] = 0.0001f * (0.5f - u01(g.seed, g.iteration, gid, TAG_H_ZERO, 1));
+                }
+                const float nrm = sqrtf(rel[0] * rel[0] + rel[1] * rel[1]);
+                float pd[2] = {1.0f, 0.0f};
+                if (nrm > 0.0f) {
+                    pd[0] = rel[0] / nrm;
+                    pd[1] = rel[1] / nrm;
+                }
+                const float ca = cosf(angle), sa = sinf(angle);
+                float feas[3];
+                feas[0] = cur_o[0] - pushing_dist * (ca * pd[0] - sa * pd[1]);
+                feas[1] = cur_o[1] - pushing_dist * (sa * pd[0] + ca * pd[1]);
+                feas[2] = atan2f(pd[1], pd[0]) - 1.57f;  // the reference's floating end-effector (HumanOracle.cpp:156)
+                // setConfiguration normalises the SO(2) component (SimEnvState.cpp:131-135)
+                double th = fmod((double)feas[2], 2.0 * MPS_PI_D);
+                if (th < -MPS_PI_D)
+                    th += 2.0 * MPS_PI_D;
+                else if (th >= MPS_PI_D)
+                    th -= 2.0 * MPS_PI_D;
+                feas[2] = (float)th;
+                n = steer(cur_r, feas, g.velocity_limits, p.accel, g.duration_max, out, p.L);
+                // HumanOracle::predictAction from the feasible state: the first control of the steer towards the
+                // object's destination, half an object size short of it; a null control when the object does not translate
+                float push[MPS_CONTROL_DIM] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                const float r2[3] = {des_o[0] - cur_o[0], des_o[1] - cur_o[1], 0.0f};
+                const float n2 = sqrtf(r2[0] * r2[0] + r2[1] * r2[1]);
+                if (n2 != 0.0f) {
+                    const float half = g.object_size[obj] / 2.0f;
+                    const float next_r[3] = {des_o[0] - r2[0] / n2 * half, des_o[1] - r2[1] / n2 * half, feas[2]};
+                    float first[MPS_CONTROL_DIM];
+                    if (steer(feas, next_r, g.velocity_limits, p.accel, g.duration_max, first, 1) > 0)
+                        for (int i = 0; i < MPS_CONTROL_DIM; ++i) push[i] = first[i];
+                }
+                if (n < p.L)
+                    for (int i = 0; i < MPS_CONTROL_DIM; ++i) out[n * MPS_CONTROL_DIM + i] = push[i];
+                ++n;
+            }
+        }
+        if (n > p.L) {
+            atomicAdd(p.truncated, 1u);
+            n = p.L;
+        }
+        p.n_ctrl[k] = n;
+    }
 }
 
 __global__ void naive_sample_kernel(NaiveSampleParams p)
@@ -75,15 +258,8 @@ __global__ void naive_sample_kernel(NaiveSampleParams p)
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.M * p.K; t += gridDim.x * blockDim.x) {
         const int m = t / p.K, k = t - m * p.K;
         const long long gid = p.instance_offset + p.inst_ids[m];
-        const float r = p.v_limit * sqrtf(u01(p.seed, p.iteration, gid, TAG_CTRL, k * 4));
-        float sn, cs;
-        __sincosf(two_pi * u01(p.seed, p.iteration, gid, TAG_CTRL, k * 4 + 1), &sn, &cs);
-        float* c = p.controls + (size_t)t * MPS_CONTROL_DIM;
-        c[0] = r * cs;
-        c[1] = r * sn;
-        c[2] = (2.0f * u01(p.seed, p.iteration, gid, TAG_CTRL, k * 4 + 2) - 1.0f) * p.w_limit;
-        c[3] = p.dur_min + (p.dur_max - p.dur_min) * u01(p.seed, p.iteration, gid, TAG_CTRL, k * 4 + 3);
-        c[4] = 0.0f;
+        sample_control(p.seed, p.iteration, gid, TAG_CTRL, k, p.v_limit, p.w_limit, p.dur_min, p.dur_max,
+                       p.controls + (size_t)t * MPS_CONTROL_DIM);
     }
 }
 
@@ -135,5 +311,18 @@ cudaError_t mps_launch_naive_pick(int M, int C, int B, const float* cand, const 
 cudaError_t mps_launch_idx_to_parent(int M, const long long* nearest, int32_t* parents, cudaStream_t stream)
 {
     idx_to_parent_kernel<<<grid_of(M), 256, 0, stream>>>(M, nearest, parents);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_hybrid_controls(const HybridGenParams& p, cudaStream_t stream)
+{
+    hybrid_controls_kernel<<<grid_of(p.K), 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t mps_launch_sample_controls(unsigned long long seed, int iteration, long long gid, int n, float v_limit,
+                                       float w_limit, float dur_min, float dur_max, float* controls, cudaStream_t stream)
+{
+    sample_controls_kernel<<<grid_of(n), 256, 0, stream>>>(seed, iteration, gid, n, v_limit, w_limit, dur_min, dur_max, controls);
     return cudaGetLastError();
 }

@@ -35,14 +35,14 @@ def test_struct_sizes_match_the_header(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "mps_b200.h"\n'
-        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(mps_scene), sizeof(mps_goal),"
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(mps_hybrid_gen), offsetof(mps_hybrid_gen, object_size), sizeof(mps_scene), sizeof(mps_goal),"
         " sizeof(mps_extend_in), sizeof(mps_extend_best), sizeof(mps_extend_out), offsetof(mps_scene, position_weight),"
         " offsetof(mps_scene, dt), offsetof(mps_scene, jam_steps), sizeof(mps_forest_extend_in), sizeof(mps_forest_naive_in),"
         " offsetof(mps_forest_naive_in, goals), offsetof(mps_forest_naive_in, duration_max), offsetof(mps_extend_in, starts));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    want = [C.sizeof(abi.Scene), C.sizeof(abi.Goal), C.sizeof(abi.ExtendIn), C.sizeof(abi.ExtendBest),
+    want = [C.sizeof(abi.HybridGen), abi.HybridGen.object_size.offset, C.sizeof(abi.Scene), C.sizeof(abi.Goal), C.sizeof(abi.ExtendIn), C.sizeof(abi.ExtendBest),
             C.sizeof(abi.ExtendOut), abi.Scene.position_weight.offset, abi.Scene.dt.offset, abi.Scene.jam_steps.offset,
             C.sizeof(abi.ForestExtendIn), C.sizeof(abi.ForestNaiveIn), abi.ForestNaiveIn.goals.offset,
             abi.ForestNaiveIn.duration_max.offset, abi.ExtendIn.starts.offset]
