@@ -1127,19 +1127,21 @@ SlicePtr SliceBasedOracleRRT::getSlice(const ompl::state::SimEnvWorldState& stat
     return rep ? _slices_list.at((size_t)rep->index) : nullptr;
 }
 
-bool SliceBasedOracleRRT::projectSliceBall(const ompl::state::SimEnvWorldState& center,
-                                           ompl::state::SimEnvWorldState* sample) const
+bool SliceBasedOracleRRT::projectSliceBall(const ompl::state::SimEnvWorldStateDistanceMeasure& measure, unsigned int n_objects,
+                                           unsigned int robot_id, float radius,
+                                           const ompl::state::SimEnvWorldState& center,
+                                           ompl::state::SimEnvWorldState* sample)
 {
     // d_arr(sample, center) <= r: inside the ball; else move every object towards the centre's arrangement by the
-    // factor r / d along the straight line (positions) and the shortest arc (angles)
-    auto dm = *_distance_measure;
+    // factor r / d along the straight line (positions) and the shortest arc (angles); the robot's sub-state stays
+    auto dm = measure;
     dm.setAll(true);
-    dm.setActive(_robot_id_cached, false);
+    dm.setActive(robot_id, false);
     double d = dm.distance(sample, &center);
-    if (d <= (double)_slice_ball_radius || d == 0.0) return true;
-    float f = (float)((double)_slice_ball_radius / d);
-    for (unsigned int i = 0; i < _state_space->getNumObjects(); ++i) {
-        if (i == _robot_id_cached) continue;
+    if (d <= (double)radius || d == 0.0) return true;
+    float f = (float)((double)radius / d);
+    for (unsigned int i = 0; i < n_objects; ++i) {
+        if (i == robot_id) continue;
         const float* c = center.getObjectState(i);
         float* s = sample->getObjectState(i);
         s[0] = c[0] + f * (s[0] - c[0]);
@@ -1149,6 +1151,13 @@ bool SliceBasedOracleRRT::projectSliceBall(const ompl::state::SimEnvWorldState& 
         s[2] = th;
     }
     return false;
+}
+
+bool SliceBasedOracleRRT::projectSliceBall(const ompl::state::SimEnvWorldState& center,
+                                           ompl::state::SimEnvWorldState* sample) const
+{
+    return projectSliceBall(*_distance_measure, _state_space->getNumObjects(), _robot_id_cached, _slice_ball_radius, center,
+                            sample);
 }
 
 void SliceBasedOracleRRT::selectTreeNode(const MotionPtr& sample, MotionPtr& selected_node, unsigned int& active_obj_id,
@@ -1527,6 +1536,25 @@ extern "C" int mps_host_ramp_steer(const float* vel_limits, const float* accel_l
     for (size_t i = 0; i < out.size() && (int32_t)i < max_controls; ++i)
         for (int c = 0; c < 5; ++c) controls_out[i * 5 + c] = out[i][c];
     return (int)out.size();
+}
+
+extern "C" int mps_host_project_slice_ball(const mps_scene* scene, const float* weights, int32_t robot_id, float radius,
+                                           const float* center, float* sample)
+{
+    if (!scene || !center || !sample) return -1;
+    const unsigned int B = (unsigned int)scene->n_bodies;
+    auto space = std::make_shared<ompl::state::SimEnvWorldStateSpace>(*scene);
+    std::vector<float> w;
+    if (weights) w.assign(weights, weights + B);
+    ompl::state::SimEnvWorldStateDistanceMeasure dm(space, w);
+    ompl::state::SimEnvWorldState c(B), s(B);
+    for (unsigned int i = 0; i < 3 * B; ++i) {
+        c.values[i] = center[i];
+        s.values[i] = sample[i];
+    }
+    const bool inside = pushing::algorithm::SliceBasedOracleRRT::projectSliceBall(dm, B, (unsigned int)robot_id, radius, c, &s);
+    for (unsigned int i = 0; i < 3 * B; ++i) sample[i] = s.values[i];
+    return inside ? 1 : 0;
 }
 
 extern "C" float mps_host_max_pushing_distance(void)

@@ -577,6 +577,10 @@ public:
     // nearest slice (README.md:33-34; declared but not implemented in the reference snapshot: our definition)
     void setSliceBallProjection(bool on, float radius) { _do_slice_ball_projection = on; _slice_ball_radius = radius; }
     bool projectSliceBall(const ompl::state::SimEnvWorldState& center, ompl::state::SimEnvWorldState* sample) const;
+    // the projection itself (needs no device): true = the sample was inside the ball and is unchanged
+    static bool projectSliceBall(const ompl::state::SimEnvWorldStateDistanceMeasure& measure, unsigned int n_objects,
+                                 unsigned int robot_id, float radius, const ompl::state::SimEnvWorldState& center,
+                                 ompl::state::SimEnvWorldState* sample);
 
 protected:
     void setup(PlanningQueryPtr pq, PlanningBlackboard& pb) override;                   // :766-781

@@ -52,6 +52,12 @@ int mps_host_shortcut(const mps_scene* scene, const mps_goal* goals, int32_t n_g
 /* RampComputer::steer (oracle/RampComputer.cpp:40-92) */
 int mps_host_ramp_steer(const float* vel_limits, const float* accel_limits, const float* duration_limits,
                         const float* current, const float* desired, float* controls_out, int32_t max_controls);
+/* SliceBasedOracleRRT's slice-ball projection (README.md:33-34, do_slice_ball_projection; declared but not
+ * implemented in the reference snapshot - this repo's definition): `sample` [3B] is moved onto the ball of `radius`
+ * around `center` under the arrangement metric (every body but the robot) when it lies outside; returns 1 when it
+ * was inside (unchanged), 0 when it was projected, < 0 on a bad argument */
+int mps_host_project_slice_ball(const mps_scene* scene, const float* weights, int32_t robot_id, float radius,
+                                const float* center, float* sample);
 /* HumanOracle::getMaximalPushingDistance (oracle/HumanOracle.cpp:161-164) */
 float mps_host_max_pushing_distance(void);
 

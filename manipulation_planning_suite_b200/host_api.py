@@ -60,6 +60,8 @@ def load_host_library():
                                         C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32, C.c_char_p, C.c_int32]
         L.mps_host_ramp_steer.argtypes = [C.POINTER(C.c_float)] * 6 + [C.c_int32]
         L.mps_host_max_pushing_distance.restype = C.c_float
+        L.mps_host_project_slice_ball.argtypes = [C.POINTER(abi.Scene), C.POINTER(C.c_float), C.c_int32, C.c_float,
+                                                  C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -154,3 +156,16 @@ def ramp_steer(current, desired, vel_limits=(0.6, 0.6, 1.5), accel_limits=(2.0, 
     n = L.mps_host_ramp_steer(v.ctypes.data_as(P), a.ctypes.data_as(P), d.ctypes.data_as(P), c.ctypes.data_as(P),
                               e.ctypes.data_as(P), out.ctypes.data_as(P), 64)
     return out[:n].copy()
+
+
+def project_slice_ball(scene: abi.Scene, center, sample, radius: float, weights=None):
+    """SliceBasedOracleRRT::projectSliceBall -> (inside, projected sample)"""
+    B = int(scene.n_bodies)
+    c = np.ascontiguousarray(center, np.float32).reshape(3 * B)
+    s = np.ascontiguousarray(sample, np.float32).reshape(3 * B).copy()
+    w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+    fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    rc = load_host_library().mps_host_project_slice_ball(C.byref(scene), fp(w), int(scene.robot_id), float(radius), fp(c), fp(s))
+    if rc < 0:
+        raise ValueError("bad argument to mps_host_project_slice_ball")
+    return bool(rc), s

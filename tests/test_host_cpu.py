@@ -117,3 +117,48 @@ def test_host_library_exports_and_struct_layouts():
                    host_api.HostParams.shortcut_type.offset, host_api.HostResult.shortcut_accepted.offset]
     p = host_api.default_params()
     assert p.shortcut_type == host_api.SHORTCUT_TYPES["LocalShortcut"] and p.max_shortcut_time == 5.0  # reference defaults
+
+
+def test_project_slice_ball_inside_on_and_outside():
+    """SliceBasedOracleRRT::projectSliceBall (host/mps_host.cpp; do_slice_ball_projection of README.md:33-34): a sample
+    inside or on the ball of the arrangement metric is left alone; outside, every object moves towards the centre's
+    arrangement along the straight line / shortest arc so that the arrangement distance becomes the radius; the robot's
+    sub-state is never touched"""
+    import oracle_binding as ob
+
+    sc, _ = scenes.make_scene(3, seed=2)
+    B = sc.n_bodies
+    arr_mask = ((1 << B) - 1) & ~(1 << sc.robot_id)
+    rng = np.random.RandomState(0)
+    center = scenes.sample_state(rng, sc)
+    for trial in range(20):
+        sample = scenes.sample_state(rng, sc)
+        d = ob.distance(sc, sample, center, mask=arr_mask)
+        on = np.float32(d)   # the radius travels as a float: the smallest one that is not below d
+        if float(on) < d:
+            on = np.nextafter(on, np.float32(np.inf))
+        for radius in (d * 1.5, float(on), d * 0.4, d * 0.05):
+            inside, out = host_api.project_slice_ball(sc, center, sample, radius)
+            assert np.array_equal(out[:3], sample[:3])                      # robot untouched
+            if radius >= d:
+                assert inside and np.array_equal(out, sample)                # inside / on the ball: unchanged
+            else:
+                assert not inside
+                assert ob.distance(sc, out, center, mask=arr_mask) == pytest.approx(radius, rel=2e-5)
+                f = radius / d
+                for i in range(1, B):
+                    # positions on the segment towards the centre, angles on the shortest arc, by the factor r / d
+                    assert out[3 * i:3 * i + 2] == pytest.approx(center[3 * i:3 * i + 2] + f * (sample[3 * i:3 * i + 2] - center[3 * i:3 * i + 2]), abs=1e-6)
+                    arc = (sample[3 * i + 2] - center[3 * i + 2] + np.pi) % (2 * np.pi) - np.pi
+                    got = (out[3 * i + 2] - center[3 * i + 2] + np.pi) % (2 * np.pi) - np.pi
+                    assert got == pytest.approx(f * arc, abs=2e-6)
+                    assert -np.pi <= out[3 * i + 2] < np.pi
+    # the centre itself: distance 0, inside
+    inside, out = host_api.project_slice_ball(sc, center, center, 0.1)
+    assert inside and np.array_equal(out, center)
+    # per-object weights enter the metric
+    w = np.array([1.0, 2.0, 0.5, 1.5], np.float32)
+    sample = scenes.sample_state(rng, sc)
+    d = ob.distance(sc, sample, center, weights=w, mask=arr_mask)
+    inside, out = host_api.project_slice_ball(sc, center, sample, d * 0.5, weights=w)
+    assert not inside and ob.distance(sc, out, center, weights=w, mask=arr_mask) == pytest.approx(0.5 * d, rel=2e-5)
