@@ -1861,7 +1861,7 @@ static int env_int(const char* name, int dflt)
 // grid of a rollout launch: as many CTAs as fit the machine, at most one group of lanes per chain
 template <class Kernel>
 static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_set, RolloutParams& p, int threads,
-                                         int groups, int num_sms, cudaStream_t stream)
+                                         int groups, int num_sms, cudaStream_t stream, int ctas_per_sm = 0)
 {
     size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
     int dev = 0;
@@ -1879,7 +1879,9 @@ static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_
     // tuning aid: MPS_ROLLOUT_CTAS_PER_SM caps the resident CTAs per SM (read once; initialisation of a local
     // static is thread-safe, contexts of different host threads may launch at the same time)
     static const int cap_per_sm = env_int("MPS_ROLLOUT_CTAS_PER_SM", 0);
-    if (cap_per_sm > 0 && blocks_per_sm > cap_per_sm) blocks_per_sm = cap_per_sm;
+    if (cap_per_sm > 0)
+        ctas_per_sm = cap_per_sm;
+    if (ctas_per_sm > 0 && blocks_per_sm > ctas_per_sm) blocks_per_sm = ctas_per_sm;
     int grid = num_sms * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
@@ -1891,28 +1893,37 @@ static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_
 
 // WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
 template <int WARPS, int MINB, int G>
-static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream)
+static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream, int ctas_per_sm = 0)
 {
     if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     static std::atomic<bool> attr_set[64];
-    return launch_rollout_kernel(rollout_kernel<WARPS, MINB, G>, attr_set, p, WARPS * 32, WARPS * (32 / G), num_sms, stream);
+    return launch_rollout_kernel(rollout_kernel<WARPS, MINB, G>, attr_set, p, WARPS * 32, WARPS * (32 / G), num_sms, stream,
+                                 ctas_per_sm);
 }
 
 cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bodies, cudaStream_t stream)
 {
     RolloutParams p = p_in;
-    // Few chains (at most ~3 CTAs of 4 warps per SM): one warp per chain, latency build.  Launches that fill
-    // the machine are bound by instruction issue: scenes with at most 8 bodies then run four chains per warp
-    // (same arithmetic per chain, so the same bits), which divides the instructions per chain.
-    // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build,
-    // MPS_ROLLOUT_GROUP = 8 | 16 | 32 the lanes per chain.
+    // Which build and grid (measured on B200, profiles/tools/few_probe.py and packed_probe.py, cfg 2's scene; W =
+    // chains per warp scheduler):
+    //   W <= 3   one chain per warp, 168-register build, ONE CTA per SM.  The launch lasts as long as its slowest
+    //            chain, and a chain is faster when its warp has a scheduler to itself; with the longest chains pulled
+    //            first (mps_launch_chain_order) the short ones queue behind them without stretching the launch
+    //            (K = 1024: 1.41 -> 1.35 ms against a grid that leaves two CTAs on 108 of the 148 SMs).
+    //   W <= 8   the same build, two CTAs per SM (K = 4096 chains of <= 4 controls: 1.93 ms; 3.05 with one CTA per
+    //            SM, 2.12 with three, 3.83 packed).
+    //   beyond   128-register build, as many CTAs as fit (issue-bound regime).
+    //   packed   four chains per warp (scenes with at most 8 bodies) pay off only for many single-control chains:
+    //            K = 16 384: 1.00 ms against 1.26, K = 65 536: 3.39 against 4.76; K = 8192: 0.87 against 0.68, and
+    //            chains of several controls (diverging groups) lose at every K measured (K = 16 384: 6.57 against 5.68).
+    // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build, MPS_ROLLOUT_GROUP =
+    // 8 | 16 | 32 the lanes per chain, MPS_ROLLOUT_CTAS_PER_SM the resident CTAs.
     static const int forced_minb = env_int("MPS_ROLLOUT_MINB", 0);
     static const int forced_g = env_int("MPS_ROLLOUT_GROUP", 0);
-    const bool few = (long long)p.K <= (long long)num_sms * ROLLOUT_WARPS * 3;
+    const double per_sched = (double)p.K / ((double)num_sms * ROLLOUT_WARPS);
     int g = forced_g;
-    // measured on B200 (profiles/tools/throughput_probe.py): four chains per warp gain 20-60 % for scenes with
-    // at most 8 bodies; two chains per warp (9..16 bodies) gain nothing on contact-rich scenes and stay opt-in
-    if (g == 0) g = few ? 32 : (n_bodies <= 8 ? 8 : 32);
+    // two chains per warp (9..16 bodies) gained nothing on contact-rich scenes and stay opt-in
+    if (g == 0) g = (n_bodies <= 8 && p.L == 1 && p.K >= 12288) ? 8 : 32;
     if (g == 8 && n_bodies > 8) g = 16;
     if (g == 16 && n_bodies > 16) g = 32;
     if (g != 32) {
@@ -1932,9 +1943,14 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     p.redo_only = 0;
     p.mcap_small = 0;
     int minb = forced_minb;
-    if (minb == 0) minb = few ? 3 : 4;
-    if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream);
-    return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream);
+    if (minb == 0) minb = per_sched <= 8.0 ? 3 : 4;
+    int ctas = 0;
+    if (p.order && per_sched <= 3.0)
+        ctas = 1;
+    else if (p.order && per_sched <= 8.0 && p.L > 1)
+        ctas = 2;  // (single-control chains vary less in length: three CTAs per SM are better there, 0.41 against 0.51 ms at K = 4096)
+    if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream, ctas);
+    return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream, ctas);
 }
 
 cudaError_t mps_launch_chain_order(const float* controls, const int32_t* n_ctrl, int K, int L, const float accel[3],

@@ -78,3 +78,21 @@ def test_kernel_source_reproduces_the_independent_physics_answers(group):
     valid, flags = eb.is_valid_batch(sc, np.stack([pk.arr(c["state"]) for c in kat["valid"]["cases"]]))
     for i, case in enumerate(kat["valid"]["cases"]):
         assert int(flags[i]) == case["flags"] and bool(valid[i]) == (case["flags"] == 0), case["name"]
+
+
+@pytest.mark.parametrize("group", [32, 8])
+def test_sparse_scene_free_flight_and_approach_match_oracle(group):
+    """objects spread over the workspace: most steps are free flight (only the robot's lane steps while the candidate
+    list is empty and nothing else moves), with approaches, contacts and separations in between"""
+    sc, start = scenes.make_scene(5, seed=1001)
+    rng = np.random.RandomState(8)
+    K, L = 20, 3
+    c = scenes.sample_controls(rng, K, L)
+    c[::2] = scenes.sample_controls_towards(rng, sc, start, K, L, noise=0.1)[::2]   # half of them aimed at objects
+    d = scenes.sample_state(rng, sc)
+    w = ob.extend(sc, start, c, dest=d, compare_f32=True)
+    r = eb.extend(sc, start, c, group=group, minb=4, dest=d, compare_f32=True)
+    _same(r, w)
+    moved = np.abs(w["all_states"][:, :, 3:] - start[None, None, 3:]).max(axis=(1, 2)) > 1e-4
+    assert 2 <= moved.sum() <= K - 2   # both kinds of chains are present
+    assert r["counters"]["steps"] == int(w["all_steps"].sum())
