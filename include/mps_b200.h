@@ -282,6 +282,10 @@ int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uin
  * tree / the slice).  One streaming pass with warp-level top-k lists; exact (see csrc/nn_scan.cu). */
 int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
                        int32_t k, int64_t* indices, double* distances, int32_t* n_found);
+/* n calls of mps_tree_nearest in a row (queries [n][3B]), timed by the host clock around the loop: the end-to-end
+ * latency of the C entry point itself (host query in, index and distance out), without a language binding on top */
+int mps_tree_nearest_timed(mps_ctx* ctx, const float* queries, int32_t n, const float* weights, uint32_t mask,
+                           int32_t slice_filter, int64_t* indices, double* distances, double* seconds);
 /* how many mps_tree_nearest_k calls had to be redone by exact successor scans (diagnostic) */
 int mps_tree_nearest_k_fallbacks(mps_ctx* ctx, int64_t* count);
 /* SliceBasedOracleRRT's two-level search (RRT.cpp:783-827: _slices_nn->nearest, then the slice's own

@@ -250,6 +250,7 @@ SYMBOLS = {
     "mps_tree_add_batch": (C.c_int, [_ctx, _P(_f32), _P(_i32), _P(_f32), _P(_i32), C.c_int64, _P(C.c_int64)]),
     "mps_tree_nearest": (C.c_int, [_ctx, _P(_f32), _P(_f32), _u32, _i32, _P(C.c_int64), _P(C.c_double)]),
     "mps_tree_nearest_k": (C.c_int, [_ctx, _P(_f32), _P(_f32), _u32, _i32, _i32, _P(C.c_int64), _P(C.c_double), _P(_i32)]),
+    "mps_tree_nearest_timed": (C.c_int, [_ctx, _P(_f32), _i32, _P(_f32), _u32, _i32, _P(C.c_int64), _P(C.c_double), _P(C.c_double)]),
     "mps_tree_nearest_k_fallbacks": (C.c_int, [_ctx, _P(C.c_int64)]),
     "mps_tree_nearest_two_level": (C.c_int, [_ctx, _ctx, _P(_f32), _P(_f32), _u32, _u32, _P(C.c_int64), _P(C.c_double),
                                              _P(C.c_int64), _P(C.c_double)]),

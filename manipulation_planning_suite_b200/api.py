@@ -407,6 +407,20 @@ class NearestNeighbors:
                                                     C.byref(n)))
         return idx[: n.value], d[: n.value]
 
+    def nearest_timed(self, queries, weights=None, mask=None, slice_filter: int = -1):
+        """n single queries through the C entry point in a C loop -> (indices, distances, seconds)"""
+        B = self.ctx.B
+        qs = _f32(queries).reshape(-1, 3 * B)
+        n = qs.shape[0]
+        w = _f32(weights, (B,))
+        full = (1 << B) - 1 if B < 32 else 0xFFFFFFFF
+        idx = np.zeros(n, np.int64)
+        d = np.zeros(n, np.float64)
+        sec = C.c_double(0)
+        self.ctx._check(self.lib.mps_tree_nearest_timed(self.ctx.h, _fp(qs), n, _fp(w), full if mask is None else int(mask),
+                                                        int(slice_filter), _fp(idx, C.c_int64), _fp(d, C.c_double), C.byref(sec)))
+        return idx, d, sec.value
+
     def nearest_k_fallbacks(self) -> int:
         n = C.c_int64(0)
         self.ctx._check(self.lib.mps_tree_nearest_k_fallbacks(self.ctx.h, C.byref(n)))

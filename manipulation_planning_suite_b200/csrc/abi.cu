@@ -800,6 +800,28 @@ int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uin
     return MPS_OK;
 }
 
+// n single queries one after the other through mps_tree_nearest (host query in, (index, distance) out), timed by the
+// host clock around the loop: the latency of the C entry point itself, without the caller's language binding
+int mps_tree_nearest_timed(mps_ctx* ctx, const float* queries, int32_t n, const float* weights, uint32_t mask,
+                           int32_t slice_filter, int64_t* indices, double* distances, double* seconds)
+{
+    if (!ctx || !queries || n < 1 || !seconds) return mps_fail(ctx, MPS_ERR_ARG, "bad argument to mps_tree_nearest_timed");
+    const int B = ctx->scene.n_bodies;
+    int64_t idx = -1;
+    double d = 0.0;
+    int rc = mps_tree_nearest(ctx, queries, weights, mask, slice_filter, &idx, &d);  // warm-up (buffers, first launch)
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; ++i) {
+        rc = mps_tree_nearest(ctx, queries + (size_t)i * 3 * B, weights, mask, slice_filter, &idx, &d);
+        if (rc) return rc;
+        if (indices) indices[i] = idx;
+        if (distances) distances[i] = d;
+    }
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return MPS_OK;
+}
+
 // SliceBasedOracleRRT's two-level search without a host round trip between the levels (RRT.cpp:783-827 when the
 // sample needs no oracle adjustment, i.e. the active object is the robot): scan 1 finds the nearest slice
 // representative in `reps` (a second context whose node index is the slice id) under rep_mask, scan 2 - enqueued

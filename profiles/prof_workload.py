@@ -1,4 +1,5 @@
-"""Small profiling workload (run under ncu): 2 cfg2 extends (K=1024 chains) + 3 cfg3 NN scans (1M nodes)."""
+"""Small profiling workload (run under ncu): 2 cfg2 extends (K=1024 chains), 3 cfg3 NN scans (1M nodes) and two exact
+top-k queries (k = 8, 32) over the same tree."""
 import os
 import sys
 
@@ -29,4 +30,6 @@ tree.nearest_upload(q[None, :])
 for _ in range(3):
     tree.nearest_launch()
 print("nn", tree.nearest_fetch())
+for k in (8, 32):
+    print("top-k", k, tree.nearest_k(q, k)[0][:4])
 ctx3.close()

@@ -26,6 +26,10 @@ WANT = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "sm__icc_requests.sum", "sm__icc_requests_lookup_hit.sum", "sm__icc_requests_lookup_miss.sum",
+    "gcc__requests.sum", "smsp__thread_inst_executed.sum", "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
 ]
 with open(prefix + "_raw_summary.txt", "w") as f:
     f.write(f"# selected raw metrics of {rep} (ncu --set full --clock-control none), one block per captured launch\n")
