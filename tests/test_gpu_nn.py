@@ -303,3 +303,33 @@ def test_two_level_query_equals_two_separate_queries():
     assert ri == n_slices - 1 and rd == 0.0 and i == -1
     ctx.close()
     rctx.close()
+
+
+def test_nearest_with_near_duplicates_at_the_angle_wrap():
+    """under a one-body mask the whole distance can be tiny while the fp32 arc of a wrapped angle difference,
+    2 pi - |dtheta|, carries an absolute error of a few 1e-7 rad; the candidate slack has to cover it, or the true
+    double-precision minimum is filtered out.  Nodes that differ from the query only by angles just across the wrap."""
+    sc, _ = scenes.make_scene(3, seed=4)
+    B = sc.n_bodies
+    rng = np.random.RandomState(3)
+    N = 4096
+    states = np.stack([scenes.sample_state(rng, sc) for _ in range(N)])
+    q = scenes.sample_state(rng, sc)
+    q[2] = np.float32(np.pi - 3e-5)
+    for i in range(0, N, 2):                       # robot sub-state: same position, angle just beyond -pi
+        states[i, 0:2] = q[0:2]
+        states[i, 2] = np.float32(-np.pi + 3e-5 + 2e-7 * (i % 97))
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.add_batch(states)
+    for mask in (1, (1 << B) - 1):
+        gi, gd = tree.nearest(q, mask=mask)
+        wi, wd = ob.nn_linear(sc, states, q, mask=mask)
+        assert (gi, gd) == (wi, wd)
+        ki, kd = tree.nearest_k(q, 16, mask=mask)
+        d = _all_distances(sc, states, q, mask=mask)
+        wi16, wd16 = _sorted_scan(d, 16)
+        assert np.array_equal(ki, wi16) and np.array_equal(kd, wd16)
+        if mask == 1:
+            assert gd < 1e-4   # the distances in play really are tiny
+    ctx.close()
