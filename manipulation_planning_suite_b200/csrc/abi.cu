@@ -1510,6 +1510,16 @@ static int forest_extend_launch(mps_ctx* ctx, int M, int K, int L, bool has_nctr
     sp.tree_slice = ctx->forest.slice;
     sp.inst_ids = rp.inst_ids;
     sp.parents = rp.parents;
+    // longest chains first, as in the plain extend (the launch lasts as long as its last chains)
+    static const bool lpt = !(getenv("MPS_ROLLOUT_LPT") && getenv("MPS_ROLLOUT_LPT")[0] == '0');
+    if (lpt && KT >= 64) {
+        int rc2 = ensure(ctx, ctx->d_order, sizeof(int32_t) * KT);
+        if (rc2) return rc2;
+        rp.order = (const int32_t*)ctx->d_order.p;
+        MPS_CUDA_CHECK(mps_launch_chain_order(rp.controls, rp.n_ctrl, rp.K, rp.L, ctx->hscene.accel, ctx->hscene.dt,
+                                              (int32_t*)ctx->d_order.p, st), ctx);
+        ctx->launches += 1;
+    }
     MPS_CUDA_CHECK(mps_launch_rollout(rp, ctx->num_sms, ctx->scene.n_bodies, st), ctx);
     MPS_CUDA_CHECK(mps_launch_select(sp, st), ctx);
     ctx->launches += 2;
