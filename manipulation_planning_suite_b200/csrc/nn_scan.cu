@@ -535,7 +535,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
 #if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 2
     cta_rank_merge(s_keys, s_out, k, &s_rej, tid);
 #endif
-    if (tid < k) tp.part_keys[(size_t)blockIdx.x * k + tid] = s_out[tid];
+    if (tid < k) {
+        tp.part_keys[(size_t)blockIdx.x * k + tid] = s_out[tid];
+        __threadfence();  // every writer of the list fences its own store before the CTA takes its ticket
+    }
+    __syncthreads();
     if (tid == 0) {
         tp.part_rej[blockIdx.x] = s_rej;
         __threadfence();
