@@ -64,49 +64,52 @@ __device__ __forceinline__ float shortest_so2(float a, float b)  // util/Math.cp
 }
 
 // RampVelocityControl::computeRamp's acceleration time for plateau velocities v (RampVelocityControl.cpp:98-118)
-__device__ __forceinline__ float accel_time_of(const float v[3], const float acc[3])
+__device__ __forceinline__ float accel_time_of(float vx, float vy, float vw, const float acc[3])
 {
-    float t = fabsf(v[0] / acc[0]);
-    t = fmaxf(t, fabsf(v[1] / acc[1]));
-    t = fmaxf(t, fabsf(v[2] / acc[2]));
+    float t = fabsf(vx / acc[0]);
+    t = fmaxf(t, fabsf(vy / acc[1]));
+    t = fmaxf(t, fabsf(vw / acc[2]));
     return t;
 }
 
-// RampComputer::steer (pushing/oracle/RampComputer.cpp:40-92): ramp controls that take the robot from cur to des along
-// the straight line of its configuration space; appends at most `room` controls to out, returns how many the steer
-// consists of (may exceed room)
-__device__ int steer(const float cur[3], const float des[3], const float vlim[3], const float acc[3], float dur_max,
-                     float* out, int room)
+__device__ __forceinline__ float norm3(float x, float y, float z, float s)
 {
-    float dir[3] = {des[0] - cur[0], des[1] - cur[1], shortest_so2(cur[2], des[2])};
-    float distance = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    return sqrtf(s * x * s * x + s * y * s * y + s * z * s * z);
+}
+
+// RampComputer::steer (pushing/oracle/RampComputer.cpp:40-92): ramp controls that take the robot from (cx, cy, cth) to
+// (dx_, dy_, dth) along the straight line of its configuration space; emit(n, vx, vy, w, duration) receives the n-th
+// control; returns how many controls the steer consists of
+template <class Emit>
+__device__ __forceinline__ int steer(float cx, float cy, float cth, float dx_, float dy_, float dth, const float vlim[3],
+                                     const float acc[3], float dur_max, Emit emit)
+{
+    float ex = dx_ - cx, ey = dy_ - cy, ez = shortest_so2(cth, dth);
+    float distance = sqrtf(ex * ex + ey * ey + ez * ez);
     if (!(distance > 0.0f)) return 0;
-    for (int i = 0; i < 3; ++i) dir[i] /= distance;
+    ex /= distance;
+    ey /= distance;
+    ez /= distance;
     float vabs = 3.402823466e+38f;
-    for (int i = 0; i < 3; ++i) vabs = fminf(vabs, vlim[i] / fabsf(dir[i]));
-    float vel[3] = {vabs * dir[0], vabs * dir[1], vabs * dir[2]};
-    float ta = accel_time_of(vel, acc);
-    auto norm3 = [](const float v[3], float s) { return sqrtf(s * v[0] * s * v[0] + s * v[1] * s * v[1] + s * v[2] * s * v[2]); };
-    float dist_accel = norm3(vel, ta);
+    vabs = fminf(vabs, vlim[0] / fabsf(ex));
+    vabs = fminf(vabs, vlim[1] / fabsf(ey));
+    vabs = fminf(vabs, vlim[2] / fabsf(ez));
+    float vx = vabs * ex, vy = vabs * ey, vw = vabs * ez;
+    float ta = accel_time_of(vx, vy, vw, acc);
+    float dist_accel = norm3(vx, vy, vw, ta);
     int n = 0;
     while (distance > 0.0f && n < 64) {
         if (dist_accel > distance) {  // the acceleration phases alone would overshoot: a slower plateau velocity
             vabs = distance / ta;
-            for (int i = 0; i < 3; ++i) vel[i] = vabs * dir[i];
-            ta = accel_time_of(vel, acc);
-            dist_accel = norm3(vel, ta);
+            vx = vabs * ex;
+            vy = vabs * ey;
+            vw = vabs * ez;
+            ta = accel_time_of(vx, vy, vw, acc);
+            dist_accel = norm3(vx, vy, vw, ta);
         }
         distance = distance - dist_accel;
-        const float max_plateau = fminf(norm3(vel, dur_max), distance);
-        const float duration = max_plateau / vabs;
-        if (n < room) {
-            float* c = out + n * MPS_CONTROL_DIM;
-            c[0] = vel[0];
-            c[1] = vel[1];
-            c[2] = vel[2];
-            c[3] = duration;
-            c[4] = 0.0f;
-        }
+        const float max_plateau = fminf(norm3(vx, vy, vw, dur_max), distance);
+        emit(n, vx, vy, vw, max_plateau / vabs);
         ++n;
         distance = distance - max_plateau;
     }
@@ -116,7 +119,9 @@ __device__ int steer(const float cur[3], const float des[3], const float vlim[3]
 // standard normal from two uniforms (Box-Muller)
 __device__ __forceinline__ float gauss01(float u1, float u2)
 {
-    return sqrtf(-2.0f * logf(1.0f - u1)) * cosf(6.28318530717958647692f * u2);
+    float sn, cs;
+    mps_sincos(6.28318530717958647692f * u2, &sn, &cs);  // the spec's own sincos: no libm slow path (and its stack frame)
+    return sqrtf(-2.0f * logf(1.0f - u1)) * cs;
 }
 
 // One thread per chain: HybridActionRRT::sampleActionSequence (pushing/algorithm/RRT.cpp:491-529) with
@@ -130,6 +135,17 @@ __global__ void hybrid_controls_kernel(HybridGenParams p)
         for (int i = 0; i < p.L * MPS_CONTROL_DIM; ++i) out[i] = 0.0f;
         const long long gid = (long long)g.k_offset + k;
         int n = 0;
+        const int L = p.L;
+        auto write_control = [out, L](int i, float vx, float vy, float vw, float duration) {
+            if (i < L) {
+                float* c = out + i * MPS_CONTROL_DIM;
+                c[0] = vx;
+                c[1] = vy;
+                c[2] = vw;
+                c[3] = duration;
+                c[4] = 0.0f;
+            }
+        };
         const float die = u01(g.seed, g.iteration, gid, TAG_H_DIE, 0);
         const float cur_r[3] = {p.start[3 * p.robot], p.start[3 * p.robot + 1], p.start[3 * p.robot + 2]};
         if (die < g.action_randomness) {
@@ -152,8 +168,8 @@ __global__ void hybrid_controls_kernel(HybridGenParams p)
                 }
             }
             if (obj == p.robot) {  // transit primitive
-                const float des_r[3] = {p.dest[3 * p.robot], p.dest[3 * p.robot + 1], p.dest[3 * p.robot + 2]};
-                n = steer(cur_r, des_r, g.velocity_limits, p.accel, g.duration_max, out, p.L);
+                n = steer(cur_r[0], cur_r[1], cur_r[2], p.dest[3 * p.robot], p.dest[3 * p.robot + 1], p.dest[3 * p.robot + 2],
+                          g.velocity_limits, p.accel, g.duration_max, write_control);
             } else {  // transfer primitive: to a feasible pushing state, then the push (the world is assumed unchanged)
                 const float cur_o[3] = {p.start[3 * obj], p.start[3 * obj + 1], p.start[3 * obj + 2]};
                 const float des_o[3] = {p.dest[3 * obj], p.dest[3 * obj + 1], p.dest[3 * obj + 2]};
@@ -173,33 +189,39 @@ __global__ void hybrid_controls_kernel(HybridGenParams p)
                     pd[0] = rel[0] / nrm;
                     pd[1] = rel[1] / nrm;
                 }
-                const float ca = cosf(angle), sa = sinf(angle);
+                float ca, sa;
+                mps_sincos(angle, &sa, &ca);
                 float feas[3];
                 feas[0] = cur_o[0] - pushing_dist * (ca * pd[0] - sa * pd[1]);
                 feas[1] = cur_o[1] - pushing_dist * (sa * pd[0] + ca * pd[1]);
                 feas[2] = atan2f(pd[1], pd[0]) - 1.57f;  // the reference's floating end-effector (HumanOracle.cpp:156)
                 // setConfiguration normalises the SO(2) component (SimEnvState.cpp:131-135)
-                double th = fmod((double)feas[2], 2.0 * MPS_PI_D);
+                double th = (double)feas[2];  // in [-pi - 1.57, pi - 1.57]: fmod(th, 2 pi) of the normalisation is th itself
                 if (th < -MPS_PI_D)
                     th += 2.0 * MPS_PI_D;
                 else if (th >= MPS_PI_D)
                     th -= 2.0 * MPS_PI_D;
                 feas[2] = (float)th;
-                n = steer(cur_r, feas, g.velocity_limits, p.accel, g.duration_max, out, p.L);
+                n = steer(cur_r[0], cur_r[1], cur_r[2], feas[0], feas[1], feas[2], g.velocity_limits, p.accel, g.duration_max,
+                          write_control);
                 // HumanOracle::predictAction from the feasible state: the first control of the steer towards the
                 // object's destination, half an object size short of it; a null control when the object does not translate
-                float push[MPS_CONTROL_DIM] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                const float r2[3] = {des_o[0] - cur_o[0], des_o[1] - cur_o[1], 0.0f};
-                const float n2 = sqrtf(r2[0] * r2[0] + r2[1] * r2[1]);
+                float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+                const float r2x = des_o[0] - cur_o[0], r2y = des_o[1] - cur_o[1];
+                const float n2 = sqrtf(r2x * r2x + r2y * r2y);
                 if (n2 != 0.0f) {
                     const float half = g.object_size[obj] / 2.0f;
-                    const float next_r[3] = {des_o[0] - r2[0] / n2 * half, des_o[1] - r2[1] / n2 * half, feas[2]};
-                    float first[MPS_CONTROL_DIM];
-                    if (steer(feas, next_r, g.velocity_limits, p.accel, g.duration_max, first, 1) > 0)
-                        for (int i = 0; i < MPS_CONTROL_DIM; ++i) push[i] = first[i];
+                    steer(feas[0], feas[1], feas[2], des_o[0] - r2x / n2 * half, des_o[1] - r2y / n2 * half, feas[2],
+                          g.velocity_limits, p.accel, g.duration_max, [&](int i, float a, float b, float c, float d) {
+                              if (i == 0) {
+                                  p0 = a;
+                                  p1 = b;
+                                  p2 = c;
+                                  p3 = d;
+                              }
+                          });
                 }
-                if (n < p.L)
-                    for (int i = 0; i < MPS_CONTROL_DIM; ++i) out[n * MPS_CONTROL_DIM + i] = push[i];
+                write_control(n, p0, p1, p2, p3);
                 ++n;
             }
         }
