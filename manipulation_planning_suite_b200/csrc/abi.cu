@@ -8,6 +8,7 @@
 #include <cfloat>
 #include <atomic>
 #include <chrono>
+#include <limits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -83,6 +84,8 @@ struct mps_ctx {
     bool nn_ready = false;
     bool nn_direct = false;  // the pending query's result lands in h_nn_out without a copy
     unsigned int nn_seq = 0;  // sequence number of the last single query (completion flag in h_nn_out)
+    unsigned long long* h_nn_parts = nullptr;  // pinned: per-CTA records of the host-folded single query
+    int h_nn_parts_grid = 0;                   // grid of the last query that wrote them
     DevBuf d_topk_keys, d_topk_rej, d_topk_out;  // top-k: per-CTA lists, dropped minima, idx[32] | dist[32] | meta[2]
     int nn_Q = 0;
 
@@ -96,12 +99,28 @@ struct mps_ctx {
     // validity
     DevBuf d_vstates, d_valid, d_vflags;
 
+    // the last CUDA call made for this context enqueued an NN scan (see MPS_CUDA_CHECK below and
+    // mps_tree_nearest_launch): the next scan may overlap its tail
+    bool nn_chain = false;
+
     // optional per-launch timing of the rollout kernel
     bool timing = false;
     std::vector<cudaEvent_t> ev0, ev1;
     int ev_count = 0;
 };
 #define MPS_EVENT_RING 512
+
+// Every CUDA call made on behalf of a context goes through this macro; each one ends the chain of back-to-back NN
+// scans (nn_chain), so a scan is only ever allowed to overlap the previous kernel of the stream when NOTHING else -
+// no append, no upload, no allocation, no other launch - was issued for the context in between.
+#undef MPS_CUDA_CHECK
+#define MPS_CUDA_CHECK(expr, ctx_)                                                        \
+    do {                                                                                  \
+        mps_ctx* chk_ctx__ = (ctx_);                                                      \
+        if (chk_ctx__) chk_ctx__->nn_chain = false;                                       \
+        cudaError_t err__ = (expr);                                                       \
+        if (err__ != cudaSuccess) return mps_fail_cuda(chk_ctx__, err__, #expr, __LINE__); \
+    } while (0)
 
 static int mps_fail(mps_ctx* ctx, int code, const std::string& msg)
 {
@@ -342,6 +361,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->d_scene) cudaFree(ctx->d_scene);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_nn_out) cudaFreeHost(ctx->h_nn_out);
+    if (ctx->h_nn_parts) cudaFreeHost(ctx->h_nn_parts);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -731,7 +751,11 @@ int mps_tree_nearest_launch(mps_ctx* ctx)
     np.tree = ctx->tree;
     np.n = ctx->tree_n;
     np.grid_x = mps_nn_grid_x(np.n, ctx->num_sms);
+    // back-to-back scans of one context (nothing else issued for it since the last one): the new scan's streaming
+    // pass may start while the previous scan's last CTAs finish (programmatic dependent launch, nn_scan.cu)
+    np.overlap_prev = ctx->nn_chain ? 1 : 0;
     MPS_CUDA_CHECK(mps_launch_nn_scan(np, ctx->stream), ctx);
+    ctx->nn_chain = true;
     ctx->launches++;
     return MPS_OK;
 }
@@ -760,43 +784,86 @@ int mps_tree_nearest_batch(mps_ctx* ctx, const float* queries, int32_t Q, const 
     return mps_tree_nearest_fetch(ctx, indices, distances);
 }
 
-// waits for the completion flag the scan's last CTA writes behind its result in pinned host memory (a few hundred
-// nanoseconds after the write instead of the microseconds a stream synchronise takes to return); falls back to the
-// synchronise if the flag has not appeared after 20 ms (a failed launch never sets it)
-static int nn_wait_flag(mps_ctx* ctx, unsigned int seq)
+// The host's half of the single query (nn_scan_kernel, host_parts): every CTA posts {distance bits, seq << 40 | index}
+// as one 16-byte store into pinned memory; the host folds the records in CTA order as they arrive, with the kernel's
+// own rule (smaller distance, then smaller index) - the same (double, index) minimum as the device-side hand-off,
+// without its ticket, fences and last-CTA pass.  A 16-byte aligned store lies in one cache line, so a record whose
+// second word carries this query's sequence number is complete.  Falls back to a stream synchronise if a record has
+// not appeared after 20 ms (a failed launch never writes it).
+static int nn_fold_parts(mps_ctx* ctx, int grid, unsigned int seq, int64_t* index, double* distance)
 {
-    volatile unsigned int* flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    const volatile unsigned long long* rec = ctx->h_nn_parts;
     const auto t0 = std::chrono::steady_clock::now();
-    unsigned spins = 0;
-    while (*flag != seq) {
-        if ((++spins & 0x3ff) == 0 &&
-            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
-            MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
-            if (*flag != seq) return mps_fail(ctx, MPS_ERR_CUDA, "nearest-neighbour scan finished without a result");
-            break;
+    double bd = 0.0;
+    long long bi = -1;
+    bool synced = false;
+    for (int c = 0; c < grid; ++c) {
+        unsigned long long w1;
+        unsigned spins = 0;
+        while ((unsigned int)((w1 = rec[2 * c + 1]) >> 40) != seq) {
+            if ((++spins & 0x3ff) == 0 && !synced &&
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
+                MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+                synced = true;
+                if ((unsigned int)(rec[2 * c + 1] >> 40) != seq)
+                    return mps_fail(ctx, MPS_ERR_CUDA, "nearest-neighbour scan finished without a result");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        const unsigned long long w0 = rec[2 * c];
+        const unsigned long long i40 = w1 & 0xffffffffffull;
+        if (i40 == 0xffffffffffull) continue;  // this CTA saw no node (slice filter, ragged grid)
+        double d;
+        memcpy(&d, &w0, 8);
+        const long long i = (long long)i40;
+        if (bi < 0 || d < bd || (d == bd && i < bi)) {
+            bd = d;
+            bi = i;
         }
     }
-    std::atomic_thread_fence(std::memory_order_acquire);
+    if (index) *index = bi;
+    if (distance) *distance = bi < 0 ? std::numeric_limits<double>::infinity() : bd;
     return MPS_OK;
 }
 
 int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
                      int64_t* index, double* distance)
 {
-    // One query, one launch, no synchronise: the query rides in the kernel parameters, the last CTA writes
-    // (index, distance) and then a sequence number straight into pinned host memory, the host waits for the number.
+    // One query, one launch, no synchronise and no device-side hand-off: the query rides in the kernel parameters, every
+    // CTA posts its result straight into pinned host memory and the host folds them (nn_fold_parts).
     int rc = mps_tree_nearest_upload(ctx, query, 1, weights, &mask, &slice_filter);
     if (rc) return rc;
+    if ((rc = tree_sync_size(ctx))) return rc;
+    const int grid = mps_nn_grid_x(ctx->tree_n, ctx->num_sms);
+    if (!ctx->h_nn_parts) {
+        const size_t bytes = 16 * (size_t)ctx->num_sms * 16;  // the largest grid (mps_tree_nearest_upload)
+        MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_nn_parts, bytes), ctx);
+        memset(ctx->h_nn_parts, 0, bytes);
+    }
+    if (grid != ctx->h_nn_parts_grid) {
+        // no scan is in flight here (every single query is waited for): records of another grid size must not be
+        // mistaken for this one's when the sequence number comes round again
+        memset(ctx->h_nn_parts, 0, 16 * (size_t)ctx->num_sms * 16);
+        ctx->h_nn_parts_grid = grid;
+    }
+    do {
+        ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
+    } while (ctx->nn_seq == 0);
+    ctx->np.host_parts = ctx->h_nn_parts;
+    ctx->np.host_seq = ctx->nn_seq;
+    ctx->nn_direct = true;
+    rc = mps_tree_nearest_launch(ctx);
+    ctx->np.host_parts = nullptr;  // a re-launch of the cached query (mps_time_launches) takes the device-side hand-off
     ctx->np.out_idx = (long long*)ctx->h_nn_out;
     ctx->np.out_dist = (double*)((char*)ctx->h_nn_out + 8);
-    ctx->np.done_flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
-    ctx->np.done_seq = ++ctx->nn_seq ? ctx->nn_seq : ++ctx->nn_seq;
-    ctx->nn_direct = true;
-    if ((rc = mps_tree_nearest_launch(ctx))) return rc;
-    if ((rc = nn_wait_flag(ctx, ctx->np.done_seq))) return rc;
-    ctx->np.done_flag = nullptr;  // a re-launch of the cached query (mps_time_launches) does not signal
-    if (index) memcpy(index, ctx->h_nn_out, 8);
-    if (distance) memcpy(distance, (char*)ctx->h_nn_out + 8, 8);
+    if (rc) return rc;
+    int64_t fi = -1;
+    double fd = 0.0;
+    if ((rc = nn_fold_parts(ctx, grid, ctx->nn_seq, &fi, &fd))) return rc;
+    memcpy(ctx->h_nn_out, &fi, 8);  // where mps_tree_nearest_fetch looks
+    memcpy((char*)ctx->h_nn_out + 8, &fd, 8);
+    if (index) *index = fi;
+    if (distance) *distance = fd;
     return MPS_OK;
 }
 
@@ -1863,6 +1930,7 @@ int mps_time_launches(mps_ctx* ctx, int32_t what, int32_t iters, float* elapsed_
         } else if (what == 1) {
             rc = mps_tree_nearest_launch(ctx);
         } else {
+            ctx->nn_chain = false;
             cudaError_t le = mps_launch_nn_topk(ctx->topk, ctx->stream);
             if (le != cudaSuccess) rc = mps_fail_cuda(ctx, le, "mps_launch_nn_topk", __LINE__);
             ctx->launches++;

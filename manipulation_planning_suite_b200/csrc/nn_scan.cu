@@ -16,6 +16,8 @@
 #include "mps_device.cuh"
 #include "nn_scan.h"
 
+#include <cstdlib>
+
 #define FULL 0xffffffffu
 // launch shape (tuned on B200, profiles/tools/nn_tune.sh): threads per CTA, CTAs per SM, bodies whose
 // 3 rows are loaded before the arithmetic starts (3 * NN_BODY_BATCH LDG.128 in flight per thread)
@@ -37,6 +39,38 @@
 #define NN_CAND_CAP 512
 
 namespace {
+
+// Programmatic dependent launch (sm_90+): a scan is launched with the programmatic-stream-serialization attribute, so
+// its CTAs may become resident while the previous kernel of the stream is still draining.  grid_dep_wait() blocks
+// until that kernel has completed and its writes are visible; grid_dep_trigger() lets the NEXT kernel of the stream
+// start its own CTAs as soon as every CTA of this one has called it (or exited).
+__device__ __forceinline__ void grid_dep_wait()
+{
+#ifndef MPS_CPU_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void grid_dep_trigger()
+{
+#ifndef MPS_CPU_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// NN_TRACE (profiles/tools/nn_trace_probe.cu): per-CTA timestamps of the scan's phases
+#ifdef NN_TRACE
+__device__ unsigned long long g_nn_trace[8 * 4096];
+__device__ __forceinline__ void nn_trace(int slot)
+{
+    if (threadIdx.x == 0 && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_nn_trace[8 * blockIdx.x + slot] = t;
+    }
+}
+#else
+#define nn_trace(slot)
+#endif
 
 __device__ __forceinline__ float sqrt_approx(float x)
 {
@@ -185,6 +219,14 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     const int warp = tid >> 5;
     const int q = blockIdx.y;
     const int B = p.tree.B;
+    // Ordering against the previous kernel of the stream (see grid_dep_wait).  overlap_prev: the host knows that
+    // kernel is another scan of this context that wrote nothing this one reads (no tree append, no chained filter) -
+    // the streaming pass then starts while that scan's last CTAs finish, and only the hand-off below (shared
+    // scratch, result block) waits for it.  Otherwise everything waits here.
+    nn_trace(0);
+    if (!p.overlap_prev) grid_dep_wait();
+    grid_dep_trigger();
+    nn_trace(2);
     // the query, its mask / slice filter and the weights come from device buffers, or (single query through
     // mps_tree_nearest) from the kernel parameters themselves
     const bool inl = p.inline_q != 0;
@@ -206,6 +248,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             }
         }
     }
+    nn_trace(7);
     if (tid < 3 * B) s_q[tid] = inl ? p.q_inline[tid] : p.queries[(size_t)q * 3 * B + tid];
     if (tid < B) {
         const float w = inl ? (p.inline_has_w ? p.w_inline[tid] : 1.0f) : (p.weights ? p.weights[tid] : 1.0f);
@@ -223,6 +266,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
         s_ncand = 0u;
     }
     __syncthreads();
+    nn_trace(1);
     const int nact = s_nact;
     const float pwf = (float)p.pw, owf = (float)p.ow;
     const size_t cap = p.tree.cap;
@@ -240,6 +284,12 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     long long best_i = -1;
 
     // ---- streaming pass: fp32 metric for every node, candidates deferred ------------------------
+    // grid-stride: at any moment the grid reads one contiguous window of every row.  Measured on B200 and dropped: one
+    // contiguous range of groups per CTA (296 x 33 separate DRAM streams: the pass 17 % slower), and dealing the
+    // groups of the partial last trip to all CTAs in warp-sized units (every CTA then stays to the end with two or
+    // three of its eight warps busy: 21.7 us against 20.9 us, and 24.2 us against 20.7 us per scan in a stream of
+    // scans, where the CTAs that leave early make room for the next scan's).  The grid is sized so that all CTAs
+    // make the same number of trips instead (mps_nn_grid_x).
     for (long long g = (long long)blockIdx.x * NN_THREADS + tid; g < groups; g += (long long)gridDim.x * NN_THREADS) {
         const long long n0 = g << 2;
         float d0, d1, d2, d3;
@@ -272,6 +322,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
         }
     }
     __syncthreads();
+    nn_trace(3);
 
     // ---- deferred exact pass: only candidates still within the final CTA bound ---------------------
     {
@@ -298,6 +349,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
         s_ri[warp] = best_i;
     }
     __syncthreads();
+    nn_trace(4);
     if (tid < 32) {
         best_d = tid < NN_THREADS / 32 ? s_rd[tid] : 0.0;
         best_i = tid < NN_THREADS / 32 ? s_ri[tid] : -1;
@@ -306,7 +358,21 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             long long oi = __shfl_down_sync(FULL, best_i, off);
             take_min(best_d, best_i, od, oi);
         }
-        if (tid == 0 && gridDim.x == 1) {
+        // everything this kernel shares with the previous one (scratch, tickets, result block) is touched from here on
+        if (tid == 0 && p.overlap_prev) grid_dep_wait();
+        if (p.host_parts) {
+            // single query the host is waiting for (mps_tree_nearest): every CTA posts its (distance, index) straight
+            // into pinned host memory as ONE 16-byte store - distance bits | sequence number << 40 | index (40 bits,
+            // all ones = none) - and the host folds the grid's records as they arrive.  No ticket, no fence, no last
+            // CTA: the cross-CTA hand-off took 3.9 us of a 25 us launch (profiles/tools/nn_trace_probe.cu).
+            if (tid == 0) {
+                const unsigned long long w1 = ((unsigned long long)(p.host_seq & 0xffffffu) << 40) |
+                                              ((unsigned long long)best_i & 0xffffffffffull);
+                *reinterpret_cast<ulonglong2*>(p.host_parts + 2 * (size_t)blockIdx.x) =
+                    make_ulonglong2((unsigned long long)__double_as_longlong(best_d), w1);
+                s_last = false;
+            }
+        } else if (tid == 0 && gridDim.x == 1) {
             // small trees: one CTA, no cross-CTA hand-off (saves ~4 dependent global round trips)
             p.out_idx[q] = best_i;
             p.out_dist[q] = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
@@ -324,13 +390,16 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
         }
     }
     __syncthreads();
-    if (s_last && tid < 32) {
+    nn_trace(5);
+    if (s_last) {
+        // the last CTA folds the per-CTA results: every thread fetches its entries at once (one round trip to L2 for
+        // the usual grid of 296; a single warp walking the list took ten dependent ones), then warp and CTA reduction
         __threadfence();
         double fd = 0.0;
         long long fi = -1;
-        for (int c = tid; c < (int)gridDim.x; c += 32) {
-            double od = *reinterpret_cast<volatile double*>(&p.part_d[(size_t)q * p.grid_x + c]);
-            long long oi = *reinterpret_cast<volatile long long*>(&p.part_i[(size_t)q * p.grid_x + c]);
+        for (int c = tid; c < (int)gridDim.x; c += NN_THREADS) {
+            double od = __ldcg(&p.part_d[(size_t)q * p.grid_x + c]);
+            long long oi = __ldcg(&p.part_i[(size_t)q * p.grid_x + c]);
             take_min(fd, fi, od, oi);
         }
         for (int off = 16; off > 0; off >>= 1) {
@@ -338,13 +407,28 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             long long oi = __shfl_down_sync(FULL, fi, off);
             take_min(fd, fi, od, oi);
         }
-        if (tid == 0) {
-            p.out_idx[q] = fi;
-            p.out_dist[q] = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
-            p.tickets[q] = 0u;
-            if (p.done_flag) {
-                __threadfence_system();
-                *p.done_flag = p.done_seq;
+        if (lane == 0) {
+            s_rd[warp] = fd;
+            s_ri[warp] = fi;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            fd = tid < NN_THREADS / 32 ? s_rd[tid] : 0.0;
+            fi = tid < NN_THREADS / 32 ? s_ri[tid] : -1;
+            for (int off = 16; off > 0; off >>= 1) {
+                double od = __shfl_down_sync(FULL, fd, off);
+                long long oi = __shfl_down_sync(FULL, fi, off);
+                take_min(fd, fi, od, oi);
+            }
+            if (tid == 0) {
+                p.out_idx[q] = fi;
+                p.out_dist[q] = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
+                p.tickets[q] = 0u;
+                if (p.done_flag) {
+                    __threadfence_system();
+                    *p.done_flag = p.done_seq;
+                }
+                nn_trace(6);
             }
         }
     }
@@ -852,21 +936,40 @@ int mps_nn_grid_x(long long n, int num_sms)
     long long groups = (n + 3) / 4;
     long long want = (groups + NN_THREADS - 1) / NN_THREADS;
     long long cap = (long long)num_sms * NN_CTAS_PER_SM;
-    if (want > cap) want = cap;
+    if (want > cap) {
+        // more than one trip per thread: the fewest CTAs that make the same number of trips as the full grid would,
+        // so that every CTA makes ALL of them (1 M nodes: 245 CTAs x 4 trips instead of 89 x 4 + 207 x 3)
+        static const int mode = getenv("MPS_NN_GRID_MODE") ? atoi(getenv("MPS_NN_GRID_MODE")) : 1;
+        const long long per_trip = cap * NN_THREADS;
+        const long long trips = (groups + per_trip - 1) / per_trip;
+        long long even = (groups + trips * NN_THREADS - 1) / (trips * NN_THREADS);
+        want = mode == 1 && even <= cap ? even : cap;
+    }
     if (want < 1) want = 1;
     return (int)want;
 }
 
-cudaError_t mps_launch_nn_scan(const NNParams& p, cudaStream_t stream)
+cudaError_t mps_launch_nn_scan(const NNParams& p_in, cudaStream_t stream)
 {
-    dim3 grid((unsigned)p.grid_x, (unsigned)p.Q, 1);
+    NNParams p = p_in;
+    if (p.filter_from) p.overlap_prev = 0;  // the filter is the previous scan's result
+    // launched with programmatic stream serialization: the CTAs may become resident (and run their prologue, or - with
+    // overlap_prev - their whole streaming pass) before the previous kernel of the stream has drained; the kernel
+    // orders itself with griddepcontrol.wait
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.grid_x, (unsigned)p.Q, 1);
+    cfg.blockDim = dim3(NN_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     // evict-first loads while the scanned rows are within ~2x the 126 MB L2, default policy beyond
     const double scanned = (double)p.n * 12.0 * p.tree.B;
-    if (scanned < 252.0e6)
-        nn_scan_kernel<true><<<grid, NN_THREADS, 0, stream>>>(p);
-    else
-        nn_scan_kernel<false><<<grid, NN_THREADS, 0, stream>>>(p);
-    return cudaGetLastError();
+    if (scanned < 252.0e6) return cudaLaunchKernelEx(&cfg, nn_scan_kernel<true>, p);
+    return cudaLaunchKernelEx(&cfg, nn_scan_kernel<false>, p);
 }
 
 cudaError_t mps_launch_nn_topk(const TopKParams& p, cudaStream_t stream)

@@ -50,7 +50,15 @@ struct NNParams {
     // (pinned host memory) so that the host can wait for the result without a stream synchronise
     volatile unsigned int* done_flag;
     unsigned int done_seq;
+    // host-folded single query: per-CTA records {distance bits, seq << 40 | index} in pinned host memory, 2 words per
+    // CTA (see nn_scan_kernel); when set, out_idx / out_dist / tickets / done_flag are not used
+    unsigned long long* host_parts;
+    unsigned int host_seq;
     float abs_eps;  // absolute slack of the fp32 candidate filter (covers the rounding of the angle wrap)
+    // programmatic dependent launch: 1 = the previous kernel of the stream is a scan of the same context and nothing
+    // it writes is read by this one before the hand-off (the streaming pass may overlap its tail); 0 = wait for the
+    // previous kernel before anything else (always safe; mps_launch_nn_scan forces it for chained filters)
+    int overlap_prev;
 };
 
 // exact k nearest neighbours of one query (k <= 32), see nn_topk_kernel

@@ -178,6 +178,51 @@ def test_single_query_paths_agree():
     ctx.close()
 
 
+def test_back_to_back_scans_overlap_without_changing_results():
+    """Scans enqueued back to back for one context may overlap (programmatic dependent launch: the next scan streams
+    while the previous one's last CTAs finish; both share the context's scratch and tickets).  Every launch of such a
+    stream must return what a lone launch returns - also when a tree append sits between two launches (the chain is
+    then broken and the scan is ordered behind the append), and when two contexts alternate on one stream."""
+    import torch
+
+    sc, _ = scenes.make_scene(10, seed=5)
+    rng = np.random.RandomState(5)
+    N = 400_000
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctxs = [api.Context(sc, stream=stream.cuda_stream) for _ in range(2)]
+        trees = [api.NearestNeighbors(c) for c in ctxs]
+        for j, t in enumerate(trees):
+            t.fill_random(N, seed=50 + j, n_slices=8)
+        states = [t.read_states(0, N) for t in trees]
+        for rep in range(3):
+            q = scenes.sample_state(rng, sc)
+            want = [ob.nn_linear(sc, states[j], q) for j in range(2)]
+            for j, t in enumerate(trees):
+                t.nearest_upload(q[None, :])
+            for i in range(24):  # alternating contexts, every launch overlapping the previous one
+                trees[i % 2].nearest_launch()
+                if i % 5 == 4:
+                    gi, gd = trees[i % 2].nearest_fetch()
+                    assert (int(gi[0]), float(gd[0])) == want[i % 2]
+            for j, t in enumerate(trees):
+                gi, gd = t.nearest_fetch()
+                assert (int(gi[0]), float(gd[0])) == want[j]
+            # a node exactly at the query, appended between two launches of the stream: the next launch must see it
+            t = trees[0]
+            t.nearest_launch()
+            first = t.add_batch(q[None, :])
+            t.nearest_launch()
+            t.nearest_launch()
+            gi, gd = t.nearest_fetch()
+            assert int(gi[0]) == N + rep and float(gd[0]) == 0.0
+            assert t.nearest(q) == (N + rep, 0.0)
+            states[0] = np.concatenate([states[0], q[None, :]])
+            del first
+        for c in ctxs:
+            c.close()
+
+
 def _all_distances(sc, states, q, weights=None, mask=None):
     """orc_distance (oracle/mps_oracle.c) for every node, vectorised in numpy with the same operations in the same
     order (double; body order) - checked against the oracle itself on a sample below"""
