@@ -601,6 +601,31 @@ def bench_nn(api, scenes, device, flush):
             torch.cuda.synchronize()
             stream_ms.append(e0s.elapsed_time(e1s) / 48)
         ms_stream = float(np.median(stream_ms))
+        # the three metrics the planners query with (SURVEY.md 8d cfg 3): all bodies (RearrangementRRT::selectTreeNode),
+        # all but the robot (ObjectArrangementDistanceFn), the robot alone (RobotStateDistanceFn); same rotation
+        full = (1 << B) - 1
+        per_mask = {}
+        for name, m in (("all_bodies", full), ("all_but_robot", full & ~(1 << sc.robot_id)), ("robot_only", 1 << sc.robot_id)):
+            for t in trees:
+                t.nearest_upload(q[None, :], masks=np.array([m], np.uint32))
+                t.nearest_launch()
+            torch.cuda.synchronize()
+            reps = []
+            for rep in range(3):
+                e0s, e1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0s.record(stream)
+                for i in range(48):
+                    trees[(i + 1) % 3].nearest_launch()
+                e1s.record(stream)
+                torch.cuda.synchronize()
+                reps.append(e0s.elapsed_time(e1s) / 48)
+            t_ms = float(np.median(reps))
+            nb = bin(m).count("1")
+            per_mask[name] = {"us_per_query": round(t_ms * 1e3, 2), "queries_per_s": round(1e3 / t_ms, 1),
+                              "GBps_algorithmic": round(N * 12 * nb / (t_ms * 1e-3) / 1e9, 1)}
+        out["per_mask"] = per_mask
+        tree.nearest_upload(q[None, :])
+        tree.nearest_launch()
         for c2, t2 in others:
             c2.close()
         # (b) the L2 filled with DIRTY lines before every launch (256 MB memset): the scan then competes with the

@@ -826,6 +826,26 @@ static int nn_fold_parts(mps_ctx* ctx, int grid, unsigned int seq, int64_t* inde
     return MPS_OK;
 }
 
+// pinned record block of the host-folded query and a fresh sequence number for a scan of `grid` CTAs
+static int nn_parts_begin(mps_ctx* ctx, int grid)
+{
+    if (!ctx->h_nn_parts) {
+        const size_t bytes = 16 * (size_t)ctx->num_sms * 16;  // the largest grid (mps_tree_nearest_upload)
+        MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_nn_parts, bytes), ctx);
+        memset(ctx->h_nn_parts, 0, bytes);
+    }
+    if (grid != ctx->h_nn_parts_grid) {
+        // no scan is in flight here (every host-folded query is waited for): records of another grid size must not be
+        // mistaken for this one's when the sequence number comes round again
+        memset(ctx->h_nn_parts, 0, 16 * (size_t)ctx->num_sms * 16);
+        ctx->h_nn_parts_grid = grid;
+    }
+    do {
+        ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
+    } while (ctx->nn_seq == 0);
+    return MPS_OK;
+}
+
 int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask, int32_t slice_filter,
                      int64_t* index, double* distance)
 {
@@ -835,20 +855,7 @@ int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uin
     if (rc) return rc;
     if ((rc = tree_sync_size(ctx))) return rc;
     const int grid = mps_nn_grid_x(ctx->tree_n, ctx->num_sms);
-    if (!ctx->h_nn_parts) {
-        const size_t bytes = 16 * (size_t)ctx->num_sms * 16;  // the largest grid (mps_tree_nearest_upload)
-        MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_nn_parts, bytes), ctx);
-        memset(ctx->h_nn_parts, 0, bytes);
-    }
-    if (grid != ctx->h_nn_parts_grid) {
-        // no scan is in flight here (every single query is waited for): records of another grid size must not be
-        // mistaken for this one's when the sequence number comes round again
-        memset(ctx->h_nn_parts, 0, 16 * (size_t)ctx->num_sms * 16);
-        ctx->h_nn_parts_grid = grid;
-    }
-    do {
-        ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
-    } while (ctx->nn_seq == 0);
+    if ((rc = nn_parts_begin(ctx, grid))) return rc;
     ctx->np.host_parts = ctx->h_nn_parts;
     ctx->np.host_seq = ctx->nn_seq;
     ctx->nn_direct = true;
@@ -914,29 +921,47 @@ int mps_tree_nearest_two_level(mps_ctx* ctx, mps_ctx* reps, const float* query, 
     p1.grid_x = mps_nn_grid_x(p1.n, ctx->num_sms);
     p1.out_idx = (long long*)ctx->d_nn_out.p;
     p1.out_dist = (double*)((char*)ctx->d_nn_out.p + 8);
-    MPS_CUDA_CHECK(mps_launch_nn_scan(p1, ctx->stream), ctx);
-    // scan 2 on the main tree, filter = scan 1's index, result + flag in pinned memory
+    // scan 2 on the main tree, filter = scan 1's index (device memory); its CTAs post their results into pinned memory
+    // and the host folds them (nn_fold_parts) - no stream synchronise.  Scan 1 mirrors its own result into pinned
+    // memory as well: scan 2 starts only after scan 1 has completed (it waits for it before reading the filter), so
+    // by the time scan 2's records arrive the mirror is there.
     if ((rc = tree_sync_size(ctx))) return rc;
     NNParams p2 = ctx->np;
     p2.tree = ctx->tree;
     p2.n = ctx->tree_n;
     p2.grid_x = mps_nn_grid_x(p2.n, ctx->num_sms);
+    if ((rc = nn_parts_begin(ctx, p2.grid_x))) return rc;
+    p1.mirror_idx = (long long*)((char*)ctx->h_nn_out + 16);
+    p1.mirror_dist = (double*)((char*)ctx->h_nn_out + 24);
+    // ... and signs it: the sequence number follows the mirror behind a system-scope fence, the host checks it below
+    volatile unsigned int* flag1 = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    p1.done_flag = flag1;
+    p1.done_seq = ctx->nn_seq;
+    MPS_CUDA_CHECK(mps_launch_nn_scan(p1, ctx->stream), ctx);
     p2.inline_mask = member_mask;
     p2.filter_from = p1.out_idx;
-    p2.out_idx = (long long*)ctx->h_nn_out;
-    p2.out_dist = (double*)((char*)ctx->h_nn_out + 8);
-    p2.done_flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
-    p2.done_seq = ++ctx->nn_seq ? ctx->nn_seq : ++ctx->nn_seq;
+    p2.host_parts = ctx->h_nn_parts;
+    p2.host_seq = ctx->nn_seq;
     MPS_CUDA_CHECK(mps_launch_nn_scan(p2, ctx->stream), ctx);
-    // scan 1's result follows to the host behind scan 2 (16 bytes; the wait below covers scan 2 only, so synchronise)
-    MPS_CUDA_CHECK(cudaMemcpyAsync((char*)ctx->h_nn_out + 16, ctx->d_nn_out.p, 16, cudaMemcpyDeviceToHost, ctx->stream), ctx);
     ctx->launches += 2;
-    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
-    if (index) memcpy(index, ctx->h_nn_out, 8);
-    if (distance) memcpy(distance, (char*)ctx->h_nn_out + 8, 8);
+    ctx->nn_ready = false;
+    int64_t fi = -1;
+    double fd = 0.0;
+    if ((rc = nn_fold_parts(ctx, p2.grid_x, ctx->nn_seq, &fi, &fd))) return rc;
+    if (*flag1 != ctx->nn_seq) {  // scan 1 finished before scan 2 started; its writes are normally long here
+        const auto t0 = std::chrono::steady_clock::now();
+        while (*flag1 != ctx->nn_seq) {
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
+                MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+                if (*flag1 != ctx->nn_seq) return mps_fail(ctx, MPS_ERR_CUDA, "slice-level scan finished without a result");
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (index) *index = fi;
+    if (distance) *distance = fd;
     if (rep_index) memcpy(rep_index, (char*)ctx->h_nn_out + 16, 8);
     if (rep_distance) memcpy(rep_distance, (char*)ctx->h_nn_out + 24, 8);
-    ctx->nn_ready = false;
     return MPS_OK;
 }
 

@@ -376,6 +376,10 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             // small trees: one CTA, no cross-CTA hand-off (saves ~4 dependent global round trips)
             p.out_idx[q] = best_i;
             p.out_dist[q] = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
+            if (p.mirror_idx && q == 0) {
+                *p.mirror_idx = best_i;
+                *p.mirror_dist = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
+            }
             if (p.done_flag) {
                 __threadfence_system();
                 *p.done_flag = p.done_seq;
@@ -423,6 +427,10 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             if (tid == 0) {
                 p.out_idx[q] = fi;
                 p.out_dist[q] = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
+                if (p.mirror_idx && q == 0) {
+                    *p.mirror_idx = fi;
+                    *p.mirror_dist = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
+                }
                 p.tickets[q] = 0u;
                 if (p.done_flag) {
                     __threadfence_system();

@@ -54,6 +54,10 @@ struct NNParams {
     // CTA (see nn_scan_kernel); when set, out_idx / out_dist / tickets / done_flag are not used
     unsigned long long* host_parts;
     unsigned int host_seq;
+    // optional second copy of (index, distance) of query 0, e.g. in pinned host memory for a scan whose result also
+    // feeds the next scan on the device (device-side hand-off only)
+    long long* mirror_idx;
+    double* mirror_dist;
     float abs_eps;  // absolute slack of the fp32 candidate filter (covers the rounding of the angle wrap)
     // programmatic dependent launch: 1 = the previous kernel of the stream is a scan of the same context and nothing
     // it writes is read by this one before the hand-off (the streaming pass may overlap its tail); 0 = wait for the

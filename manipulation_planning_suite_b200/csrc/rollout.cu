@@ -1260,6 +1260,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
         for (int i = threadIdx.x; i < (int)(sizeof(DevScene) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    if (p.active_warps > 0 && (int)(threadIdx.x >> 5) >= p.active_warps) return;
     const Ln ln = make_ln<G>();
     const int lane = ln.g;  // lane within the chain's group = body index
     const int group = (threadIdx.x >> 5) * (32 / G) + ((threadIdx.x & 31) / G);
@@ -1918,6 +1919,8 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     //            chains of several controls (diverging groups) lose at every K measured (K = 16 384: 6.57 against 5.68).
     // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build, MPS_ROLLOUT_GROUP =
     // 8 | 16 | 32 the lanes per chain, MPS_ROLLOUT_CTAS_PER_SM the resident CTAs.
+    static const int forced_active = env_int("MPS_ROLLOUT_ACTIVE_WARPS", 0);
+    p.active_warps = forced_active;
     static const int forced_minb = env_int("MPS_ROLLOUT_MINB", 0);
     static const int forced_g = env_int("MPS_ROLLOUT_GROUP", 0);
     const double per_sched = (double)p.K / ((double)num_sms * ROLLOUT_WARPS);

@@ -15,6 +15,7 @@ struct RolloutParams {
     size_t warp_bytes_small;  // the same with mcap_small slots
     int mcap_small;         // manifold slots per chain of a packed launch (0: the scene's capacity)
     int redo_only;          // set by the launcher: only the chains flagged in `redo` are run
+    int active_warps;       // tuning aid (MPS_ROLLOUT_ACTIVE_WARPS): > 0 = only this many warps of a CTA pull chains
     uint8_t* redo;          // [K] chains a packed launch left to the one-chain-per-warp kernel
     const float* start;     // [3B], or [K][3B] when start_stride != 0
     size_t start_stride;    // 0 or 3B
