@@ -74,6 +74,10 @@ namespace {
 #ifndef MPS_REG_ROUNDS
 #define MPS_REG_ROUNDS 1
 #endif
+// ... and in the build for launches of one CTA per SM (MINB = 1: up to 255 registers)
+#ifndef MPS_REG_ROUNDS_SOLO
+#define MPS_REG_ROUNDS_SOLO 4
+#endif
 #define MF_FIELDS (4 * MF_VEC4)
 
 struct Shape {
@@ -983,6 +987,37 @@ __device__ __forceinline__ void general_sweep(const DevScene& sc, const WarpMem&
     }
 }
 
+// One round's manifold of this lane as the register-resident sweeps hold it (see physics_step)
+struct RoundRegs {
+    MRows R;
+    float4 acc;
+    int j;
+    bool act, st, isa, two;
+};
+
+__device__ __forceinline__ RoundRegs load_round(const WarpMem& W, unsigned e, int lane)
+{
+    RoundRegs r;
+    r.act = e != 0u;
+    r.st = (e & 0x8000u) != 0u;
+    r.j = r.act ? (int)((e >> 8) & 0x3fu) : lane;
+    r.isa = r.st || lane < r.j;
+    r.R = load_rows(W.man + (r.act ? (int)(e & 0xffu) : 0) * MF_VEC4);
+    r.acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    r.two = r.act && ((__float_as_int(r.R.m0.x) >> 16) & 0xff) > 1;
+    return r;
+}
+
+// vel_iters sweeps over NR rounds, rows and accumulated impulses in registers
+template <bool TWO, int NR>
+__device__ __forceinline__ void sweep_in_registers(RoundRegs (&r)[NR], Body& bd, const Ln ln, int iters)
+{
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) solve_core<TWO>(r[k].R, r[k].acc, bd, ln, r[k].act, r[k].j, r[k].st, r[k].isa);
+    }
+}
+
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
 template <int G, int RR>
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, const Ln ln, float ux,
@@ -1095,7 +1130,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
             };
             if (rounds < 0) {
                 general_sweep<G>(sc, W, bd, ln, dr.nm, st);
-            } else if (RR > 0 && rounds <= RR) {
+            } else if (RR > 0 && rounds <= (RR < 2 ? RR : 2)) {
                 // One or two rounds (most contact steps): the rows of this lane's manifolds stay in registers
                 // for the whole sweep and so do the accumulated impulses, which start at zero every step and
                 // are not read after the sweep - a pass is three shuffles and arithmetic, no shared memory.
@@ -1137,6 +1172,21 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                         }
                     }
                 }
+            } else if (RR >= 3 && rounds == 3) {
+                // (build with the whole register file to itself, one CTA per SM: three and four rounds in registers too)
+                RoundRegs r[3] = {load_round(W, cache.ent[0], lane), load_round(W, cache.ent[1], lane),
+                                  load_round(W, cache.ent[2], lane)};
+                if (__any_sync(ln.m, r[0].two || r[1].two || r[2].two))
+                    sweep_in_registers<true, 3>(r, bd, ln, iters);
+                else
+                    sweep_in_registers<false, 3>(r, bd, ln, iters);
+            } else if (RR >= 4 && rounds == 4) {
+                RoundRegs r[4] = {load_round(W, cache.ent[0], lane), load_round(W, cache.ent[1], lane),
+                                  load_round(W, cache.ent[2], lane), load_round(W, cache.ent[3], lane)};
+                if (__any_sync(ln.m, r[0].two || r[1].two || r[2].two || r[3].two))
+                    sweep_in_registers<true, 4>(r, bd, ln, iters);
+                else
+                    sweep_in_registers<false, 4>(r, bd, ln, iters);
             } else if (RR < 2 && rounds <= 4 && !two_step) {
                 // (not in the build that keeps two rounds in registers: there this path only serves three and four
                 // rounds, and a second copy of it cost more in instruction fetch than it saved - cfg2 2.05 -> 2.09 ms)
@@ -1242,7 +1292,9 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
     return dist;
 }
 
-// MINB = CTAs per SM the register allocation is held to, G = lanes per chain.  Built: <4, 3, 32> (up to 168
+// MINB = CTAs per SM the register allocation is held to, G = lanes per chain.  Built: <4, 1, 32> (248 registers) for
+// launches of one CTA per SM (K <= 3 chains per scheduler, cfg 2's extend): sweeps of up to four rounds keep their
+// rows in registers (cfg2 1.333 -> 1.301 ms); <4, 3, 32> (up to 168
 // registers) for launches with few chains, where one warp per scheduler runs alone and only its own
 // dependent-instruction latency matters; <4, 4, 32> (128 registers) for launches that fill the machine;
 // <4, 4, 8> and <4, 4, 16> with four / two chains per warp (see mps_launch_rollout).  None spills.
@@ -1396,7 +1448,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 }
                 bool bad, over;
                 float pen;
-                physics_step<G, (MINB <= 3 ? 2 : (G < 32 ? MPS_REG_ROUNDS : 0))>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
+                physics_step<G, (MINB == 1 ? MPS_REG_ROUNDS_SOLO : MINB <= 3 ? 2 : (G < 32 ? MPS_REG_ROUNDS : 0))>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
                 if (over && small_cap) {
                     redo = true;
                     break;
@@ -1952,6 +2004,9 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
         ctas = 1;
     else if (p.order && per_sched <= 8.0 && p.L > 1)
         ctas = 2;  // (single-control chains vary less in length: three CTAs per SM are better there, 0.41 against 0.51 ms at K = 4096)
+    // one CTA per SM: the build that may use the whole register file (sweeps of up to four rounds in registers)
+    static const int solo_build = env_int("MPS_ROLLOUT_SOLO_BUILD", 1);
+    if (minb == 3 && ctas == 1 && solo_build) return launch_rollout_t<ROLLOUT_WARPS, 1, 32>(p, num_sms, stream, ctas);
     if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream, ctas);
     return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream, ctas);
 }

@@ -107,7 +107,9 @@ int emu_extend(const mps_scene* sc, const mps_extend_in* in, const mps_extend_ou
     if (group == 32) {
         rp.mcap_small = 0;
         rp.redo_only = 0;
-        if (minb == 3)
+        if (minb == 1)
+            run_rollout<2, 1, 32>(rp, ctas);
+        else if (minb == 3)
             run_rollout<2, 3, 32>(rp, ctas);
         else
             run_rollout<2, 4, 32>(rp, ctas);
