@@ -273,7 +273,9 @@ int mps_tree_add(mps_ctx* ctx, const float* state, int32_t parent, const float* 
 int mps_tree_add_batch(mps_ctx* ctx, const float* states, const int32_t* parents, const float* controls,
                        const int32_t* slice_ids, int64_t n, int64_t* first_index);
 /* nearest node under d = sum_i mask_i w_i (pw |dxy| + ow arc(dtheta)), double arithmetic,
- * ties -> lowest index.  slice_filter >= 0 restricts to nodes of that slice; -1 = all. */
+ * ties -> lowest index.  slice_filter >= 0 restricts to nodes of that slice; -1 = all.
+ * One launch, no stream synchronise: the scan's CTAs post their partial results into pinned host memory and the
+ * call folds them (same minimum as the device-side reduction of the staged / batched calls). */
 int mps_tree_nearest(mps_ctx* ctx, const float* query, const float* weights, uint32_t mask,
                      int32_t slice_filter, int64_t* index, double* distance);
 /* ompl::NearestNeighbors<MotionPtr>::nearestK of the interface the planners hold their tree through
