@@ -1019,7 +1019,7 @@ __device__ __forceinline__ void sweep_in_registers(RoundRegs (&r)[NR], Body& bd,
 }
 
 // one physics step.  bad / overflow / max_pen come back warp-uniform.
-template <int G, int RR>
+template <int G, int RR, bool ROLLED>
 __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& W, Body& bd, const Ln ln, float ux,
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
                                              StepStats& st, StepCache& cache)
@@ -1187,6 +1187,25 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     sweep_in_registers<true, 4>(r, bd, ln, iters);
                 else
                     sweep_in_registers<false, 4>(r, bd, ln, iters);
+            } else if (ROLLED && rounds <= 4) {
+                // Launches that fill the machine are bound by instruction fetch (the step's code is larger than the
+                // instruction cache and 16 warps per SM sit in different places of it): ONE copy of each pass variant in
+                // a rolled loop over the rounds instead of four inlined copies.  Measured on B200 in the unpacked
+                // 128-register build (profiles/r02_rolled_sweeps.txt): contact-rich launches gain (9 bodies, K = 40 960:
+                // 5.18 -> 6.06 M rollouts/s; chains of two controls 3.76 -> 4.68; 15 bodies 5.98 -> 7.45), launches with
+                // few contacts pay the loop's selects and branch (11 bodies 12.3 -> 11.5, 17 bodies 8.53 -> 8.24).
+                const unsigned e0 = cache.ent[0], e1 = cache.ent[1], e2 = cache.ent[2], e3 = cache.ent[3];
+                if (!two_step) {
+                    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                        for (int r = 0; r < rounds; ++r) pass1(r == 0 ? e0 : r == 1 ? e1 : r == 2 ? e2 : e3);
+                    }
+                } else {
+                    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+                        for (int r = 0; r < rounds; ++r) pass(r == 0 ? e0 : r == 1 ? e1 : r == 2 ? e2 : e3);
+                    }
+                }
             } else if (RR < 2 && rounds <= 4 && !two_step) {
                 // (not in the build that keeps two rounds in registers: there this path only serves three and four
                 // rounds, and a second copy of it cost more in instruction fetch than it saved - cfg2 2.05 -> 2.09 ms)
@@ -1298,7 +1317,7 @@ __device__ __forceinline__ double warp_distance(const DevScene& sc, const Body& 
 // registers) for launches with few chains, where one warp per scheduler runs alone and only its own
 // dependent-instruction latency matters; <4, 4, 32> (128 registers) for launches that fill the machine;
 // <4, 4, 8> and <4, 4, 16> with four / two chains per warp (see mps_launch_rollout).  None spills.
-template <int WARPS, int MINB, int G>
+template <int WARPS, int MINB, int G, bool ROLLED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams p)
 {
     MPS_DYN_SMEM(smem_dyn);
@@ -1448,7 +1467,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) rollout_kernel(RolloutParams
                 }
                 bool bad, over;
                 float pen;
-                physics_step<G, (MINB == 1 ? MPS_REG_ROUNDS_SOLO : MINB <= 3 ? 2 : (G < 32 ? MPS_REG_ROUNDS : 0))>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
+                physics_step<G, (MINB == 1 ? MPS_REG_ROUNDS_SOLO : MINB <= 3 ? 2 : (G < 32 ? MPS_REG_ROUNDS : 0)), ROLLED>(sc, W, bd, ln, ux, uy, uw, bad, over, pen, st, cache);
                 if (over && small_cap) {
                     redo = true;
                     break;
@@ -1945,12 +1964,12 @@ static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_
 }
 
 // WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
-template <int WARPS, int MINB, int G>
+template <int WARPS, int MINB, int G, bool ROLLED = false>
 static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream, int ctas_per_sm = 0)
 {
     if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     static std::atomic<bool> attr_set[64];
-    return launch_rollout_kernel(rollout_kernel<WARPS, MINB, G>, attr_set, p, WARPS * 32, WARPS * (32 / G), num_sms, stream,
+    return launch_rollout_kernel(rollout_kernel<WARPS, MINB, G, ROLLED>, attr_set, p, WARPS * 32, WARPS * (32 / G), num_sms, stream,
                                  ctas_per_sm);
 }
 
@@ -2008,6 +2027,12 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     static const int solo_build = env_int("MPS_ROLLOUT_SOLO_BUILD", 1);
     if (minb == 3 && ctas == 1 && solo_build) return launch_rollout_t<ROLLOUT_WARPS, 1, 32>(p, num_sms, stream, ctas);
     if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream, ctas);
+    // launches that fill the machine: the build with the sweeps rolled over the rounds (see physics_step; measured over
+    // seven shapes, profiles/r02_rolled_sweeps.txt: -6 .. +25 %, +7 % on average) for scenes of up to 12 bodies - the
+    // 17-body clutter of config 4 loses 3 % with it, config 5's sweep (9 bodies) gains 4 %.  MPS_ROLLED_MAX_BODIES = 0 / 32
+    // select one build for everything, for comparison.
+    static const int rolled_max = env_int("MPS_ROLLED_MAX_BODIES", 12);
+    if (n_bodies <= rolled_max) return launch_rollout_t<ROLLOUT_WARPS, 4, 32, true>(p, num_sms, stream, ctas);
     return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream, ctas);
 }
 

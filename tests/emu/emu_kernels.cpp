@@ -35,11 +35,11 @@ void run_grid(RolloutParams& p, int groups, int ctas, Body body)
     emu::launch(dim3(grid), dim3(WARPS * 32), smem, body);
 }
 
-template <int WARPS, int MINB, int G>
+template <int WARPS, int MINB, int G, bool ROLLED = false>
 void run_rollout(RolloutParams p, int ctas)
 {
     if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
-    run_grid<WARPS>(p, WARPS * (32 / G), ctas, [&]() { rollout_kernel<WARPS, MINB, G>(p); });
+    run_grid<WARPS>(p, WARPS * (32 / G), ctas, [&]() { rollout_kernel<WARPS, MINB, G, ROLLED>(p); });
 }
 
 }  // namespace
@@ -47,8 +47,8 @@ void run_rollout(RolloutParams p, int ctas)
 extern "C" {
 
 // K chains + argmin, as mps_extend (abi.cu) drives rollout_kernel and select_kernel.
-//   group: lanes per chain (32, 16, 8); minb: register-budget instantiation (3 | 4) of the one-chain-per-warp
-//   build; mcap_small: manifold slots of a packed launch (0 = the scene's); warps: warps per emulated CTA;
+//   group: lanes per chain (32, 16, 8); minb: register-budget instantiation (1 | 3 | 4, 5 = 4 with rolled sweeps) of the
+//   one-chain-per-warp build; mcap_small: manifold slots of a packed launch (0 = the scene's); warps: warps per emulated CTA;
 //   ctas: CTAs of the emulated grid (chains are pulled from the work counter as on the device)
 int emu_extend(const mps_scene* sc, const mps_extend_in* in, const mps_extend_out* out, int group, int minb,
                int mcap_small, int ctas, uint64_t* counters_out)
@@ -109,6 +109,8 @@ int emu_extend(const mps_scene* sc, const mps_extend_in* in, const mps_extend_ou
         rp.redo_only = 0;
         if (minb == 1)
             run_rollout<2, 1, 32>(rp, ctas);
+        else if (minb == 5)  // the 128-register build with the sweeps rolled over the rounds
+            run_rollout<2, 4, 32, true>(rp, ctas);
         else if (minb == 3)
             run_rollout<2, 3, 32>(rp, ctas);
         else
