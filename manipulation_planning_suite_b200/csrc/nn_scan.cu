@@ -62,10 +62,10 @@ __device__ __forceinline__ void grid_dep_trigger()
 __device__ unsigned long long g_nn_trace[8 * 4096];
 __device__ __forceinline__ void nn_trace(int slot)
 {
-    if (threadIdx.x == 0 && blockIdx.y == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        g_nn_trace[8 * blockIdx.x + slot] = t;
+        g_nn_trace[8 * blockIdx.y + slot] = t;
     }
 }
 #else
@@ -217,7 +217,12 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int q = blockIdx.y;
+    // grid = (queries, CTAs per query): the CTAs that scan the same part of the tree for different queries of a batch are
+    // neighbours in launch order, so a part of the tree is fetched from HBM once and served to the other queries from
+    // L2 (with the queries in grid.y every query streamed the whole tree on its own: 18.4 us per query at Q = 32,
+    // the cost of a lone scan)
+    const int q = blockIdx.x;
+    const unsigned int cta = blockIdx.y, ncta = gridDim.y;
     const int B = p.tree.B;
     // Ordering against the previous kernel of the stream (see grid_dep_wait).  overlap_prev: the host knows that
     // kernel is another scan of this context that wrote nothing this one reads (no tree append, no chained filter) -
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     // the rows of this thread's first group are requested before the prologue's barrier (they depend on nothing the
     // prologue computes): the first LDG.128 of the streaming pass then finds them on their way
     if (!p.inst_ids && (tid & 7) == 0) {
-        const long long g0 = (long long)blockIdx.x * NN_THREADS + tid;
+        const long long g0 = (long long)cta * NN_THREADS + tid;
         if ((g0 << 2) < p.n) {
             const float* base = p.tree.states + (g0 << 2);
             for (int i = 0; i < B; ++i) {
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     // three of its eight warps busy: 21.7 us against 20.9 us, and 24.2 us against 20.7 us per scan in a stream of
     // scans, where the CTAs that leave early make room for the next scan's).  The grid is sized so that all CTAs
     // make the same number of trips instead (mps_nn_grid_x).
-    for (long long g = (long long)blockIdx.x * NN_THREADS + tid; g < groups; g += (long long)gridDim.x * NN_THREADS) {
+    for (long long g = (long long)cta * NN_THREADS + tid; g < groups; g += (long long)ncta * NN_THREADS) {
         const long long n0 = g << 2;
         float d0, d1, d2, d3;
         group_distances<STREAM>(p, s_act, s_q, s_w, nact, cap, col0, n0, N, filter, pwf, owf, d0, d1, d2, d3);
@@ -368,11 +373,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             if (tid == 0) {
                 const unsigned long long w1 = ((unsigned long long)(p.host_seq & 0xffffffu) << 40) |
                                               ((unsigned long long)best_i & 0xffffffffffull);
-                *reinterpret_cast<ulonglong2*>(p.host_parts + 2 * (size_t)blockIdx.x) =
+                *reinterpret_cast<ulonglong2*>(p.host_parts + 2 * (size_t)cta) =
                     make_ulonglong2((unsigned long long)__double_as_longlong(best_d), w1);
                 s_last = false;
             }
-        } else if (tid == 0 && gridDim.x == 1) {
+        } else if (tid == 0 && ncta == 1) {
             // small trees: one CTA, no cross-CTA hand-off (saves ~4 dependent global round trips)
             p.out_idx[q] = best_i;
             p.out_dist[q] = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
@@ -386,11 +391,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
             }
             s_last = false;
         } else if (tid == 0) {
-            p.part_d[(size_t)q * p.grid_x + blockIdx.x] = best_d;
-            p.part_i[(size_t)q * p.grid_x + blockIdx.x] = best_i;
+            p.part_d[(size_t)q * p.grid_x + cta] = best_d;
+            p.part_i[(size_t)q * p.grid_x + cta] = best_i;
             __threadfence();
             unsigned int t = atomicAdd(&p.tickets[q], 1u);
-            s_last = (t == gridDim.x - 1);
+            s_last = (t == ncta - 1);
         }
     }
     __syncthreads();
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
         __threadfence();
         double fd = 0.0;
         long long fi = -1;
-        for (int c = tid; c < (int)gridDim.x; c += NN_THREADS) {
+        for (int c = tid; c < (int)ncta; c += NN_THREADS) {
             double od = __ldcg(&p.part_d[(size_t)q * p.grid_x + c]);
             long long oi = __ldcg(&p.part_i[(size_t)q * p.grid_x + c]);
             take_min(fd, fi, od, oi);
@@ -965,7 +970,7 @@ cudaError_t mps_launch_nn_scan(const NNParams& p_in, cudaStream_t stream)
     // overlap_prev - their whole streaming pass) before the previous kernel of the stream has drained; the kernel
     // orders itself with griddepcontrol.wait
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)p.grid_x, (unsigned)p.Q, 1);
+    cfg.gridDim = dim3((unsigned)p.Q, (unsigned)p.grid_x, 1);  // see nn_scan_kernel
     cfg.blockDim = dim3(NN_THREADS, 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
