@@ -670,7 +670,8 @@ def bench_nn(api, scenes, device, flush):
         out["batch"] = {"queries_per_launch": Q, "us_per_query": round(ms_batch / Q * 1e3, 2),
                         "queries_per_s": round(Q / ms_batch * 1e3, 1),
                         "GBps_algorithmic": round(N * 3 * B * 4 * Q / (ms_batch * 1e-3) / 1e9, 1),
-                        "note": "every query streams the whole tree; rows shared through L2 by the CTAs of different queries"}
+                        "note": "tiles of eight queries per CTA share every load (nn_scan_tile_kernel): arithmetic-bound, "
+                                "the tree is read from HBM once per tile; GBps_algorithmic counts 132 MB per query"}
         if hasattr(tree, "nearest_k"):
             out["top_k"] = bench_nn_topk(tree, qs, flush, stream, torch, N, B)
         if hasattr(tree, "nearest_two_level"):

@@ -86,11 +86,13 @@ __device__ __forceinline__ float sqrt_approx(float x)
 __device__ __forceinline__ float body_term_f32(float x, float y, float th, float qx, float qy, float qth, float pwf,
                                                float owf)
 {
+    // (the library is compiled without implicit fusion: the fused multiply-adds of this filter are spelled out - it
+    // only has to stay within the slack of the exact metric, and it is a fifth of the instructions of a batched scan)
     float dx = x - qx;
     float dy = y - qy;
     float d = fabsf(th - qth);
-    float arc = d > MPS_PI_F ? MPS_TWO_PI_F - d : d;
-    return pwf * sqrt_approx(dx * dx + dy * dy) + owf * arc;
+    float arc = fminf(d, MPS_TWO_PI_F - d);
+    return fmaf(pwf, sqrt_approx(fmaf(dx, dx, dy * dy)), owf * arc);
 }
 
 // the reference's double expression for one node (rare path)
@@ -447,6 +449,267 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
     }
 }
 
+
+// ---- batches: a tile of NN_QT queries per CTA ----------------------------------------------------------------------
+// mps_tree_nearest_batch with many queries (Q >= NN_QT, plain tree).  A thread loads its four nodes of a body's rows
+// ONCE and evaluates the fp32 metric for the NN_QT queries of the CTA's tile, the accumulators of all of them in
+// registers: the scan of a batch is bound by L2 bandwidth when every query reads the rows for itself (13.4 us per
+// query), by arithmetic when a tile shares them.  Per query everything else is the single-query scan's: CTA bound,
+// deferred candidates re-evaluated in double, (double, index) minimum, ticket hand-off, last CTA folds.  A candidate
+// list that overflows (adversarial orderings) sends the query to a second pass of the CTA over its nodes with the
+// final bound, evaluated exactly on the spot.
+#define NN_QT 8
+#define NN_TILE_CAND 128
+
+template <bool STREAM>
+__global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_tile_kernel(const __grid_constant__ NNParams p)
+{
+    __shared__ float4 s_qw[NN_QT][MPS_MAX_BODIES];  // per query and body: (qx, qy, qtheta, weight or 0 when masked out)
+    __shared__ float s_qf[NN_QT][3 * MPS_MAX_BODIES];  // the queries as the exact pass reads them
+    __shared__ float s_wb[MPS_MAX_BODIES];
+    __shared__ uint32_t s_mask[NN_QT];
+    __shared__ int s_filter[NN_QT];
+    __shared__ int s_act[MPS_MAX_BODIES];
+    __shared__ int s_nact, s_any_filter;
+    __shared__ unsigned int s_bound[NN_QT], s_ncand[NN_QT];
+    __shared__ unsigned int s_cand_d[NN_QT][NN_TILE_CAND];
+    __shared__ long long s_cand_i[NN_QT][NN_TILE_CAND];
+    __shared__ double s_rd[NN_THREADS / 32];
+    __shared__ long long s_ri[NN_THREADS / 32];
+    __shared__ bool s_last[NN_QT];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int q0 = blockIdx.x * NN_QT;
+    const int nq = min(NN_QT, p.Q - q0);
+    const unsigned int cta = blockIdx.y, ncta = gridDim.y;
+    const int B = p.tree.B;
+    grid_dep_wait();
+    grid_dep_trigger();
+    const uint32_t full = B < 32 ? (1u << B) - 1u : 0xffffffffu;
+    if (tid < NN_QT) {
+        const bool live = tid < nq;
+        s_mask[tid] = live ? ((p.masks ? p.masks[q0 + tid] : 0xffffffffu) & full) : 0u;
+        s_filter[tid] = live && p.filters ? p.filters[q0 + tid] : -1;
+        s_bound[tid] = 0x7f800000u;
+        s_ncand[tid] = 0u;
+    }
+    if (tid < B) s_wb[tid] = p.weights ? p.weights[tid] : 1.0f;
+    __syncthreads();
+    for (int e = tid; e < NN_QT * B; e += NN_THREADS) {
+        const int qq = e / B, i = e - qq * B;
+        float qx = 0.0f, qy = 0.0f, qth = 0.0f;
+        if (qq < nq) {
+            const float* src = p.queries + (size_t)(q0 + qq) * 3 * B + 3 * i;
+            qx = src[0];
+            qy = src[1];
+            qth = src[2];
+        }
+        s_qf[qq][3 * i] = qx;
+        s_qf[qq][3 * i + 1] = qy;
+        s_qf[qq][3 * i + 2] = qth;
+        s_qw[qq][i] = make_float4(qx, qy, qth, ((s_mask[qq] >> i) & 1u) ? s_wb[i] : 0.0f);
+    }
+    if (tid == 0) {
+        uint32_t any = 0u;
+        int anyf = 0;
+        for (int qq = 0; qq < nq; ++qq) {
+            any |= s_mask[qq];
+            anyf |= s_filter[qq] >= 0 ? 1 : 0;
+        }
+        int n = 0;
+        for (int i = 0; i < B; ++i)
+            if ((any >> i) & 1u) s_act[n++] = i;
+        s_nact = n;
+        s_any_filter = anyf;
+    }
+    __syncthreads();
+    const int nact = s_nact;
+    const bool any_filter = s_any_filter != 0;
+    const float pwf = (float)p.pw, owf = (float)p.ow;
+    const size_t cap = p.tree.cap;
+    const long long N = p.n;
+    const long long groups = (N + 3) >> 2;
+    const float inf = __uint_as_float(0x7f800000u);
+
+    // ---- streaming pass ----------------------------------------------------------------------------------------------
+    for (long long g = (long long)cta * NN_THREADS + tid; g < groups; g += (long long)ncta * NN_THREADS) {
+        const long long n0 = g << 2;
+        float d[NN_QT][4];
+#pragma unroll
+        for (int qq = 0; qq < NN_QT; ++qq) d[qq][0] = d[qq][1] = d[qq][2] = d[qq][3] = 0.0f;
+        for (int a0 = 0; a0 < nact; a0 += 2) {
+            float4 X[2], Y[2], T[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int a = a0 + u < nact ? a0 + u : nact - 1;
+                const float* row = p.tree.states + (size_t)(3 * s_act[a]) * cap + n0;
+                X[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row)) : __ldg(reinterpret_cast<const float4*>(row));
+                Y[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + cap))
+                              : __ldg(reinterpret_cast<const float4*>(row + cap));
+                T[u] = STREAM ? __ldcs(reinterpret_cast<const float4*>(row + 2 * cap))
+                              : __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (a0 + u < nact) {
+                    const int i = s_act[a0 + u];
+#pragma unroll
+                    for (int qq = 0; qq < NN_QT; ++qq) {
+                        const float4 qw = s_qw[qq][i];
+                        d[qq][0] = fmaf(qw.w, body_term_f32(X[u].x, Y[u].x, T[u].x, qw.x, qw.y, qw.z, pwf, owf), d[qq][0]);
+                        d[qq][1] = fmaf(qw.w, body_term_f32(X[u].y, Y[u].y, T[u].y, qw.x, qw.y, qw.z, pwf, owf), d[qq][1]);
+                        d[qq][2] = fmaf(qw.w, body_term_f32(X[u].z, Y[u].z, T[u].z, qw.x, qw.y, qw.z, pwf, owf), d[qq][2]);
+                        d[qq][3] = fmaf(qw.w, body_term_f32(X[u].w, Y[u].w, T[u].w, qw.x, qw.y, qw.z, pwf, owf), d[qq][3]);
+                    }
+                }
+            }
+        }
+        int4 sl = make_int4(0, 0, 0, 0);
+        if (any_filter) sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + n0));
+        const bool t1 = n0 + 1 >= N, t2 = n0 + 2 >= N, t3 = n0 + 3 >= N;
+        const unsigned am = __activemask();
+#pragma unroll
+        for (int qq = 0; qq < NN_QT; ++qq) {
+            if (qq >= nq) break;  // uniform
+            float d0 = d[qq][0], d1 = d[qq][1], d2 = d[qq][2], d3 = d[qq][3];
+            const int f = s_filter[qq];
+            if (f >= 0) {
+                if (sl.x != f) d0 = inf;
+                if (sl.y != f) d1 = inf;
+                if (sl.z != f) d2 = inf;
+                if (sl.w != f) d3 = inf;
+            }
+            if (t1) d1 = inf;
+            if (t2) d2 = inf;
+            if (t3) d3 = inf;
+            const float dm = fminf(fminf(d0, d1), fminf(d2, d3));
+            const unsigned wmin = __reduce_min_sync(am, __float_as_uint(dm));
+            if (lane == (__ffs(am) - 1)) atomicMin(&s_bound[qq], wmin);
+            __syncwarp(am);
+            const float b = fminf(__uint_as_float(*reinterpret_cast<volatile unsigned int*>(&s_bound[qq])),
+                                  __uint_as_float(wmin));
+            const float thr = b * (1.0f + NN_REL_EPS) + p.abs_eps;
+            if (dm <= thr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float dj = j == 0 ? d0 : j == 1 ? d1 : j == 2 ? d2 : d3;
+                    if (dj <= thr && dj < inf) {
+                        const unsigned slot = atomicAdd(&s_ncand[qq], 1u);  // beyond the capacity: second pass below
+                        if (slot < NN_TILE_CAND) {
+                            s_cand_d[qq][slot] = __float_as_uint(dj);
+                            s_cand_i[qq][slot] = n0 + j;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- per query: exact pass, CTA minimum, hand-off ---------------------------------------------------------------
+    for (int qq = 0; qq < nq; ++qq) {
+        const int q = q0 + qq;
+        const uint32_t mask = s_mask[qq];
+        const float thr = __uint_as_float(s_bound[qq]) * (1.0f + NN_REL_EPS) + p.abs_eps;
+        double best_d = __longlong_as_double(0x7ff0000000000000ll);
+        long long best_i = -1;
+        if (s_ncand[qq] <= NN_TILE_CAND) {
+            const int ncand = (int)s_ncand[qq];
+            for (int c = warp; c < ncand; c += NN_THREADS / 32) {
+                if (__uint_as_float(s_cand_d[qq][c]) <= thr) {
+                    const long long n = s_cand_i[qq][c];
+                    const double e = warp_exact_distance(p.tree, n, s_qf[qq], s_wb, mask, p.pw, p.ow, lane);
+                    if (lane == 0) take_min(best_d, best_i, e, n);
+                }
+            }
+        } else {
+            // the list overflowed: once more over this CTA's nodes for this query with the final bound, every node
+            // within the slack evaluated exactly on the spot
+            const int f = s_filter[qq];
+            for (long long g = (long long)cta * NN_THREADS + tid; g < groups; g += (long long)ncta * NN_THREADS) {
+                const long long n0 = g << 2;
+                float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                for (int a = 0; a < nact; ++a) {
+                    const int i = s_act[a];
+                    const float4 qw = s_qw[qq][i];
+                    const float* row = p.tree.states + (size_t)(3 * i) * cap + n0;
+                    const float4 X = __ldg(reinterpret_cast<const float4*>(row)), Y = __ldg(reinterpret_cast<const float4*>(row + cap));
+                    const float4 T = __ldg(reinterpret_cast<const float4*>(row + 2 * cap));
+                    dd[0] = fmaf(qw.w, body_term_f32(X.x, Y.x, T.x, qw.x, qw.y, qw.z, pwf, owf), dd[0]);
+                    dd[1] = fmaf(qw.w, body_term_f32(X.y, Y.y, T.y, qw.x, qw.y, qw.z, pwf, owf), dd[1]);
+                    dd[2] = fmaf(qw.w, body_term_f32(X.z, Y.z, T.z, qw.x, qw.y, qw.z, pwf, owf), dd[2]);
+                    dd[3] = fmaf(qw.w, body_term_f32(X.w, Y.w, T.w, qw.x, qw.y, qw.z, pwf, owf), dd[3]);
+                }
+                int4 sl = make_int4(f, f, f, f);
+                if (f >= 0) sl = __ldg(reinterpret_cast<const int4*>(p.tree.slice + n0));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sj = j == 0 ? sl.x : j == 1 ? sl.y : j == 2 ? sl.z : sl.w;
+                    if (n0 + j < N && sj == f && dd[j] <= thr) {
+                        const double e = exact_distance(p.tree, n0 + j, s_qf[qq], s_wb, mask, p.pw, p.ow);
+                        take_min(best_d, best_i, e, n0 + j);
+                    }
+                }
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            double od = __shfl_down_sync(FULL, best_d, off);
+            long long oi = __shfl_down_sync(FULL, best_i, off);
+            take_min(best_d, best_i, od, oi);
+        }
+        if (lane == 0) {
+            s_rd[warp] = best_d;
+            s_ri[warp] = best_i;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NN_THREADS / 32; ++w) take_min(best_d, best_i, s_rd[w], s_ri[w]);
+            if (ncta == 1) {
+                p.out_idx[q] = best_i;
+                p.out_dist[q] = best_i < 0 ? __longlong_as_double(0x7ff0000000000000ll) : best_d;
+                s_last[qq] = false;
+            } else {
+                p.part_d[(size_t)q * p.grid_x + cta] = best_d;
+                p.part_i[(size_t)q * p.grid_x + cta] = best_i;
+                __threadfence();
+                s_last[qq] = atomicAdd(&p.tickets[q], 1u) == ncta - 1;
+            }
+        }
+        __syncthreads();
+    }
+    // the last CTA of a query folds its per-CTA results
+    for (int qq = 0; qq < nq; ++qq) {
+        if (!s_last[qq]) continue;  // uniform
+        const int q = q0 + qq;
+        __threadfence();
+        double fd = 0.0;
+        long long fi = -1;
+        for (int c = tid; c < (int)ncta; c += NN_THREADS) {
+            double od = __ldcg(&p.part_d[(size_t)q * p.grid_x + c]);
+            long long oi = __ldcg(&p.part_i[(size_t)q * p.grid_x + c]);
+            take_min(fd, fi, od, oi);
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            double od = __shfl_down_sync(FULL, fd, off);
+            long long oi = __shfl_down_sync(FULL, fi, off);
+            take_min(fd, fi, od, oi);
+        }
+        if (lane == 0) {
+            s_rd[warp] = fd;
+            s_ri[warp] = fi;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NN_THREADS / 32; ++w) take_min(fd, fi, s_rd[w], s_ri[w]);
+            p.out_idx[q] = fi;
+            p.out_dist[q] = fi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : fd;
+            p.tickets[q] = 0u;
+        }
+        __syncthreads();
+    }
+}
 
 #endif  // MPS_CPU_EMU
 
@@ -981,6 +1244,13 @@ cudaError_t mps_launch_nn_scan(const NNParams& p_in, cudaStream_t stream)
     cfg.numAttrs = 1;
     // evict-first loads while the scanned rows are within ~2x the 126 MB L2, default policy beyond
     const double scanned = (double)p.n * 12.0 * p.tree.B;
+    static const int tile_min_q = getenv("MPS_NN_TILE_MIN_Q") ? atoi(getenv("MPS_NN_TILE_MIN_Q")) : NN_QT;
+    if (p.Q >= tile_min_q && !p.inline_q && !p.inst_ids && !p.host_parts && p.queries) {
+        // a batch on the plain tree: tiles of NN_QT queries share every load (nn_scan_tile_kernel)
+        cfg.gridDim = dim3((unsigned)((p.Q + NN_QT - 1) / NN_QT), (unsigned)p.grid_x, 1);
+        if (scanned < 252.0e6) return cudaLaunchKernelEx(&cfg, nn_scan_tile_kernel<true>, p);
+        return cudaLaunchKernelEx(&cfg, nn_scan_tile_kernel<false>, p);
+    }
     if (scanned < 252.0e6) return cudaLaunchKernelEx(&cfg, nn_scan_kernel<true>, p);
     return cudaLaunchKernelEx(&cfg, nn_scan_kernel<false>, p);
 }

@@ -178,6 +178,57 @@ def test_single_query_paths_agree():
     ctx.close()
 
 
+@pytest.mark.parametrize("n_objects,N,Q", [(10, 60_011, 37), (6, 1_003, 8), (16, 20_000, 70)])
+def test_tiled_batches_match_linear_scan(n_objects, N, Q):
+    """Batches of >= 8 queries take the tiled scan (eight queries per CTA share every load): per-query masks, slice
+    filters, weights, duplicate nodes (ties to the lowest index), queries that sit on nodes, a ragged last tile."""
+    sc, _ = scenes.make_scene(n_objects, seed=N)
+    B = sc.n_bodies
+    rng = np.random.RandomState(N)
+    states = np.stack([scenes.sample_state(rng, sc) for _ in range(N)])
+    states[N // 2:N // 2 + 50] = states[:50]  # duplicates at higher indices
+    slices = rng.randint(0, 5, size=N).astype(np.int32)
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.add_batch(states, slice_ids=slices)
+    qs = np.stack([scenes.sample_state(rng, sc) for _ in range(Q)])
+    qs[3] = states[17]
+    qs[Q - 1] = states[N // 2 + 7]  # an exact hit on a duplicated node: the lower index wins
+    masks = np.array([_masks(B)[i % 3] for i in range(Q)], np.uint32)
+    filters = np.array([(-1, 2, 4, 9)[i % 4] for i in range(Q)], np.int32)  # slice 9 has no members
+    weights = rng.uniform(0.5, 2.0, size=B).astype(np.float32)
+    for w in (None, weights):
+        for m, f in ((None, None), (masks, None), (masks, filters)):
+            gi, gd = tree.nearest_batch(qs, weights=w, masks=m, slice_filters=f)
+            for i in range(Q):
+                wi, wd = ob.nn_linear(sc, states, qs[i], weights=w, mask=None if m is None else int(m[i]),
+                                      slice_ids=slices, slice_filter=-1 if f is None else int(f[i]))
+                assert gi[i] == wi, (i, gi[i], wi)
+                if wi >= 0:
+                    assert gd[i] == wd
+    ctx.close()
+
+
+def test_tiled_batch_with_overflowing_candidate_lists():
+    """Every node improves on the previous one for every query of the tile: the candidate lists overflow and the
+    CTAs take their second, exact pass."""
+    sc, _ = scenes.make_scene(3, seed=1)
+    B = sc.n_bodies
+    N = 40000
+    states = np.zeros((N, 3 * B), np.float32)
+    states[:, 0] = np.linspace(0.9, 1e-6, N).astype(np.float32)
+    qs = np.zeros((11, 3 * B), np.float32)
+    qs[:, 1] = np.linspace(0.0, 0.01, 11).astype(np.float32)
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.add_batch(states)
+    gi, gd = tree.nearest_batch(qs)
+    for i in range(len(qs)):
+        wi, wd = ob.nn_linear(sc, states, qs[i])
+        assert gi[i] == wi and gd[i] == wd
+    ctx.close()
+
+
 def test_back_to_back_scans_overlap_without_changing_results():
     """Scans enqueued back to back for one context may overlap (programmatic dependent launch: the next scan streams
     while the previous one's last CTAs finish; both share the context's scratch and tickets).  Every launch of such a
