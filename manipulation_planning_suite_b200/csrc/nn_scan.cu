@@ -1246,8 +1246,18 @@ cudaError_t mps_launch_nn_scan(const NNParams& p_in, cudaStream_t stream)
     const double scanned = (double)p.n * 12.0 * p.tree.B;
     static const int tile_min_q = getenv("MPS_NN_TILE_MIN_Q") ? atoi(getenv("MPS_NN_TILE_MIN_Q")) : NN_QT;
     if (p.Q >= tile_min_q && !p.inline_q && !p.inst_ids && !p.host_parts && p.queries) {
-        // a batch on the plain tree: tiles of NN_QT queries share every load (nn_scan_tile_kernel)
-        cfg.gridDim = dim3((unsigned)((p.Q + NN_QT - 1) / NN_QT), (unsigned)p.grid_x, 1);
+        // a batch on the plain tree: tiles of NN_QT queries share every load (nn_scan_tile_kernel).  CTAs per tile: as
+        // many as make the whole grid one wave of the machine (the single scan's grid per tile would be 3.3 waves at
+        // Q = 32, the last one a third full, and the warps of a CTA waited at the barrier behind the pass for those
+        // that had one trip more: 1.4 barrier stalls per issued instruction)
+        const int tiles = (p.Q + NN_QT - 1) / NN_QT;
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+        int gx = sms * NN_CTAS_PER_SM / tiles;
+        if (gx < 1) gx = 1;
+        if (gx < p.grid_x) p.grid_x = gx;
+        cfg.gridDim = dim3((unsigned)tiles, (unsigned)p.grid_x, 1);
         if (scanned < 252.0e6) return cudaLaunchKernelEx(&cfg, nn_scan_tile_kernel<true>, p);
         return cudaLaunchKernelEx(&cfg, nn_scan_tile_kernel<false>, p);
     }
