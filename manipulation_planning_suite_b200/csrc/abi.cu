@@ -826,6 +826,26 @@ static int nn_fold_parts(mps_ctx* ctx, int grid, unsigned int seq, int64_t* inde
     return MPS_OK;
 }
 
+// waits for a sequence number a kernel writes into pinned host memory behind its results (a few hundred nanoseconds
+// after the write, where a stream synchronise takes microseconds to return); falls back to the synchronise if the
+// number has not appeared after 20 ms (a failed launch never writes it)
+static int nn_wait_flag(mps_ctx* ctx, volatile unsigned int* flag, unsigned int seq)
+{
+    if (*flag != seq) {
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (*flag != seq) {
+            if ((++spins & 0x3ff) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
+                MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+                if (*flag != seq) return mps_fail(ctx, MPS_ERR_CUDA, "nearest-neighbour scan finished without a result");
+                break;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return MPS_OK;
+}
+
 // pinned record block of the host-folded query and a fresh sequence number for a scan of `grid` CTAs
 static int nn_parts_begin(mps_ctx* ctx, int grid)
 {
@@ -948,16 +968,7 @@ int mps_tree_nearest_two_level(mps_ctx* ctx, mps_ctx* reps, const float* query, 
     int64_t fi = -1;
     double fd = 0.0;
     if ((rc = nn_fold_parts(ctx, p2.grid_x, ctx->nn_seq, &fi, &fd))) return rc;
-    if (*flag1 != ctx->nn_seq) {  // scan 1 finished before scan 2 started; its writes are normally long here
-        const auto t0 = std::chrono::steady_clock::now();
-        while (*flag1 != ctx->nn_seq) {
-            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
-                MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
-                if (*flag1 != ctx->nn_seq) return mps_fail(ctx, MPS_ERR_CUDA, "slice-level scan finished without a result");
-            }
-        }
-    }
-    std::atomic_thread_fence(std::memory_order_acquire);
+    if ((rc = nn_wait_flag(ctx, flag1, ctx->nn_seq))) return rc;  // scan 1 finished before scan 2 started: normally long there
     if (index) *index = fi;
     if (distance) *distance = fd;
     if (rep_index) memcpy(rep_index, (char*)ctx->h_nn_out + 16, 8);
@@ -990,16 +1001,21 @@ int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, u
     tp.k = k;
     tp.part_keys = (unsigned long long*)ctx->d_topk_keys.p;
     tp.part_rej = (unsigned int*)ctx->d_topk_rej.p;
-    tp.out_idx = (long long*)ctx->d_topk_out.p;
-    tp.out_dist = (double*)((char*)ctx->d_topk_out.p + 8 * NN_TOPK_MAX);
-    tp.out_meta = (int*)((char*)ctx->d_topk_out.p + 16 * NN_TOPK_MAX);
+    // the last CTA writes the result block straight into pinned host memory and signs it: no copy, no synchronise
+    tp.out_idx = (long long*)ctx->h_nn_out;
+    tp.out_dist = (double*)((char*)ctx->h_nn_out + 8 * NN_TOPK_MAX);
+    tp.out_meta = (int*)((char*)ctx->h_nn_out + 16 * NN_TOPK_MAX);
+    tp.done_flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    do {
+        ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
+    } while (ctx->nn_seq == 0);
+    tp.done_seq = ctx->nn_seq;
     ctx->topk = tp;
     ctx->topk_ready = true;
     MPS_CUDA_CHECK(mps_launch_nn_topk(tp, ctx->stream), ctx);
     ctx->launches++;
+    if ((rc = nn_wait_flag(ctx, tp.done_flag, tp.done_seq))) return rc;
     char host[16 * NN_TOPK_MAX + 16];
-    MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nn_out, ctx->d_topk_out.p, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream), ctx);
-    MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
     memcpy(host, ctx->h_nn_out, sizeof(host));
     int meta[2];
     memcpy(meta, host + 16 * NN_TOPK_MAX, sizeof(meta));

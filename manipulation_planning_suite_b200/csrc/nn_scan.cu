@@ -1003,6 +1003,11 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
         tp.out_meta[1] = status;
         p.tickets[0] = 0u;
     }
+    if (tp.done_flag) {
+        __threadfence_system();  // every writer of the result block, before the CTA signs it
+        __syncthreads();
+        if (tid == 0) *tp.done_flag = tp.done_seq;
+    }
 }
 
 // successor scan in double: the smallest (distance, index) above (after_d, after_i).  Plain: one thread per node,

@@ -76,6 +76,10 @@ struct TopKParams {
     long long* out_idx;             // [k] ascending by (double distance, index)
     double* out_dist;               // [k]
     int* out_meta;                  // [0] results written (<= k), [1] status: 0 exact, 1 ambiguous (caller falls back)
+    // results in pinned host memory: the last CTA writes done_seq here behind them (system-scope fence), the host waits
+    // for the number instead of synchronising the stream
+    volatile unsigned int* done_flag;
+    unsigned int done_seq;
 };
 
 // lexicographic successor scan in double (rare fallback of the top-k path, and its checker):
