@@ -84,6 +84,7 @@ struct mps_ctx {
     bool nn_ready = false;
     bool nn_direct = false;  // the pending query's result lands in h_nn_out without a copy
     unsigned int nn_seq = 0;  // sequence number of the last single query (completion flag in h_nn_out)
+    char* h_valid = nullptr;                   // pinned: states in, results + signature out (mps_is_valid_batch, few states)
     unsigned long long* h_nn_parts = nullptr;  // pinned: per-CTA records of the host-folded single query
     int h_nn_parts_grid = 0;                   // grid of the last query that wrote them
     DevBuf d_topk_keys, d_topk_rej, d_topk_out;  // top-k: per-CTA lists, dropped minima, idx[32] | dist[32] | meta[2]
@@ -362,6 +363,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_nn_out) cudaFreeHost(ctx->h_nn_out);
     if (ctx->h_nn_parts) cudaFreeHost(ctx->h_nn_parts);
+    if (ctx->h_valid) cudaFreeHost(ctx->h_valid);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev1) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1401,11 +1403,45 @@ int mps_is_valid_batch(mps_ctx* ctx, const float* states, int32_t n, uint8_t* va
     MPS_CUDA_CHECK(cudaSetDevice(ctx->device), ctx);
     const size_t sb = sizeof(float) * 3 * ctx->scene.n_bodies * (size_t)n;
     int rc;
+    if (n <= 16) {
+        // A planner validates its samples one or a few at a time (RRT.cpp:171-190): one CTA reads the states from
+        // pinned host memory, writes the results there and signs them; the host waits for the signature (43 -> 17 us
+        // per call against copy in, launch, two copies out and a stream synchronise).
+        const size_t vb = ((size_t)n + 15) & ~(size_t)15;
+        if (!ctx->h_valid) {
+            // its own pinned block (the staging buffer may still feed an asynchronous upload): 16 states of 32 bodies
+            MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_valid, 16 * 3 * MPS_MAX_BODIES * sizeof(float) + 256), ctx);
+        }
+        char* h = ctx->h_valid;
+        memcpy(h, states, sb);
+        ValidityParams vp;
+        memset(&vp, 0, sizeof(vp));
+        vp.scene = ctx->d_scene;
+        vp.scene_bytes = ctx->scene_bytes;
+        vp.warp_bytes = ctx->warp_bytes;
+        vp.states = (const float*)h;
+        vp.n = n;
+        vp.valid = (uint8_t*)(h + sb);
+        vp.flags = (uint32_t*)(h + sb + vb);
+        vp.done_flag = (volatile unsigned int*)(h + sb + vb + sizeof(uint32_t) * (size_t)n);
+        do {
+            ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
+        } while (ctx->nn_seq == 0);
+        vp.done_seq = ctx->nn_seq;
+        *vp.done_flag = 0u;
+        MPS_CUDA_CHECK(mps_launch_validity(vp, ctx->num_sms, ctx->stream), ctx);
+        ctx->launches++;
+        if ((rc = nn_wait_flag(ctx, vp.done_flag, vp.done_seq))) return rc;
+        if (valid) memcpy(valid, h + sb, (size_t)n);
+        if (flags) memcpy(flags, h + sb + vb, sizeof(uint32_t) * (size_t)n);
+        return MPS_OK;
+    }
     if ((rc = ensure(ctx, ctx->d_vstates, sb))) return rc;
     if ((rc = ensure(ctx, ctx->d_valid, (size_t)n))) return rc;
     if ((rc = ensure(ctx, ctx->d_vflags, sizeof(uint32_t) * (size_t)n))) return rc;
     MPS_CUDA_CHECK(cudaMemcpyAsync(ctx->d_vstates.p, states, sb, cudaMemcpyHostToDevice, ctx->stream), ctx);
     ValidityParams vp;
+    memset(&vp, 0, sizeof(vp));
     vp.scene = ctx->d_scene;
     vp.scene_bytes = ctx->scene_bytes;
     vp.warp_bytes = ctx->warp_bytes;
@@ -1750,6 +1786,7 @@ int mps_forest_naive_step(mps_ctx* ctx, const mps_forest_naive_in* in, mps_exten
     MPS_CUDA_CHECK(mps_launch_naive_sample(sp, st), ctx);
     // 2. validity of the candidates, first valid one becomes the sample (= dest of the extend, query of the NN)
     ValidityParams vp;
+    memset(&vp, 0, sizeof(vp));
     vp.scene = ctx->d_scene;
     vp.scene_bytes = ctx->scene_bytes;
     vp.warp_bytes = ctx->warp_bytes;

@@ -1903,6 +1903,11 @@ __global__ void __launch_bounds__(WARPS * 32) validity_kernel(ValidityParams p)
             p.valid[i] = f == 0u ? 1 : 0;
         }
     }
+    if (p.done_flag) {  // single CTA (mps_launch_validity)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *p.done_flag = p.done_seq;
+    }
 }
 
 }  // namespace
@@ -2074,6 +2079,7 @@ cudaError_t mps_launch_validity(const ValidityParams& p, int num_sms, cudaStream
     int grid = num_sms * 4;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
+    if (p.done_flag) grid = 1;  // the CTA that signs the results must be the only one
     validity_kernel<ROLLOUT_WARPS><<<grid, ROLLOUT_WARPS * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -104,6 +104,10 @@ struct ValidityParams {
     int n;
     uint8_t* valid;
     uint32_t* flags;
+    // few states, one CTA, everything in pinned host memory: the CTA signs its results with done_seq (system-scope
+    // fence) and the host waits for the number - no copy in either direction, no stream synchronise
+    volatile unsigned int* done_flag;
+    unsigned int done_seq;
 };
 
 size_t mps_rollout_warp_bytes(const DevScene& sc);

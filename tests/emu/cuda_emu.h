@@ -210,6 +210,7 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v)
 }
 inline void __syncthreads() { emu::cta_barrier(); }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 
 // ---- scalar intrinsics ------------------------------------------------------------------------
 inline unsigned __float_as_uint(float f) { return emu::from_bits<unsigned>(emu::to_bits(f)); }

@@ -174,6 +174,7 @@ int emu_is_valid_batch(const mps_scene* sc, const float* states, int n, uint8_t*
     DevScene ds;
     derive_scene(sc, &ds);
     ValidityParams vp;
+    memset(&vp, 0, sizeof(vp));
     vp.scene = &ds;
     vp.scene_bytes = mps_rollout_scene_bytes();
     vp.warp_bytes = mps_rollout_warp_bytes(ds);

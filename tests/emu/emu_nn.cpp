@@ -4,8 +4,6 @@
 #define MPS_CPU_EMU 1
 #include "cuda_emu.h"
 
-inline void __threadfence_system() {}
-
 #include "../../manipulation_planning_suite_b200/csrc/nn_scan.cu"
 
 #include <vector>
