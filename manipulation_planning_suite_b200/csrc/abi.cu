@@ -1346,8 +1346,20 @@ int mps_extend(mps_ctx* ctx, const mps_extend_in* in, const mps_extend_out* out)
     return mps_extend_fetch(ctx, out);
 }
 
+// small pinned block shared by the synchronous low-latency calls (mps_is_valid_batch with few states, mps_propagate):
+// 16 states of 32 bodies + results + a signature word
+static int ensure_small_pinned(mps_ctx* ctx)
+{
+    if (!ctx->h_valid) MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_valid, 16 * 3 * MPS_MAX_BODIES * sizeof(float) + 256), ctx);
+    return MPS_OK;
+}
+
 int mps_propagate(mps_ctx* ctx, const float* state_in, float* control, float* state_out, int32_t* ok, uint32_t* flags)
 {
+    // SimEnvStatePropagator::propagate as the reference calls it: one state, one control.  The rollout writes the
+    // resulting state, rest time and flags straight into pinned host memory and the select kernel - the last work of
+    // the extend - signs them; the host waits for the signature (three copies and a stream synchronise less: 151 ->
+    // 124 us per call through ctypes, most of the rest being the rollout itself).
     if (!ctx || !state_in || !control || !state_out) return mps_fail(ctx, MPS_ERR_ARG, "NULL argument to mps_propagate");
     mps_extend_in in;
     memset(&in, 0, sizeof(in));
@@ -1355,18 +1367,33 @@ int mps_propagate(mps_ctx* ctx, const float* state_in, float* control, float* st
     in.controls = control;
     in.K = 1;
     in.L = 1;
-    float rest = 0.0f;
-    uint32_t f = 0;
-    mps_extend_out out;
-    memset(&out, 0, sizeof(out));
-    std::vector<float> res(3 * (size_t)ctx->scene.n_bodies);
-    out.all_states = res.data();
-    out.all_rest = &rest;
-    out.all_flags = &f;
-    int rc = mps_extend(ctx, &in, &out);
+    int rc = mps_extend_upload(ctx, &in);
     if (rc) return rc;
-    memcpy(state_out, res.data(), sizeof(float) * res.size());
-    control[4] = rest;
+    if ((rc = ensure_small_pinned(ctx))) return rc;
+    const int B = ctx->scene.n_bodies;
+    float* h_state = (float*)ctx->h_valid;
+    float* h_rest = h_state + 3 * MPS_MAX_BODIES;
+    uint32_t* h_flags = (uint32_t*)(h_rest + 1);
+    volatile unsigned int* h_sig = (volatile unsigned int*)(h_rest + 2);
+    ctx->rp.out_states = h_state;
+    ctx->rp.out_rest = h_rest;
+    ctx->rp.out_flags = h_flags;
+    ctx->sp.states = h_state;
+    ctx->sp.rest = h_rest;
+    ctx->sp.flags = h_flags;
+    do {
+        ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
+    } while (ctx->nn_seq == 0);
+    ctx->sp.done_flag = h_sig;
+    ctx->sp.done_seq = ctx->nn_seq;
+    *h_sig = 0u;
+    rc = mps_extend_launch(ctx);
+    ctx->extend_ready = false;  // the staged buffers do not hold this extend's outputs: nothing to fetch or relaunch
+    if (rc) return rc;
+    if ((rc = nn_wait_flag(ctx, h_sig, ctx->nn_seq))) return rc;
+    memcpy(state_out, h_state, sizeof(float) * 3 * (size_t)B);
+    control[4] = *h_rest;
+    const uint32_t f = *h_flags;
     if (ok) *ok = (f & MPS_F_OK) ? 1 : 0;
     if (flags) *flags = f;
     return MPS_OK;
@@ -1408,10 +1435,8 @@ int mps_is_valid_batch(mps_ctx* ctx, const float* states, int32_t n, uint8_t* va
         // pinned host memory, writes the results there and signs them; the host waits for the signature (43 -> 17 us
         // per call against copy in, launch, two copies out and a stream synchronise).
         const size_t vb = ((size_t)n + 15) & ~(size_t)15;
-        if (!ctx->h_valid) {
-            // its own pinned block (the staging buffer may still feed an asynchronous upload): 16 states of 32 bodies
-            MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_valid, 16 * 3 * MPS_MAX_BODIES * sizeof(float) + 256), ctx);
-        }
+        // (its own pinned block: the staging buffer may still feed an asynchronous upload)
+        if ((rc = ensure_small_pinned(ctx))) return rc;
         char* h = ctx->h_valid;
         memcpy(h, states, sb);
         ValidityParams vp;

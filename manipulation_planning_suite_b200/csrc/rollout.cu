@@ -1774,6 +1774,11 @@ __global__ void __launch_bounds__(1024) select_kernel(SelectParams p)
             p.tree_slice[col0 + i] = -1;
         }
     }
+    if (p.done_flag) {  // single instance: this CTA is the last work of the extend
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) *p.done_flag = p.done_seq;
+    }
 }
 
 // Exchange step of the K-sharded extend: every rank holds the all-gathered winner records in rank

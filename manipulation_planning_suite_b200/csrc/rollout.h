@@ -77,6 +77,10 @@ struct SelectParams {
     float* tree_controls;
     int32_t* tree_parent;
     int32_t* tree_slice;
+    // M == 1 only: after everything else the CTA writes done_seq here (pinned host memory, system-scope fence first),
+    // so that a caller whose outputs live in pinned memory can wait for the number instead of synchronising the stream
+    volatile unsigned int* done_flag;
+    unsigned int done_seq;
 };
 
 // exchange step of the multi-GPU extend: pick the global winner among the gathered per-rank records
