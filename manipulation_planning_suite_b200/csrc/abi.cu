@@ -48,6 +48,7 @@ struct mps_ctx {
     DevScene* d_scene = nullptr;
     size_t scene_bytes = 0, warp_bytes = 0, warp_bytes_small = 0;
     int mcap_small = 0;
+    RolloutTuning tuning = {};                 // launcher knobs, read from the environment at creation
     std::string err;
     unsigned long long launches = 0;
 
@@ -319,6 +320,7 @@ int mps_ctx_create_on_stream(const mps_scene* scene, int device, void* cuda_stre
         if (const char* e = getenv("MPS_ROLLOUT_SMALL_CAP")) ctx->mcap_small = atoi(e);  // test hook
         if (ctx->mcap_small >= ctx->hscene.Mcap) ctx->mcap_small = 0;
         ctx->warp_bytes_small = ctx->mcap_small ? mps_rollout_group_bytes(ctx->hscene, ctx->mcap_small) : ctx->warp_bytes;
+        ctx->tuning = mps_rollout_tuning_from_env();
         memset(&ctx->tree, 0, sizeof(ctx->tree));
         ctx->tree.B = scene->n_bodies;
         memset(&ctx->forest, 0, sizeof(ctx->forest));
@@ -1298,7 +1300,7 @@ int mps_extend_launch(mps_ctx* ctx)
     }
     const bool timed = ctx->timing && ctx->ev_count < MPS_EVENT_RING;
     if (timed) MPS_CUDA_CHECK(cudaEventRecord(ctx->ev0[ctx->ev_count], ctx->stream), ctx);
-    MPS_CUDA_CHECK(mps_launch_rollout(ctx->rp, ctx->num_sms, ctx->scene.n_bodies, ctx->stream), ctx);
+    MPS_CUDA_CHECK(mps_launch_rollout(ctx->rp, ctx->tuning, ctx->num_sms, ctx->scene.n_bodies, ctx->stream), ctx);
     if (timed) {
         MPS_CUDA_CHECK(cudaEventRecord(ctx->ev1[ctx->ev_count], ctx->stream), ctx);
         ctx->ev_count++;
@@ -1689,7 +1691,7 @@ static int forest_extend_launch(mps_ctx* ctx, int M, int K, int L, bool has_nctr
                                               (int32_t*)ctx->d_order.p, st), ctx);
         ctx->launches += 1;
     }
-    MPS_CUDA_CHECK(mps_launch_rollout(rp, ctx->num_sms, ctx->scene.n_bodies, st), ctx);
+    MPS_CUDA_CHECK(mps_launch_rollout(rp, ctx->tuning, ctx->num_sms, ctx->scene.n_bodies, st), ctx);
     MPS_CUDA_CHECK(mps_launch_select(sp, st), ctx);
     ctx->launches += 2;
     ctx->extend_ready = false;  // the plain extend's cached parameters no longer describe the buffers

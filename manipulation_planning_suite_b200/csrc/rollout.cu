@@ -1943,7 +1943,7 @@ static int env_int(const char* name, int dflt)
 // grid of a rollout launch: as many CTAs as fit the machine, at most one group of lanes per chain
 template <class Kernel>
 static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_set, RolloutParams& p, int threads,
-                                         int groups, int num_sms, cudaStream_t stream, int ctas_per_sm = 0)
+                                         int groups, int num_sms, cudaStream_t stream, int ctas_per_sm, int cap_per_sm)
 {
     size_t smem = p.scene_bytes + (size_t)groups * p.warp_bytes;
     int dev = 0;
@@ -1958,9 +1958,7 @@ static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_
     if (e != cudaSuccess) return e;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int want = (p.K + groups - 1) / groups;
-    // tuning aid: MPS_ROLLOUT_CTAS_PER_SM caps the resident CTAs per SM (read once; initialisation of a local
-    // static is thread-safe, contexts of different host threads may launch at the same time)
-    static const int cap_per_sm = env_int("MPS_ROLLOUT_CTAS_PER_SM", 0);
+    // tuning aid: MPS_ROLLOUT_CTAS_PER_SM caps the resident CTAs per SM
     if (cap_per_sm > 0)
         ctas_per_sm = cap_per_sm;
     if (ctas_per_sm > 0 && blocks_per_sm > ctas_per_sm) blocks_per_sm = ctas_per_sm;
@@ -1975,15 +1973,29 @@ static cudaError_t launch_rollout_kernel(Kernel kernel, std::atomic<bool>* attr_
 
 // WARPS warps per CTA, MINB CTAs per SM for the register budget, G lanes per chain
 template <int WARPS, int MINB, int G, bool ROLLED = false>
-static cudaError_t launch_rollout_t(RolloutParams& p, int num_sms, cudaStream_t stream, int ctas_per_sm = 0)
+static cudaError_t launch_rollout_t(RolloutParams& p, const RolloutTuning& tune, int num_sms, cudaStream_t stream,
+                                    int ctas_per_sm = 0)
 {
     if (G < 32 && p.mcap_small > 0) p.warp_bytes = p.warp_bytes_small;
     static std::atomic<bool> attr_set[64];
     return launch_rollout_kernel(rollout_kernel<WARPS, MINB, G, ROLLED>, attr_set, p, WARPS * 32, WARPS * (32 / G), num_sms, stream,
-                                 ctas_per_sm);
+                                 ctas_per_sm, tune.ctas_per_sm);
 }
 
-cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bodies, cudaStream_t stream)
+RolloutTuning mps_rollout_tuning_from_env()
+{
+    RolloutTuning t;
+    t.group = env_int("MPS_ROLLOUT_GROUP", 0);
+    t.minb = env_int("MPS_ROLLOUT_MINB", 0);
+    t.ctas_per_sm = env_int("MPS_ROLLOUT_CTAS_PER_SM", 0);
+    t.active_warps = env_int("MPS_ROLLOUT_ACTIVE_WARPS", 0);
+    t.solo_build = env_int("MPS_ROLLOUT_SOLO_BUILD", 1);
+    t.rolled_max_bodies = env_int("MPS_ROLLED_MAX_BODIES", 12);
+    return t;
+}
+
+cudaError_t mps_launch_rollout(const RolloutParams& p_in, const RolloutTuning& tune, int num_sms, int n_bodies,
+                               cudaStream_t stream)
 {
     RolloutParams p = p_in;
     // Which build and grid (measured on B200, profiles/tools/few_probe.py and packed_probe.py, cfg 2's scene; W =
@@ -2000,14 +2012,20 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     //            chains of several controls (diverging groups) lose at every K measured (K = 16 384: 6.57 against 5.68).
     // Tuning aids: MPS_ROLLOUT_MINB = 3 | 4 pins the register budget of the unpacked build, MPS_ROLLOUT_GROUP =
     // 8 | 16 | 32 the lanes per chain, MPS_ROLLOUT_CTAS_PER_SM the resident CTAs.
-    static const int forced_active = env_int("MPS_ROLLOUT_ACTIVE_WARPS", 0);
-    p.active_warps = forced_active;
-    static const int forced_minb = env_int("MPS_ROLLOUT_MINB", 0);
-    static const int forced_g = env_int("MPS_ROLLOUT_GROUP", 0);
+    p.active_warps = tune.active_warps;
+    const int forced_minb = tune.minb;
+    const int forced_g = tune.group;
     const double per_sched = (double)p.K / ((double)num_sms * ROLLOUT_WARPS);
     int g = forced_g;
-    // two chains per warp (9..16 bodies) gained nothing on contact-rich scenes and stay opt-in
-    if (g == 0) g = (n_bodies <= 8 && p.L == 1 && p.K >= 12288) ? 8 : 32;
+    // two chains per warp (9 .. 16 bodies): with the sweeps rolled over the rounds they gain 5 .. 12 % in single-control
+    // launches of K >= 16 384 from ONE start state on scenes of 9 .. 12 bodies (profiles/r02_g16_rolled.txt) and lose
+    // below that K, with chains of several controls, with 13 and more bodies, and in multi-instance launches (every
+    // instance its own start state: the two chains of a warp share less of the instruction stream; config 5's sweep
+    // 2.08 -> 2.28 s)
+    if (g == 0)
+        g = (n_bodies <= 8 && p.L == 1 && p.K >= 12288)                                      ? 8
+            : (n_bodies >= 9 && n_bodies <= 12 && p.L == 1 && p.K >= 16384 && p.K_per == 0) ? 16
+                                                                                              : 32;
     if (g == 8 && n_bodies > 8) g = 16;
     if (g == 16 && n_bodies > 16) g = 32;
     if (g != 32) {
@@ -2017,12 +2035,14 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
         if (e != cudaSuccess) return e;
         RolloutParams q = p;
         q.redo_only = 0;
-        e = g == 8 ? launch_rollout_t<4, 4, 8>(q, num_sms, stream) : launch_rollout_t<ROLLOUT_WARPS, 4, 16>(q, num_sms, stream);
+        // (two chains per warp always with the sweeps rolled over the rounds: 9 .. 15 bodies, +16 .. 28 % over the inlined
+        // sweeps of the same packing, profiles/r02_g16_rolled.txt)
+        e = g == 8 ? launch_rollout_t<4, 4, 8>(q, tune, num_sms, stream) : launch_rollout_t<ROLLOUT_WARPS, 4, 16, true>(q, tune, num_sms, stream);
         if (e != cudaSuccess) return e;
         if (p.mcap_small <= 0) return cudaSuccess;
         p.redo_only = 1;
         p.mcap_small = 0;
-        return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream);
+        return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, tune, num_sms, stream);
     }
     p.redo_only = 0;
     p.mcap_small = 0;
@@ -2034,16 +2054,16 @@ cudaError_t mps_launch_rollout(const RolloutParams& p_in, int num_sms, int n_bod
     else if (p.order && per_sched <= 8.0 && p.L > 1)
         ctas = 2;  // (single-control chains vary less in length: three CTAs per SM are better there, 0.41 against 0.51 ms at K = 4096)
     // one CTA per SM: the build that may use the whole register file (sweeps of up to four rounds in registers)
-    static const int solo_build = env_int("MPS_ROLLOUT_SOLO_BUILD", 1);
-    if (minb == 3 && ctas == 1 && solo_build) return launch_rollout_t<ROLLOUT_WARPS, 1, 32>(p, num_sms, stream, ctas);
-    if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, num_sms, stream, ctas);
+    const int solo_build = tune.solo_build;
+    if (minb == 3 && ctas == 1 && solo_build) return launch_rollout_t<ROLLOUT_WARPS, 1, 32>(p, tune, num_sms, stream, ctas);
+    if (minb == 3) return launch_rollout_t<ROLLOUT_WARPS, 3, 32>(p, tune, num_sms, stream, ctas);
     // launches that fill the machine: the build with the sweeps rolled over the rounds (see physics_step; measured over
     // seven shapes, profiles/r02_rolled_sweeps.txt: -6 .. +25 %, +7 % on average) for scenes of up to 12 bodies - the
     // 17-body clutter of config 4 loses 3 % with it, config 5's sweep (9 bodies) gains 4 %.  MPS_ROLLED_MAX_BODIES = 0 / 32
     // select one build for everything, for comparison.
-    static const int rolled_max = env_int("MPS_ROLLED_MAX_BODIES", 12);
-    if (n_bodies <= rolled_max) return launch_rollout_t<ROLLOUT_WARPS, 4, 32, true>(p, num_sms, stream, ctas);
-    return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, num_sms, stream, ctas);
+    const int rolled_max = tune.rolled_max_bodies;
+    if (n_bodies <= rolled_max) return launch_rollout_t<ROLLOUT_WARPS, 4, 32, true>(p, tune, num_sms, stream, ctas);
+    return launch_rollout_t<ROLLOUT_WARPS, 4, 32>(p, tune, num_sms, stream, ctas);
 }
 
 cudaError_t mps_launch_chain_order(const float* controls, const int32_t* n_ctrl, int K, int L, const float accel[3],

@@ -117,7 +117,17 @@ struct ValidityParams {
 size_t mps_rollout_warp_bytes(const DevScene& sc);
 size_t mps_rollout_group_bytes(const DevScene& sc, int mcap);
 size_t mps_rollout_scene_bytes();
-cudaError_t mps_launch_rollout(const RolloutParams& p, int num_sms, int n_bodies, cudaStream_t stream);
+// Tuning aids of the rollout launcher (0 = the launcher's own rule).  Read from the environment when a context is
+// created, not per process: every context can be given its own, which is how the GPU tests force each build.
+//   MPS_ROLLOUT_GROUP = 8 | 16 | 32 lanes per chain, MPS_ROLLOUT_MINB = 3 | 4 register budget of the unpacked build,
+//   MPS_ROLLOUT_CTAS_PER_SM resident CTAs, MPS_ROLLOUT_ACTIVE_WARPS warps of a CTA that pull chains,
+//   MPS_ROLLOUT_SOLO_BUILD = 0 no <4,1,32> build, MPS_ROLLED_MAX_BODIES largest scene that takes the rolled sweeps.
+struct RolloutTuning {
+    int group, minb, ctas_per_sm, active_warps, solo_build, rolled_max_bodies;
+};
+RolloutTuning mps_rollout_tuning_from_env();
+cudaError_t mps_launch_rollout(const RolloutParams& p, const RolloutTuning& tune, int num_sms, int n_bodies,
+                               cudaStream_t stream);
 cudaError_t mps_launch_chain_order(const float* controls, const int32_t* n_ctrl, int K, int L, const float accel[3],
                                    float dt, int32_t* order, cudaStream_t stream);
 cudaError_t mps_launch_select(const SelectParams& p, cudaStream_t stream);

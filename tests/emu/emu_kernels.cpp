@@ -121,7 +121,7 @@ int emu_extend(const mps_scene* sc, const mps_extend_in* in, const mps_extend_ou
         if (group == 8)
             run_rollout<2, 4, 8>(q, ctas);
         else
-            run_rollout<2, 4, 16>(q, ctas);
+            run_rollout<2, 4, 16, true>(q, ctas);  // two chains per warp: always the rolled sweeps
         if (rp.mcap_small > 0) {
             rp.redo_only = 1;
             rp.mcap_small = 0;

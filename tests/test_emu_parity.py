@@ -10,7 +10,7 @@ import emu_binding as eb
 import oracle_binding as ob
 from manipulation_planning_suite_b200 import scenes
 
-VARIANTS = [(32, 1, 0), (32, 3, 0), (32, 4, 0), (32, 5, 0), (8, 4, 14), (8, 4, 2)]
+VARIANTS = [(32, 1, 0), (32, 3, 0), (32, 4, 0), (32, 5, 0), (8, 4, 14), (8, 4, 2), (16, 4, 14), (16, 4, 2)]
 
 
 def _same(r, w):
@@ -37,7 +37,7 @@ def test_cfg2_shape_chains_match_oracle(group, minb, mcap_small):
     assert r["counters"]["steps"] >= int(w["all_steps"].sum())
 
 
-@pytest.mark.parametrize("n_objects,group,minb", [(3, 32, 4), (3, 8, 4), (10, 32, 4), (16, 32, 4), (12, 16, 4),
+@pytest.mark.parametrize("n_objects,group,minb", [(3, 32, 4), (3, 8, 4), (10, 32, 4), (16, 32, 4), (12, 16, 4), (8, 16, 4), (9, 16, 4),
                                                   (10, 32, 1), (16, 32, 1), (16, 32, 3), (10, 32, 5), (16, 32, 5)])
 def test_single_control_rollouts_match_oracle(n_objects, group, minb):
     sc, _ = scenes.make_scene(n_objects, seed=1000 + n_objects)

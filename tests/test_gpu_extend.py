@@ -400,6 +400,60 @@ def test_baseline_config4_shape_determinism_and_sampled_parity():
     ctx.close()
 
 
+@pytest.mark.parametrize("env,n_objects,K,L", [
+    ({"MPS_ROLLOUT_MINB": "3", "MPS_ROLLOUT_SOLO_BUILD": "0"}, 6, 200, 3),   # <4,3,32>, one CTA per SM
+    ({"MPS_ROLLOUT_MINB": "3"}, 10, 150, 2),                                  # <4,1,32>: up to four rounds in registers
+    ({"MPS_ROLLOUT_MINB": "4", "MPS_ROLLED_MAX_BODIES": "0"}, 10, 150, 2),    # <4,4,32>, sweeps inlined per round
+    ({"MPS_ROLLOUT_MINB": "4", "MPS_ROLLED_MAX_BODIES": "32"}, 10, 150, 2),   # <4,4,32,rolled>
+    ({"MPS_ROLLOUT_MINB": "4", "MPS_ROLLED_MAX_BODIES": "32"}, 16, 100, 1),
+    ({"MPS_ROLLOUT_GROUP": "16"}, 8, 150, 2),                                 # <4,4,16,rolled>
+    ({"MPS_ROLLOUT_GROUP": "8"}, 6, 150, 2),                                  # <4,4,8>
+])
+def test_every_build_of_the_rollout_kernel_matches_oracle(monkeypatch, env, n_objects, K, L):
+    """The launcher picks one of six instantiations of rollout_kernel by launch shape; here each is forced through the
+    launcher's knobs (read when the context is created) on the same kind of contact-rich batch: same bits as the
+    oracle whatever the build."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc, _ = scenes.make_scene(n_objects, seed=50 + n_objects)
+    start = scenes.cluttered_start(sc, 60 + n_objects)
+    rng = np.random.RandomState(n_objects)
+    controls = scenes.sample_controls_towards(rng, sc, start, K, L)
+    n_ctrl = rng.randint(1, L + 1, size=K).astype(np.int32)
+    dest = scenes.sample_state(rng, sc)
+    r = compare_extend(sc, start, controls, n_ctrl=n_ctrl, dest=dest)
+    assert r["got"].all_steps.sum() > 2000
+    assert ((r["want"]["all_flags"] & abi.MPS_F_OK) != 0).any()
+
+
+def test_nine_bodies_many_rollouts_two_chains_per_warp_sampled_parity():
+    """A 9-body scene, K >= 16 384 single-control rollouts from one start state: the launcher packs two chains per
+    warp (rollout_kernel<4,4,16,rolled>) on its own: run-to-run identical, the winner is the first chain with the
+    smallest distance among the valid ones, and 256 sampled chains equal the oracle's bit for bit."""
+    sc, _ = scenes.make_scene(8, seed=1005)
+    start = scenes.cluttered_start(sc, 1005)
+    rng = np.random.RandomState(8)
+    K = 16384 + 37
+    controls = scenes.sample_controls_towards(rng, sc, start, K, 1)
+    dest = scenes.sample_state(rng, sc)
+    ctx = api.Context(sc)
+    a = ctx.extend(start, controls, dump=True, dest=dest)
+    b = ctx.extend(start, controls, dump=True, dest=dest)
+    assert a.k == b.k and a.distance == b.distance
+    assert np.array_equal(a.all_states, b.all_states) and np.array_equal(a.all_flags, b.all_flags)
+    ok = (a.all_flags[:, 0] & abi.MPS_F_OK) != 0
+    assert 0.05 < ok.mean() <= 1.0
+    d = np.where(ok, a.all_dist, np.inf)
+    assert a.k == int(np.argmin(d)) and a.distance == d.min()
+    idx = rng.choice(K, 256, replace=False)
+    want = ob.extend(sc, start, controls[idx], dest=dest, threads=8)
+    assert np.array_equal(a.all_flags[idx], want["all_flags"]) and np.array_equal(a.all_dist[idx], want["all_dist"])
+    assert np.array_equal(a.all_steps[idx], want["all_steps"]) and np.array_equal(a.all_rest[idx], want["all_rest"])
+    _, _, exact, n = assert_states_close(a.all_states[idx], want["all_states"], want["all_flags"])
+    assert exact == n
+    ctx.close()
+
+
 def test_sharded_extend_world_1_equals_ctx_extend_and_appends_on_the_device():
     """ShardedExtend on one rank: rollouts, record copy, merge kernel and the tree append all on the device, only the
     24-byte head comes back; same winner, same appended nodes as ctx.extend(append_to_tree=True)."""
