@@ -77,6 +77,7 @@ struct mps_ctx {
     // nn
     DevBuf d_queries, d_masks, d_filters, d_nnw, d_nn_out, d_part_d, d_part_i, d_tickets;
     void* h_nn_out = nullptr;  // pinned: idx[Q] | dist[Q]
+    unsigned long long* h_topk_rec = nullptr;  // pinned: the top-k scan's self-signed result records (nothing else writes here)
     size_t h_nn_out_bytes = 0;
     NNParams np;
     TopKParams topk;
@@ -364,6 +365,7 @@ void mps_ctx_destroy(mps_ctx* ctx)
     if (ctx->d_scene) cudaFree(ctx->d_scene);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_nn_out) cudaFreeHost(ctx->h_nn_out);
+    if (ctx->h_topk_rec) cudaFreeHost(ctx->h_topk_rec);
     if (ctx->h_nn_parts) cudaFreeHost(ctx->h_nn_parts);
     if (ctx->h_valid) cudaFreeHost(ctx->h_valid);
     for (cudaEvent_t e : ctx->ev0) cudaEventDestroy(e);
@@ -850,6 +852,26 @@ static int nn_wait_flag(mps_ctx* ctx, volatile unsigned int* flag, unsigned int 
     return MPS_OK;
 }
 
+// waits for a self-signed 16-byte record {payload, seq << 40 | payload} a kernel stores into pinned host memory with ONE
+// store (complete as soon as its second word carries the sequence number); same fallback as nn_wait_flag
+static int nn_wait_record(mps_ctx* ctx, const volatile unsigned long long* rec, unsigned int seq)
+{
+    if ((unsigned int)(rec[1] >> 40) != seq) {
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while ((unsigned int)(rec[1] >> 40) != seq) {
+            if ((++spins & 0x3ff) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 0.02) {
+                MPS_CUDA_CHECK(cudaStreamSynchronize(ctx->stream), ctx);
+                if ((unsigned int)(rec[1] >> 40) != seq)
+                    return mps_fail(ctx, MPS_ERR_CUDA, "nearest-neighbour scan finished without a result");
+                break;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return MPS_OK;
+}
+
 // pinned record block of the host-folded query and a fresh sequence number for a scan of `grid` CTAs
 static int nn_parts_begin(mps_ctx* ctx, int grid)
 {
@@ -1005,11 +1027,13 @@ int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, u
     tp.k = k;
     tp.part_keys = (unsigned long long*)ctx->d_topk_keys.p;
     tp.part_rej = (unsigned int*)ctx->d_topk_rej.p;
-    // the last CTA writes the result block straight into pinned host memory and signs it: no copy, no synchronise
-    tp.out_idx = (long long*)ctx->h_nn_out;
-    tp.out_dist = (double*)((char*)ctx->h_nn_out + 8 * NN_TOPK_MAX);
-    tp.out_meta = (int*)((char*)ctx->h_nn_out + 16 * NN_TOPK_MAX);
-    tp.done_flag = (volatile unsigned int*)((char*)ctx->h_nn_out + ctx->h_nn_out_bytes);
+    // the last CTA writes the results straight into pinned host memory as self-signed 16-byte records (one store each:
+    // a record that carries this query's sequence number is complete): no copy, no fence, no synchronise
+    if (!ctx->h_topk_rec) {
+        MPS_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_topk_rec, 16 * (NN_TOPK_MAX + 1)), ctx);
+        memset(ctx->h_topk_rec, 0, 16 * (NN_TOPK_MAX + 1));
+    }
+    tp.out_rec = ctx->h_topk_rec;
     do {
         ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
     } while (ctx->nn_seq == 0);
@@ -1018,16 +1042,19 @@ int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, u
     ctx->topk_ready = true;
     MPS_CUDA_CHECK(mps_launch_nn_topk(tp, ctx->stream), ctx);
     ctx->launches++;
-    if ((rc = nn_wait_flag(ctx, tp.done_flag, tp.done_seq))) return rc;
-    char host[16 * NN_TOPK_MAX + 16];
-    memcpy(host, ctx->h_nn_out, sizeof(host));
-    int meta[2];
-    memcpy(meta, host + 16 * NN_TOPK_MAX, sizeof(meta));
-    int found = meta[0];
+    const volatile unsigned long long* rec = ctx->h_topk_rec;
+    if ((rc = nn_wait_record(ctx, rec + 2 * NN_TOPK_MAX, tp.done_seq))) return rc;
+    const unsigned long long meta = rec[2 * NN_TOPK_MAX];
+    int found = (int)(unsigned int)(meta & 0xffffffffull);
+    const int status = (int)(unsigned int)(meta >> 32);
     static const bool force_fallback = getenv("MPS_NN_TOPK_FALLBACK") && getenv("MPS_NN_TOPK_FALLBACK")[0] == '1';
-    if (meta[1] == 0 && !force_fallback) {
-        memcpy(indices, host, 8 * (size_t)found);
-        if (distances) memcpy(distances, host + 8 * NN_TOPK_MAX, 8 * (size_t)found);
+    if (status == 0 && !force_fallback) {
+        for (int r = 0; r < found; ++r) {
+            if ((rc = nn_wait_record(ctx, rec + 2 * r, tp.done_seq))) return rc;
+            const unsigned long long w0 = rec[2 * r], w1 = rec[2 * r + 1];
+            indices[r] = (int64_t)(w1 & 0xffffffffffull);
+            if (distances) memcpy(&distances[r], &w0, 8);
+        }
     } else {
         // successor scans: (d, i) strictly above the previous result, k times
         NextParams nx;

@@ -751,26 +751,6 @@ __device__ __forceinline__ unsigned long long warp_list_insert(unsigned long lon
     return dropped;
 }
 
-// the keys a warp holds are offered one by one to the list; rej collects the fp32 bits of what does not stay
-__device__ __forceinline__ void warp_list_offer(unsigned long long& mine, unsigned long long& kth, unsigned int& rej,
-                                                unsigned long long key, bool valid, int k, int lane)
-{
-    unsigned bal = __ballot_sync(FULL, valid && key < kth);
-    if (valid && !(key < kth)) rej = min(rej, (unsigned int)(key >> 32));
-    while (bal) {
-        const int src = __ffs(bal) - 1;
-        bal &= bal - 1u;
-        const unsigned long long k64 = shfl_u64(key, src);
-        if (k64 < kth) {
-            const unsigned long long dropped = warp_list_insert(mine, k64, k, lane);
-            if (dropped != NN_KEY_SENTINEL) rej = min(rej, (unsigned int)(dropped >> 32));
-            kth = shfl_u64(mine, k - 1);
-        } else {
-            rej = min(rej, (unsigned int)(k64 >> 32));  // the list tightened since the ballot
-        }
-    }
-}
-
 // the 32 smallest keys of two ascending 32-entry lists (one entry per lane), ascending
 __device__ __forceinline__ unsigned long long warp_merge32(unsigned long long a, unsigned long long b, int lane)
 {
@@ -783,6 +763,60 @@ __device__ __forceinline__ unsigned long long warp_merge32(unsigned long long a,
         m = (up == (m < o)) ? o : m;  // lower lane keeps the smaller, upper lane the larger
     }
     return m;
+}
+
+// one key per lane -> ascending over the lanes (bitonic network, 15 compare-exchange stages)
+__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long v, int lane)
+{
+#pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(FULL, v, j);
+            const bool take_max = ((lane & j) != 0) != ((lane & k2) != 0);  // upper lane of the pair, block ascending
+            v = (take_max == (v < o)) ? o : v;
+        }
+    }
+    return v;
+}
+
+// more candidates than this in one offer: sort them and merge the two lists instead of inserting one by one (an
+// insertion is ~4 dependent shuffles, the sort + merge 21 stages whatever the number of candidates)
+#ifndef NN_OFFER_SERIAL_MAX
+#define NN_OFFER_SERIAL_MAX 5
+#endif
+
+// the keys a warp holds (one per lane) are offered to the list; rej collects the fp32 bits of what does not stay
+__device__ __forceinline__ void warp_list_offer(unsigned long long& mine, unsigned long long& kth, unsigned int& rej,
+                                                unsigned long long key, bool valid, int k, int lane)
+{
+    const bool cand = valid && key < kth;
+    unsigned bal = __ballot_sync(FULL, cand);
+    if (valid && !cand) rej = min(rej, (unsigned int)(key >> 32));
+    if (__popc(bal) > NN_OFFER_SERIAL_MAX) {
+        // many candidates (the first trips of a warp, before its list has tightened)
+        const unsigned long long c = warp_sort32(cand ? key : NN_KEY_SENTINEL, lane);
+        const unsigned long long old = mine;
+        mine = warp_merge32(mine, c, lane);
+        if (lane >= k) mine = NN_KEY_SENTINEL;
+        kth = shfl_u64(mine, k - 1);
+        // what did not stay: list entries and offered keys above the new k-th (keys are unique)
+        if (old != NN_KEY_SENTINEL && old > kth) rej = min(rej, (unsigned int)(old >> 32));
+        if (cand && key > kth) rej = min(rej, (unsigned int)(key >> 32));
+        return;
+    }
+    while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1u;
+        const unsigned long long k64 = shfl_u64(key, src);
+        if (k64 < kth) {
+            const unsigned long long dropped = warp_list_insert(mine, k64, k, lane);
+            if (dropped != NN_KEY_SENTINEL) rej = min(rej, (unsigned int)(dropped >> 32));
+            kth = shfl_u64(mine, k - 1);
+        } else {
+            rej = min(rej, (unsigned int)(k64 >> 32));  // the list tightened since the ballot
+        }
+    }
 }
 
 // CTA merge of the warps' lists (s_keys[w * 32 + l] = entry l of warp w's ascending list, sentinels at the end):
@@ -837,6 +871,10 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
     __shared__ unsigned int s_ncand;
     __shared__ long long s_ci[NN_TOPK_CAND];
     __shared__ double s_cd[NN_TOPK_CAND];
+    __shared__ unsigned int s_nhot, s_nbuf;
+    __shared__ unsigned short s_hot[NN_TOPK_HOT];            // lists whose head lies within the bound (last CTA)
+    __shared__ unsigned long long s_buf[NN_TOPK_BUF];        // their keys within the bound
+    __shared__ double s_term[NN_TOPK_CAND * MPS_MAX_BODIES];  // body terms of the candidates' exact distances
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -881,7 +919,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
         for (int j = 0; j < 4; ++j) {
             const float dj = j == 0 ? d0 : j == 1 ? d1 : j == 2 ? d2 : d3;
             const unsigned long long key = ((unsigned long long)__float_as_uint(dj) << 32) | (unsigned long long)(unsigned int)(n0 + j);
-#if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 3
+#if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 3 || NN_TOPK_PROBE >= 4
             warp_list_offer(mine, kth, rej, key, dj < inf, k, lane);
 #else
             rej = min(rej, (unsigned int)(key >> 32));
@@ -892,7 +930,7 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
     s_keys[tid] = mine;
     if (lane == 0) atomicMin(&s_rej, rej);
     __syncthreads();
-#if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 2
+#if !defined(NN_TOPK_PROBE) || NN_TOPK_PROBE < 2 || NN_TOPK_PROBE >= 4
     cta_rank_merge(s_keys, s_out, k, &s_rej, tid);
 #endif
     if (tid < k) {
@@ -908,84 +946,125 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
     }
     __syncthreads();
     if (!s_last) return;
-#if defined(NN_TOPK_PROBE) && NN_TOPK_PROBE >= 1
+#if defined(NN_TOPK_PROBE) && NN_TOPK_PROBE >= 1 && NN_TOPK_PROBE <= 3
     if (tid == 0) p.tickets[0] = 0u;
     return;
 #endif
 
-    // ---- last CTA: the k-th smallest fp32 distance of all CTAs' lists, then the exact fix-up -------------------------
+    // ---- last CTA: the k smallest fp32 keys of all CTAs' lists, then the exact fix-up ---------------------------------
+    // The lists are ascending, so the k-th smallest of their HEADS, U, bounds the k-th smallest key of the whole tree from
+    // above (k keys <= U exist), and every key that can matter - the k smallest and whatever lies within the slack of the
+    // k-th - is <= U' = U inflated by the slack and sits in a list whose head is <= U' (usually k lists or a few more out
+    // of 245).  Three dependent trips to L2 (heads, the hot lists' keys, the dropped minima) instead of a merge chain
+    // over all lists.
     __threadfence();
-    const int total = (int)gridDim.x * k;
-    const volatile unsigned long long* keys = tp.part_keys;
-    // Every CTA's list is ascending: two lists merge into the 32 smallest of both in six shuffles (the reversed
-    // second list against the first gives a bitonic sequence holding the 32 smallest, five compare-exchange stages
-    // sort it).  Each warp folds its share of the lists into one, two chains at a time; three more merges through
-    // shared memory leave the k smallest fp32 keys of the whole tree in s_out.
+    const int lists = (int)gridDim.x;
+    const unsigned long long* keys = tp.part_keys;  // read through L2 (__ldcg): written by other SMs before their tickets
     {
-        const int lists = (int)gridDim.x;
-        auto load_list = [&](int l) -> unsigned long long {
-            return (l < lists && lane < k) ? keys[(size_t)l * k + lane] : NN_KEY_SENTINEL;
-        };
-        // four independent merge chains per warp (the chain is the latency; four of them share the issue slots), the
-        // next four lists already on their way from L2 while the current four are merged
-        unsigned long long acc0 = NN_KEY_SENTINEL, acc1 = NN_KEY_SENTINEL, acc2 = NN_KEY_SENTINEL, acc3 = NN_KEY_SENTINEL;
-        const int step = 4 * (NN_THREADS / 32);
-        int l = warp * 4;
-        unsigned long long n0 = load_list(l), n1 = load_list(l + 1), n2 = load_list(l + 2), n3 = load_list(l + 3);
-        for (; l < lists; l += step) {
-            const unsigned long long b0 = n0, b1 = n1, b2 = n2, b3 = n3;
-            n0 = load_list(l + step);
-            n1 = load_list(l + step + 1);
-            n2 = load_list(l + step + 2);
-            n3 = load_list(l + step + 3);
-            acc0 = warp_merge32(acc0, b0, lane);
-            acc1 = warp_merge32(acc1, b1, lane);
-            acc2 = warp_merge32(acc2, b2, lane);
-            acc3 = warp_merge32(acc3, b3, lane);
+        unsigned long long hmine = NN_KEY_SENTINEL, hkth = NN_KEY_SENTINEL;
+        unsigned int hrej = 0u;
+        for (int l0 = warp * 32; l0 < lists; l0 += NN_THREADS) {
+            const int l = l0 + lane;
+            const unsigned long long h = l < lists ? __ldcg(keys + (size_t)l * k) : NN_KEY_SENTINEL;
+            warp_list_offer(hmine, hkth, hrej, h, h != NN_KEY_SENTINEL, k, lane);
         }
-        acc0 = warp_merge32(acc0, acc1, lane);
-        acc2 = warp_merge32(acc2, acc3, lane);
-        acc0 = warp_merge32(acc0, acc2, lane);
-        s_keys[tid] = acc0;
+        s_keys[tid] = hmine;
+        if (tid < NN_TOPK_MAX) s_out[tid] = NN_KEY_SENTINEL;
+        if (tid == 0) {
+            s_rej = 0x7f800000u;
+            s_nhot = 0u;
+            s_nbuf = 0u;
+        }
         __syncthreads();
         for (int stride = 1; stride < NN_THREADS / 32; stride <<= 1) {
             if ((warp & (2 * stride - 1)) == 0) {
-                acc0 = warp_merge32(acc0, s_keys[(warp + stride) * 32 + lane], lane);
-                s_keys[tid] = acc0;
+                hmine = warp_merge32(hmine, s_keys[(warp + stride) * 32 + lane], lane);
+                s_keys[tid] = hmine;
             }
             __syncthreads();
         }
-        if (tid < NN_TOPK_MAX) s_out[tid] = s_keys[tid];
-        if (tid == 0) s_rej = 0x7f800000u;
-        __syncthreads();
     }
-    int have = 0;
-    for (int i = 0; i < k; ++i) have += s_out[i] != NN_KEY_SENTINEL ? 1 : 0;
-    const unsigned int lo = have > 0 ? (unsigned int)(s_out[have - 1] >> 32) : 0x7f800000u;
-    int status = 0;
-    float thr = inf;
-    if (have > 0) thr = __uint_as_float(lo) * (1.0f + NN_REL_EPS) + p.abs_eps;
+    const unsigned long long U = s_keys[k - 1];  // sentinel: fewer than k non-empty lists, every key matters
+    const float thrU = U == NN_KEY_SENTINEL ? inf : __uint_as_float((unsigned int)(U >> 32)) * (1.0f + NN_REL_EPS) + p.abs_eps;
+    for (int l = tid; l < lists; l += NN_THREADS) {
+        const unsigned long long h = __ldcg(keys + (size_t)l * k);
+        if (h != NN_KEY_SENTINEL && __uint_as_float((unsigned int)(h >> 32)) <= thrU) {
+            const unsigned int slot = atomicAdd(&s_nhot, 1u);
+            if (slot < NN_TOPK_HOT) s_hot[slot] = (unsigned short)l;
+        }
+    }
     __syncthreads();
+    int status = 0;
+    if (s_nhot > NN_TOPK_HOT || lists > 65535) status = 1;
+    const int nhot = (int)min(s_nhot, (unsigned int)NN_TOPK_HOT);
+    for (int i = tid; i < nhot * k; i += NN_THREADS) {
+        const int hl = i / k;
+        const unsigned long long key = __ldcg(keys + (size_t)s_hot[hl] * k + (i - hl * k));
+        if (key != NN_KEY_SENTINEL && __uint_as_float((unsigned int)(key >> 32)) <= thrU) {
+            const unsigned int slot = atomicAdd(&s_nbuf, 1u);
+            if (slot < NN_TOPK_BUF) s_buf[slot] = key;
+        }
+    }
     // smallest distance any CTA dropped: it must lie beyond the slack
     unsigned int gr = 0x7f800000u;
-    for (int c = tid; c < (int)gridDim.x; c += NN_THREADS) gr = min(gr, *reinterpret_cast<volatile unsigned int*>(&tp.part_rej[c]));
+    for (int c = tid; c < lists; c += NN_THREADS) gr = min(gr, __ldcg(tp.part_rej + c));
     gr = __reduce_min_sync(FULL, gr);
     if (lane == 0) atomicMin(&s_rej, gr);
-    // candidates: every reported key within the slack
-    for (int i = tid; i < total; i += NN_THREADS) {
-        const unsigned long long key = keys[i];
-        if (key != NN_KEY_SENTINEL && __uint_as_float((unsigned int)(key >> 32)) <= thr) {
+    __syncthreads();
+#if defined(NN_TOPK_PROBE) && NN_TOPK_PROBE == 4
+    if (tid == 0) p.tickets[0] = 0u;
+    return;
+#endif
+    if (s_nbuf > NN_TOPK_BUF) status = 1;  // more near-equal distances than the buffer holds: the caller falls back
+    const int m = (int)min(s_nbuf, (unsigned int)NN_TOPK_BUF);
+    // the k smallest of the buffer by ranking (keys are unique)
+    for (int i = tid; i < m; i += NN_THREADS) {
+        const unsigned long long mk = s_buf[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += s_buf[j] < mk ? 1 : 0;
+        if (rank < k) s_out[rank] = mk;
+    }
+    __syncthreads();
+    const int have = m < k ? m : k;
+    const unsigned int lo = have > 0 ? (unsigned int)(s_out[have - 1] >> 32) : 0x7f800000u;
+    float thr = inf;
+    if (have > 0) thr = __uint_as_float(lo) * (1.0f + NN_REL_EPS) + p.abs_eps;
+    // candidates: every buffered key within the slack of the k-th (thr <= thrU: all of them are in the buffer)
+    for (int i = tid; i < m; i += NN_THREADS) {
+        const unsigned long long key = s_buf[i];
+        if (__uint_as_float((unsigned int)(key >> 32)) <= thr) {
             const unsigned int slot = atomicAdd(&s_ncand, 1u);
             if (slot < NN_TOPK_CAND) s_ci[slot] = (long long)(unsigned int)(key & 0xffffffffull);
         }
     }
     __syncthreads();
+#if defined(NN_TOPK_PROBE) && NN_TOPK_PROBE == 5
+    if (tid == 0) p.tickets[0] = 0u;
+    return;
+#endif
     if (have == k && __uint_as_float(s_rej) <= thr) status = 1;
     if (s_ncand > NN_TOPK_CAND) status = 1;
     const int nc = (int)min(s_ncand, (unsigned int)NN_TOPK_CAND);
-    for (int c = warp; c < nc; c += NN_THREADS / 32) {
-        const double e = warp_exact_distance(p.tree, s_ci[c], s_q, s_wb, mask, p.pw, p.ow, lane);
-        if (lane == 0) s_cd[c] = e;
+    // the reference's double expression for every candidate: thread = (candidate, body), all loads in flight at once;
+    // the terms are then added in body order (the rounding of the sequential loop, as in warp_exact_distance)
+    for (int w = tid; w < nc * B; w += NN_THREADS) {
+        const int c = w / B, b = w - c * B;
+        double term = 0.0;
+        if ((mask >> b) & 1u) {
+            const long long n = s_ci[c];
+            const float x = p.tree.states[(size_t)(3 * b) * cap + n];
+            const float y = p.tree.states[(size_t)(3 * b + 1) * cap + n];
+            const float th = p.tree.states[(size_t)(3 * b + 2) * cap + n];
+            term = (double)s_wb[b] * mps_body_distance(x, y, th, s_q[3 * b], s_q[3 * b + 1], s_q[3 * b + 2], p.pw, p.ow);
+        }
+        s_term[w] = term;
+    }
+    __syncthreads();
+    if (tid < nc) {
+        double dist = 0.0;
+        for (int b = 0; b < B; ++b)
+            if ((mask >> b) & 1u) dist += s_term[tid * B + b];
+        s_cd[tid] = dist;
     }
     __syncthreads();
     if (tid < nc) {
@@ -994,16 +1073,28 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_topk_kernel(cons
         int rank = 0;
         for (int j = 0; j < nc; ++j) rank += (s_cd[j] < md || (s_cd[j] == md && s_ci[j] < mi)) ? 1 : 0;
         if (rank < k) {
-            tp.out_idx[rank] = mi;
-            tp.out_dist[rank] = md;
+            if (tp.out_rec) {
+                *reinterpret_cast<ulonglong2*>(tp.out_rec + 2 * rank) =
+                    make_ulonglong2((unsigned long long)__double_as_longlong(md),
+                                    ((unsigned long long)(tp.done_seq & 0xffffffu) << 40) | ((unsigned long long)mi & 0xffffffffffull));
+            } else {
+                tp.out_idx[rank] = mi;
+                tp.out_dist[rank] = md;
+            }
         }
     }
     if (tid == 0) {
-        tp.out_meta[0] = nc < k ? nc : k;
-        tp.out_meta[1] = status;
+        if (tp.out_rec) {
+            *reinterpret_cast<ulonglong2*>(tp.out_rec + 2 * NN_TOPK_MAX) =
+                make_ulonglong2((unsigned long long)(unsigned int)(nc < k ? nc : k) | ((unsigned long long)(unsigned int)status << 32),
+                                (unsigned long long)(tp.done_seq & 0xffffffu) << 40);
+        } else {
+            tp.out_meta[0] = nc < k ? nc : k;
+            tp.out_meta[1] = status;
+        }
         p.tickets[0] = 0u;
     }
-    if (tp.done_flag) {
+    if (tp.done_flag && !tp.out_rec) {
         __threadfence_system();  // every writer of the result block, before the CTA signs it
         __syncthreads();
         if (tid == 0) *tp.done_flag = tp.done_seq;

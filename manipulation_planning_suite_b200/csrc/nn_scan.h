@@ -68,6 +68,8 @@ struct NNParams {
 // exact k nearest neighbours of one query (k <= 32), see nn_topk_kernel
 #define NN_TOPK_MAX 32
 #define NN_TOPK_CAND 64
+#define NN_TOPK_HOT 512   // lists the last CTA looks into (grid <= 2 CTAs x 148 SMs)
+#define NN_TOPK_BUF 1024  // keys within the bound of the k-th smallest list head (k hot lists x k keys at most, without ties)
 struct TopKParams {
     NNParams nn;                    // tree, n, the query (inline), pw / ow, grid_x, tickets
     int k;
@@ -80,6 +82,11 @@ struct TopKParams {
     // for the number instead of synchronising the stream
     volatile unsigned int* done_flag;
     unsigned int done_seq;
+    // or (out_rec != nullptr; out_idx / out_dist / out_meta / done_flag unused): self-signed 16-byte records in pinned host
+    // memory, one store each - [r] = {distance bits, done_seq << 40 | index} for result r, [NN_TOPK_MAX] = {results
+    // written | status << 32, done_seq << 40}; a record that carries the sequence number is complete, so nothing has to
+    // be fenced (the system-scope fence before the flag cost ~2 us of the last CTA's tail)
+    unsigned long long* out_rec;
 };
 
 // lexicographic successor scan in double (rare fallback of the top-k path, and its checker):

@@ -228,6 +228,8 @@ inline long long clock64() { return 0; }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 template <class T>
+inline T __ldcg(const T* p) { return *p; }
+template <class T>
 inline T __ldcs(const T* p) { return *p; }
 template <class T>
 inline T atomicAdd(T* p, T v)
