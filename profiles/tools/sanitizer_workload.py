@@ -27,3 +27,15 @@ c = scenes.sample_controls_towards(rng, sc, start, 64, 2)
 tree2 = api.NearestNeighbors(ctx)
 sh.upload(start, c, dest=q, append_to_tree=True, parent=0)
 sh.launch(); h = sh.head(); print("sharded", h.k, h.tree_index)
+# packed launches: two chains per warp with the rolled sweeps (9 bodies), four per warp (7 bodies), forced per context
+import os
+for grp, nobj in (("16", 8), ("8", 6)):
+    os.environ["MPS_ROLLOUT_GROUP"] = grp
+    s2, _ = scenes.make_scene(nobj, seed=30 + nobj)
+    st2 = scenes.cluttered_start(s2, 40 + nobj)
+    c2 = scenes.sample_controls_towards(rng, s2, st2, 70, 2)
+    cx = api.Context(s2)
+    r2 = cx.extend(st2, c2, dest=scenes.sample_state(rng, s2))
+    print("packed", grp, r2.k, r2.n_ok)
+    cx.close()
+os.environ.pop("MPS_ROLLOUT_GROUP")
