@@ -677,6 +677,18 @@ __device__ __forceinline__ DetectResult detect(const DevScene& sc, const WarpMem
         nm += __popc(tmask);
     }
     DetectResult r;
+    // nothing touches (most steps): no lane has a flag, a penetration or a manifold to publish.  Only in the packed
+    // builds (four chains per warp, 7 bodies, K = 65 536: 19.4 -> 20.7 M rollouts/s); one chain per warp loses 1 .. 3 %
+    // with the extra branch (profiles/r02_variants_shortcuts_coldcalls.txt)
+    if (G < 32 && n_touch == 0u) {
+        r.bad = false;
+        r.overflow = false;
+        r.max_pen = 0.0f;
+        r.nm = 0;
+        r.candidates = (unsigned)ncand;
+        r.touching = 0u;
+        return r;
+    }
     const unsigned fl = __reduce_or_sync(ln.m, (lane_bad ? 1u : 0u) | (lane_over ? 2u : 0u));
     r.bad = (fl & 1u) != 0u;
     r.overflow = (fl & 2u) != 0u;
