@@ -1034,9 +1034,13 @@ int mps_tree_nearest_k(mps_ctx* ctx, const float* query, const float* weights, u
         memset(ctx->h_topk_rec, 0, 16 * (NN_TOPK_MAX + 1));
     }
     tp.out_rec = ctx->h_topk_rec;
+    const unsigned int seq_before = ctx->nn_seq;
     do {
         ctx->nn_seq = (ctx->nn_seq + 1) & 0xffffffu;
     } while (ctx->nn_seq == 0);
+    // the 24-bit sequence number came round: a record slot that no query has rewritten since (a larger k long ago) must
+    // not be taken for this query's (nothing is in flight here: every top-k query is waited for)
+    if (ctx->nn_seq < seq_before) memset(ctx->h_topk_rec, 0, 16 * (NN_TOPK_MAX + 1));
     tp.done_seq = ctx->nn_seq;
     ctx->topk = tp;
     ctx->topk_ready = true;
