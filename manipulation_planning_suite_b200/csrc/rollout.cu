@@ -67,7 +67,9 @@ namespace {
 //   [5] couplings t0-n0, t0-n1, t1-n0, t1-n1
 //   [6] accumulated impulses (n0, t0, n1, t1) of owner lane a   [7] the same, owner lane b's private copy
 // A missing second point carries zero rows.
+#ifndef MF_VEC4
 #define MF_VEC4 8
+#endif
 // sweeps of at most this many rounds keep the manifold rows in registers (see physics_step): two in the build
 // with the large register budget, MPS_REG_ROUNDS in the packed 128-register builds, none in the unpacked
 // 128-register build (measured on B200: +6 % on cfg2, +8 % packed at B = 7, -5 % unpacked at B = 17)
