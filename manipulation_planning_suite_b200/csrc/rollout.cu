@@ -81,6 +81,15 @@ namespace {
 #define MPS_REG_ROUNDS_SOLO 4
 #endif
 #define MF_FIELDS (4 * MF_VEC4)
+// Unrolling of the iteration loop of the register-resident sweeps.  The iterations are serial (Gauss-Seidel), so
+// unrolling only removes the loop's branch and costs code the step has to fetch: measured on B200
+// (profiles/r02_variants_shortcuts_coldcalls.txt) against the compiler's own choice (about 2): not unrolled, cfg 2
+// +0.7 %, two chains per warp +6 .. 9 %, four chains per warp -7 % (kept at 2 there); unrolled 4 / 8 times cfg 2 loses
+// 7 / 25 %.
+template <int G>
+struct SweepUnroll {
+    static constexpr int value = G == 8 ? 2 : 1;
+};
 
 struct Shape {
     int shape;
@@ -1026,6 +1035,7 @@ __device__ __forceinline__ RoundRegs load_round(const WarpMem& W, unsigned e, in
 template <bool TWO, int NR>
 __device__ __forceinline__ void sweep_in_registers(RoundRegs (&r)[NR], Body& bd, const Ln ln, int iters)
 {
+#pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < NR; ++k) solve_core<TWO>(r[k].R, r[k].acc, bd, ln, r[k].act, r[k].j, r[k].st, r[k].isa);
@@ -1038,6 +1048,7 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                                              float uy, float uw, bool& bad, bool& overflow, float& max_pen,
                                              StepStats& st, StepCache& cache)
 {
+    constexpr int kSweepUnroll = SweepUnroll<G>::value;
     const int lane = ln.g;
     const int B = sc.B;
     if (lane == sc.robot) {
@@ -1163,8 +1174,10 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     const bool two = G < 32 || __any_sync(ln.m, two_a);
                     PH_T(tl0);
                     if (two) {
+#pragma unroll kSweepUnroll
                         for (int it = 0; it < iters; ++it) solve_core<true>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
                     } else {
+#pragma unroll kSweepUnroll
                         for (int it = 0; it < iters; ++it) solve_core<false>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
                     }
                     PH_T(tl1);
@@ -1175,11 +1188,13 @@ __device__ __forceinline__ void physics_step(const DevScene& sc, const WarpMem& 
                     const bool two_b = act_b && ((__float_as_int(Rb.m0.x) >> 16) & 0xff) > 1;
                     const bool two = G < 32 || __any_sync(ln.m, two_a || two_b);
                     if (two) {
+#pragma unroll kSweepUnroll
                         for (int it = 0; it < iters; ++it) {
                             solve_core<true>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
                             solve_core<true>(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
                         }
                     } else {
+#pragma unroll kSweepUnroll
                         for (int it = 0; it < iters; ++it) {
                             solve_core<false>(Ra, acc_a, bd, ln, act_a, j_a, st_a, isa_a);
                             solve_core<false>(Rb, acc_b, bd, ln, act_b, j_b, st_b, isa_b);
