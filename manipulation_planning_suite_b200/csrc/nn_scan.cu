@@ -461,6 +461,57 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_kernel(cons
 #define NN_QT 8
 #define NN_TILE_CAND 128
 
+// Packed fp32 (sm_100a FFMA2 / FADD2 / FMUL2): two IEEE operations per instruction, bit for bit the scalar ones.  The tiled
+// scan is bound by issue slots once its loads are pipelined (72 % busy, FMA pipe 50 %), and a packed instruction takes one
+// slot for two nodes (profiles/r02_ffma2_probe.txt: same flops, half the instructions).
+#ifndef NN_TILE_F32X2
+#define NN_TILE_F32X2 1  // 0: the scalar arithmetic (same bits; 5.71 against 5.38 us per query at Q = 128)
+#endif
+#if NN_TILE_F32X2
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// two nodes of one body against one query: the operations of body_term_f32 and of the accumulation, pairwise
+__device__ __forceinline__ f32x2_t body_term_pair(f32x2_t acc, float x0, float x1, float y0, float y1, float t0, float t1,
+                                                  const float4 qw, f32x2_t pw2, f32x2_t ow2)
+{
+    const f32x2_t dx = sub2(pk2(x0, x1), pk2(qw.x, qw.x));
+    const f32x2_t dy = sub2(pk2(y0, y1), pk2(qw.y, qw.y));
+    float s0, s1;
+    upk2(fma2(dx, dx, mul2(dy, dy)), s0, s1);
+    const float d0 = fabsf(t0 - qw.z), d1 = fabsf(t1 - qw.z);
+    const float a0 = fminf(d0, MPS_TWO_PI_F - d0), a1 = fminf(d1, MPS_TWO_PI_F - d1);
+    const f32x2_t term = fma2(pw2, pk2(sqrt_approx(s0), sqrt_approx(s1)), mul2(ow2, pk2(a0, a1)));
+    return fma2(pk2(qw.w, qw.w), term, acc);
+}
+#endif
+
 template <bool STREAM>
 __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_tile_kernel(const __grid_constant__ NNParams p)
 {
@@ -536,9 +587,16 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_tile_kernel
     // ---- streaming pass ----------------------------------------------------------------------------------------------
     for (long long g = (long long)cta * NN_THREADS + tid; g < groups; g += (long long)ncta * NN_THREADS) {
         const long long n0 = g << 2;
+#if NN_TILE_F32X2
+        f32x2_t dp[NN_QT][2];
+        const f32x2_t pw2 = pk2(pwf, pwf), ow2 = pk2(owf, owf);
+#pragma unroll
+        for (int qq = 0; qq < NN_QT; ++qq) dp[qq][0] = dp[qq][1] = pk2(0.0f, 0.0f);
+#else
         float d[NN_QT][4];
 #pragma unroll
         for (int qq = 0; qq < NN_QT; ++qq) d[qq][0] = d[qq][1] = d[qq][2] = d[qq][3] = 0.0f;
+#endif
         // the rows of the next two bodies are on their way while the current two are evaluated for the eight queries
         // (the pass was waiting for its loads half of the time: 7.2 -> 6.5 us per query at Q = 32, 6.2 -> 5.7 at Q = 128)
         auto load2 = [&](int a0, float4 (&X)[2], float4 (&Y)[2], float4 (&T)[2]) {
@@ -565,10 +623,15 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_tile_kernel
 #pragma unroll
                     for (int qq = 0; qq < NN_QT; ++qq) {
                         const float4 qw = s_qw[qq][i];
+#if NN_TILE_F32X2
+                        dp[qq][0] = body_term_pair(dp[qq][0], X[u].x, X[u].y, Y[u].x, Y[u].y, T[u].x, T[u].y, qw, pw2, ow2);
+                        dp[qq][1] = body_term_pair(dp[qq][1], X[u].z, X[u].w, Y[u].z, Y[u].w, T[u].z, T[u].w, qw, pw2, ow2);
+#else
                         d[qq][0] = fmaf(qw.w, body_term_f32(X[u].x, Y[u].x, T[u].x, qw.x, qw.y, qw.z, pwf, owf), d[qq][0]);
                         d[qq][1] = fmaf(qw.w, body_term_f32(X[u].y, Y[u].y, T[u].y, qw.x, qw.y, qw.z, pwf, owf), d[qq][1]);
                         d[qq][2] = fmaf(qw.w, body_term_f32(X[u].z, Y[u].z, T[u].z, qw.x, qw.y, qw.z, pwf, owf), d[qq][2]);
                         d[qq][3] = fmaf(qw.w, body_term_f32(X[u].w, Y[u].w, T[u].w, qw.x, qw.y, qw.z, pwf, owf), d[qq][3]);
+#endif
                     }
                 }
             }
@@ -586,7 +649,13 @@ __global__ void __launch_bounds__(NN_THREADS, NN_MIN_BLOCKS) nn_scan_tile_kernel
 #pragma unroll
         for (int qq = 0; qq < NN_QT; ++qq) {
             if (qq >= nq) break;  // uniform
+#if NN_TILE_F32X2
+            float d0, d1, d2, d3;
+            upk2(dp[qq][0], d0, d1);
+            upk2(dp[qq][1], d2, d3);
+#else
             float d0 = d[qq][0], d1 = d[qq][1], d2 = d[qq][2], d3 = d[qq][3];
+#endif
             const int f = s_filter[qq];
             if (f >= 0) {
                 if (sl.x != f) d0 = inf;
