@@ -339,6 +339,29 @@ def test_nearest_k_equals_sorted_double_scan(n_objects, N):
     ctx.close()
 
 
+def test_nearest_k_on_an_empty_tree_and_a_slice_without_members():
+    """nearestK with nothing to return: an empty tree, a slice filter no node carries; then fewer nodes than k."""
+    sc, _ = scenes.make_scene(3, seed=5)
+    ctx = api.Context(sc)
+    tree = api.NearestNeighbors(ctx)
+    tree.clear()
+    q = np.zeros(3 * sc.n_bodies, np.float32)
+    gi, gd = tree.nearest_k(q, 4)
+    assert len(gi) == 0 and len(gd) == 0
+    tree.add(q, slice_id=3)
+    gi, gd = tree.nearest_k(q, 4, slice_filter=4)
+    assert len(gi) == 0
+    gi, gd = tree.nearest_k(q, 4, slice_filter=3)
+    assert list(gi) == [0] and gd[0] == 0.0
+    q2 = q.copy()
+    q2[0] = 0.25
+    tree.add(q2, slice_id=3)
+    gi, gd = tree.nearest_k(q, 32)
+    assert list(gi) == [0, 1] and gd[0] == 0.0 and gd[1] == ob.distance(sc, q2, q)
+    assert tree.nearest_k_fallbacks() == 0
+    ctx.close()
+
+
 def test_nearest_k_at_one_million_nodes_and_with_duplicates():
     sc, _ = scenes.make_scene(10, seed=1003)
     B = sc.n_bodies
