@@ -672,6 +672,20 @@ def bench_nn(api, scenes, device, flush):
                         "GBps_algorithmic": round(N * 3 * B * 4 * Q / (ms_batch * 1e-3) / 1e9, 1),
                         "note": "tiles of eight queries per CTA share every load (nn_scan_tile_kernel): arithmetic-bound, "
                                 "the tree is read from HBM once per tile; GBps_algorithmic counts 132 MB per query"}
+        # the same with 128 queries per launch (16 tiles: the grid is still one wave of the machine)
+        Q2 = 128
+        rng2 = np.random.RandomState(12)
+        tree.nearest_upload(np.stack([scenes.sample_state(rng2, sc) for _ in range(Q2)]))
+        tree.nearest_launch()
+        torch.cuda.synchronize()
+        flush.zero_()
+        e0.record(stream)
+        tree.nearest_launch()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_b2 = e0.elapsed_time(e1)
+        out["batch_128"] = {"queries_per_launch": Q2, "us_per_query": round(ms_b2 / Q2 * 1e3, 2),
+                            "queries_per_s": round(Q2 / ms_b2 * 1e3, 1)}
         if hasattr(tree, "nearest_k"):
             out["top_k"] = bench_nn_topk(tree, qs, flush, stream, torch, N, B)
         if hasattr(tree, "nearest_two_level"):
