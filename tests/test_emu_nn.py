@@ -36,6 +36,28 @@ def test_top_k_equals_sorted_double_scan(k):
         assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
 
 
+@pytest.mark.parametrize("k,grid_x", [(1, 7), (2, 5), (3, 9), (17, 4), (31, 2), (32, 6)])
+def test_top_k_head_bound_with_more_lists_than_k_and_fewer(k, grid_x):
+    """The last CTA bounds the answer by the k-th smallest list HEAD and reads only the lists within the slack of it: grids
+    with more lists than k (the bound is a real key) and with fewer (no bound: every list is read), sparse weights so that
+    many distances are close; every offer path of the warp lists (one-by-one insertion and sort + merge)."""
+    sc, _ = scenes.make_scene(4, seed=6)
+    rng = np.random.RandomState(100 * k + grid_x)
+    N = 2500 + 37 * grid_x
+    states = np.stack([scenes.sample_state(rng, sc) for _ in range(N)])
+    states[::7, 2::3] = np.float32(np.pi) - np.float32(1e-6)   # angles at the wrap
+    for trial in range(3):
+        q = scenes.sample_state(rng, sc)
+        if trial == 1:
+            q[2::3] = -np.float32(np.pi) + np.float32(2e-6)
+        mask = None if trial == 0 else int(rng.randint(1, 1 << sc.n_bodies))
+        w = None if trial == 2 else rng.uniform(0.0, 2.0, size=sc.n_bodies).astype(np.float32)
+        gi, gd, status = eb.nearest_k(sc, states, q, k, weights=w, mask=mask, grid_x=grid_x)
+        wi, wd = sorted_scan(sc, states, q, k, weights=w, mask=mask)
+        assert status == 0
+        assert np.array_equal(gi, wi) and np.array_equal(gd, wd), (k, grid_x, trial)
+
+
 def test_top_k_with_slice_filter_small_trees_and_ragged_sizes():
     sc, _ = scenes.make_scene(3, seed=4)
     rng = np.random.RandomState(9)
